@@ -1,0 +1,75 @@
+"""ctypes binding of libb2v.so — the C ABI declared in include/b2v.h.
+
+The library is mandatory: there is no CPU fallback. A missing or stale build raises
+ImportError-style RuntimeError at first use, loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libb2v.so"
+
+OK, ERR_ARG, ERR_CUDA, ERR_RANGE, ERR_NOCONV = 0, 1, 2, 3, 4
+I16, U8, F64 = 0, 1, 2
+MIP_MAX, MIP_MIN, MIP_MEAN = 0, 1, 2
+
+i64, i32, vp, cint = C.c_int64, C.c_int32, C.c_void_p, C.c_int
+
+# name -> (restype, argtypes). Must list every symbol of include/b2v.h (tests check).
+PROTOTYPES = {
+    "b2v_last_error": (C.c_char_p, []),
+    "b2v_version": (cint, []),
+    "b2v_launch_count": (i64, []),
+    "b2v_launch_count_reset": (None, []),
+    "b2v_copy3d_h2d": (cint, [vp, vp, i64, i64, i64, i64, i64, i64, vp]),
+    "b2v_copy3d_d2h": (cint, [vp, vp, i64, i64, i64, i64, i64, i64, vp]),
+    "b2v_threshold_i16": (cint, [vp, i64, i32, i32, vp, cint, vp]),
+    "b2v_threshold_i16_masklayout": (cint, [vp, i64, i64, i64, i32, i32, vp, cint, cint, vp]),
+    "b2v_mip_workspace_bytes": (i64, [cint, i64, i64, i64, cint, cint]),
+    "b2v_mip": (cint, [vp, cint, i64, i64, i64, cint, cint, vp, vp, vp]),
+    "b2v_minmax_workspace_bytes": (i64, [i64]),
+    "b2v_minmax_f32": (cint, [vp, cint, i64, vp, vp, vp]),
+}
+
+_lib = None
+
+
+class B2VError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension is mandatory (no CPU fallback). "
+            "Build it with `python -m invesalius3_b200._build` or __graft_entry__.build()."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = stale build
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    """Map a B2V_* status to the exception the reference boundary would raise."""
+    if rc == OK:
+        return
+    msg = load().b2v_last_error().decode("utf-8", "replace")
+    if rc == ERR_ARG:
+        raise ValueError(msg)
+    if rc == ERR_RANGE:
+        raise ValueError(msg)
+    raise B2VError(f"b2v status {rc}: {msg}")
+
+
+def call(name: str, *args):
+    fn = getattr(load(), name)
+    check(fn(*args))

@@ -1,0 +1,203 @@
+"""Device-resident API: the hot path on torch CUDA tensors.
+
+PyTorch is used for device memory, streams and (in dist.py) torch.distributed only;
+every computation is a kernel of libb2v.so reached through the C ABI (include/b2v.h).
+All functions enqueue on torch's current stream and do not synchronise unless stated.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DT = {torch.int16: _lib.I16, torch.uint8: _lib.U8, torch.float64: _lib.F64}
+_NP2T = {np.dtype(np.int16): torch.int16, np.dtype(np.uint8): torch.uint8, np.dtype(np.float64): torch.float64,
+         np.dtype(np.uint32): torch.int32, np.dtype(np.int32): torch.int32, np.dtype(np.float32): torch.float32,
+         np.dtype(np.int64): torch.int64}
+_KIND = {"max": _lib.MIP_MAX, "min": _lib.MIP_MIN, "mean": _lib.MIP_MEAN}
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("invesalius3_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _dense(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be dense C-order; pack strided views with to_device()")
+    return t
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"Invalid image type: {t.dtype}") from None
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor | None:
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device) if nbytes > 0 else None
+
+
+# ----------------------------------------------------------------------------- transfers
+def _box_pitches(a: np.ndarray):
+    """(row_pitch, plane_pitch) in bytes if `a` (3-D) is an x-contiguous box view."""
+    if a.ndim != 3 or a.size == 0:
+        return None
+    sz, sy, sx = a.strides
+    if sx != a.itemsize or sy < a.shape[2] * a.itemsize or sz <= 0 or sy <= 0:
+        return None
+    if sz % sy != 0 or sz // sy < a.shape[1]:
+        if a.shape[0] == 1:
+            return sy, sy * a.shape[1]
+        return None
+    return sy, sz
+
+
+def to_device(a: np.ndarray, device=None) -> torch.Tensor:
+    """Host array (any strides, memmap views included) -> dense device tensor.
+
+    x-contiguous 3-D box views such as `mask.matrix[1:, 1:, 1:]` are packed by the DMA
+    engine (b2v_copy3d_h2d) straight from the view; anything else is made contiguous on
+    the host first."""
+    require_cuda()
+    device = torch.device("cuda" if device is None else device)
+    tdt = _NP2T.get(a.dtype)
+    if tdt is None:
+        raise TypeError(f"unsupported dtype {a.dtype}")
+    t = torch.empty(a.shape, dtype=tdt, device=device)
+    if a.size == 0:
+        return t
+    pit = _box_pitches(a)
+    with torch.cuda.device(device):
+        if pit is not None:
+            dz, dy, dx = a.shape
+            _lib.call("b2v_copy3d_h2d", _p(t), C.c_void_p(a.ctypes.data), dz, dy, dx, a.itemsize, pit[0], pit[1],
+                      _stream())
+        else:
+            c = np.ascontiguousarray(a)
+            _lib.call("b2v_copy3d_h2d", _p(t), C.c_void_p(c.ctypes.data), 1, 1, c.size, c.itemsize,
+                      c.size * c.itemsize, c.size * c.itemsize, _stream())
+            torch.cuda.current_stream().synchronize()  # `c` may be a temporary
+    return t
+
+
+def to_host(t: torch.Tensor, out: np.ndarray) -> None:
+    """Dense device tensor -> host array `out` (written in place, any strides). Synchronises."""
+    assert tuple(t.shape) == tuple(out.shape), (t.shape, out.shape)
+    if out.size == 0:
+        return
+    if not out.flags.writeable:
+        raise ValueError("output array is read-only")
+    pit = _box_pitches(out)
+    with torch.cuda.device(t.device):
+        if pit is not None:
+            dz, dy, dx = out.shape
+            _lib.call("b2v_copy3d_d2h", C.c_void_p(out.ctypes.data), _p(t), dz, dy, dx, out.itemsize, pit[0], pit[1],
+                      _stream())
+            torch.cuda.current_stream().synchronize()
+        elif out.flags.c_contiguous:
+            _lib.call("b2v_copy3d_d2h", C.c_void_p(out.ctypes.data), _p(t), 1, 1, out.size, out.itemsize,
+                      out.size * out.itemsize, out.size * out.itemsize, _stream())
+            torch.cuda.current_stream().synchronize()
+        else:
+            tmp = np.empty(out.shape, dtype=out.dtype)
+            _lib.call("b2v_copy3d_d2h", C.c_void_p(tmp.ctypes.data), _p(t), 1, 1, tmp.size, tmp.itemsize,
+                      tmp.size * tmp.itemsize, tmp.size * tmp.itemsize, _stream())
+            torch.cuda.current_stream().synchronize()
+            out[...] = tmp
+
+
+# ----------------------------------------------------------------------------- threshold
+def _int_range(lo, hi):
+    """Inclusive bounds on an integer image: a float bound is equivalent to ceil/floor."""
+    lo = int(np.ceil(lo))
+    hi = int(np.floor(hi))
+    lo = max(lo, -(2 ** 31) + 1)
+    hi = min(hi, 2 ** 31 - 1)
+    return lo, hi
+
+
+def threshold(img: torch.Tensor, lo, hi, out: torch.Tensor | None = None,
+              preserve_markers: bool = False) -> torch.Tensor:
+    """out = 255*[lo <= img <= hi] as uint8, same shape; with preserve_markers the old
+    values 1, 2, 253, 254 of `out` survive (slice_.py:1238-1246 / :1731-1737)."""
+    _dense(img, "img")
+    if img.dtype != torch.int16:
+        raise TypeError("threshold: image must be int16")
+    if out is None:
+        if preserve_markers:
+            raise ValueError("preserve_markers needs the previous mask in `out`")
+        out = torch.empty(img.shape, dtype=torch.uint8, device=img.device)
+    _dense(out, "out")
+    if out.dtype != torch.uint8 or out.shape != img.shape:
+        raise TypeError("threshold: out must be uint8 with the image's shape")
+    lo, hi = _int_range(lo, hi)
+    with torch.cuda.device(img.device):
+        _lib.call("b2v_threshold_i16", _p(img), img.numel(), lo, hi, _p(out), int(preserve_markers), _stream())
+    return out
+
+
+def threshold_masklayout(img: torch.Tensor, lo, hi, mask_padded: torch.Tensor, preserve_markers: bool,
+                         only_dirty: bool) -> torch.Tensor:
+    """Threshold into the padded Mask layout [dz+1][dy+1][dx+1] incl. axial flags."""
+    _dense(img, "img")
+    _dense(mask_padded, "mask_padded")
+    dz, dy, dx = img.shape
+    if img.dtype != torch.int16 or mask_padded.dtype != torch.uint8:
+        raise TypeError("threshold_masklayout: int16 image and uint8 mask expected")
+    if tuple(mask_padded.shape) != (dz + 1, dy + 1, dx + 1):
+        raise ValueError("mask_padded must have shape (dz+1, dy+1, dx+1)")
+    lo, hi = _int_range(lo, hi)
+    with torch.cuda.device(img.device):
+        _lib.call("b2v_threshold_i16_masklayout", _p(img), dz, dy, dx, lo, hi, _p(mask_padded),
+                  int(preserve_markers), int(only_dirty), _stream())
+    return mask_padded
+
+
+# ----------------------------------------------------------------------------- projections
+def mip(img: torch.Tensor, axis: int, kind: str = "max", out: torch.Tensor | None = None) -> torch.Tensor:
+    """MaxIP / MinIP / MeanIP == tmp_array.max/min/mean(axis) (slice_.py:881-886)."""
+    _dense(img, "img")
+    if img.dim() != 3:
+        raise ValueError("mip: 3-D volume expected")
+    code = dtype_code(img)
+    k = _KIND[kind]
+    dz, dy, dx = img.shape
+    oshape = [(dy, dx), (dz, dx), (dz, dy)][axis]
+    odt = torch.float64 if kind == "mean" else img.dtype
+    if out is None:
+        out = torch.empty(oshape, dtype=odt, device=img.device)
+    _dense(out, "out")
+    if tuple(out.shape) != oshape or out.dtype != odt:
+        raise TypeError("mip: bad output shape/dtype")
+    lib = _lib.load()
+    ws = _workspace(lib.b2v_mip_workspace_bytes(code, dz, dy, dx, axis, k), img.device)
+    with torch.cuda.device(img.device):
+        _lib.call("b2v_mip", _p(img), code, dz, dy, dx, axis, k, _p(out), _p(ws), _stream())
+    return out
+
+
+def minmax(img: torch.Tensor) -> torch.Tensor:
+    """float32 [min, max] of the whole buffer, left on the device (mips.rs:113-122)."""
+    _dense(img, "img")
+    code = dtype_code(img)
+    lib = _lib.load()
+    ws = _workspace(lib.b2v_minmax_workspace_bytes(img.numel()), img.device)
+    out = torch.empty(2, dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.call("b2v_minmax_f32", _p(img), code, img.numel(), _p(out), _p(ws), _stream())
+    return out
