@@ -88,6 +88,44 @@ int b2v_mip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int 
 int64_t b2v_minmax_workspace_bytes(int64_t n);
 int b2v_minmax_f32(const void* img, int dtype, int64_t n, float* minmax_out, void* workspace, void* stream);
 
+/* ---- seeded flood fill / region grow -------------------------------------------
+ * invesalius_rs.floodfill_threshold(data, seeds, t0, t1, fill, strct, out)
+ *   invesalius_rs/__init__.py:21-40 -> src/floodfill_py.rs:137-185 -> src/floodfill.rs:96-166
+ * data: dense [dz][dy][dx] of dtype code `dtype`; out: uint8, same shape, read-write.
+ * seeds_host: HOST array of nseeds (x, y, z) triples (int64). A seed is used only if
+ * t0 <= data[seed] <= t1. Voxels of `out` already equal to `fill` are walls. Result: every
+ * voxel reachable from the valid seeds gets out = fill; everything else is untouched.
+ * strct_host: HOST uint8 [odz][ody][odx], each dim <= 3; offset of entry (kk,jj,ii) is
+ * (kk - odz/2, jj - ody/2, ii - odx/2) as in floodfill.rs:110-112.
+ * A seed outside the volume returns B2V_ERR_RANGE (the reference panics).
+ * SYNCHRONISES the stream (round control reads one flag per batch of rounds).
+ * rounds_out (optional, host): number of flood rounds launched.
+ * Algorithmic bytes: 4 B/voxel (int16 data 2 + out read 1 + out write 1). */
+int64_t b2v_floodfill_workspace_bytes(int64_t dz, int64_t dy, int64_t dx, int64_t nseeds);
+int b2v_floodfill_threshold(const void* data, int dtype, int64_t dz, int64_t dy, int64_t dx,
+                            const int64_t* seeds_host, int64_t nseeds, double t0, double t1, uint8_t fill,
+                            const uint8_t* strct_host, int64_t odz, int64_t ody, int64_t odx, uint8_t* out,
+                            void* workspace, void* stream, int* rounds_out);
+/* invesalius_rs.floodfill_threshold_inplace(data, seeds, t0, t1, fill, strct)
+ *   __init__.py:43-54 -> floodfill_py.rs:187-231 -> floodfill.rs:168-237
+ * Same walk, but `data` is both the tested and the written array (visited <=> data == fill). */
+int b2v_floodfill_threshold_inplace(void* data, int dtype, int64_t dz, int64_t dy, int64_t dx,
+                                    const int64_t* seeds_host, int64_t nseeds, double t0, double t1, double fill,
+                                    const uint8_t* strct_host, int64_t odz, int64_t ody, int64_t odx,
+                                    void* workspace, void* stream, int* rounds_out);
+/* invesalius_rs.floodfill(data, i, j, k, v, fill, out): floodfill_py.rs:87-135 -> floodfill.rs:5-49.
+ * 6-connected walk over data == v starting at (x=i, y=j, z=k); the seed is marked
+ * unconditionally. */
+int b2v_floodfill_equal(const void* data, int dtype, int64_t dz, int64_t dy, int64_t dx, int64_t i, int64_t j,
+                        int64_t k, double v, uint8_t fill, uint8_t* out, void* workspace, void* stream,
+                        int* rounds_out);
+/* invesalius_rs.fill_holes_automatically(mask, labels, nlabels, max_size) -> bool
+ *   floodfill_py.rs:233-249 -> floodfill.rs:51-94. mask uint8 [n] rw, labels uint32 [n].
+ * modified_out (host) receives the bool. SYNCHRONISES the stream. 6 B/voxel. */
+int64_t b2v_fill_holes_workspace_bytes(uint32_t nlabels);
+int b2v_fill_holes(uint8_t* mask, const uint32_t* labels, int64_t n, uint32_t nlabels, uint32_t max_size,
+                   void* workspace, void* stream, int* modified_out);
+
 #ifdef __cplusplus
 }
 #endif

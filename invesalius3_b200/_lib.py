@@ -16,6 +16,7 @@ I16, U8, F64 = 0, 1, 2
 MIP_MAX, MIP_MIN, MIP_MEAN = 0, 1, 2
 
 i64, i32, vp, cint = C.c_int64, C.c_int32, C.c_void_p, C.c_int
+dbl, u8, u32, f32 = C.c_double, C.c_uint8, C.c_uint32, C.c_float
 
 # name -> (restype, argtypes). Must list every symbol of include/b2v.h (tests check).
 PROTOTYPES = {
@@ -31,6 +32,14 @@ PROTOTYPES = {
     "b2v_mip": (cint, [vp, cint, i64, i64, i64, cint, cint, vp, vp, vp]),
     "b2v_minmax_workspace_bytes": (i64, [i64]),
     "b2v_minmax_f32": (cint, [vp, cint, i64, vp, vp, vp]),
+    "b2v_floodfill_workspace_bytes": (i64, [i64, i64, i64, i64]),
+    "b2v_floodfill_threshold": (cint, [vp, cint, i64, i64, i64, vp, i64, dbl, dbl, u8, vp, i64, i64, i64, vp, vp, vp,
+                                       C.POINTER(cint)]),
+    "b2v_floodfill_threshold_inplace": (cint, [vp, cint, i64, i64, i64, vp, i64, dbl, dbl, dbl, vp, i64, i64, i64, vp,
+                                               vp, C.POINTER(cint)]),
+    "b2v_floodfill_equal": (cint, [vp, cint, i64, i64, i64, i64, i64, i64, dbl, u8, vp, vp, vp, C.POINTER(cint)]),
+    "b2v_fill_holes_workspace_bytes": (i64, [u32]),
+    "b2v_fill_holes": (cint, [vp, vp, i64, u32, u32, vp, vp, C.POINTER(cint)]),
 }
 
 _lib = None

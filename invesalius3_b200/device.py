@@ -201,3 +201,88 @@ def minmax(img: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(img.device):
         _lib.call("b2v_minmax_f32", _p(img), code, img.numel(), _p(out), _p(ws), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------- flood fill
+def _seed_array(seeds) -> np.ndarray:
+    s = np.array([tuple(int(c) for c in p) for p in seeds], dtype=np.int64).reshape(-1, 3)
+    if (s < 0).any():
+        raise OverflowError("can't convert negative int to unsigned")
+    return np.ascontiguousarray(s)
+
+
+def _strct_array(strct) -> np.ndarray:
+    st = np.ascontiguousarray(strct, dtype=np.uint8)
+    if st.ndim != 3:
+        raise TypeError("strct must be a 3-D array")
+    return st
+
+
+def floodfill_threshold(data: torch.Tensor, seeds, t0, t1, fill: int, strct, out: torch.Tensor) -> int:
+    """Region grow from `seeds` ((x, y, z) triples) through voxels with t0 <= data <= t1 that
+    are not already `fill` in `out`; reached voxels get out = fill (floodfill.rs:96-166).
+    Returns the number of flood rounds. Synchronises the stream."""
+    _dense(data, "data"); _dense(out, "out")
+    if out.dtype != torch.uint8 or out.shape != data.shape or data.dim() != 3:
+        raise TypeError("floodfill_threshold: out must be uint8 with data's 3-D shape")
+    code = dtype_code(data)
+    s, st = _seed_array(seeds), _strct_array(strct)
+    dz, dy, dx = data.shape
+    lib = _lib.load()
+    ws = _workspace(lib.b2v_floodfill_workspace_bytes(dz, dy, dx, len(s)), data.device)
+    rounds = C.c_int(0)
+    with torch.cuda.device(data.device):
+        _lib.call("b2v_floodfill_threshold", _p(data), code, dz, dy, dx, C.c_void_p(s.ctypes.data), len(s),
+                  float(t0), float(t1), int(fill), C.c_void_p(st.ctypes.data), *st.shape, _p(out), _p(ws), _stream(),
+                  C.byref(rounds))
+    return rounds.value
+
+
+def floodfill_threshold_inplace(data: torch.Tensor, seeds, t0, t1, fill, strct) -> int:
+    """floodfill.rs:168-237: as floodfill_threshold, reading and writing `data` itself."""
+    _dense(data, "data")
+    if data.dim() != 3:
+        raise TypeError("floodfill_threshold_inplace: 3-D volume expected")
+    code = dtype_code(data)
+    s, st = _seed_array(seeds), _strct_array(strct)
+    dz, dy, dx = data.shape
+    lib = _lib.load()
+    ws = _workspace(lib.b2v_floodfill_workspace_bytes(dz, dy, dx, len(s)), data.device)
+    rounds = C.c_int(0)
+    with torch.cuda.device(data.device):
+        _lib.call("b2v_floodfill_threshold_inplace", _p(data), code, dz, dy, dx, C.c_void_p(s.ctypes.data), len(s),
+                  float(t0), float(t1), float(fill), C.c_void_p(st.ctypes.data), *st.shape, _p(ws), _stream(),
+                  C.byref(rounds))
+    return rounds.value
+
+
+def floodfill(data: torch.Tensor, i: int, j: int, k: int, v, fill: int, out: torch.Tensor) -> int:
+    """floodfill.rs:5-49: 6-connected fill of data == v from (x=i, y=j, z=k); seed always marked."""
+    _dense(data, "data"); _dense(out, "out")
+    if out.dtype != torch.uint8 or out.shape != data.shape or data.dim() != 3:
+        raise TypeError("floodfill: out must be uint8 with data's 3-D shape")
+    code = dtype_code(data)
+    dz, dy, dx = data.shape
+    lib = _lib.load()
+    ws = _workspace(lib.b2v_floodfill_workspace_bytes(dz, dy, dx, 1), data.device)
+    rounds = C.c_int(0)
+    with torch.cuda.device(data.device):
+        _lib.call("b2v_floodfill_equal", _p(data), code, dz, dy, dx, int(i), int(j), int(k), float(v), int(fill),
+                  _p(out), _p(ws), _stream(), C.byref(rounds))
+    return rounds.value
+
+
+def fill_holes_automatically(mask: torch.Tensor, labels: torch.Tensor, nlabels: int, max_size: int) -> bool:
+    """floodfill.rs:51-94. labels: int32 tensor holding the uint32 label image."""
+    _dense(mask, "mask"); _dense(labels, "labels")
+    if mask.dtype != torch.uint8:
+        raise TypeError("Invalid mask type")
+    if labels.dtype != torch.int32 or labels.shape != mask.shape:
+        raise TypeError("labels must be a uint32 (int32-typed tensor) image of the mask's shape")
+    lib = _lib.load()
+    ws = _workspace(lib.b2v_fill_holes_workspace_bytes(int(nlabels)), mask.device)
+    mod = C.c_int(0)
+    with torch.cuda.device(mask.device):
+        _lib.call("b2v_fill_holes", _p(mask), _p(labels), mask.numel(), int(nlabels), int(max_size), _p(ws),
+                  _stream(), C.byref(mod))
+    return bool(mod.value)

@@ -1,0 +1,147 @@
+"""Mirror of the reference's native package `invesalius_rs` (numpy in, numpy out).
+
+Same names, argument order, in-place output convention and error behaviour as
+`invesalius_rs/__init__.py:11-111` + the PyO3 layer (`src/*_py.rs`), so the callers in
+`invesalius/data/{slice_,styles,mask}.py` can bind this module under the aliases they
+already use (`import invesalius_rs as floodfill / mips`), see INTEGRATION.md.
+
+Every function packs its (possibly strided, memmap-backed) arguments into dense device
+tensors, runs the sm_100a kernels of libb2v.so and writes results back into the
+caller's arrays. There is no CPU fallback.
+
+Error mapping (reference -> here):
+  PyO3 extraction TypeError / OverflowError  -> same exception types
+  "Invalid image or output type" TypeError   -> same
+  Rust panic (out-of-bounds seed, unrepresentable MIDA result, label > nlabels)
+      pyo3_runtime.PanicException             -> ValueError (IndexError for seeds)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import device as dev
+from ._lib import B2VError  # noqa: F401
+
+_SUFFIX = {np.dtype(np.int16): "i16", np.dtype(np.uint8): "u8", np.dtype(np.float64): "f64"}
+_RANGE = {"i16": (-32768, 32767), "u8": (0, 255)}
+
+
+def _suffix(a, what="image"):
+    if not isinstance(a, np.ndarray):
+        raise TypeError(f"{what} must be a numpy array")
+    try:
+        return _SUFFIX[a.dtype]
+    except KeyError:
+        raise TypeError(f"Invalid {what} type: {a.dtype}") from None
+
+
+def _extract(v, suf):
+    """PyO3 `extract::<T>()`: integers must fit T; a float is only accepted for f64."""
+    if suf == "f64":
+        return float(v)
+    if isinstance(v, (float, np.floating)):
+        raise TypeError("'float' object cannot be interpreted as an integer")
+    v = int(v)
+    lo, hi = _RANGE[suf]
+    if not lo <= v <= hi:
+        raise OverflowError("out of range integral type conversion attempted")
+    return v
+
+
+def _need3(a, name):
+    if a.ndim != 3:
+        raise TypeError(f"{name} must be 3-dimensional")
+
+
+def _seed_check(exc):
+    if "outside the volume" in str(exc):
+        raise IndexError(str(exc)) from None
+    raise exc
+
+
+# ------------------------------------------------------------------------------- flood fill
+def floodfill_threshold(data, seeds, t0, t1, fill, strct, out):
+    """invesalius_rs/__init__.py:21-40."""
+    suf = _suffix(data, "data")
+    _need3(data, "data")
+    if not isinstance(out, np.ndarray) or out.dtype != np.uint8 or out.ndim != 3:
+        raise TypeError("Invalid output type")
+    if out.shape != data.shape:
+        raise ValueError("data and out shapes differ")
+    tuple_seeds = [tuple(s) for s in seeds]
+    strct_u8 = np.ascontiguousarray(strct, dtype=np.uint8)
+    if suf == "i16":
+        t0, t1, fill = int(t0), int(t1), int(fill)
+    elif suf == "f64":
+        t0, t1, fill = float(t0), float(t1), float(fill)
+    t0, t1 = _extract(t0, suf), _extract(t1, suf)
+    fill = _extract(fill, "u8")
+    if not out.flags.writeable:
+        raise ValueError("out is read-only")
+    aliased = np.shares_memory(data, out)
+    d = dev.to_device(data)
+    o = d if (aliased and suf == "u8") else dev.to_device(out)
+    try:
+        if aliased and suf == "u8":
+            # data is out (styles.py:2932-2940): degenerates to the in-place walk
+            dev.floodfill_threshold_inplace(d, tuple_seeds, t0, t1, fill, strct_u8)
+        else:
+            dev.floodfill_threshold(d, tuple_seeds, t0, t1, fill, strct_u8, o)
+    except ValueError as e:
+        _seed_check(e)
+    dev.to_host(o, out)
+
+
+def floodfill_threshold_inplace(data, seeds, t0, t1, fill, strct):
+    """invesalius_rs/__init__.py:43-54."""
+    suf = _suffix(data, "data")
+    _need3(data, "data")
+    tuple_seeds = [tuple(s) for s in seeds]
+    strct_u8 = np.ascontiguousarray(strct, dtype=np.uint8)
+    t0, t1, fill = _extract(t0, suf), _extract(t1, suf), _extract(fill, suf)
+    if not data.flags.writeable:
+        raise ValueError("data is read-only")
+    d = dev.to_device(data)
+    try:
+        dev.floodfill_threshold_inplace(d, tuple_seeds, t0, t1, fill, strct_u8)
+    except ValueError as e:
+        _seed_check(e)
+    dev.to_host(d, data)
+
+
+def floodfill(data, i, j, k, v, fill, out):
+    """floodfill_py.rs:87-135 (exported as-is by __init__.py:11)."""
+    suf = _suffix(data, "data")
+    _need3(data, "data")
+    if not isinstance(out, np.ndarray) or out.dtype != np.uint8 or out.shape != data.shape:
+        raise TypeError("Invalid output type")
+    v, fill = _extract(v, suf), _extract(fill, "u8")
+    for c in (i, j, k):
+        if int(c) < 0:
+            raise OverflowError("can't convert negative int to unsigned")
+    d, o = dev.to_device(data), dev.to_device(out)
+    try:
+        dev.floodfill(d, int(i), int(j), int(k), v, fill, o)
+    except ValueError as e:
+        _seed_check(e)
+    dev.to_host(o, out)
+
+
+def fill_holes_automatically(mask, labels, nlabels, max_size) -> bool:
+    """floodfill_py.rs:233-249; caller invesalius/data/mask.py:519-562."""
+    if not isinstance(mask, np.ndarray) or mask.dtype != np.uint8:
+        raise TypeError("Invalid mask type")
+    if not isinstance(labels, np.ndarray) or labels.dtype != np.uint32:
+        raise TypeError("labels must be a uint32 array")
+    _need3(mask, "mask")
+    if labels.shape != mask.shape:
+        raise ValueError("mask and labels shapes differ")
+    nlabels, max_size = int(nlabels), int(max_size)
+    if not (0 <= nlabels < 2 ** 32 and 0 <= max_size < 2 ** 32):
+        raise OverflowError("out of range integral type conversion attempted")
+    m = dev.to_device(mask)
+    lab = dev.to_device(labels)
+    modified = dev.fill_holes_automatically(m, lab, nlabels, max_size)
+    if modified:
+        dev.to_host(m, mask)
+    return modified

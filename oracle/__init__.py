@@ -126,9 +126,15 @@ def floodfill_threshold(data, seeds, t0, t1, fill, strct, out):
     elif suf == "f64":
         t0, t1, fill = float(t0), float(t1), float(fill)
     t0, t1 = _extract(t0, suf), _extract(t1, suf)
-    if isinstance(fill, float):
-        raise TypeError("'float' object cannot be interpreted as an integer")
+    # NB: for float64 data the reference wrapper has just turned `fill` into a float, which
+    # the PyO3 signature `fill: u8` then rejects -> the f64 branch always raises TypeError.
     fill = _extract(fill, "u8")
+    _floodfill_threshold_core(data, seeds, t0, t1, fill, strct_u8, out)
+
+
+def _floodfill_threshold_core(data, seeds, t0, t1, fill, strct_u8, out):
+    """generic_floodfill_threshold itself (floodfill.rs:96-166), past the Python/PyO3 coercions."""
+    suf = _suffix(data)
     s = _seeds(seeds)
     fn = getattr(lib(), f"orc_floodfill_threshold_{suf}")
     ct = _CT[suf]
@@ -246,3 +252,23 @@ def fast_countour_mip(image, n, axis, wl, ww, tmip, out):
 
 def _mida_f64_f64(image, axis, wl, ww, out):
     raise NotImplementedError("f64 contour-MIDA is outside the GPU core's dtype set")
+
+
+# --------------------------------------------------------------------------- marching cubes
+def marching_cubes(volume, iso, spacing=(1.0, 1.0, 1.0), origin_index=(0, 0, 0), flip_y=True):
+    """Canonical marching cubes (parity unpinned: stands in for vtkContourFilter,
+    surface_process.py:172-186). volume: dense int16/uint8 [nz][ny][nx];
+    spacing = (sx, sy, sz); origin_index = (ox, oy, oz) added to the (x, y, z) indices.
+    Returns (vertices float32 [V,3], triangles int64 [T,3])."""
+    v = np.ascontiguousarray(volume)
+    dt = {np.dtype(np.int16): 0, np.dtype(np.uint8): 1}[v.dtype]
+    nz, ny, nx = v.shape
+    nv, nt = C.c_int64(0), C.c_int64(0)
+    args = [_ptr(v), dt, C.c_int64(nz), C.c_int64(ny), C.c_int64(nx), C.c_double(iso), C.c_float(spacing[0]),
+            C.c_float(spacing[1]), C.c_float(spacing[2]), C.c_int64(origin_index[0]), C.c_int64(origin_index[1]),
+            C.c_int64(origin_index[2]), int(bool(flip_y))]
+    lib().orc_marching_cubes(*args, None, None, C.byref(nv), C.byref(nt))
+    verts = np.zeros((nv.value, 3), np.float32)
+    tris = np.zeros((nt.value, 3), np.int64)
+    lib().orc_marching_cubes(*args, _ptr(verts), _ptr(tris), C.byref(nv), C.byref(nt))
+    return verts, tris

@@ -387,3 +387,99 @@ DEF_LMIP(orc_lmip_f64, double)
 DEF_FCM(orc_fcm_i16, int16_t, WRAP_I16, cast_f32_i16)
 DEF_FCM(orc_fcm_u8, uint8_t, WRAP_U8, cast_f32_u8)
 DEF_FCM(orc_fcm_f64, double, DIFF_F64, cast_f32_f64)
+
+/* ------------------------------------------------------------------------- */
+/* marching cubes — canonical restatement of the per-piece contour step of      */
+/* invesalius/data/surface_process.py:71-201 (vtkContourFilter on a padded,     */
+/* y-flipped vtkImageData; geometry from converters.py:34-101).                 */
+/*                                                                              */
+/* PARITY UNPINNED: VTK is neither installed nor vendored and the reference has */
+/* no golden mesh. The canonical order defined here (and in DESIGN.md) is:      */
+/*   inside(p)   <=> (double)S[p] >= iso                                        */
+/*   vertices    voxels in raveled order; per voxel the crossing edges towards   */
+/*               +x, +y, +z in that order; t = (iso - s0)/(s1 - s0) in float32   */
+/*   position    x = ((i + ox) [+ t]) * sx ; y = -(((j + oy) [+ t]) * sy) when   */
+/*               flip_y ; z = ((k + oz) [+ t]) * sz   (all float32, no FMA)       */
+/*   triangles   cells in raveled order, table order within a cell (the table    */
+/*               is generated by tools/gen_mc_tables.py); winding reversed when  */
+/*               flip_y so normals keep pointing from inside to outside          */
+/* ------------------------------------------------------------------------- */
+#include "../invesalius3_b200/csrc/mc_tables.h"
+
+static inline double mc_val(const void* vol, int dtype, int64_t i) {
+  return dtype == 0 ? (double)((const int16_t*)vol)[i] : (double)((const uint8_t*)vol)[i];
+}
+
+/* Pass `verts`/`tris` NULL to only count. Returns 0; counts in *nv, *nt. */
+int orc_marching_cubes(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso, float sx, float sy,
+                       float sz, int64_t ox, int64_t oy, int64_t oz, int flip_y, float* verts, int64_t* tris,
+                       int64_t* nv_out, int64_t* nt_out) {
+  int64_t n = nz * ny * nx;
+  int64_t* voff = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1));
+  uint8_t* in = (uint8_t*)malloc((size_t)n);
+  for (int64_t i = 0; i < n; ++i) in[i] = mc_val(vol, dtype, i) >= iso;
+  int64_t nv = 0;
+  const int64_t step[3] = {1, nx, nx * ny};
+  for (int64_t z = 0; z < nz; ++z)
+    for (int64_t y = 0; y < ny; ++y)
+      for (int64_t x = 0; x < nx; ++x) {
+        int64_t p = (z * ny + y) * nx + x;
+        voff[p] = nv;
+        int64_t idx[3] = {x, y, z};
+        const int64_t lim[3] = {nx, ny, nz};
+        for (int a = 0; a < 3; ++a) {
+          if (idx[a] + 1 >= lim[a]) continue;
+          int64_t q = p + step[a];
+          if (in[p] == in[q]) continue;
+          if (verts) {
+            float s0 = (float)mc_val(vol, dtype, p), s1 = (float)mc_val(vol, dtype, q);
+            float t = ((float)iso - s0) / (s1 - s0);
+            float fx = (float)(x + ox), fy = (float)(y + oy), fz = (float)(z + oz);
+            if (a == 0) fx = fx + t; else if (a == 1) fy = fy + t; else fz = fz + t;
+            float px = fx * sx, py = fy * sy, pz = fz * sz;
+            if (flip_y) py = -py;
+            verts[3 * nv] = px; verts[3 * nv + 1] = py; verts[3 * nv + 2] = pz;
+          }
+          ++nv;
+        }
+      }
+  voff[n] = nv;
+  int64_t nt = 0;
+  for (int64_t z = 0; z + 1 < nz; ++z)
+    for (int64_t y = 0; y + 1 < ny; ++y)
+      for (int64_t x = 0; x + 1 < nx; ++x) {
+        int64_t p = (z * ny + y) * nx + x;
+        int c = 0;
+        for (int k = 0; k < 8; ++k) c |= in[p + (k & 1) + ((k >> 1) & 1) * nx + ((k >> 2) & 1) * nx * ny] << k;
+        int ntri = B2V_MC_NTRI[c];
+        for (int t = 0; t < ntri; ++t) {
+          if (tris) {
+            int64_t id[3];
+            for (int m = 0; m < 3; ++m) {
+              int e = B2V_MC_TRI[c][3 * t + m];
+              int a = e >> 2, j = e & 3, cu = j & 1, cv = j >> 1;
+              int u = a == 0 ? 1 : 0, v = a == 2 ? 1 : 2;
+              int64_t off[3] = {0, 0, 0};
+              off[u] = cu; off[v] = cv;
+              int64_t q = p + off[0] + off[1] * nx + off[2] * nx * ny;
+              /* rank of axis a among the owner's crossing edges (x, y, z order) */
+              int64_t qi[3] = {x + off[0], y + off[1], z + off[2]};
+              const int64_t lim[3] = {nx, ny, nz};
+              int rank = 0;
+              for (int b = 0; b < a; ++b)
+                if (qi[b] + 1 < lim[b] && in[q] != in[q + step[b]]) ++rank;
+              id[m] = voff[q] + rank;
+            }
+            tris[3 * nt] = id[0];
+            tris[3 * nt + 1] = flip_y ? id[2] : id[1];
+            tris[3 * nt + 2] = flip_y ? id[1] : id[2];
+          }
+          ++nt;
+        }
+      }
+  free(voff);
+  free(in);
+  *nv_out = nv;
+  *nt_out = nt;
+  return 0;
+}
