@@ -126,6 +126,27 @@ int64_t b2v_fill_holes_workspace_bytes(uint32_t nlabels);
 int b2v_fill_holes(uint8_t* mask, const uint32_t* labels, int64_t n, uint32_t nlabels, uint32_t max_size,
                    void* workspace, void* stream, int* modified_out);
 
+/* ---- marching cubes ---------------------------------------------------------------
+ * Replaces the contour step of create_surface_piece, invesalius/data/surface_process.py:
+ * 156-186 (vtkImageFlip about the origin + vtkContourFilter at iso 127 on the uint8 mask,
+ * or at tmin / tmax on the int16 image); geometry as converters.to_vtk, converters.py:34-101.
+ * vol: dense [nz][ny][nx] uint8 or int16. inside(p) <=> vol[p] >= iso.
+ * Two calls sharing one caller-owned workspace:
+ *   b2v_mc_count  classifies, scans and returns the vertex / triangle counts (host);
+ *                 SYNCHRONISES the stream.
+ *   b2v_mc_emit   writes verts float32 [V][3] and tris int32 [T][3] (shared vertices).
+ * Vertex (i + ox [+t], j + oy [+t], k + oz [+t]) * (sx, sy, sz), y negated when flip_y
+ * (and the winding reversed, so normals keep pointing from inside to outside);
+ * t = (iso - s0) / (s1 - s0) in float32. Canonical ordering: see DESIGN.md.
+ * Algorithmic bytes: 1 B/voxel (uint8) or 2 B/voxel (int16) + 12 B per vertex + 12 B per
+ * triangle. */
+int64_t b2v_mc_workspace_bytes(int64_t nz, int64_t ny, int64_t nx);
+int b2v_mc_count(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso, void* workspace,
+                 void* stream, int64_t* nverts_host, int64_t* ntris_host);
+int b2v_mc_emit(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso, const void* workspace,
+                float sx, float sy, float sz, int32_t ox, int32_t oy, int32_t oz, int flip_y, float* verts,
+                int32_t* tris, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

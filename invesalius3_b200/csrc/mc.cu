@@ -1,0 +1,525 @@
+// Marching cubes: classify -> scan -> emit, on a bit-packed inside volume.
+// Replaces the per-piece vtkContourFilter step of invesalius/data/surface_process.py:71-201
+// (geometry: converters.py:34-101). Canonical output order is defined in DESIGN.md and
+// restated by the CPU checker; VTK itself is not available, so parity to VTK is unpinned.
+//
+//   1. bits   (HBM-bound, the only pass over the volume: 1 B/voxel uint8, 2 B/voxel int16):
+//             inside(p) = S[p] >= iso packed 32 voxels per word along x.
+//   2. count  (on bits, L2 resident): per word the crossing masks towards +x/+y/+z, the
+//             number of owned vertices (popcounts) and of triangles (table lookups over
+//             the active cells only).
+//   3. scan   exclusive prefix sums of both counts (block sums -> one block -> apply).
+//   4. emit   one warp per word with work: lane = voxel (vertices) and lane = cell
+//             (triangles); a vertex id is  voff[owner word] + popcounts below the owner bit.
+#include "b2v_common.cuh"
+#define B2V_MC_QUAL __device__
+#include "mc_tables.h"
+
+namespace {
+
+struct McGeom {
+  int64_t nz, ny, nx;
+  int wx;           // words per row
+  int64_t nwords;
+};
+
+McGeom make_geom(int64_t nz, int64_t ny, int64_t nx) {
+  McGeom g;
+  g.nz = nz; g.ny = ny; g.nx = nx;
+  g.wx = (int)ceil_div64(nx, 32);
+  g.nwords = nz * ny * g.wx;
+  return g;
+}
+
+constexpr int kScanBlock = 256;
+
+struct McWs {
+  uint32_t* bits;    // [nwords]
+  uint4* info;       // [nwords] (cx, cy, cz, vertex offset)
+  uint32_t* toff;    // [nwords] triangle offset
+  uint32_t* bsum_v;  // [nblocks]
+  uint32_t* bsum_t;  // [nblocks]
+  unsigned long long* totals;  // [2] V, T
+  int64_t nblocks;
+  int64_t bytes;
+};
+
+McWs carve(void* base, const McGeom& g) {
+  McWs w;
+  auto align = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
+  char* p = (char*)base;
+  int64_t off = 0;
+  w.nblocks = ceil_div64(g.nwords, kScanBlock);
+  w.bits = (uint32_t*)(p + off); off += align(g.nwords * 4 + 4);
+  w.info = (uint4*)(p + off); off += align(g.nwords * 16);
+  w.toff = (uint32_t*)(p + off); off += align(g.nwords * 4);
+  w.bsum_v = (uint32_t*)(p + off); off += align(w.nblocks * 4);
+  w.bsum_t = (uint32_t*)(p + off); off += align(w.nblocks * 4);
+  w.totals = (unsigned long long*)(p + off); off += 256;
+  w.bytes = off;
+  return w;
+}
+
+// ---- 1. inside bits ---------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_mc_bits(const T* __restrict__ vol, McGeom g, int ithr,
+                                                 uint32_t* __restrict__ bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t wi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < g.nwords; wi += nwarps) {
+    int64_t row = wi / g.wx;
+    int64_t x = (wi - row * g.wx) * 32 + lane;
+    bool in = x < g.nx && (int)vol[row * g.nx + x] >= ithr;
+    uint32_t b = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) bits[wi] = b;
+  }
+}
+
+// uint8, nx % 16 == 0, aligned: one 128-bit load = 16 voxels per lane, 2 lanes per word
+__global__ void __launch_bounds__(256) k_mc_bits_u8_vec(const uint8_t* __restrict__ vol, McGeom g, int ithr,
+                                                        uint32_t* __restrict__ bits) {
+  const int gx = g.wx * 2;  // 16-voxel groups per row (padded)
+  const int64_t ngroups = g.nz * g.ny * gx;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x; g0 < ngroups; g0 += stride) {
+    int64_t gi = g0 + threadIdx.x;
+    uint32_t b = 0;
+    int64_t row = 0;
+    int q = 0;
+    if (gi < ngroups) {
+      row = gi / gx;
+      q = (int)(gi - row * gx);
+      int64_t x = (int64_t)q * 16;
+      if (x < g.nx) {
+        uint4 v = ld_stream((const uint4*)(vol + row * g.nx + x));
+        uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) b |= (uint32_t)((int)((wv[k >> 2] >> (8 * (k & 3))) & 0xff) >= ithr) << k;
+      }
+    }
+    uint32_t word = b << (16 * (lane & 1));
+    word |= __shfl_xor_sync(0xffffffffu, word, 1);
+    if ((lane & 1) == 0 && gi < ngroups) bits[row * g.wx + (q >> 1)] = word;
+  }
+}
+
+// int16, nx % 8 == 0, aligned: 8 voxels per lane, 4 lanes per word
+__global__ void __launch_bounds__(256) k_mc_bits_i16_vec(const int16_t* __restrict__ vol, McGeom g, int ithr,
+                                                         uint32_t* __restrict__ bits) {
+  const int gx = g.wx * 4;
+  const int64_t ngroups = g.nz * g.ny * gx;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x; g0 < ngroups; g0 += stride) {
+    int64_t gi = g0 + threadIdx.x;
+    uint32_t b = 0;
+    int64_t row = 0;
+    int q = 0;
+    if (gi < ngroups) {
+      row = gi / gx;
+      q = (int)(gi - row * gx);
+      int64_t x = (int64_t)q * 8;
+      if (x < g.nx) {
+        int4 v = ld_stream((const int4*)(vol + row * g.nx + x));
+        int vv[8] = {(int16_t)(v.x & 0xffff), v.x >> 16, (int16_t)(v.y & 0xffff), v.y >> 16,
+                     (int16_t)(v.z & 0xffff), v.z >> 16, (int16_t)(v.w & 0xffff), v.w >> 16};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b |= (uint32_t)(vv[k] >= ithr) << k;
+      }
+    }
+    uint32_t word = b << (8 * (lane & 3));
+    word |= __shfl_xor_sync(0xffffffffu, word, 1);
+    word |= __shfl_xor_sync(0xffffffffu, word, 2);
+    if ((lane & 3) == 0 && gi < ngroups) bits[row * g.wx + (q >> 2)] = word;
+  }
+}
+
+// ---- 2. count -------------------------------------------------------------------------------
+struct Rows {       // the four bit rows a cell row touches, word w and bit 0 of word w+1
+  uint32_t i00, i01, i10, i11;  // [cz][cy]
+  uint32_t n00, n01, n10, n11;  // next word in x (0 past the row end)
+};
+
+__device__ __forceinline__ Rows load_rows(const uint32_t* __restrict__ bits, const McGeom& g, int64_t z, int64_t y,
+                                          int w) {
+  Rows r;
+  const bool hy = y + 1 < g.ny, hz = z + 1 < g.nz, hn = w + 1 < g.wx;
+  const int64_t b00 = (z * g.ny + y) * g.wx + w;
+  const int64_t b01 = b00 + g.wx, b10 = b00 + (int64_t)g.ny * g.wx, b11 = b10 + g.wx;
+  r.i00 = __ldg(bits + b00);
+  r.i01 = hy ? __ldg(bits + b01) : 0u;
+  r.i10 = hz ? __ldg(bits + b10) : 0u;
+  r.i11 = (hy && hz) ? __ldg(bits + b11) : 0u;
+  r.n00 = hn ? __ldg(bits + b00 + 1) : 0u;
+  r.n01 = (hn && hy) ? __ldg(bits + b01 + 1) : 0u;
+  r.n10 = (hn && hz) ? __ldg(bits + b10 + 1) : 0u;
+  r.n11 = (hn && hy && hz) ? __ldg(bits + b11 + 1) : 0u;
+  return r;
+}
+
+// bit i of the result = bit i+1 of the 64-bit (hi:lo)
+__device__ __forceinline__ uint32_t shift_in(uint32_t lo, uint32_t hi) { return (lo >> 1) | (hi << 31); }
+
+// bits i with x = 32 w + i and x + 1 < nx
+__device__ __forceinline__ uint32_t valid_x1(const McGeom& g, int w) {
+  int64_t rem = g.nx - 1 - (int64_t)w * 32;  // number of valid bits
+  return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+}
+
+__device__ __forceinline__ int cell_case(const Rows& r, int i) {
+  uint32_t a = __funnelshift_r(r.i00, r.n00, i) & 3u;
+  uint32_t b = __funnelshift_r(r.i01, r.n01, i) & 3u;
+  uint32_t c = __funnelshift_r(r.i10, r.n10, i) & 3u;
+  uint32_t d = __funnelshift_r(r.i11, r.n11, i) & 3u;
+  return (int)(a | (b << 2) | (c << 4) | (d << 6));
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_mc_count(const uint32_t* __restrict__ bits, McGeom g,
+                                                         uint4* __restrict__ info, uint32_t* __restrict__ toff,
+                                                         uint32_t* __restrict__ bsum_v,
+                                                         uint32_t* __restrict__ bsum_t) {
+  __shared__ unsigned char s_ntri[256];
+  __shared__ uint32_t s_red[2][kScanBlock / 32];
+  s_ntri[threadIdx.x] = B2V_MC_NTRI[threadIdx.x];
+  __syncthreads();
+  const int64_t wi = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  uint32_t nv = 0, nt = 0;
+  if (wi < g.nwords) {
+    int64_t row = wi / g.wx;
+    int w = (int)(wi - row * g.wx);
+    int64_t z = row / g.ny, y = row - z * g.ny;
+    Rows r = load_rows(bits, g, z, y, w);
+    const uint32_t vx = valid_x1(g, w);
+    const bool hy = y + 1 < g.ny, hz = z + 1 < g.nz;
+    uint32_t cx = (r.i00 ^ shift_in(r.i00, r.n00)) & vx;
+    uint32_t cy = hy ? (r.i00 ^ r.i01) : 0u;
+    uint32_t cz = hz ? (r.i00 ^ r.i10) : 0u;
+    nv = __popc(cx) + __popc(cy) + __popc(cz);
+    if (hy && hz) {
+      uint32_t s00 = shift_in(r.i00, r.n00), s01 = shift_in(r.i01, r.n01), s10 = shift_in(r.i10, r.n10),
+               s11 = shift_in(r.i11, r.n11);
+      uint32_t any = r.i00 | r.i01 | r.i10 | r.i11 | s00 | s01 | s10 | s11;
+      uint32_t all = r.i00 & r.i01 & r.i10 & r.i11 & s00 & s01 & s10 & s11;
+      uint32_t act = any & ~all & vx;
+      while (act) {
+        int i = __ffs(act) - 1;
+        act &= act - 1;
+        nt += s_ntri[cell_case(r, i)];
+      }
+    }
+    info[wi] = make_uint4(cx, cy, cz, nv);
+    toff[wi] = nt;
+  }
+  // block sums
+  uint32_t a = nv, b = nt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_red[0][threadIdx.x >> 5] = a;
+    s_red[1][threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t sa = 0, sb = 0;
+#pragma unroll
+    for (int k = 0; k < kScanBlock / 32; ++k) {
+      sa += s_red[0][k];
+      sb += s_red[1][k];
+    }
+    bsum_v[blockIdx.x] = sa;
+    bsum_t[blockIdx.x] = sb;
+  }
+}
+
+// ---- 3. scan -------------------------------------------------------------------------------
+// one block: exclusive scan of the block sums (in place, as 64-bit running totals truncated
+// to 32 bits on store; the host rejects totals >= 2^32), totals[0..1] = V, T
+__global__ void __launch_bounds__(1024) k_mc_scan_bsums(uint32_t* bsum_v, uint32_t* bsum_t, int64_t nblocks,
+                                                        unsigned long long* totals) {
+  __shared__ unsigned long long s_w[2][32];
+  __shared__ unsigned long long s_carry[2];
+  if (threadIdx.x == 0) s_carry[0] = s_carry[1] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t base = 0; base < nblocks; base += 1024) {
+    int64_t i = base + threadIdx.x;
+    unsigned long long v = i < nblocks ? bsum_v[i] : 0ull, t = i < nblocks ? bsum_t[i] : 0ull;
+    unsigned long long iv = v, it = t;  // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long pv = __shfl_up_sync(0xffffffffu, iv, o), pt = __shfl_up_sync(0xffffffffu, it, o);
+      if (lane >= o) { iv += pv; it += pt; }
+    }
+    if (lane == 31) { s_w[0][wid] = iv; s_w[1][wid] = it; }
+    __syncthreads();
+    if (wid == 0) {
+      unsigned long long a = s_w[0][lane], b = s_w[1][lane];
+      unsigned long long ia = a, ib = b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long pa = __shfl_up_sync(0xffffffffu, ia, o), pb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += pa; ib += pb; }
+      }
+      s_w[0][lane] = ia - a;  // exclusive over warps
+      s_w[1][lane] = ib - b;
+    }
+    __syncthreads();
+    unsigned long long ev = s_carry[0] + s_w[0][wid] + iv - v;
+    unsigned long long et = s_carry[1] + s_w[1][wid] + it - t;
+    if (i < nblocks) {
+      bsum_v[i] = (uint32_t)ev;
+      bsum_t[i] = (uint32_t)et;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) {
+      s_carry[0] = ev + v;
+      s_carry[1] = et + t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    totals[0] = s_carry[0];
+    totals[1] = s_carry[1];
+  }
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_mc_scan_apply(uint4* __restrict__ info, uint32_t* __restrict__ toff,
+                                                              int64_t nwords, const uint32_t* __restrict__ bsum_v,
+                                                              const uint32_t* __restrict__ bsum_t) {
+  __shared__ uint32_t s_w[2][kScanBlock / 32];
+  const int64_t wi = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t v = wi < nwords ? info[wi].w : 0u, t = wi < nwords ? toff[wi] : 0u;
+  uint32_t iv = v, it = t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t pv = __shfl_up_sync(0xffffffffu, iv, o), pt = __shfl_up_sync(0xffffffffu, it, o);
+    if (lane >= o) { iv += pv; it += pt; }
+  }
+  if (lane == 31) { s_w[0][wid] = iv; s_w[1][wid] = it; }
+  __syncthreads();
+  uint32_t ov = bsum_v[blockIdx.x], ot = bsum_t[blockIdx.x];
+  for (int k = 0; k < wid; ++k) { ov += s_w[0][k]; ot += s_w[1][k]; }
+  if (wi < nwords) {
+    info[wi].w = ov + iv - v;
+    toff[wi] = ot + it - t;
+  }
+}
+
+// ---- 4. emit -------------------------------------------------------------------------------
+struct McXform {
+  float sx, sy, sz;
+  int ox, oy, oz;
+  int flip_y;
+  float iso;
+};
+
+// per edge id: axis and owner offset, packed (a | ox<<2 | oy<<3 | oz<<4)
+__device__ __forceinline__ int edge_code(int e) {
+  int a = e >> 2, cu = e & 1, cv = (e >> 1) & 1;
+  int ox = 0, oy = 0, oz = 0;
+  if (a == 0) { oy = cu; oz = cv; }
+  else if (a == 1) { ox = cu; oz = cv; }
+  else { ox = cu; oy = cv; }
+  return a | (ox << 2) | (oy << 3) | (oz << 4);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_mc_emit(const T* __restrict__ vol, McGeom g, const uint32_t* __restrict__ bits,
+                                                 const uint4* __restrict__ info, const uint32_t* __restrict__ toff,
+                                                 const unsigned long long* __restrict__ totals, McXform xf,
+                                                 float* __restrict__ verts, int* __restrict__ tris) {
+  __shared__ signed char s_tri[256][16];  // 15 edge ids + triangle count
+  for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+    int c = i >> 4, k = i & 15;
+    s_tri[c][k] = k < 15 ? B2V_MC_TRI[c][k] : (signed char)B2V_MC_NTRI[c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t low = (1u << lane) - 1u;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t totV = (uint32_t)totals[0], totT = (uint32_t)totals[1];
+  for (int64_t wi0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; wi0 < g.nwords;
+       wi0 += nwarps * 32) {
+    // lane j looks at word wi0 + j: does it own vertices or triangles?
+    int64_t mine = wi0 + lane;
+    bool work = false;
+    if (mine < g.nwords) {
+      uint32_t v0 = info[mine].w, t0 = toff[mine];
+      uint32_t v1 = mine + 1 < g.nwords ? info[mine + 1].w : totV;
+      uint32_t t1 = mine + 1 < g.nwords ? toff[mine + 1] : totT;
+      work = v1 != v0 || t1 != t0;
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, work);
+    while (todo) {
+      int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int64_t wi = wi0 + src;
+      const int64_t row = wi / g.wx;
+      const int w = (int)(wi - row * g.wx);
+      const int64_t z = row / g.ny, y = row - z * g.ny;
+      const int64_t x = (int64_t)w * 32 + lane;
+      const uint4 inf = info[wi];
+      // ---- vertices owned by voxel (z, y, x)
+      {
+        const int bx = (inf.x >> lane) & 1, by = (inf.y >> lane) & 1, bz = (inf.z >> lane) & 1;
+        if (bx | by | bz) {
+          uint32_t vid = inf.w + __popc(inf.x & low) + __popc(inf.y & low) + __popc(inf.z & low);
+          const int64_t p = row * g.nx + x;
+          const float s0 = (float)vol[p];
+          const float fx = (float)((int)x + xf.ox), fy = (float)((int)y + xf.oy), fz = (float)((int)z + xf.oz);
+          const float num = __fsub_rn(xf.iso, s0);
+          if (bx) {
+            float t = __fdiv_rn(num, __fsub_rn((float)vol[p + 1], s0));
+            float py = __fmul_rn(fy, xf.sy);
+            float* o = verts + 3ll * vid;
+            o[0] = __fmul_rn(__fadd_rn(fx, t), xf.sx);
+            o[1] = xf.flip_y ? -py : py;
+            o[2] = __fmul_rn(fz, xf.sz);
+            ++vid;
+          }
+          if (by) {
+            float t = __fdiv_rn(num, __fsub_rn((float)vol[p + g.nx], s0));
+            float py = __fmul_rn(__fadd_rn(fy, t), xf.sy);
+            float* o = verts + 3ll * vid;
+            o[0] = __fmul_rn(fx, xf.sx);
+            o[1] = xf.flip_y ? -py : py;
+            o[2] = __fmul_rn(fz, xf.sz);
+            ++vid;
+          }
+          if (bz) {
+            float t = __fdiv_rn(num, __fsub_rn((float)vol[p + g.nx * g.ny], s0));
+            float py = __fmul_rn(fy, xf.sy);
+            float* o = verts + 3ll * vid;
+            o[0] = __fmul_rn(fx, xf.sx);
+            o[1] = xf.flip_y ? -py : py;
+            o[2] = __fmul_rn(__fadd_rn(fz, t), xf.sz);
+          }
+        }
+      }
+      // ---- triangles of cell (z, y, x)
+      if (y + 1 < g.ny && z + 1 < g.nz) {
+        Rows r = load_rows(bits, g, z, y, w);
+        int c = (x + 1 < g.nx) ? cell_case(r, lane) : 0;
+        int ntri = s_tri[c][15];
+        // exclusive prefix of ntri over the lanes
+        int inc = ntri;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int pv = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += pv;
+        }
+        if (ntri) {
+          int64_t tbase = (int64_t)toff[wi] + (inc - ntri);
+          for (int t = 0; t < ntri; ++t) {
+            int id[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+              int code = edge_code(s_tri[c][3 * t + m]);
+              int a = code & 3;
+              int64_t qx = x + ((code >> 2) & 1), qy = y + ((code >> 3) & 1), qz = z + ((code >> 4) & 1);
+              int64_t ow = (qz * g.ny + qy) * g.wx + (qx >> 5);
+              int ob = (int)(qx & 31);
+              uint4 oi = __ldg(info + ow);
+              uint32_t ol = (1u << ob) - 1u;
+              int v = (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
+              if (a > 0) v += (oi.x >> ob) & 1;
+              if (a > 1) v += (oi.y >> ob) & 1;
+              id[m] = v;
+            }
+            int* o = tris + 3 * (tbase + t);
+            o[0] = id[0];
+            o[1] = xf.flip_y ? id[2] : id[1];
+            o[2] = xf.flip_y ? id[1] : id[2];
+          }
+        }
+      }
+    }
+  }
+}
+
+int grid_for(int64_t items, int per_block) {
+  int64_t blocks = ceil_div64(items, per_block);
+  int64_t cap = (int64_t)b2v_sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// inside(p) <=> (double)S >= iso  <=>  S >= ceil(iso) for integer S
+int int_threshold(double iso, int lo, int hi) {
+  double c = ceil(iso);
+  if (c <= (double)lo) return lo;          // everything inside
+  if (c > (double)hi) return hi + 1;       // nothing inside
+  return (int)c;
+}
+
+}  // namespace
+
+extern "C" int64_t b2v_mc_workspace_bytes(int64_t nz, int64_t ny, int64_t nx) {
+  if (nz <= 0 || ny <= 0 || nx <= 0) return 0;
+  return carve(nullptr, make_geom(nz, ny, nx)).bytes;
+}
+
+extern "C" int b2v_mc_count(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
+                            void* workspace, void* stream, int64_t* nverts_host, int64_t* ntris_host) {
+  B2V_REQUIRE(vol && workspace && nverts_host && ntris_host, B2V_ERR_ARG, "mc_count: null pointer");
+  B2V_REQUIRE(nz > 0 && ny > 0 && nx > 0, B2V_ERR_ARG, "mc_count: empty volume");
+  B2V_REQUIRE(dtype == B2V_U8 || dtype == B2V_I16, B2V_ERR_ARG, "mc_count: dtype must be uint8 or int16");
+  B2V_REQUIRE(iso == iso, B2V_ERR_ARG, "mc_count: iso is NaN");
+  McGeom g = make_geom(nz, ny, nx);
+  B2V_REQUIRE(g.nwords < (1ll << 31), B2V_ERR_ARG, "mc_count: volume too large for one call; shard along z");
+  McWs w = carve(workspace, g);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if (dtype == B2V_U8) {
+    int thr = int_threshold(iso, 0, 255);
+    if (nx % 16 == 0 && b2v_aligned16(vol))
+      k_mc_bits_u8_vec<<<grid_for(g.nwords * 2, 256), 256, 0, s>>>((const uint8_t*)vol, g, thr, w.bits);
+    else
+      k_mc_bits<uint8_t><<<grid_for(g.nwords, 8), 256, 0, s>>>((const uint8_t*)vol, g, thr, w.bits);
+  } else {
+    int thr = int_threshold(iso, -32768, 32767);
+    if (nx % 8 == 0 && b2v_aligned16(vol))
+      k_mc_bits_i16_vec<<<grid_for(g.nwords * 4, 256), 256, 0, s>>>((const int16_t*)vol, g, thr, w.bits);
+    else
+      k_mc_bits<int16_t><<<grid_for(g.nwords, 8), 256, 0, s>>>((const int16_t*)vol, g, thr, w.bits);
+  }
+  if ((rc = b2v_check_launch("k_mc_bits"))) return rc;
+  k_mc_count<<<(unsigned)w.nblocks, kScanBlock, 0, s>>>(w.bits, g, w.info, w.toff, w.bsum_v, w.bsum_t);
+  if ((rc = b2v_check_launch("k_mc_count"))) return rc;
+  k_mc_scan_bsums<<<1, 1024, 0, s>>>(w.bsum_v, w.bsum_t, w.nblocks, w.totals);
+  if ((rc = b2v_check_launch("k_mc_scan_bsums"))) return rc;
+  k_mc_scan_apply<<<(unsigned)w.nblocks, kScanBlock, 0, s>>>(w.info, w.toff, g.nwords, w.bsum_v, w.bsum_t);
+  if ((rc = b2v_check_launch("k_mc_scan_apply"))) return rc;
+  unsigned long long tot[2] = {0, 0};
+  B2V_CUDA(cudaMemcpyAsync(tot, w.totals, sizeof(tot), cudaMemcpyDeviceToHost, s));
+  B2V_CUDA(cudaStreamSynchronize(s));
+  B2V_REQUIRE(tot[0] < (1ull << 31) && tot[1] < (1ull << 31), B2V_ERR_RANGE,
+              "mc_count: %llu vertices / %llu triangles exceed int32 indices; shard along z", tot[0], tot[1]);
+  *nverts_host = (int64_t)tot[0];
+  *ntris_host = (int64_t)tot[1];
+  return B2V_OK;
+}
+
+extern "C" int b2v_mc_emit(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
+                           const void* workspace, float sx, float sy, float sz, int32_t ox, int32_t oy, int32_t oz,
+                           int flip_y, float* verts, int32_t* tris, void* stream) {
+  B2V_REQUIRE(vol && workspace, B2V_ERR_ARG, "mc_emit: null pointer");
+  B2V_REQUIRE(dtype == B2V_U8 || dtype == B2V_I16, B2V_ERR_ARG, "mc_emit: dtype must be uint8 or int16");
+  McGeom g = make_geom(nz, ny, nx);
+  McWs w = carve(const_cast<void*>(workspace), g);
+  cudaStream_t s = (cudaStream_t)stream;
+  McXform xf = {sx, sy, sz, ox, oy, oz, flip_y ? 1 : 0, (float)iso};
+  if (dtype == B2V_U8)
+    k_mc_emit<uint8_t><<<grid_for(g.nwords, 256), 256, 0, s>>>((const uint8_t*)vol, g, w.bits, w.info, w.toff,
+                                                                w.totals, xf, verts, tris);
+  else
+    k_mc_emit<int16_t><<<grid_for(g.nwords, 256), 256, 0, s>>>((const int16_t*)vol, g, w.bits, w.info, w.toff,
+                                                                w.totals, xf, verts, tris);
+  return b2v_check_launch("k_mc_emit");
+}

@@ -168,15 +168,18 @@ def main():
         "// 256-case marching-cubes triangulation derived from first principles (see the generator",
         "// for the corner / edge numbering and the ambiguous-face rule).",
         "#pragma once",
+        "#ifndef B2V_MC_QUAL  // mc.cu defines this as __device__",
+        "#define B2V_MC_QUAL",
+        "#endif",
         f"#define B2V_MC_MAXTRI {maxt}",
         "// number of triangles per case",
-        "static const unsigned char B2V_MC_NTRI[256] = {",
+        "B2V_MC_QUAL static const unsigned char B2V_MC_NTRI[256] = {",
     ]
     for i in range(0, 256, 32):
         lines.append("  " + ", ".join(str(len(t)) for t in tris[i:i + 32]) + ",")
     lines.append("};")
     lines.append("// edge ids (0..11) of each triangle's corners, -1 padded")
-    lines.append(f"static const signed char B2V_MC_TRI[256][{3 * maxt}] = {{")
+    lines.append(f"B2V_MC_QUAL static const signed char B2V_MC_TRI[256][{3 * maxt}] = {{")
     for case, t in enumerate(tris):
         flat = [e for tri in t for e in tri]
         flat += [-1] * (3 * maxt - len(flat))
@@ -188,7 +191,7 @@ def main():
         inside = [(case >> k) & 1 for k in range(8)]
         masks.append(sum(1 << e for e, (a, b) in enumerate(EDGE_CORNERS) if inside[a] != inside[b]))
     lines.append("// bit e set <=> edge e crosses the iso-surface")
-    lines.append("static const unsigned short B2V_MC_EDGEMASK[256] = {")
+    lines.append("B2V_MC_QUAL static const unsigned short B2V_MC_EDGEMASK[256] = {")
     for i in range(0, 256, 16):
         lines.append("  " + ", ".join(f"0x{m:03x}" for m in masks[i:i + 16]) + ",")
     lines.append("};")
