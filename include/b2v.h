@@ -126,6 +126,29 @@ int64_t b2v_fill_holes_workspace_bytes(uint32_t nlabels);
 int b2v_fill_holes(uint8_t* mask, const uint32_t* labels, int64_t n, uint32_t nlabels, uint32_t max_size,
                    void* workspace, void* stream, int* modified_out);
 
+/* ---- ray-sequential projections -----------------------------------------------------
+ * workspace for the three functions below: b2v_proj_workspace_bytes(dz*dy*dx) bytes.
+ * All three SYNCHRONISE the stream (they report B2V_ERR_RANGE where the reference's
+ * NumCast panics: NaN / out-of-range MIDA result, contour intensity overflowing T).
+ * out shape: axis 0 -> [dy][dx], axis 1 -> [dz][dx], axis 2 -> [dz][dy].
+ *
+ * invesalius_rs.mida(image, axis, wl, ww, out): __init__.py:91-95 -> mips_py.rs:161-202 ->
+ * mips.rs:102-168. dtype pairs (int16,int16), (uint8,uint8), (float64,uint8); anything else
+ * is B2V_ERR_ARG ("Invalid image or output type"). wl / ww are taken AS THE IMAGE TYPE
+ * (mips_py.rs:174-175). 4 B/voxel for int16 (min/max pass + ray pass). */
+int64_t b2v_proj_workspace_bytes(int64_t n);
+int b2v_mida(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double wl, double ww,
+             void* out, int out_dtype, void* workspace, void* stream);
+/* lmip(image, axis, tmin, tmax, out): mips.rs:7-86 (called as mips.lmip by slice_.py:892,
+ * 980,1063 although the crate forgets to export it). out has the image dtype. */
+int b2v_lmip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double tmin, double tmax,
+             void* out, void* workspace, void* stream);
+/* invesalius_rs.fast_countour_mip(image, n, axis, wl, ww, tmip, out): __init__.py:98-101 ->
+ * mips_py.rs:204-253 -> mips.rs:215-279. int16 or uint8, out of the same dtype. tmip 0: max,
+ * 1: lmip(700, 3033), 2: mida. The reference's temp volume is never materialised. */
+int b2v_fast_countour_mip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, float n, int axis,
+                          double wl, double ww, int tmip, void* out, void* workspace, void* stream);
+
 /* ---- marching cubes ---------------------------------------------------------------
  * Replaces the contour step of create_surface_piece, invesalius/data/surface_process.py:
  * 156-186 (vtkImageFlip about the origin + vtkContourFilter at iso 127 on the uint8 mask,

@@ -1,0 +1,532 @@
+// Ray-sequential projections: MIDA, LMIP and the contour-enhanced variants.
+// Reference semantics: invesalius_rs/src/mips.rs
+//   mida_internal               :102-168 (+ get_opacity :88-100)     b2v_mida
+//   lmip                        :7-86                                 b2v_lmip
+//   fast_countour_mip_internal  :215-279 (finite_difference :170-195,
+//                               calc_fcm_intensity :197-213)          b2v_fast_countour_mip
+// All float arithmetic is float32 with the reference's operation order and no FMA
+// (explicit __f*_rn intrinsics); casts to the output type truncate toward zero and a value
+// that does not fit (NaN included) is reported as B2V_ERR_RANGE, where the reference panics.
+//
+// One ray per thread. Rays along z or y (axis 0/1) keep x contiguous across the threads
+// of a warp, so every step is a coalesced row access; rays along x (axis 2) are staged
+// through a padded shared-memory tile (128 rays x 32 samples) that is loaded row-wise
+// (coalesced) and walked column-wise (bank-conflict free). A block stops loading as soon
+// as all of its rays have terminated (alpha >= 1 in MIDA, first local maximum in LMIP).
+// HBM: 2 B/voxel for the ray pass + 2 B/voxel for the global min/max pass MIDA needs.
+//
+// The contour variants never materialise the reference's temp volume: a sampler computes
+// the T-typed contour intensity of a voxel on the fly from its six neighbours.
+#include <math.h>
+
+#include "b2v_common.cuh"
+
+namespace {
+
+struct Dims {
+  int64_t nz, ny, nx;
+};
+
+// ---- samplers -----------------------------------------------------------------------------
+template <typename T>
+struct PlainSampler {
+  const T* __restrict__ vol;
+  Dims d;
+  __device__ __forceinline__ T at(int64_t z, int64_t y, int64_t x, int* status) const {
+    return vol[(z * d.ny + y) * d.nx + x];
+  }
+};
+
+template <typename T> __device__ __forceinline__ float wrapdiff(T a, T b);
+template <> __device__ __forceinline__ float wrapdiff<int16_t>(int16_t a, int16_t b) {
+  return (float)(int16_t)((int)a - (int)b);
+}
+template <> __device__ __forceinline__ float wrapdiff<uint8_t>(uint8_t a, uint8_t b) {
+  return (float)(uint8_t)((int)a - (int)b);
+}
+
+template <typename T> __device__ __forceinline__ bool cast_f32(float f, T* o);
+template <> __device__ __forceinline__ bool cast_f32<int16_t>(float f, int16_t* o) {
+  if (!(f > -32769.0f && f < 32768.0f)) return false;
+  *o = (int16_t)f;
+  return true;
+}
+template <> __device__ __forceinline__ bool cast_f32<uint8_t>(float f, uint8_t* o) {
+  if (!(f > -1.0f && f < 256.0f)) return false;
+  *o = (uint8_t)f;
+  return true;
+}
+
+// calc_fcm_intensity (mips.rs:197-213) cast to T (mips.rs:241)
+template <typename T>
+struct FcmSampler {
+  const T* __restrict__ vol;
+  Dims d;
+  float n;
+  float dirx, diry, dirz;  // dir[0], dir[1], dir[2] of mips.rs:229-235 (x, y, z components)
+  __device__ __forceinline__ T at(int64_t z, int64_t y, int64_t x, int* status) const {
+    const int64_t px = x == 0 ? 0 : x - 1, fx = x == d.nx - 1 ? d.nx - 1 : x + 1;
+    const int64_t py = y == 0 ? 0 : y - 1, fy = y == d.ny - 1 ? d.ny - 1 : y + 1;
+    const int64_t pz = z == 0 ? 0 : z - 1, fz = z == d.nz - 1 ? d.nz - 1 : z + 1;
+    const int64_t row = (z * d.ny + y) * d.nx;
+    const float two_h = 2.0f;  // 2.0 * h with h = 1
+    float gx = __fdiv_rn(wrapdiff<T>(vol[row + fx], vol[row + px]), two_h);
+    float gy = __fdiv_rn(wrapdiff<T>(vol[(z * d.ny + fy) * d.nx + x], vol[(z * d.ny + py) * d.nx + x]), two_h);
+    float gz = __fdiv_rn(wrapdiff<T>(vol[(fz * d.ny + y) * d.nx + x], vol[(pz * d.ny + y) * d.nx + x]), two_h);
+    float gm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz)));
+    float val = 0.0f;
+    if (gm != 0.0f) {
+      float dd = __fadd_rn(__fadd_rn(__fmul_rn(gx, dirx), __fmul_rn(gy, diry)), __fmul_rn(gz, dirz));
+      float base = __fsub_rn(1.0f, fabsf(__fdiv_rn(dd, gm)));
+      // powf of the reference is libm's (<1 ulp); a double pow rounded once is within the
+      // same ulp. See DESIGN.md (contour-MIP tolerance).
+      float sf = (float)pow((double)base, (double)n);
+      val = __fmul_rn(gm, sf);
+    }
+    T o = 0;
+    if (!cast_f32<T>(val, &o)) *status = B2V_ERR_RANGE;
+    return o;
+  }
+};
+
+// ---- per-ray operators --------------------------------------------------------------------
+__device__ __forceinline__ float opacity(float vl, float wl, float ww) {
+  float half = __fdiv_rn(ww, 2.0f);
+  float mn = __fsub_rn(wl, half), mx = __fadd_rn(wl, half);
+  if (vl < mn) return 0.0f;
+  if (vl > mx) return 1.0f;
+  return __fdiv_rn(__fsub_rn(vl, mn), __fsub_rn(mx, mn));
+}
+
+template <typename T, typename U>
+struct MidaOp {
+  float img_min, range, inv, wl, ww;
+  float fmax, alpha_p, colour_p, final_colour;
+  __device__ __forceinline__ void init() { fmax = alpha_p = colour_p = final_colour = 0.0f; }
+  __device__ __forceinline__ void first(T) {}
+  // returns true when the ray is finished
+  __device__ __forceinline__ bool step(T raw) {
+    float vl = (float)raw;
+    float fpi = __fmul_rn(inv, __fsub_rn(vl, img_min));
+    float dl = 0.0f;
+    if (fpi > fmax) {
+      dl = __fsub_rn(fpi, fmax);
+      fmax = fpi;
+    }
+    float bt = __fsub_rn(1.0f, dl);
+    float alpha = opacity(vl, wl, ww);
+    float one_m = __fsub_rn(1.0f, __fmul_rn(bt, alpha_p));
+    float colour = __fadd_rn(__fmul_rn(bt, colour_p), __fmul_rn(__fmul_rn(one_m, fpi), alpha));
+    float cur = __fadd_rn(__fmul_rn(bt, alpha_p), __fmul_rn(one_m, alpha));
+    colour_p = colour;
+    alpha_p = cur;
+    final_colour = colour;
+    return cur >= 1.0f;
+  }
+  __device__ __forceinline__ bool result(U* o) const {
+    return cast_result(__fadd_rn(__fmul_rn(range, final_colour), img_min), o);
+  }
+  __device__ __forceinline__ static bool cast_result(float f, int16_t* o) { return cast_f32<int16_t>(f, o); }
+  __device__ __forceinline__ static bool cast_result(float f, uint8_t* o) { return cast_f32<uint8_t>(f, o); }
+};
+
+template <typename T>
+struct LmipOp {
+  T tmin, tmax, max_val;
+  bool start;
+  __device__ __forceinline__ void init() {}
+  __device__ __forceinline__ void first(T v) {
+    max_val = v;
+    start = v >= tmin && v <= tmax;
+  }
+  __device__ __forceinline__ bool step(T val) {
+    if (val > max_val) max_val = val;
+    else if (val < max_val && start) return true;
+    if (val >= tmin && val <= tmax) start = true;
+    return false;
+  }
+  __device__ __forceinline__ bool result(T* o) const {
+    *o = max_val;
+    return true;
+  }
+};
+
+template <typename T>
+struct MaxOp {  // fold_axis with Bounded::min_value() (mips.rs:250-254)
+  T m;
+  __device__ __forceinline__ void init() {}
+  __device__ __forceinline__ void first(T v) { m = v; }
+  __device__ __forceinline__ bool step(T v) {
+    if (v > m) m = v;
+    return false;
+  }
+  __device__ __forceinline__ bool result(T* o) const {
+    *o = m;
+    return true;
+  }
+};
+
+// ---- ray walkers ---------------------------------------------------------------------------
+// axis 0: out[y][x], ray along z; axis 1: out[z][x], ray along y. One thread per (r, x).
+template <typename T, typename U, typename S, typename Op>
+__global__ void __launch_bounds__(128) k_rays_keepx(S smp, int axis, Op op0, U* __restrict__ out, int* status) {
+  const Dims d = smp.d;
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = blockIdx.y;
+  if (x >= d.nx) return;
+  const int64_t n_l = axis == 0 ? d.nz : d.ny;
+  Op op = op0;
+  op.init();
+  int st = 0;
+  {
+    T v0 = axis == 0 ? smp.at(0, r, x, &st) : smp.at(r, 0, x, &st);
+    op.first(v0);
+  }
+  for (int64_t l = 0; l < n_l; ++l) {
+    T v = axis == 0 ? smp.at(l, r, x, &st) : smp.at(r, l, x, &st);
+    if (op.step(v)) break;
+  }
+  U o;
+  if (op.result(&o)) out[r * d.nx + x] = o; else st = B2V_ERR_RANGE;
+  if (st) *status = st;
+}
+
+// axis 2: out[z][y], ray along x. 128 rays per block, 32 samples per tile.
+constexpr int kRays = 128, kChunk = 32;
+template <typename T> struct Pitch { static constexpr int value = kChunk + 4 / sizeof(T) * 1; };
+template <> struct Pitch<int16_t> { static constexpr int value = kChunk + 2; };   // 17 words
+template <> struct Pitch<uint8_t> { static constexpr int value = kChunk + 4; };   // 9 words
+template <> struct Pitch<double> { static constexpr int value = kChunk + 1; };
+
+template <typename T, typename U, typename S, typename Op>
+__global__ void __launch_bounds__(kRays) k_rays_alongx(S smp, Op op0, U* __restrict__ out, int* status) {
+  __shared__ T tile[kRays][Pitch<T>::value];
+  const Dims d = smp.d;
+  const int64_t nrows = d.nz * d.ny;
+  const int64_t row0 = (int64_t)blockIdx.x * kRays;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t myrow = row0 + tid;
+  const bool live = myrow < nrows;
+  Op op = op0;
+  op.init();
+  int st = 0;
+  bool done = !live;
+  for (int64_t x0 = 0; x0 < d.nx; x0 += kChunk) {
+    // each warp loads whole 32-sample row segments: coalesced 64 B (int16) per instruction
+    for (int rr = warp; rr < kRays; rr += kRays / 32) {
+      int64_t row = row0 + rr;
+      int64_t x = x0 + lane;
+      T v = 0;
+      if (row < nrows && x < d.nx) {
+        int64_t z = row / d.ny, y = row - z * d.ny;
+        v = smp.at(z, y, x, &st);
+      }
+      tile[rr][lane] = v;
+    }
+    __syncthreads();
+    if (!done) {
+      if (x0 == 0) op.first(tile[tid][0]);
+      int lim = (int)((d.nx - x0) < kChunk ? (d.nx - x0) : kChunk);
+      for (int k = 0; k < lim; ++k)
+        if (op.step(tile[tid][k])) {
+          done = true;
+          break;
+        }
+    }
+    if (__syncthreads_and(done)) break;
+  }
+  if (live) {
+    U o;
+    if (op.result(&o)) out[myrow] = o; else st = B2V_ERR_RANGE;
+  }
+  if (st) *status = st;
+}
+
+// min / max of the sampled (T-typed) volume, for contour-MIDA
+template <typename T, typename S>
+__global__ void __launch_bounds__(256) k_sampled_minmax(S smp, int* __restrict__ mm, int* status) {
+  const Dims d = smp.d;
+  const int64_t n = d.nz * d.ny * d.nx;
+  int mn = 2147483647, mx = -2147483647 - 1, st = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t x = i % d.nx, yz = i / d.nx, y = yz % d.ny, z = yz / d.ny;
+    int v = (int)smp.at(z, y, x, &st);
+    mn = min(mn, v);
+    mx = max(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&mm[0], mn);
+    atomicMax(&mm[1], mx);
+  }
+  if (st) *status = st;
+}
+
+__global__ void k_mm_init(int* mm, int* status) {
+  mm[0] = 2147483647;
+  mm[1] = -2147483647 - 1;
+  *status = 0;
+}
+__global__ void k_mm_to_float(const int* mm, float* out) {
+  out[0] = (float)mm[0];
+  out[1] = (float)mm[1];
+}
+__global__ void k_status_init(int* status) { *status = 0; }
+
+template <typename T, typename U, typename S, typename Op>
+int launch_rays(S smp, int axis, Op op, U* out, int* status, cudaStream_t s) {
+  const Dims d = smp.d;
+  if (axis == 2) {
+    int64_t nrows = d.nz * d.ny;
+    k_rays_alongx<T, U, S, Op><<<(unsigned)ceil_div64(nrows, kRays), kRays, 0, s>>>(smp, op, out, status);
+    return b2v_check_launch("k_rays_alongx");
+  }
+  int64_t nr = axis == 0 ? d.ny : d.nz;
+  B2V_REQUIRE(nr <= 65535, B2V_ERR_ARG, "projection: more than 65535 output rows");
+  dim3 grid((unsigned)ceil_div64(d.nx, 128), (unsigned)nr);
+  k_rays_keepx<T, U, S, Op><<<grid, 128, 0, s>>>(smp, axis, op, out, status);
+  return b2v_check_launch("k_rays_keepx");
+}
+
+// MidaOp needs (min, range, 1/range) which live on the device: a tiny kernel finishes the
+// operator there instead of synchronising.
+template <typename T, typename U, typename S>
+__global__ void __launch_bounds__(128) k_mida_keepx(S smp, int axis, const float* __restrict__ mm, float wl, float ww,
+                                                    U* __restrict__ out, int* status);
+
+template <typename T, typename U>
+__device__ __forceinline__ MidaOp<T, U> make_mida(const float* mm, float wl, float ww) {
+  MidaOp<T, U> op;
+  op.img_min = mm[0];
+  op.range = __fsub_rn(mm[1], mm[0]);
+  op.inv = __fdiv_rn(1.0f, op.range);
+  op.wl = wl;
+  op.ww = ww;
+  return op;
+}
+
+template <typename T, typename U, typename S>
+__global__ void __launch_bounds__(128) k_mida_keepx(S smp, int axis, const float* __restrict__ mm, float wl, float ww,
+                                                    U* __restrict__ out, int* status) {
+  const Dims d = smp.d;
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = blockIdx.y;
+  if (x >= d.nx) return;
+  const int64_t n_l = axis == 0 ? d.nz : d.ny;
+  MidaOp<T, U> op = make_mida<T, U>(mm, wl, ww);
+  op.init();
+  int st = 0;
+  for (int64_t l = 0; l < n_l; ++l) {
+    T v = axis == 0 ? smp.at(l, r, x, &st) : smp.at(r, l, x, &st);
+    if (op.step(v)) break;
+  }
+  U o;
+  if (op.result(&o)) out[r * d.nx + x] = o; else st = B2V_ERR_RANGE;
+  if (st) *status = st;
+}
+
+template <typename T, typename U, typename S>
+__global__ void __launch_bounds__(kRays) k_mida_alongx(S smp, const float* __restrict__ mm, float wl, float ww,
+                                                       U* __restrict__ out, int* status) {
+  __shared__ T tile[kRays][Pitch<T>::value];
+  const Dims d = smp.d;
+  const int64_t nrows = d.nz * d.ny;
+  const int64_t row0 = (int64_t)blockIdx.x * kRays;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t myrow = row0 + tid;
+  const bool live = myrow < nrows;
+  MidaOp<T, U> op = make_mida<T, U>(mm, wl, ww);
+  op.init();
+  int st = 0;
+  bool done = !live;
+  for (int64_t x0 = 0; x0 < d.nx; x0 += kChunk) {
+    for (int rr = warp; rr < kRays; rr += kRays / 32) {
+      int64_t row = row0 + rr;
+      int64_t x = x0 + lane;
+      T v = 0;
+      if (row < nrows && x < d.nx) {
+        int64_t z = row / d.ny, y = row - z * d.ny;
+        v = smp.at(z, y, x, &st);
+      }
+      tile[rr][lane] = v;
+    }
+    __syncthreads();
+    if (!done) {
+      int lim = (int)((d.nx - x0) < kChunk ? (d.nx - x0) : kChunk);
+      for (int k = 0; k < lim; ++k)
+        if (op.step(tile[tid][k])) {
+          done = true;
+          break;
+        }
+    }
+    if (__syncthreads_and(done)) break;
+  }
+  if (live) {
+    U o;
+    if (op.result(&o)) out[myrow] = o; else st = B2V_ERR_RANGE;
+  }
+  if (st) *status = st;
+}
+
+template <typename T, typename U, typename S>
+int launch_mida(S smp, int axis, const float* mm, float wl, float ww, U* out, int* status, cudaStream_t s) {
+  const Dims d = smp.d;
+  if (axis == 2) {
+    k_mida_alongx<T, U, S><<<(unsigned)ceil_div64(d.nz * d.ny, kRays), kRays, 0, s>>>(smp, mm, wl, ww, out, status);
+    return b2v_check_launch("k_mida_alongx");
+  }
+  int64_t nr = axis == 0 ? d.ny : d.nz;
+  B2V_REQUIRE(nr <= 65535, B2V_ERR_ARG, "mida: more than 65535 output rows");
+  dim3 grid((unsigned)ceil_div64(d.nx, 128), (unsigned)nr);
+  k_mida_keepx<T, U, S><<<grid, 128, 0, s>>>(smp, axis, mm, wl, ww, out, status);
+  return b2v_check_launch("k_mida_keepx");
+}
+
+int finish_status(int* status_dev, cudaStream_t s, const char* what) {
+  int st = 0;
+  B2V_CUDA(cudaMemcpyAsync(&st, status_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+  B2V_CUDA(cudaStreamSynchronize(s));
+  B2V_REQUIRE(st == 0, B2V_ERR_RANGE, "%s: a value is not representable in the output type (the reference panics here)",
+              what);
+  return B2V_OK;
+}
+
+struct ProjWs {
+  float* mm_f;   // [2]
+  int* mm_i;     // [2]
+  int* status;   // [1]
+  void* minmax_ws;
+};
+ProjWs carve(void* ws) {
+  ProjWs w;
+  char* p = (char*)ws;
+  w.mm_f = (float*)p;
+  w.mm_i = (int*)(p + 64);
+  w.status = (int*)(p + 128);
+  w.minmax_ws = p + 256;
+  return w;
+}
+
+bool check_axis_dims(int64_t dz, int64_t dy, int64_t dx, int axis) {
+  return dz > 0 && dy > 0 && dx > 0 && axis >= 0 && axis <= 2;
+}
+
+}  // namespace
+
+extern "C" int64_t b2v_proj_workspace_bytes(int64_t n) { return 256 + b2v_minmax_workspace_bytes(n); }
+
+extern "C" int b2v_mida(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double wl,
+                        double ww, void* out, int out_dtype, void* workspace, void* stream) {
+  B2V_REQUIRE(img && out && workspace, B2V_ERR_ARG, "mida: null pointer");
+  B2V_REQUIRE(check_axis_dims(dz, dy, dx, axis), B2V_ERR_ARG, "mida: bad shape or axis");
+  cudaStream_t s = (cudaStream_t)stream;
+  ProjWs w = carve(workspace);
+  Dims d = {dz, dy, dx};
+  int rc;
+  k_status_init<<<1, 1, 0, s>>>(w.status);
+  if ((rc = b2v_check_launch("k_status_init"))) return rc;
+  if ((rc = b2v_minmax_f32(img, dtype, dz * dy * dx, w.mm_f, w.minmax_ws, stream))) return rc;
+  if (dtype == B2V_I16 && out_dtype == B2V_I16) {
+    PlainSampler<int16_t> smp = {(const int16_t*)img, d};
+    rc = launch_mida<int16_t, int16_t>(smp, axis, w.mm_f, (float)(int16_t)wl, (float)(int16_t)ww, (int16_t*)out,
+                                       w.status, s);
+  } else if (dtype == B2V_U8 && out_dtype == B2V_U8) {
+    PlainSampler<uint8_t> smp = {(const uint8_t*)img, d};
+    rc = launch_mida<uint8_t, uint8_t>(smp, axis, w.mm_f, (float)(uint8_t)wl, (float)(uint8_t)ww, (uint8_t*)out,
+                                       w.status, s);
+  } else if (dtype == B2V_F64 && out_dtype == B2V_U8) {
+    PlainSampler<double> smp = {(const double*)img, d};
+    rc = launch_mida<double, uint8_t>(smp, axis, w.mm_f, (float)wl, (float)ww, (uint8_t*)out, w.status, s);
+  } else {
+    B2V_REQUIRE(false, B2V_ERR_ARG, "Invalid image or output type");
+  }
+  if (rc) return rc;
+  return finish_status(w.status, s, "mida");
+}
+
+extern "C" int b2v_lmip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double tmin,
+                        double tmax, void* out, void* workspace, void* stream) {
+  B2V_REQUIRE(img && out && workspace, B2V_ERR_ARG, "lmip: null pointer");
+  B2V_REQUIRE(check_axis_dims(dz, dy, dx, axis), B2V_ERR_ARG, "lmip: bad shape or axis");
+  cudaStream_t s = (cudaStream_t)stream;
+  ProjWs w = carve(workspace);
+  Dims d = {dz, dy, dx};
+  int rc;
+  k_status_init<<<1, 1, 0, s>>>(w.status);
+  if ((rc = b2v_check_launch("k_status_init"))) return rc;
+  if (dtype == B2V_I16) {
+    PlainSampler<int16_t> smp = {(const int16_t*)img, d};
+    LmipOp<int16_t> op;
+    op.tmin = (int16_t)tmin; op.tmax = (int16_t)tmax;
+    rc = launch_rays<int16_t, int16_t>(smp, axis, op, (int16_t*)out, w.status, s);
+  } else if (dtype == B2V_U8) {
+    PlainSampler<uint8_t> smp = {(const uint8_t*)img, d};
+    LmipOp<uint8_t> op;
+    op.tmin = (uint8_t)tmin; op.tmax = (uint8_t)tmax;
+    rc = launch_rays<uint8_t, uint8_t>(smp, axis, op, (uint8_t*)out, w.status, s);
+  } else if (dtype == B2V_F64) {
+    PlainSampler<double> smp = {(const double*)img, d};
+    LmipOp<double> op;
+    op.tmin = tmin; op.tmax = tmax;
+    rc = launch_rays<double, double>(smp, axis, op, (double*)out, w.status, s);
+  } else {
+    B2V_REQUIRE(false, B2V_ERR_ARG, "Invalid image or output type");
+  }
+  return rc;
+}
+
+namespace {
+template <typename T>
+int run_fcm(const T* img, Dims d, float n, int axis, double wl, double ww, int tmip, T* out, ProjWs w,
+            cudaStream_t s) {
+  FcmSampler<T> smp = {img, d, n, axis == 2 ? 1.0f : 0.0f, axis == 1 ? 1.0f : 0.0f, axis == 0 ? 1.0f : 0.0f};
+  int rc;
+  if (tmip == 0) {
+    MaxOp<T> op = {};
+    rc = launch_rays<T, T>(smp, axis, op, out, w.status, s);
+  } else if (tmip == 1) {
+    // lmip(tmp, axis, 700, 3033): NumCast::from(700) does not fit uint8 -> the reference panics
+    B2V_REQUIRE(sizeof(T) == 2, B2V_ERR_RANGE, "fast_countour_mip: LMIP bounds 700/3033 do not fit uint8");
+    LmipOp<T> op;
+    op.tmin = (T)700; op.tmax = (T)3033;
+    rc = launch_rays<T, T>(smp, axis, op, out, w.status, s);
+  } else {
+    k_mm_init<<<1, 1, 0, s>>>(w.mm_i, w.status);
+    if ((rc = b2v_check_launch("k_mm_init"))) return rc;
+    int64_t nvox = d.nz * d.ny * d.nx;
+    int64_t blocks = ceil_div64(nvox, 256 * 8);
+    int64_t cap = (int64_t)b2v_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_sampled_minmax<T, FcmSampler<T>><<<(unsigned)blocks, 256, 0, s>>>(smp, w.mm_i, w.status);
+    if ((rc = b2v_check_launch("k_sampled_minmax"))) return rc;
+    k_mm_to_float<<<1, 1, 0, s>>>(w.mm_i, w.mm_f);
+    if ((rc = b2v_check_launch("k_mm_to_float"))) return rc;
+    rc = launch_mida<T, T>(smp, axis, w.mm_f, (float)(T)wl, (float)(T)ww, out, w.status, s);
+  }
+  return rc;
+}
+}  // namespace
+
+extern "C" int b2v_fast_countour_mip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, float n,
+                                     int axis, double wl, double ww, int tmip, void* out, void* workspace,
+                                     void* stream) {
+  B2V_REQUIRE(img && out && workspace, B2V_ERR_ARG, "fast_countour_mip: null pointer");
+  B2V_REQUIRE(check_axis_dims(dz, dy, dx, axis), B2V_ERR_ARG, "fast_countour_mip: bad shape or axis");
+  B2V_REQUIRE(tmip >= 0 && tmip <= 2, B2V_ERR_ARG, "fast_countour_mip: tmip must be 0, 1 or 2");
+  cudaStream_t s = (cudaStream_t)stream;
+  ProjWs w = carve(workspace);
+  Dims d = {dz, dy, dx};
+  int rc;
+  k_status_init<<<1, 1, 0, s>>>(w.status);
+  if ((rc = b2v_check_launch("k_status_init"))) return rc;
+  if (dtype == B2V_I16) rc = run_fcm<int16_t>((const int16_t*)img, d, n, axis, wl, ww, tmip, (int16_t*)out, w, s);
+  else if (dtype == B2V_U8) rc = run_fcm<uint8_t>((const uint8_t*)img, d, n, axis, wl, ww, tmip, (uint8_t*)out, w, s);
+  else B2V_REQUIRE(false, B2V_ERR_ARG, "fast_countour_mip: only int16 and uint8 volumes are supported on the device");
+  if (rc) return rc;
+  return finish_status(w.status, s, "fast_countour_mip");
+}

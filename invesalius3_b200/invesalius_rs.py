@@ -145,3 +145,73 @@ def fill_holes_automatically(mask, labels, nlabels, max_size) -> bool:
     if modified:
         dev.to_host(m, mask)
     return modified
+
+
+# ------------------------------------------------------------------------------- projections
+def _need_2d_out(out, shape3, axis):
+    want = [(shape3[1], shape3[2]), (shape3[0], shape3[2]), (shape3[0], shape3[1])][axis]
+    if out.ndim != 2 or tuple(out.shape) != want:
+        raise ValueError(f"out must have shape {want}")
+    if not out.flags.writeable:
+        raise ValueError("out is read-only")
+
+
+def _axis(axis):
+    axis = int(axis)
+    if axis < 0:
+        raise OverflowError("can't convert negative int to unsigned")
+    return axis
+
+
+def mida(image, axis, wl, ww, out):
+    """invesalius_rs/__init__.py:91-95 (wl, ww pass through int(); mips_py.rs:161-202)."""
+    from . import projection
+    axis = _axis(axis)
+    if not isinstance(image, np.ndarray) or not isinstance(out, np.ndarray):
+        raise TypeError("Invalid image or output type")
+    pair = (image.dtype, out.dtype)
+    if pair not in ((np.int16, np.int16), (np.uint8, np.uint8), (np.float64, np.uint8)):
+        raise TypeError("Invalid image or output type")
+    _need3(image, "image")
+    suf = _SUFFIX[image.dtype]
+    wl, ww = _extract(int(wl), suf), _extract(int(ww), suf)
+    if axis > 2:
+        return  # mips.rs:128-132 treats any other axis like 2 only inside the match default
+    _need_2d_out(out, image.shape, axis)
+    res = projection.mida(dev.to_device(image), axis, wl, ww)
+    dev.to_host(res[None], out[None])
+
+
+def lmip(image, axis, tmin, tmax, out):
+    """mips.rs:7-86; the call sites are slice_.py:892, 980, 1063 (`mips.lmip`)."""
+    from . import projection
+    axis = _axis(axis)
+    suf = _suffix(image)
+    if not isinstance(out, np.ndarray) or out.dtype != image.dtype:
+        raise TypeError("Invalid image or output type")
+    _need3(image, "image")
+    tmin, tmax = _extract(tmin, suf), _extract(tmax, suf)
+    if axis > 2:
+        return  # mips.rs:84 `_ => ()`
+    _need_2d_out(out, image.shape, axis)
+    res = projection.lmip(dev.to_device(image), axis, tmin, tmax)
+    dev.to_host(res[None], out[None])
+
+
+def fast_countour_mip(image, n, axis, wl, ww, tmip, out):
+    """invesalius_rs/__init__.py:98-101 -> mips_py.rs:204-253."""
+    from . import projection
+    axis, tmip = _axis(axis), _axis(tmip)
+    if not isinstance(image, np.ndarray) or not isinstance(out, np.ndarray) or image.dtype != out.dtype \
+            or image.dtype not in _SUFFIX:
+        raise TypeError("Invalid image or output type")
+    _need3(image, "image")
+    suf = _SUFFIX[image.dtype]
+    wl, ww = _extract(int(wl), suf), _extract(int(ww), suf)
+    if suf == "f64":
+        raise NotImplementedError("fast_countour_mip: float64 volumes are not supported by the device core")
+    if axis > 2 or tmip > 2:
+        raise ValueError("fast_countour_mip: axis and tmip must be 0, 1 or 2")
+    _need_2d_out(out, image.shape, axis)
+    res = projection.fast_countour_mip(dev.to_device(image), float(n), axis, wl, ww, tmip)
+    dev.to_host(res[None], out[None])

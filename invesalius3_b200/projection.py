@@ -1,0 +1,66 @@
+"""MIDA / LMIP / contour-MIP on device tensors (C ABI: b2v_mida, b2v_lmip,
+b2v_fast_countour_mip). Each call synchronises once (error status of the casts)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .device import _dense, _p, _stream, _workspace, dtype_code
+
+_OUT_SHAPE = lambda s, axis: [(s[1], s[2]), (s[0], s[2]), (s[0], s[1])][axis]  # noqa: E731
+
+
+def _prep(image: torch.Tensor, axis: int, out: torch.Tensor | None, out_dtype):
+    _dense(image, "image")
+    if image.dim() != 3:
+        raise TypeError("image must be 3-dimensional")
+    if axis not in (0, 1, 2):
+        raise ValueError("axis must be 0, 1 or 2")
+    shape = _OUT_SHAPE(image.shape, axis)
+    if out is None:
+        out = torch.empty(shape, dtype=out_dtype, device=image.device)
+    _dense(out, "out")
+    if tuple(out.shape) != shape:
+        raise ValueError(f"out must have shape {shape}")
+    ws = _workspace(_lib.load().b2v_proj_workspace_bytes(image.numel()), image.device)
+    return out, ws
+
+
+def mida(image: torch.Tensor, axis: int, wl, ww, out: torch.Tensor | None = None) -> torch.Tensor:
+    """mips.rs:102-168. wl/ww are interpreted as the image dtype, like the PyO3 layer."""
+    odt = {torch.int16: torch.int16, torch.uint8: torch.uint8, torch.float64: torch.uint8}.get(image.dtype)
+    if odt is None:
+        raise TypeError("Invalid image or output type")
+    out, ws = _prep(image, axis, out, odt)
+    if out.dtype not in (torch.int16, torch.uint8):
+        raise TypeError("Invalid image or output type")
+    dz, dy, dx = image.shape
+    with torch.cuda.device(image.device):
+        _lib.call("b2v_mida", _p(image), dtype_code(image), dz, dy, dx, axis, float(wl), float(ww), _p(out),
+                  dtype_code(out), _p(ws), _stream())
+    return out
+
+
+def lmip(image: torch.Tensor, axis: int, tmin, tmax, out: torch.Tensor | None = None) -> torch.Tensor:
+    """mips.rs:7-86."""
+    out, ws = _prep(image, axis, out, image.dtype)
+    if out.dtype != image.dtype:
+        raise TypeError("Invalid image or output type")
+    dz, dy, dx = image.shape
+    with torch.cuda.device(image.device):
+        _lib.call("b2v_lmip", _p(image), dtype_code(image), dz, dy, dx, axis, float(tmin), float(tmax), _p(out), _p(ws),
+                  _stream())
+    return out
+
+
+def fast_countour_mip(image: torch.Tensor, n: float, axis: int, wl, ww, tmip: int,
+                      out: torch.Tensor | None = None) -> torch.Tensor:
+    """mips.rs:215-279 (tmip 0 max, 1 LMIP(700, 3033), 2 MIDA)."""
+    out, ws = _prep(image, axis, out, image.dtype)
+    if out.dtype != image.dtype:
+        raise TypeError("Invalid image or output type")
+    dz, dy, dx = image.shape
+    with torch.cuda.device(image.device):
+        _lib.call("b2v_fast_countour_mip", _p(image), dtype_code(image), dz, dy, dx, float(n), axis, float(wl),
+                  float(ww), int(tmip), _p(out), _p(ws), _stream())
+    return out
