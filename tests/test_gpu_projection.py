@@ -138,4 +138,6 @@ def test_mida_1024_slab_properties():
         out = projection.mida(t, axis, 0, 2)
         first = [t[0], t[:, 0], t[:, :, 0]][axis]
         # alpha = 1 at the first sample => colour = fpi; out = trunc(range*fpi + min) within 1 of v
-        assert int((out.to(torch.int32) - first.to(torch.int32)).abs().max()) <= 1 or axis == 0
+        diff = (out.to(torch.int32) - first.to(torch.int32)).abs()
+        diff[0, 0] = 0  # the ray through the planted -1000 voxel does not saturate at once
+        assert int(diff.max()) <= 1, axis
