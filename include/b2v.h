@@ -170,6 +170,40 @@ int b2v_mc_emit(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, 
                 float sx, float sy, float sz, int32_t ox, int32_t oy, int32_t oz, int flip_y, float* verts,
                 int32_t* tris, void* stream);
 
+/* ---- Z-sharded volumes (one shard per GPU; invesalius3_b200/dist.py drives these) ---------
+ * The reference's only decomposition is the Z-piece split of the surface step
+ * (invesalius/data/surface.py:1360-1381: pieces of 20 slices + 1 overlap, stitched by
+ * vtkAppendPolyData + vtkCleanPolyData, surface_process.py:229-268). Here every shard holds
+ * a slab plus one halo plane per inner side.
+ *
+ * Flood fill in stages (bit 0 BEGIN: build + seeds, bit 1 CONVERGE: rounds from *round_io,
+ * bit 2 FINISH: write). Between CONVERGE calls the caller exchanges the reached bits of the
+ * shared planes with its neighbours (byte offsets from b2v_floodfill_layout: [0] passable
+ * bits, [1] reached bits, [2] round flags (int32 each), [3] bytes per z-plane, [4] tiles,
+ * [5] round capacity) and ORs them in with b2v_floodfill_merge_plane, which re-activates
+ * the touched tiles for round `round` and raises flags[round]. */
+int b2v_floodfill_threshold_staged(int stages, const void* data, int dtype, int64_t dz, int64_t dy, int64_t dx,
+                                   const int64_t* seeds_host, int64_t nseeds, double t0, double t1, uint8_t fill,
+                                   const uint8_t* strct_host, int64_t odz, int64_t ody, int64_t odx, uint8_t* out,
+                                   void* workspace, void* stream, int* round_io);
+int b2v_floodfill_layout(int64_t dz, int64_t dy, int64_t dx, int64_t nseeds, int64_t* layout_out);
+int b2v_floodfill_merge_plane(int64_t dz, int64_t dy, int64_t dx, int64_t nseeds, void* workspace, int64_t z,
+                              const uint32_t* plane_bits, int round, void* stream);
+/* Marching cubes on a slab whose last plane is shared with the next shard: that plane's
+ * vertices are owned (numbered, emitted) by the next shard. b2v_mc_layout: [0] byte offset
+ * of the per-word records {cx, cy, cz, vertex offset} in the workspace, [1] bytes of records
+ * per z-plane. The emitting shard receives the next shard's plane-0 records and global
+ * vertex base; concatenating the shards' outputs in rank order reproduces the single-GPU
+ * output bit for bit (the boundary stitch). */
+int b2v_mc_count_shard(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
+                       int skip_last_plane, void* workspace, void* stream, int64_t* nverts_host,
+                       int64_t* ntris_host);
+int b2v_mc_emit_shard(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
+                      const void* workspace, float sx, float sy, float sz, int32_t ox, int32_t oy, int32_t oz,
+                      int flip_y, int skip_last_plane, int32_t vertex_base, const void* next_shard_plane0_records,
+                      int32_t next_shard_vertex_base, float* verts, int32_t* tris, void* stream);
+int b2v_mc_layout(int64_t nz, int64_t ny, int64_t nx, int64_t* layout_out);
+
 #ifdef __cplusplus
 }
 #endif

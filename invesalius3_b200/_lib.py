@@ -47,6 +47,14 @@ PROTOTYPES = {
     "b2v_mc_workspace_bytes": (i64, [i64, i64, i64]),
     "b2v_mc_count": (cint, [vp, cint, i64, i64, i64, dbl, vp, vp, C.POINTER(i64), C.POINTER(i64)]),
     "b2v_mc_emit": (cint, [vp, cint, i64, i64, i64, dbl, vp, f32, f32, f32, i32, i32, i32, cint, vp, vp, vp]),
+    "b2v_floodfill_threshold_staged": (cint, [cint, vp, cint, i64, i64, i64, vp, i64, dbl, dbl, u8, vp, i64, i64, i64,
+                                              vp, vp, vp, C.POINTER(cint)]),
+    "b2v_floodfill_layout": (cint, [i64, i64, i64, i64, C.POINTER(i64)]),
+    "b2v_floodfill_merge_plane": (cint, [i64, i64, i64, i64, vp, i64, vp, cint, vp]),
+    "b2v_mc_count_shard": (cint, [vp, cint, i64, i64, i64, dbl, cint, vp, vp, C.POINTER(i64), C.POINTER(i64)]),
+    "b2v_mc_emit_shard": (cint, [vp, cint, i64, i64, i64, dbl, vp, f32, f32, f32, i32, i32, i32, cint, cint, i32, vp,
+                                 i32, vp, vp, vp]),
+    "b2v_mc_layout": (cint, [i64, i64, i64, C.POINTER(i64)]),
 }
 
 _lib = None

@@ -397,10 +397,11 @@ int grid_for(int64_t items, int per_block) {
 }
 
 // rounds until no tile is active. Synchronises the stream (reads one flag per batch).
-int run_rounds(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s, int* rounds_out) {
+int run_rounds(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s, int r0, int* rounds_out) {
   const int ntiles = b.ntz * b.nty * b.ntw;
   const size_t smem = (size_t)(b.tz + 2) * (b.ty + 2) * (b.tw + 2) * sizeof(uint32_t);
-  int r = 0, batch = 4, rc;
+  int r = r0, batch = 4, rc;
+  B2V_REQUIRE(r0 >= 0 && r0 + batch < kMaxRounds, B2V_ERR_NOCONV, "floodfill: round counter exhausted (%d)", r0);
   while (true) {
     for (int k = 0; k < batch; ++k, ++r) {
       k_ff_round<<<ntiles, kFloodThreads, smem, s>>>(w.fg, w.reach, b, sb, w.active[r & 1], w.active[(r + 1) & 1],
@@ -418,44 +419,104 @@ int run_rounds(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s,
   return B2V_OK;
 }
 
+enum { STAGE_BEGIN = 1, STAGE_CONVERGE = 2, STAGE_FINISH = 4, STAGE_ALL = 7 };
+
+// stages: BEGIN builds the bit volumes and plants the seeds; CONVERGE runs rounds from
+// *round_io until no tile is active (and stores the next free round there); FINISH writes
+// `fill` into every reached voxel. The one-shot entry points run all three.
 template <typename T, int MODE>
 int flood(T* data, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64_t* seeds_host, int64_t nseeds,
           typename Thr<T>::type t0, typename Thr<T>::type t1, typename Thr<T>::type fill_t, uint8_t fill_o,
-          uint32_t sb, void* workspace, cudaStream_t s, int* rounds_out) {
+          uint32_t sb, void* workspace, cudaStream_t s, int stages, int* round_io) {
   B2V_REQUIRE(data && workspace && (MODE == MODE_INPLACE || out), B2V_ERR_ARG, "floodfill: null pointer");
   B2V_REQUIRE(dz > 0 && dy > 0 && dx > 0, B2V_ERR_ARG, "floodfill: empty volume");
   B2V_REQUIRE(dz * dy * ceil_div64(dx, 32) < (1ll << 31), B2V_ERR_ARG, "floodfill: volume too large");
   int rc;
-  if ((rc = check_seeds(seeds_host, nseeds, dz, dy, dx))) return rc;
-  if (rounds_out) *rounds_out = 0;
-  if (nseeds == 0) return B2V_OK;
   BitVol b = make_bitvol(dz, dy, dx);
   Workspace w = carve(workspace, b, nseeds);
   const int64_t nwords = dz * dy * b.wx;
-  const int64_t ntiles = (int64_t)b.ntz * b.nty * b.ntw;
-  // control region (active flags, round flags) starts clean
-  B2V_CUDA(cudaMemsetAsync(w.active[0], 0, (size_t)((char*)w.seeds - (char*)w.active[0]), s));
-  B2V_CUDA(cudaMemcpyAsync(w.seeds, seeds_host, (size_t)nseeds * 24, cudaMemcpyHostToDevice, s));
-  (void)ntiles;
-  bool vec = sizeof(T) == 2 && MODE != MODE_INPLACE && dx % 8 == 0 && b2v_aligned16(data) &&
-             ((uintptr_t)out & 7u) == 0;
-  if (vec) {
-    k_ff_build_i16_vec<MODE><<<grid_for(nwords * 4, 256), 256, 0, s>>>((const int16_t*)data, out, b, (int)t0, (int)t1,
-                                                                       fill_o, w.fg, w.reach);
-  } else {
-    k_ff_build<T, MODE><<<grid_for(nwords, 8), 256, 0, s>>>(data, out, b, t0, t1, fill_t, fill_o, w.fg, w.reach);
+  if (stages & STAGE_BEGIN) {
+    if ((rc = check_seeds(seeds_host, nseeds, dz, dy, dx))) return rc;
+    if (round_io) *round_io = 0;
+    if (nseeds == 0 && stages == STAGE_ALL) return B2V_OK;
+    // control region (active flags, round flags) starts clean
+    B2V_CUDA(cudaMemsetAsync(w.active[0], 0, (size_t)((char*)w.seeds - (char*)w.active[0]), s));
+    if (nseeds) B2V_CUDA(cudaMemcpyAsync(w.seeds, seeds_host, (size_t)nseeds * 24, cudaMemcpyHostToDevice, s));
+    bool vec = sizeof(T) == 2 && MODE != MODE_INPLACE && dx % 8 == 0 && b2v_aligned16(data) &&
+               ((uintptr_t)out & 7u) == 0;
+    if (vec) {
+      k_ff_build_i16_vec<MODE><<<grid_for(nwords * 4, 256), 256, 0, s>>>((const int16_t*)data, out, b, (int)t0,
+                                                                         (int)t1, fill_o, w.fg, w.reach);
+    } else {
+      k_ff_build<T, MODE><<<grid_for(nwords, 8), 256, 0, s>>>(data, out, b, t0, t1, fill_t, fill_o, w.fg, w.reach);
+    }
+    if ((rc = b2v_check_launch("k_ff_build"))) return rc;
+    if (nseeds) {
+      k_ff_seeds<T><<<(unsigned)ceil_div64(nseeds, 128), 128, 0, s>>>(data, b, w.seeds, nseeds, t0, t1,
+                                                                      MODE == MODE_EQUAL ? 1 : 0, w.fg, w.reach,
+                                                                      w.active[0], w.flags);
+      if ((rc = b2v_check_launch("k_ff_seeds"))) return rc;
+    }
   }
-  if ((rc = b2v_check_launch("k_ff_build"))) return rc;
-  k_ff_seeds<T><<<(unsigned)ceil_div64(nseeds, 128), 128, 0, s>>>(data, b, w.seeds, nseeds, t0, t1,
-                                                                  MODE == MODE_EQUAL ? 1 : 0, w.fg, w.reach,
-                                                                  w.active[0], w.flags);
-  if ((rc = b2v_check_launch("k_ff_seeds"))) return rc;
-  if ((rc = run_rounds(b, w, sb, s, rounds_out))) return rc;
-  if (MODE == MODE_INPLACE)
-    k_ff_write<T><<<grid_for(nwords, 8), 256, 0, s>>>(w.reach, b, (T)fill_t, data);
-  else
-    k_ff_write<uint8_t><<<grid_for(nwords, 8), 256, 0, s>>>(w.reach, b, fill_o, out);
-  return b2v_check_launch("k_ff_write");
+  if (stages & STAGE_CONVERGE) {
+    int r0 = round_io ? *round_io : 0, r1 = r0;
+    if ((rc = run_rounds(b, w, sb, s, r0, &r1))) return rc;
+    if (round_io) *round_io = r1;
+  }
+  if (stages & STAGE_FINISH) {
+    if (MODE == MODE_INPLACE)
+      k_ff_write<T><<<grid_for(nwords, 8), 256, 0, s>>>(w.reach, b, (T)fill_t, data);
+    else
+      k_ff_write<uint8_t><<<grid_for(nwords, 8), 256, 0, s>>>(w.reach, b, fill_o, out);
+    if ((rc = b2v_check_launch("k_ff_write"))) return rc;
+  }
+  return B2V_OK;
+}
+
+// OR an externally supplied plane of reached bits (a neighbour shard's copy of the same
+// voxels) into plane z; tiles that gain bits become active for round `round`.
+__global__ void __launch_bounds__(256) k_ff_merge_plane(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b,
+                                                        int64_t z, const uint32_t* __restrict__ ext,
+                                                        uint8_t* active, int* flags, int round) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t plane = b.dy * b.wx;
+  if (i >= plane) return;
+  int64_t wi = z * plane + i;
+  uint32_t cur = reach[wi];
+  uint32_t nw = cur | (ext[i] & fg[wi]);
+  if (nw != cur) {
+    reach[wi] = nw;
+    int64_t y = i / b.wx;
+    int w = (int)(i - y * b.wx);
+    int tile = ((int)(z / b.tz) * b.nty + (int)(y / b.ty)) * b.ntw + w / b.tw;
+    active[tile] = 1;
+    flags[round] = 1;
+    // the tiles sharing this word's faces must look again as well
+    int tz = (int)(z / b.tz), ty = (int)(y / b.ty), tw = w / b.tw;
+    for (int oz = -1; oz <= 1; ++oz)
+      for (int oy = -1; oy <= 1; ++oy)
+        for (int ow = -1; ow <= 1; ++ow) {
+          int nz = tz + oz, ny = ty + oy, nwi = tw + ow;
+          if (nz >= 0 && nz < b.ntz && ny >= 0 && ny < b.nty && nwi >= 0 && nwi < b.ntw)
+            active[(nz * b.nty + ny) * b.ntw + nwi] = 1;
+        }
+  }
+}
+
+template <int MODE>
+int flood_dispatch(void* data, int dtype, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64_t* seeds_host,
+                   int64_t nseeds, double t0, double t1, double fill_t, uint8_t fill_o, uint32_t sb, void* workspace,
+                   cudaStream_t s, int stages, int* round_io) {
+  if (dtype == B2V_I16)
+    return flood<int16_t, MODE>((int16_t*)data, out, dz, dy, dx, seeds_host, nseeds, (int)t0, (int)t1, (int)fill_t,
+                                fill_o, sb, workspace, s, stages, round_io);
+  if (dtype == B2V_U8)
+    return flood<uint8_t, MODE>((uint8_t*)data, out, dz, dy, dx, seeds_host, nseeds, (int)t0, (int)t1, (int)fill_t,
+                                fill_o, sb, workspace, s, stages, round_io);
+  if (dtype == B2V_F64)
+    return flood<double, MODE>((double*)data, out, dz, dy, dx, seeds_host, nseeds, t0, t1, fill_t, fill_o, sb,
+                               workspace, s, stages, round_io);
+  B2V_REQUIRE(false, B2V_ERR_ARG, "floodfill: unknown dtype code %d", dtype);
 }
 
 }  // namespace
@@ -473,17 +534,9 @@ extern "C" int b2v_floodfill_threshold(const void* data, int dtype, int64_t dz, 
   uint32_t sb;
   int rc;
   if ((rc = strct_bits(strct_host, odz, ody, odx, &sb))) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == B2V_I16)
-    return flood<int16_t, MODE_THRESHOLD>((int16_t*)data, out, dz, dy, dx, seeds_host, nseeds, (int)t0, (int)t1, 0,
-                                          fill, sb, workspace, s, rounds_out);
-  if (dtype == B2V_U8)
-    return flood<uint8_t, MODE_THRESHOLD>((uint8_t*)data, out, dz, dy, dx, seeds_host, nseeds, (int)t0, (int)t1, 0,
-                                          fill, sb, workspace, s, rounds_out);
-  if (dtype == B2V_F64)
-    return flood<double, MODE_THRESHOLD>((double*)data, out, dz, dy, dx, seeds_host, nseeds, t0, t1, 0.0, fill, sb,
-                                         workspace, s, rounds_out);
-  B2V_REQUIRE(false, B2V_ERR_ARG, "floodfill_threshold: unknown dtype code %d", dtype);
+  if (rounds_out) *rounds_out = 0;
+  return flood_dispatch<MODE_THRESHOLD>(const_cast<void*>(data), dtype, out, dz, dy, dx, seeds_host, nseeds, t0, t1,
+                                        0.0, fill, sb, workspace, (cudaStream_t)stream, STAGE_ALL, rounds_out);
 }
 
 extern "C" int b2v_floodfill_threshold_inplace(void* data, int dtype, int64_t dz, int64_t dy, int64_t dx,
@@ -493,17 +546,9 @@ extern "C" int b2v_floodfill_threshold_inplace(void* data, int dtype, int64_t dz
   uint32_t sb;
   int rc;
   if ((rc = strct_bits(strct_host, odz, ody, odx, &sb))) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == B2V_I16)
-    return flood<int16_t, MODE_INPLACE>((int16_t*)data, nullptr, dz, dy, dx, seeds_host, nseeds, (int)t0, (int)t1,
-                                        (int)fill, 0, sb, workspace, s, rounds_out);
-  if (dtype == B2V_U8)
-    return flood<uint8_t, MODE_INPLACE>((uint8_t*)data, nullptr, dz, dy, dx, seeds_host, nseeds, (int)t0, (int)t1,
-                                        (int)fill, 0, sb, workspace, s, rounds_out);
-  if (dtype == B2V_F64)
-    return flood<double, MODE_INPLACE>((double*)data, nullptr, dz, dy, dx, seeds_host, nseeds, t0, t1, fill, 0, sb,
-                                       workspace, s, rounds_out);
-  B2V_REQUIRE(false, B2V_ERR_ARG, "floodfill_threshold_inplace: unknown dtype code %d", dtype);
+  if (rounds_out) *rounds_out = 0;
+  return flood_dispatch<MODE_INPLACE>(data, dtype, nullptr, dz, dy, dx, seeds_host, nseeds, t0, t1, fill, 0, sb,
+                                      workspace, (cudaStream_t)stream, STAGE_ALL, rounds_out);
 }
 
 extern "C" int b2v_floodfill_equal(const void* data, int dtype, int64_t dz, int64_t dy, int64_t dx, int64_t i,
@@ -512,17 +557,48 @@ extern "C" int b2v_floodfill_equal(const void* data, int dtype, int64_t dz, int6
   // 6-connected: (0,0,+-1), (0,+-1,0), (+-1,0,0)
   const uint32_t sb = (1u << 12) | (1u << 14) | (1u << 10) | (1u << 16) | (1u << 4) | (1u << 22);
   int64_t seed[3] = {i, j, k};
-  cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == B2V_I16)
-    return flood<int16_t, MODE_EQUAL>((int16_t*)data, out, dz, dy, dx, seed, 1, (int)v, (int)v, 0, fill, sb, workspace,
-                                      s, rounds_out);
-  if (dtype == B2V_U8)
-    return flood<uint8_t, MODE_EQUAL>((uint8_t*)data, out, dz, dy, dx, seed, 1, (int)v, (int)v, 0, fill, sb, workspace,
-                                      s, rounds_out);
-  if (dtype == B2V_F64)
-    return flood<double, MODE_EQUAL>((double*)data, out, dz, dy, dx, seed, 1, v, v, 0.0, fill, sb, workspace, s,
-                                     rounds_out);
-  B2V_REQUIRE(false, B2V_ERR_ARG, "floodfill: unknown dtype code %d", dtype);
+  if (rounds_out) *rounds_out = 0;
+  return flood_dispatch<MODE_EQUAL>(const_cast<void*>(data), dtype, out, dz, dy, dx, seed, 1, v, v, 0.0, fill, sb,
+                                    workspace, (cudaStream_t)stream, STAGE_ALL, rounds_out);
+}
+
+// ---- staged interface for Z-sharded volumes (dist.py) ---------------------------------------
+extern "C" int b2v_floodfill_threshold_staged(int stages, const void* data, int dtype, int64_t dz, int64_t dy,
+                                              int64_t dx, const int64_t* seeds_host, int64_t nseeds, double t0,
+                                              double t1, uint8_t fill, const uint8_t* strct_host, int64_t odz,
+                                              int64_t ody, int64_t odx, uint8_t* out, void* workspace, void* stream,
+                                              int* round_io) {
+  uint32_t sb;
+  int rc;
+  if ((rc = strct_bits(strct_host, odz, ody, odx, &sb))) return rc;
+  B2V_REQUIRE(stages > 0 && stages <= STAGE_ALL && round_io, B2V_ERR_ARG, "floodfill_staged: bad stage mask");
+  return flood_dispatch<MODE_THRESHOLD>(const_cast<void*>(data), dtype, out, dz, dy, dx, seeds_host, nseeds, t0, t1,
+                                        0.0, fill, sb, workspace, (cudaStream_t)stream, stages, round_io);
+}
+
+extern "C" int b2v_floodfill_layout(int64_t dz, int64_t dy, int64_t dx, int64_t nseeds, int64_t* layout_out) {
+  B2V_REQUIRE(dz > 0 && dy > 0 && dx > 0 && layout_out, B2V_ERR_ARG, "floodfill_layout: bad arguments");
+  BitVol b = make_bitvol(dz, dy, dx);
+  Workspace w = carve(nullptr, b, nseeds);
+  layout_out[0] = (int64_t)((char*)w.fg - (char*)nullptr);
+  layout_out[1] = (int64_t)((char*)w.reach - (char*)nullptr);
+  layout_out[2] = (int64_t)((char*)w.flags - (char*)nullptr);
+  layout_out[3] = (int64_t)b.dy * b.wx * 4;  // bytes per z-plane of a bit volume
+  layout_out[4] = (int64_t)b.ntz * b.nty * b.ntw;
+  layout_out[5] = kMaxRounds;
+  return B2V_OK;
+}
+
+extern "C" int b2v_floodfill_merge_plane(int64_t dz, int64_t dy, int64_t dx, int64_t nseeds, void* workspace,
+                                         int64_t z, const uint32_t* plane_bits, int round, void* stream) {
+  B2V_REQUIRE(workspace && plane_bits && z >= 0 && z < dz && round >= 0 && round < kMaxRounds, B2V_ERR_ARG,
+              "floodfill_merge_plane: bad arguments");
+  BitVol b = make_bitvol(dz, dy, dx);
+  Workspace w = carve(workspace, b, nseeds);
+  int64_t plane = b.dy * b.wx;
+  k_ff_merge_plane<<<(unsigned)ceil_div64(plane, 256), 256, 0, (cudaStream_t)stream>>>(
+      w.fg, w.reach, b, z, plane_bits, w.active[round & 1], w.flags, round);
+  return b2v_check_launch("k_ff_merge_plane");
 }
 
 // ---- fill holes -------------------------------------------------------------------------------

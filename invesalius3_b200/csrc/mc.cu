@@ -175,7 +175,7 @@ __device__ __forceinline__ int cell_case(const Rows& r, int i) {
   return (int)(a | (b << 2) | (c << 4) | (d << 6));
 }
 
-__global__ void __launch_bounds__(kScanBlock) k_mc_count(const uint32_t* __restrict__ bits, McGeom g,
+__global__ void __launch_bounds__(kScanBlock) k_mc_count(const uint32_t* __restrict__ bits, McGeom g, int skip_last,
                                                          uint4* __restrict__ info, uint32_t* __restrict__ toff,
                                                          uint32_t* __restrict__ bsum_v,
                                                          uint32_t* __restrict__ bsum_t) {
@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(kScanBlock) k_mc_count(const uint32_t* __restr
     uint32_t cx = (r.i00 ^ shift_in(r.i00, r.n00)) & vx;
     uint32_t cy = hy ? (r.i00 ^ r.i01) : 0u;
     uint32_t cz = hz ? (r.i00 ^ r.i10) : 0u;
-    nv = __popc(cx) + __popc(cy) + __popc(cz);
+    // a Z shard does not own the vertices of its last (shared) plane: the next shard does
+    nv = (skip_last && z == g.nz - 1) ? 0 : __popc(cx) + __popc(cy) + __popc(cz);
     if (hy && hz) {
       uint32_t s00 = shift_in(r.i00, r.n00), s01 = shift_in(r.i01, r.n01), s10 = shift_in(r.i10, r.n10),
                s11 = shift_in(r.i11, r.n11);
@@ -332,7 +333,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_mc_emit(const T* __restrict__ vol, McGeom g, const uint32_t* __restrict__ bits,
                                                  const uint4* __restrict__ info, const uint32_t* __restrict__ toff,
                                                  const unsigned long long* __restrict__ totals, McXform xf,
-                                                 float* __restrict__ verts, int* __restrict__ tris) {
+                                                 int skip_last, int vbase, const uint4* __restrict__ foreign,
+                                                 int foreign_base, float* __restrict__ verts,
+                                                 int* __restrict__ tris) {
   __shared__ signed char s_tri[256][16];  // 15 edge ids + triangle count
   for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
     int c = i >> 4, k = i & 15;
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(256) k_mc_emit(const T* __restrict__ vol, McGe
       // ---- vertices owned by voxel (z, y, x)
       {
         const int bx = (inf.x >> lane) & 1, by = (inf.y >> lane) & 1, bz = (inf.z >> lane) & 1;
-        if (bx | by | bz) {
+        if ((bx | by | bz) && !(skip_last && z == g.nz - 1)) {
           uint32_t vid = inf.w + __popc(inf.x & low) + __popc(inf.y & low) + __popc(inf.z & low);
           const int64_t p = row * g.nx + x;
           const float s0 = (float)vol[p];
@@ -422,11 +425,19 @@ __global__ void __launch_bounds__(256) k_mc_emit(const T* __restrict__ vol, McGe
               int code = edge_code(s_tri[c][3 * t + m]);
               int a = code & 3;
               int64_t qx = x + ((code >> 2) & 1), qy = y + ((code >> 3) & 1), qz = z + ((code >> 4) & 1);
-              int64_t ow = (qz * g.ny + qy) * g.wx + (qx >> 5);
               int ob = (int)(qx & 31);
-              uint4 oi = __ldg(info + ow);
               uint32_t ol = (1u << ob) - 1u;
-              int v = (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
+              uint4 oi;
+              int v;
+              if (skip_last && qz == g.nz - 1) {
+                // owned by the next shard: its records of that plane, its numbering
+                oi = __ldg(foreign + qy * g.wx + (qx >> 5));
+                v = foreign_base;
+              } else {
+                oi = __ldg(info + (qz * g.ny + qy) * g.wx + (qx >> 5));
+                v = vbase;
+              }
+              v += (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
               if (a > 0) v += (oi.x >> ob) & 1;
               if (a > 1) v += (oi.y >> ob) & 1;
               id[m] = v;
@@ -465,8 +476,8 @@ extern "C" int64_t b2v_mc_workspace_bytes(int64_t nz, int64_t ny, int64_t nx) {
   return carve(nullptr, make_geom(nz, ny, nx)).bytes;
 }
 
-extern "C" int b2v_mc_count(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
-                            void* workspace, void* stream, int64_t* nverts_host, int64_t* ntris_host) {
+static int mc_count_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso, int skip_last,
+                         void* workspace, void* stream, int64_t* nverts_host, int64_t* ntris_host) {
   B2V_REQUIRE(vol && workspace && nverts_host && ntris_host, B2V_ERR_ARG, "mc_count: null pointer");
   B2V_REQUIRE(nz > 0 && ny > 0 && nx > 0, B2V_ERR_ARG, "mc_count: empty volume");
   B2V_REQUIRE(dtype == B2V_U8 || dtype == B2V_I16, B2V_ERR_ARG, "mc_count: dtype must be uint8 or int16");
@@ -490,7 +501,7 @@ extern "C" int b2v_mc_count(const void* vol, int dtype, int64_t nz, int64_t ny, 
       k_mc_bits<int16_t><<<grid_for(g.nwords, 8), 256, 0, s>>>((const int16_t*)vol, g, thr, w.bits);
   }
   if ((rc = b2v_check_launch("k_mc_bits"))) return rc;
-  k_mc_count<<<(unsigned)w.nblocks, kScanBlock, 0, s>>>(w.bits, g, w.info, w.toff, w.bsum_v, w.bsum_t);
+  k_mc_count<<<(unsigned)w.nblocks, kScanBlock, 0, s>>>(w.bits, g, skip_last, w.info, w.toff, w.bsum_v, w.bsum_t);
   if ((rc = b2v_check_launch("k_mc_count"))) return rc;
   k_mc_scan_bsums<<<1, 1024, 0, s>>>(w.bsum_v, w.bsum_t, w.nblocks, w.totals);
   if ((rc = b2v_check_launch("k_mc_scan_bsums"))) return rc;
@@ -506,20 +517,63 @@ extern "C" int b2v_mc_count(const void* vol, int dtype, int64_t nz, int64_t ny, 
   return B2V_OK;
 }
 
-extern "C" int b2v_mc_emit(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
-                           const void* workspace, float sx, float sy, float sz, int32_t ox, int32_t oy, int32_t oz,
-                           int flip_y, float* verts, int32_t* tris, void* stream) {
+static int mc_emit_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
+                        const void* workspace, float sx, float sy, float sz, int32_t ox, int32_t oy, int32_t oz,
+                        int flip_y, int skip_last, int32_t vbase, const void* foreign, int32_t foreign_base,
+                        float* verts, int32_t* tris, void* stream) {
   B2V_REQUIRE(vol && workspace, B2V_ERR_ARG, "mc_emit: null pointer");
   B2V_REQUIRE(dtype == B2V_U8 || dtype == B2V_I16, B2V_ERR_ARG, "mc_emit: dtype must be uint8 or int16");
+  B2V_REQUIRE(!skip_last || foreign, B2V_ERR_ARG, "mc_emit: a shard that skips its last plane needs the next shard's records");
   McGeom g = make_geom(nz, ny, nx);
   McWs w = carve(const_cast<void*>(workspace), g);
   cudaStream_t s = (cudaStream_t)stream;
   McXform xf = {sx, sy, sz, ox, oy, oz, flip_y ? 1 : 0, (float)iso};
   if (dtype == B2V_U8)
     k_mc_emit<uint8_t><<<grid_for(g.nwords, 256), 256, 0, s>>>((const uint8_t*)vol, g, w.bits, w.info, w.toff,
-                                                                w.totals, xf, verts, tris);
+                                                                w.totals, xf, skip_last, vbase, (const uint4*)foreign,
+                                                                foreign_base, verts, tris);
   else
     k_mc_emit<int16_t><<<grid_for(g.nwords, 256), 256, 0, s>>>((const int16_t*)vol, g, w.bits, w.info, w.toff,
-                                                                w.totals, xf, verts, tris);
+                                                                w.totals, xf, skip_last, vbase, (const uint4*)foreign,
+                                                                foreign_base, verts, tris);
   return b2v_check_launch("k_mc_emit");
+}
+
+extern "C" int b2v_mc_count(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
+                            void* workspace, void* stream, int64_t* nverts_host, int64_t* ntris_host) {
+  return mc_count_impl(vol, dtype, nz, ny, nx, iso, 0, workspace, stream, nverts_host, ntris_host);
+}
+
+extern "C" int b2v_mc_emit(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
+                           const void* workspace, float sx, float sy, float sz, int32_t ox, int32_t oy, int32_t oz,
+                           int flip_y, float* verts, int32_t* tris, void* stream) {
+  return mc_emit_impl(vol, dtype, nz, ny, nx, iso, workspace, sx, sy, sz, ox, oy, oz, flip_y, 0, 0, nullptr, 0, verts,
+                      tris, stream);
+}
+
+// ---- Z-sharded variants (dist.py): the slab passed in ends with the plane it shares with
+// the next shard; that plane's vertices belong to the next shard (skip_last_plane).
+extern "C" int b2v_mc_count_shard(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
+                                  int skip_last_plane, void* workspace, void* stream, int64_t* nverts_host,
+                                  int64_t* ntris_host) {
+  return mc_count_impl(vol, dtype, nz, ny, nx, iso, skip_last_plane ? 1 : 0, workspace, stream, nverts_host,
+                       ntris_host);
+}
+
+extern "C" int b2v_mc_emit_shard(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
+                                 const void* workspace, float sx, float sy, float sz, int32_t ox, int32_t oy,
+                                 int32_t oz, int flip_y, int skip_last_plane, int32_t vertex_base,
+                                 const void* next_shard_plane0_records, int32_t next_shard_vertex_base, float* verts,
+                                 int32_t* tris, void* stream) {
+  return mc_emit_impl(vol, dtype, nz, ny, nx, iso, workspace, sx, sy, sz, ox, oy, oz, flip_y, skip_last_plane ? 1 : 0,
+                      vertex_base, next_shard_plane0_records, next_shard_vertex_base, verts, tris, stream);
+}
+
+extern "C" int b2v_mc_layout(int64_t nz, int64_t ny, int64_t nx, int64_t* layout_out) {
+  B2V_REQUIRE(nz > 0 && ny > 0 && nx > 0 && layout_out, B2V_ERR_ARG, "mc_layout: bad arguments");
+  McGeom g = make_geom(nz, ny, nx);
+  McWs w = carve(nullptr, g);
+  layout_out[0] = (int64_t)((char*)w.info - (char*)nullptr);   // byte offset of the per-word records
+  layout_out[1] = (int64_t)ny * g.wx * 16;                      // bytes of records per z-plane
+  return B2V_OK;
 }

@@ -1,0 +1,212 @@
+"""world_size-2 gloo tests (CPU) of the Z-shard protocols in invesalius3_b200/dist.py:
+halo exchange, flood-fill plane exchange loop and termination, MIP reductions, and the
+marching-cubes numbering / boundary stitch. The compute is delegated to a CPU checker
+backend built on the oracle (tests may use the oracle; the product backend is CUDA)."""
+import numpy as np
+import pytest
+import torch
+
+from dist_common import ext_slab, global_volume, run_ranks
+
+THR = (226, 3071)
+
+
+class CpuBackend:
+    """Implements dist.py's backend protocol with NumPy + the oracle."""
+
+    def __init__(self):
+        import oracle
+        self.o = oracle
+
+    # ---- threshold / projections
+    def threshold(self, img, lo, hi, out=None, preserve_markers=False):
+        a = img.numpy()
+        m = np.zeros(a.shape, np.uint8) if out is None else out.numpy()
+        self.o.threshold(a, lo, hi, m, preserve_markers)
+        return torch.from_numpy(m)
+
+    def mip(self, img, axis, kind):
+        a = img.numpy()
+        return torch.from_numpy(np.ascontiguousarray({"max": a.max, "min": a.min, "mean": a.mean}[kind](axis)))
+
+    def sum_axis0(self, img):
+        return torch.from_numpy(img.numpy().astype(np.int64).sum(axis=0))
+
+    # ---- flood fill
+    def ff_begin(self, data, out, seeds, t0, t1, fill, strct):
+        d, o = data.numpy(), out.numpy()
+        passable = (d >= t0) & (d <= t1) & (o != fill)
+        reached = np.zeros(d.shape, bool)
+        for (x, y, z) in seeds:
+            if t0 <= d[z, y, x] <= t1:
+                passable[z, y, x] = True
+                reached[z, y, x] = True
+        return dict(passable=passable, reached=reached, out=o, fill=fill, strct=np.ascontiguousarray(strct, np.uint8),
+                    changed=0)
+
+    def ff_converge(self, st):
+        seeds = [(int(x), int(y), int(z)) for z, y, x in np.argwhere(st["reached"])]
+        if not seeds:
+            return
+        grown = np.zeros(st["reached"].shape, np.uint8)
+        self.o._floodfill_threshold_core(st["passable"].astype(np.uint8), seeds, 1, 1, 1, st["strct"], grown)
+        st["reached"] |= grown.astype(bool)
+
+    def ff_get_planes(self, st, zs):
+        return torch.from_numpy(np.stack([st["reached"][z] for z in zs]).astype(np.int32))
+
+    def ff_merge_planes(self, st, zs, planes):
+        st["changed"] = 0
+        for z, pl in zip(zs, planes):
+            new = pl.numpy().astype(bool) & st["passable"][z] & ~st["reached"][z]
+            if new.any():
+                st["reached"][z] |= new
+                st["changed"] = 1
+
+    def ff_changed(self, st):
+        return torch.tensor([st["changed"]], dtype=torch.int32)
+
+    def ff_finish(self, st):
+        st["out"][st["reached"]] = st["fill"]
+
+    # ---- marching cubes
+    def mc_count(self, vol, iso, skip_last):
+        a = vol.numpy()
+        inside = a >= iso
+        cx = np.zeros(a.shape, bool); cy = cx.copy(); cz = cx.copy()
+        cx[:, :, :-1] = inside[:, :, :-1] != inside[:, :, 1:]
+        cy[:, :-1, :] = inside[:, :-1, :] != inside[:, 1:, :]
+        cz[:-1] = inside[:-1] != inside[1:]
+        nv = cx.astype(np.int64) + cy + cz
+        voff_full = np.cumsum(nv.ravel()) - nv.ravel()
+        V_full = int(nv.sum())
+        V_own = int(voff_full.reshape(a.shape)[-1, 0, 0]) if skip_last else V_full
+        _, T = self.o.marching_cubes(a, iso)
+        return dict(vol=a, iso=iso, skip_last=skip_last, cx=cx, cy=cy, cz=cz,
+                    voff=voff_full.reshape(a.shape), V=V_own, T=len(T), V_full=V_full)
+
+    def mc_plane0_records(self, st):
+        return torch.from_numpy(np.stack([st["voff"][0], st["cx"][0].astype(np.int64), st["cy"][0].astype(np.int64),
+                                          st["cz"][0].astype(np.int64)]))
+
+    def mc_emit(self, st, spacing, origin_index, flip_y, vbase, foreign, foreign_base):
+        V, T = self.o.marching_cubes(st["vol"], st["iso"], spacing, origin_index, flip_y)
+        T = T.copy()
+        own = T < st["V"]
+        out = np.where(own, T + vbase, 0)
+        if (~own).any():
+            f = foreign.numpy()
+            nz, ny, nx = st["vol"].shape
+            base_last = int(st["voff"][-1, 0, 0])
+            # reverse lookup: which (y, x, axis) of the last plane is local vertex id i?
+            lut = {}
+            for y in range(ny):
+                for x in range(nx):
+                    k = int(st["voff"][-1, y, x])
+                    for ax, c in enumerate((st["cx"][-1, y, x], st["cy"][-1, y, x])):  # no +z edge in the last plane
+                        if c:
+                            lut[k] = (y, x, ax)
+                            k += 1
+            for idx in np.argwhere(~own):
+                i = int(T[tuple(idx)])
+                assert i >= base_last
+                y, x, ax = lut[i]
+                rank_in_voxel = int(f[1, y, x]) if ax == 1 else 0
+                out[tuple(idx)] = foreign_base + int(f[0, y, x]) + rank_in_voxel
+        return torch.from_numpy(V[: st["V"]].copy()), torch.from_numpy(out.astype(np.int32))
+
+
+def _setup(rank, world):
+    from invesalius3_b200 import dist as d
+    g = global_volume()
+    shard = d.ZShard(g.shape[0], rank, world)
+    return d, g, shard
+
+
+def rank_halo_and_mip(rank, world, device):
+    d, g, shard = _setup(rank, world)
+    be = CpuBackend()
+    ext = torch.from_numpy(ext_slab(g, shard).copy())
+    want = ext.clone()
+    if shard.has_lo: ext[0] = -7
+    if shard.has_hi: ext[-1] = -7
+    d.exchange_halo(ext, shard)
+    assert torch.equal(ext, want)
+    own = torch.from_numpy(np.ascontiguousarray(g[shard.z0:shard.z1]))
+    res = {}
+    for axis in (0, 1, 2):
+        for kind in ("max", "min", "mean"):
+            res[(axis, kind)] = d.mip(own, axis, kind, shard, backend=be).numpy()
+    m = d.threshold(own, *THR, shard, backend=be).numpy()
+    return res, (shard.z0, shard.z1, m)
+
+
+def test_halo_mip_threshold_two_ranks(orc):
+    out = run_ranks("rank_halo_and_mip", "test_dist_gloo")
+    g = global_volume()
+    for rank in (0, 1):
+        res, (z0, z1, m) = out[rank]
+        for (axis, kind), got in res.items():
+            want = {"max": g.max, "min": g.min, "mean": g.mean}[kind](axis)
+            assert got.dtype == want.dtype and np.array_equal(got, want), (rank, axis, kind)
+        want = np.zeros(g.shape, np.uint8)
+        orc.threshold(g, *THR, want, False)
+        assert np.array_equal(m, want[z0:z1])
+
+
+def ff_cases(g):
+    from scipy.ndimage import generate_binary_structure
+    def first(z):
+        yy, xx = np.nonzero((g[z] >= 100) & (g[z] <= 3071) & (np.arange(g.shape[1])[:, None] != 10))
+        return (int(xx[0]), int(yy[0]), z)
+    return ((generate_binary_structure(3, 1), [first(2)]),
+            (generate_binary_structure(3, 3), [first(21), first(11), (0, 0, 0)]))
+
+
+def rank_floodfill(rank, world, device):
+    d, g, shard = _setup(rank, world)
+    be = CpuBackend()
+    results = []
+    for strct, seeds in ff_cases(g):
+        data = torch.from_numpy(ext_slab(g, shard))
+        out_g = np.zeros(g.shape, np.uint8)
+        out_g[:, 10, :] = 254                       # a pre-filled wall crossing the shard boundary
+        out = torch.from_numpy(ext_slab(out_g, shard).copy())
+        outer = d.floodfill_threshold(data, seeds, 100, 3071, 254, strct, out, shard, backend=be)
+        results.append((shard.z0, shard.z1, shard.interior(out).numpy().copy(), outer))
+    return results
+
+
+def test_floodfill_two_ranks(orc):
+    out = run_ranks("rank_floodfill", "test_dist_gloo")
+    g = global_volume()
+    for case, (strct, seeds) in enumerate(ff_cases(g)):
+        want = np.zeros(g.shape, np.uint8); want[:, 10, :] = 254
+        orc.floodfill_threshold(g, seeds, 100, 3071, 254, strct, want)
+        got = np.concatenate([out[r][case][2] for r in (0, 1)])
+        assert np.array_equal(got, want), case
+        grown = (want == 254); grown[:, 10, :] = False
+        z_split = out[0][case][1]
+        assert grown[:z_split].sum() > 50 and grown[z_split:].sum() > 50   # the region crosses the boundary
+        assert out[0][case][3] == out[1][case][3] >= (2 if case == 0 else 1)
+
+
+def rank_mc(rank, world, device):
+    d, g, shard = _setup(rank, world)
+    be = CpuBackend()
+    mask = ((g >= THR[0]) & (g <= THR[1])).astype(np.uint8) * 255
+    vol = torch.from_numpy(ext_slab(mask, shard, lo=False, hi=True))
+    v, t, vbase, tv, tt = d.marching_cubes(vol, 127, (0.5, 0.75, 1.5), (-1, -1, 3), True, shard, backend=be)
+    return v.numpy(), t.numpy(), vbase, tv, tt
+
+
+def test_marching_cubes_two_ranks(orc):
+    out = run_ranks("rank_mc", "test_dist_gloo")
+    g = global_volume()
+    mask = ((g >= THR[0]) & (g <= THR[1])).astype(np.uint8) * 255
+    V, T = orc.marching_cubes(mask, 127, (0.5, 0.75, 1.5), (-1, -1, 3), True)
+    gv = np.concatenate([out[0][0], out[1][0]])
+    gt = np.concatenate([out[0][1], out[1][1]])
+    assert out[0][3] == len(V) and out[0][4] == len(T) and out[1][2] == len(out[0][0])
+    assert np.array_equal(gv, V)
+    assert np.array_equal(gt.astype(np.int64), T)

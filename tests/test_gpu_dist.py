@@ -1,0 +1,79 @@
+"""Z-sharded ops with the CUDA backend: 2 ranks. On a 1-GPU box both ranks share the device
+and talk through gloo (tensors staged via the host); with >= 2 GPUs the same functions also
+run over NCCL, one rank per GPU. Results must equal the oracle on the whole volume."""
+import numpy as np
+import pytest
+import torch
+
+from dist_common import ext_slab, global_volume, run_ranks
+from test_dist_gloo import THR, ff_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def rank_all(rank, world, device):
+    from invesalius3_b200 import dist as d
+    g = global_volume((37, 40, 96), seed=3)
+    shard = d.ZShard(g.shape[0], rank, world)
+    res = {}
+    own = torch.from_numpy(np.ascontiguousarray(g[shard.z0:shard.z1])).to(_dev())
+    for axis in (0, 1, 2):
+        for kind in ("max", "min", "mean"):
+            res[("mip", axis, kind)] = d.mip(own, axis, kind, shard).cpu().numpy()
+    res["thr"] = (shard.z0, shard.z1, d.threshold(own, *THR, shard).cpu().numpy())
+    # flood fill
+    for ci, (strct, seeds) in enumerate(ff_cases(g)):
+        data = torch.from_numpy(ext_slab(g, shard)).to(_dev())
+        dext = torch.empty_like(data)
+        d.shard_copy = None
+        out_g = np.zeros(g.shape, np.uint8); out_g[:, 10, :] = 254
+        out = torch.from_numpy(ext_slab(out_g, shard).copy()).to(_dev())
+        # halo planes arrive by exchange, not from the global array
+        if shard.has_lo: data[0] = 0; out[0] = 0
+        if shard.has_hi: data[-1] = 0; out[-1] = 0
+        d.exchange_halo(data, shard); d.exchange_halo(out, shard)
+        outer = d.floodfill_threshold(data, seeds, 100, 3071, 254, strct, out, shard)
+        res[("ff", ci)] = (shard.interior(out).cpu().numpy(), outer)
+    # marching cubes on the thresholded mask
+    mask = ((g >= THR[0]) & (g <= THR[1])).astype(np.uint8) * 255
+    vol = torch.from_numpy(ext_slab(mask, shard, lo=False, hi=True)).to(_dev())
+    v, t, vbase, tv, tt = d.marching_cubes(vol, 127, (0.5, 0.75, 1.5), (-1, -1, 3), True, shard)
+    res["mc"] = (v.cpu().numpy(), t.cpu().numpy(), vbase, tv, tt)
+    return res
+
+
+def _check(out, orc):
+    g = global_volume((37, 40, 96), seed=3)
+    for rank in (0, 1):
+        for axis in (0, 1, 2):
+            for kind in ("max", "min", "mean"):
+                want = {"max": g.max, "min": g.min, "mean": g.mean}[kind](axis)
+                assert np.array_equal(out[rank][("mip", axis, kind)], want), (rank, axis, kind)
+        z0, z1, m = out[rank]["thr"]
+        want = np.zeros(g.shape, np.uint8)
+        orc.threshold(g, *THR, want, False)
+        assert np.array_equal(m, want[z0:z1])
+    for ci, (strct, seeds) in enumerate(ff_cases(g)):
+        want = np.zeros(g.shape, np.uint8); want[:, 10, :] = 254
+        orc.floodfill_threshold(g, seeds, 100, 3071, 254, strct, want)
+        got = np.concatenate([out[r][("ff", ci)][0] for r in (0, 1)])
+        assert np.array_equal(got, want), ci
+    mask = ((g >= THR[0]) & (g <= THR[1])).astype(np.uint8) * 255
+    V, T = orc.marching_cubes(mask, 127, (0.5, 0.75, 1.5), (-1, -1, 3), True)
+    gv = np.concatenate([out[0]["mc"][0], out[1]["mc"][0]])
+    gt = np.concatenate([out[0]["mc"][1], out[1]["mc"][1]])
+    assert out[0]["mc"][3] == len(V) and out[0]["mc"][4] == len(T)
+    assert np.array_equal(gv, V) and np.array_equal(gt.astype(np.int64), T)
+
+
+def test_sharded_ops_two_ranks_one_gpu_gloo(orc):
+    _check(run_ranks("rank_all", "test_gpu_dist", device="cuda"), orc)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_ops_two_ranks_nccl(orc):
+    _check(run_ranks("rank_all", "test_gpu_dist", device="nccl"), orc)
