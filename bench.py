@@ -44,11 +44,16 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def make_volume(n):
+def make_volume(n, world=1, zrange=None):
+    """The job's volume is (n*world) x n x n, Z-sharded; returns the planes `zrange` (default:
+    all) and the global seed (x, y, z) in the middle slice."""
     from invesalius3_b200 import phantom
-    vol = phantom.ct((n, n, n), seed=2)
-    seed = phantom.first_seed_in_range(vol, int(n * SEED_SLICE_FRAC), *THR)
-    return vol, seed
+    DZ = n * world
+    zmid = int(DZ * SEED_SLICE_FRAC)
+    mid = phantom.ct((DZ, n, n), seed=2, zrange=(zmid, zmid + 1))
+    sx, sy, _ = phantom.first_seed_in_range(mid, 0, *THR)
+    vol = phantom.ct((DZ, n, n), seed=2, zrange=zrange)
+    return vol, (sx, sy, zmid)
 
 
 # ------------------------------------------------------------------ CPU reference path
@@ -153,39 +158,74 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     n = args.size
-    vol, seed = make_volume(n)            # every rank holds one n^3 shard of the job (weak scaling)
+    from invesalius3_b200 import dist as zd
+    shard = zd.ZShard(n * world, rank, world)
+    ext_np, seed = make_volume(n, world, (shard.ze0, shard.ze1))   # own planes + halo planes
+    vol = shard.interior(torch.from_numpy(ext_np)).numpy()          # this rank's n^3 shard
     strct = generate_binary_structure(3, 1)
     N = vol.size
+    nz_ext = ext_np.shape[0]
 
     # pinned host buffers for the e2e leg (numpy views of torch pinned tensors)
-    h_vol = torch.from_numpy(vol).pin_memory()
+    h_ext = torch.from_numpy(ext_np).pin_memory()
+    h_vol = shard.interior(h_ext)
     h_mask = torch.zeros((n + 1, n + 1, n + 1), dtype=torch.uint8).pin_memory()
-    h_out = torch.zeros((n, n, n), dtype=torch.uint8).pin_memory()
+    h_out = torch.zeros((nz_ext, n, n), dtype=torch.uint8).pin_memory()
     np_vol, np_mask, np_out = h_vol.numpy(), h_mask.numpy(), h_out.numpy()
 
-    d_vol = h_vol.cuda(non_blocking=True)
+    d_ext = h_ext.cuda(non_blocking=True)
+    d_vol = shard.interior(d_ext)
     d_mask = torch.empty((n, n, n), dtype=torch.uint8, device="cuda")
-    d_out = torch.empty((n, n, n), dtype=torch.uint8, device="cuda")
+    d_out = torch.empty((nz_ext, n, n), dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
     info = {}
+    local_seed = (seed[0], seed[1], seed[2] - shard.ze0)
+
+    def do_flood(data_ext, out_ext):
+        if world == 1:
+            info["rounds"] = dev.floodfill_threshold(data_ext, [seed], THR[0], THR[1], FILL, strct, out_ext)
+        else:
+            info["rounds"] = zd.floodfill_threshold(data_ext, [seed], THR[0], THR[1], FILL, strct, out_ext, shard)
+
+    def do_surface(out_ext):
+        if world == 1:
+            v, f = marching_cubes(out_ext, 127, SPACING, (0, 0, 0), True)
+            info["V"], info["T"] = int(v.shape[0]), int(f.shape[0])
+        else:
+            v, f, _, info["V"], info["T"] = zd.marching_cubes(out_ext[int(shard.has_lo):], 127, SPACING, (0, 0, 0),
+                                                              True, shard)
+        return v, f
+
+    def flood_and_surface(data_ext, out_ext):
+        do_flood(data_ext, out_ext)
+        return do_surface(out_ext)
 
     def step_device(ev=None):
         if ev: ev[0].record()
         dev.threshold(d_vol, THR[0], THR[1], out=d_mask)
         if ev: ev[1].record()
         d_out.zero_()
-        info["rounds"] = dev.floodfill_threshold(d_vol, [seed], THR[0], THR[1], FILL, strct, d_out)
+        do_flood(d_ext, d_out)
         if ev: ev[2].record()
-        v, f = marching_cubes(d_out, 127, SPACING, (0, 0, 0), True)
+        do_surface(d_out)
         if ev: ev[3].record()
-        info["V"], info["T"] = int(v.shape[0]), int(f.shape[0])
 
     def step_e2e():
-        slice_ops.set_mask_threshold(np_vol, np_mask, THR)
-        np_out[...] = 0
-        invesalius_rs.floodfill_threshold(np_vol, [seed], THR[0], THR[1], FILL, strct, np_out)
-        v, f = surface_process.contour(np_out, [127], SPACING, 0, True)
-        return v, f
+        if world == 1:
+            slice_ops.set_mask_threshold(np_vol, np_mask, THR)
+            np_out[...] = 0
+            invesalius_rs.floodfill_threshold(np_vol, [seed], THR[0], THR[1], FILL, strct, np_out)
+            v, f = surface_process.contour(np_out, [127], SPACING, 0, True)
+            return v, f
+        # N > 1: the sharded pipeline fed from / drained to pinned host memory
+        t_ext = dev.to_device(h_ext.numpy())
+        m = dev.threshold(shard.interior(t_ext), THR[0], THR[1])
+        dev.to_host(m, np_mask[1:, 1:, 1:])
+        np_mask[1:, 0, 0] = 1
+        o_ext = torch.zeros((nz_ext, n, n), dtype=torch.uint8, device="cuda")
+        v, f = flood_and_surface(t_ext, o_ext)
+        dev.to_host(shard.interior(o_ext), shard.interior(h_out).numpy())
+        return v.cpu().numpy(), f.cpu().numpy()
 
     def barrier():
         if world > 1:
@@ -232,7 +272,10 @@ def run_gpu(args):
         v, f = step_e2e()
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-    h2d = 2 * N * 2 + 2 * N            # image twice (threshold, flood fill), out in, out again for MC
+    if world == 1:
+        h2d = 2 * N * 2 + 2 * N            # image twice (threshold, flood fill), out in, out again for MC
+    else:
+        h2d = ext_np.nbytes                # the extended slab once; the pipeline stays on the device
     d2h = 2 * N + v.nbytes + f.nbytes  # mask, out, mesh
     e2e_value = world * N / e2e_s / 1e6
 
@@ -243,31 +286,36 @@ def run_gpu(args):
     peak, peak_kind = measured_peak()
     # dominant stage and its roofline (algorithmic bytes: SURVEY.md 8d / DESIGN.md)
     alg = {"threshold": 3.0 * N, "floodfill": 4.0 * N,
-           "marching_cubes": 1.0 * N + 12.0 * info["V"] + 12.0 * info["T"]}
+           "marching_cubes": 1.0 * N + (12.0 * info["V"] + 12.0 * info["T"]) / world}
     names = list(alg)
     dom = int(np.argmax(stage_ms))
     achieved = alg[names[dom]] / (stage_ms[dom] * 1e-3) / 1e9
     cores = os.cpu_count() or 1
-    cpu_v, cpu_sample_desc = time_cpu(vol, seed, min(n, args.cpu_slices), 1, cores)
+    cpu_baseline = None
+    if world == 1:   # the CPU baseline is an N=1 figure (rank 0's host cores)
+        cpu_v, cpu_sample_desc = time_cpu(vol, seed, min(n, args.cpu_slices), 1, cores)
+        cpu_baseline = {"value": round(cpu_v, 2), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": cpu_sample_desc}
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
         "config": {"workload": f"{n}^3 synthetic int16 CT phantom (seed 2): threshold [226,3071] -> "
                                "6-connected flood fill from one seed -> marching cubes iso 127 on the grown mask",
+                   "volume": f"{n * world}x{n}x{n} (Z-sharded, one halo plane per inner side)",
                    "shard": f"{n}^3 voxels per GPU", "l2": "inputs (256 MiB int16 + 128 MiB uint8) exceed the 126 MB L2",
                    "flood_rounds": info["rounds"], "vertices": info["V"], "triangles": info["T"],
                    "stage_ms": {k: round(float(m), 4) for k, m in zip(names, stage_ms)}},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_s * 1e3, 3),
-                "api": "slice_ops.set_mask_threshold + invesalius_rs.floodfill_threshold + surface_process.contour "
-                       "on pinned numpy buffers"},
+                "api": ("slice_ops.set_mask_threshold + invesalius_rs.floodfill_threshold + surface_process.contour "
+                        "on pinned numpy buffers") if world == 1 else
+                       "dist.* sharded pipeline fed from / drained to pinned host buffers"},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak,
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                      "per_stage_GBs": {k: round(alg[k] / (m * 1e-3) / 1e9, 1) for k, m in zip(names, stage_ms)}},
-        "cpu_baseline": {"value": round(cpu_v, 2), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": cpu_sample_desc},
+        "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
     if world > 1:

@@ -291,7 +291,9 @@ def mip(img_slab, axis, kind, shard: ZShard, gather=True, backend=None):
         if kind == "mean":
             part = be.sum_axis0(img_slab)
             _all_reduce(shard, part, dist.ReduceOp.SUM)
-            return part.to(torch.float64) / shard.DZ
+            # tensor / tensor is a true IEEE division (tensor / python-scalar multiplies by the
+            # reciprocal on CUDA and would differ from NumPy's mean in the last bit)
+            return part.to(torch.float64) / torch.full((), float(shard.DZ), dtype=torch.float64, device=part.device)
         part = be.mip(img_slab, 0, kind).to(torch.int32)   # NCCL has no int16
         _all_reduce(shard, part, dist.ReduceOp.MAX if kind == "max" else dist.ReduceOp.MIN)
         return part.to(img_slab.dtype)

@@ -25,7 +25,8 @@ def lib() -> C.CDLL:
     global _LIB
     if _LIB is None:
         so = _HERE / "liboracle.so"
-        if not so.exists() or so.stat().st_mtime < (_HERE / "oracle.c").stat().st_mtime:
+        srcs = list(_HERE.glob("*.c"))
+        if not so.exists() or any(so.stat().st_mtime < s.stat().st_mtime for s in srcs):
             subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
         _LIB = C.CDLL(str(so))
     return _LIB

@@ -1,0 +1,123 @@
+/* watershed.c — CPU restatement of skimage.segmentation.watershed as the reference uses it
+ * (invesalius/data/watershed_process.py:39,52: watershed(gradient, markers.astype(int16),
+ * bstruct), no mask, no compactness, no watershed line).
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle.c).
+ *
+ * scikit-image 0.24.0 is a third-party dependency that is absent from this image and from
+ * /root/reference (pyproject.toml:35), so this follows its published algorithm
+ * (skimage/segmentation/_watershed_cy.pyx::watershed_raveled + heap_general.pxi) from
+ * memory — PARITY UNPINNED:
+ *   - every marker voxel is pushed (raveled order) with key (value = image, age = 0);
+ *   - the heap is a plain array binary heap ordered by (value, age);
+ *   - pop the smallest; for each neighbour in the order of _offsets_to_raveled_neighbors
+ *     (footprint entries sorted by squared distance from the centre, stable, centre
+ *     dropped): skip if out of the image or already labelled; otherwise label it with the
+ *     popped voxel's label AT PUSH TIME and push it with (image[neighbour], ++age).
+ * The SciPy callees (watershed_ift, morphological_gradient) are present in this image and
+ * are called directly by oracle/__init__.py, so they need no restatement.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+  double value;
+  int64_t age;
+  int64_t index;
+} elem_t;
+
+typedef struct {
+  elem_t* a;
+  int64_t n, cap;
+} heap_t;
+
+static int smaller(const elem_t* x, const elem_t* y) {
+  if (x->value != y->value) return x->value < y->value;
+  return x->age < y->age;
+}
+static void heap_push(heap_t* h, elem_t e) {
+  if (h->n == h->cap) {
+    h->cap *= 2;
+    h->a = (elem_t*)realloc(h->a, sizeof(elem_t) * (size_t)h->cap);
+  }
+  int64_t child = h->n++;
+  h->a[child] = e;
+  while (child > 0) {
+    int64_t parent = (child + 1) / 2 - 1;
+    if (smaller(&h->a[child], &h->a[parent])) {
+      elem_t t = h->a[child]; h->a[child] = h->a[parent]; h->a[parent] = t;
+      child = parent;
+    } else break;
+  }
+}
+static elem_t heap_pop(heap_t* h) {
+  elem_t top = h->a[0];
+  if (h->n <= 1) { h->n = 0; return top; }
+  h->n -= 1;
+  h->a[0] = h->a[h->n];
+  int64_t parent = 0, child = 1;
+  while (child < h->n) {
+    if (child + 1 < h->n && smaller(&h->a[child + 1], &h->a[child])) child += 1;
+    if (smaller(&h->a[child], &h->a[parent])) {
+      elem_t t = h->a[child]; h->a[child] = h->a[parent]; h->a[parent] = t;
+      parent = child;
+      child = 2 * child + 1;
+    } else break;
+  }
+  return top;
+}
+
+/* image uint16 [nz][ny][nx]; markers int16; strct uint8 [sz][sy][sx] (odd dims); out int16 */
+int orc_watershed_skimage(const uint16_t* image, const int16_t* markers, int64_t nz, int64_t ny, int64_t nx,
+                          const uint8_t* strct, int64_t sz, int64_t sy, int64_t sx, int16_t* out) {
+  int64_t n = nz * ny * nx;
+  /* neighbour list sorted by squared distance (stable), centre removed */
+  int64_t cz = sz / 2, cy = sy / 2, cx = sx / 2;
+  int64_t cnt = 0;
+  int64_t(*nb)[4] = (int64_t(*)[4])malloc(sizeof(int64_t) * 4 * (size_t)(sz * sy * sx));
+  for (int64_t k = 0; k < sz; ++k)
+    for (int64_t j = 0; j < sy; ++j)
+      for (int64_t i = 0; i < sx; ++i)
+        if (strct[(k * sy + j) * sx + i]) {
+          int64_t dz = k - cz, dy = j - cy, dx = i - cx;
+          if (dz == 0 && dy == 0 && dx == 0) continue;
+          nb[cnt][0] = dz; nb[cnt][1] = dy; nb[cnt][2] = dx; nb[cnt][3] = dz * dz + dy * dy + dx * dx;
+          ++cnt;
+        }
+  for (int64_t a = 1; a < cnt; ++a) { /* stable insertion sort by distance */
+    int64_t t[4];
+    memcpy(t, nb[a], sizeof(t));
+    int64_t b = a - 1;
+    while (b >= 0 && nb[b][3] > t[3]) { memcpy(nb[b + 1], nb[b], sizeof(t)); --b; }
+    memcpy(nb[b + 1], t, sizeof(t));
+  }
+  memcpy(out, markers, sizeof(int16_t) * (size_t)n);
+  heap_t h;
+  h.cap = 1 << 16;
+  h.n = 0;
+  h.a = (elem_t*)malloc(sizeof(elem_t) * (size_t)h.cap);
+  for (int64_t p = 0; p < n; ++p)
+    if (out[p]) {
+      elem_t e = {(double)image[p], 0, p};
+      heap_push(&h, e);
+    }
+  int64_t age = 1;
+  while (h.n > 0) {
+    elem_t e = heap_pop(&h);
+    int64_t z = e.index / (ny * nx), r = e.index % (ny * nx), y = r / nx, x = r % nx;
+    for (int64_t k = 0; k < cnt; ++k) {
+      int64_t zz = z + nb[k][0], yy = y + nb[k][1], xx = x + nb[k][2];
+      if (zz < 0 || zz >= nz || yy < 0 || yy >= ny || xx < 0 || xx >= nx) continue; /* padded border: mask False */
+      int64_t q = (zz * ny + yy) * nx + xx;
+      if (out[q]) continue;
+      age += 1;
+      out[q] = out[e.index];
+      elem_t ne = {(double)image[q], age, q};
+      heap_push(&h, ne);
+    }
+  }
+  free(h.a);
+  free(nb);
+  return 0;
+}
