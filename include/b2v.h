@@ -170,6 +170,29 @@ int b2v_mc_emit(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, 
                 float sx, float sy, float sz, int32_t ox, int32_t oy, int32_t oz, int flip_y, float* verts,
                 int32_t* tris, void* stream);
 
+/* ---- watershed -------------------------------------------------------------------------
+ * do_watershed, invesalius/data/watershed_process.py:19-60.
+ * b2v_ws_lut_i16: get_LUT_value(image, ww, wl).astype('uint16'), invesalius/data/
+ *   imagedata_utils.py:555-564 (float64 piecewise, truncated into int16, reinterpreted).
+ * b2v_ws_shift_i16: (image - image.min()).astype('uint16') (watershed_process.py:50,55);
+ *   workspace: b2v_ws_workspace_bytes.
+ * b2v_ws_morph_gradient_u16: scipy.ndimage.morphological_gradient(pre, size=(sz,sy,sx)),
+ *   mode 'reflect' (watershed_process.py:36,49). Bit-exact against SciPy.
+ * b2v_ws_flood: mode 0 = scipy.ndimage.watershed_ift cost model (max |dI| along the path),
+ *   mode 1 = skimage.segmentation.watershed cost model (max I along the path). markers
+ *   int16 (0 = unlabeled); labels int16 out. Exact minimax costs; labels follow cost-optimal
+ *   edges, ties resolved by hop count then smaller label (the reference's ties follow its
+ *   queue order: see DESIGN.md section 6). SYNCHRONISES the stream. strct_host: uint8, dims
+ *   1 or 3. 14 B/voxel for the whole do_watershed as the reference defines it. */
+int b2v_ws_lut_i16(const int16_t* img, int64_t n, double window, double level, uint16_t* out, void* stream);
+int b2v_ws_shift_i16(const int16_t* img, int64_t n, uint16_t* out, void* workspace, void* stream);
+int b2v_ws_morph_gradient_u16(const uint16_t* in, int64_t nz, int64_t ny, int64_t nx, int sz, int sy, int sx,
+                              uint16_t* out, void* stream);
+int64_t b2v_ws_workspace_bytes(int64_t nz, int64_t ny, int64_t nx);
+int b2v_ws_flood(const uint16_t* img, const int16_t* markers, int64_t nz, int64_t ny, int64_t nx,
+                 const uint8_t* strct_host, int64_t odz, int64_t ody, int64_t odx, int mode, int16_t* labels,
+                 void* workspace, void* stream, int* rounds_out);
+
 /* ---- Z-sharded volumes (one shard per GPU; invesalius3_b200/dist.py drives these) ---------
  * The reference's only decomposition is the Z-piece split of the surface step
  * (invesalius/data/surface.py:1360-1381: pieces of 20 slices + 1 overlap, stitched by
