@@ -222,16 +222,23 @@ __global__ void __launch_bounds__(kFloodThreads)
     active_cur[tile] = 0;  // this buffer becomes `next` of the following round
     s_faces = 0;
   }
-  // halo load (zero outside the volume)
+  // halo load (zero outside the volume); passable bits of the interior ride along for the
+  // directional sweeps (halo entries of sF stay 0: halo words are never written)
   const int nh = (tz + 2) * py * pw;
+  uint32_t* sF = sR + nh;
   for (int i = tid; i < nh; i += kFloodThreads) {
     int hw = i % pw, hy = (i / pw) % py, hz = i / (pw * py);
     int64_t z = z0 + hz - 1, y = y0 + hy - 1;
     int w = w0 + hw - 1;
-    uint32_t v = 0;
-    if (z >= 0 && z < b.dz && y >= 0 && y < b.dy && w >= 0 && w < b.wx)
-      v = __ldcg(&reach[(z * b.dy + y) * b.wx + w]);
+    uint32_t v = 0, f = 0;
+    if (z >= 0 && z < b.dz && y >= 0 && y < b.dy && w >= 0 && w < b.wx) {
+      int64_t gi = (z * b.dy + y) * b.wx + w;
+      v = __ldcg(&reach[gi]);
+      bool interior = hz >= 1 && hz <= tz && hy >= 1 && hy <= ty && hw >= 1 && hw <= tw;
+      if (interior) f = __ldg(&fg[gi]);
+    }
     sR[i] = v;
+    sF[i] = f;
   }
   // owned words: fg and the initial reach value stay in registers
   constexpr int kOwn = kTileWords / kFloodThreads;
@@ -247,7 +254,6 @@ __global__ void __launch_bounds__(kFloodThreads)
       int64_t z = z0 + iz, y = y0 + iy;
       int w = w0 + iw;
       if (z < b.dz && y < b.dy && w < b.wx) {
-        fgr[k] = __ldg(&fg[(z * b.dy + y) * b.wx + w]);
         hidx[k] = ((iz + 1) * py + (iy + 1)) * pw + (iw + 1);
       }
     }
@@ -255,13 +261,95 @@ __global__ void __launch_bounds__(kFloodThreads)
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < kOwn; ++k)
-    if (hidx[k] >= 0) r0[k] = sR[hidx[k]];
+    if (hidx[k] >= 0) {
+      r0[k] = sR[hidx[k]];
+      fgr[k] = sF[hidx[k]];
+    }
 
   const bool xfill = ((sb >> 12) & 1u) && ((sb >> 14) & 1u);  // (0,0,-1) and (0,0,+1)
+  // axis-aligned offsets present in the structuring element (flood moves p -> p + off)
+  const bool yfwd = (sb >> 16) & 1u, ybwd = (sb >> 10) & 1u;   // (0,+1,0), (0,-1,0)
+  const bool zfwd = (sb >> 22) & 1u, zbwd = (sb >> 4) & 1u;    // (+1,0,0), (-1,0,0)
   int changed;
   int iters = 0;
   do {
     changed = 0;
+    // ---- directional sweeps: each carries reached bits across the whole tile along one
+    // axis in a single pass (a Jacobi step moves them by one row / one word only)
+    if (xfill) {
+      for (int r = tid; r < tz * ty; r += kFloodThreads) {
+        const int base = ((r / ty + 1) * py + (r % ty + 1)) * pw + 1;
+        uint32_t carry = sR[base - 1] >> 31;
+        for (int w = 0; w < tw; ++w) {
+          uint32_t f = sF[base + w], cur = sR[base + w];
+          uint32_t v = f ? run_fill((cur | carry) & f, f) : 0u;
+          if (v != cur) { sR[base + w] = v; changed = 1; }
+          carry = v >> 31;
+        }
+        carry = sR[base + tw] & 1u;
+        for (int w = tw - 1; w >= 0; --w) {
+          uint32_t f = sF[base + w], cur = sR[base + w];
+          uint32_t v = f ? run_fill((cur | (carry << 31)) & f, f) : 0u;
+          if (v != cur) { sR[base + w] = v; changed = 1; }
+          carry = v & 1u;
+        }
+      }
+      __syncthreads();
+    }
+    if (yfwd || ybwd) {
+      for (int c = tid; c < tz * tw; c += kFloodThreads) {
+        const int base = ((c / tw + 1) * py) * pw + (c % tw + 1);  // row hy = 0 of this column
+        if (yfwd) {
+          uint32_t prev = sR[base];
+          for (int y = 1; y <= ty; ++y) {
+            uint32_t f = sF[base + y * pw], cur = sR[base + y * pw];
+            uint32_t v = (cur | prev) & f;
+            if (xfill && v) v = run_fill(v, f);
+            if (v != cur) { sR[base + y * pw] = v; changed = 1; }
+            prev = v;
+          }
+        }
+        if (ybwd) {
+          uint32_t prev = sR[base + (ty + 1) * pw];
+          for (int y = ty; y >= 1; --y) {
+            uint32_t f = sF[base + y * pw], cur = sR[base + y * pw];
+            uint32_t v = (cur | prev) & f;
+            if (xfill && v) v = run_fill(v, f);
+            if (v != cur) { sR[base + y * pw] = v; changed = 1; }
+            prev = v;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (zfwd || zbwd) {
+      const int pz = py * pw;
+      for (int c = tid; c < ty * tw; c += kFloodThreads) {
+        const int base = (c / tw + 1) * pw + (c % tw + 1);  // plane hz = 0 of this column
+        if (zfwd) {
+          uint32_t prev = sR[base];
+          for (int z = 1; z <= tz; ++z) {
+            uint32_t f = sF[base + z * pz], cur = sR[base + z * pz];
+            uint32_t v = (cur | prev) & f;
+            if (xfill && v) v = run_fill(v, f);
+            if (v != cur) { sR[base + z * pz] = v; changed = 1; }
+            prev = v;
+          }
+        }
+        if (zbwd) {
+          uint32_t prev = sR[base + (tz + 1) * pz];
+          for (int z = tz; z >= 1; --z) {
+            uint32_t f = sF[base + z * pz], cur = sR[base + z * pz];
+            uint32_t v = (cur | prev) & f;
+            if (xfill && v) v = run_fill(v, f);
+            if (v != cur) { sR[base + z * pz] = v; changed = 1; }
+            prev = v;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- generic step: every offset of the structuring element, one hop
 #pragma unroll
     for (int k = 0; k < kOwn; ++k) {
       if (hidx[k] < 0 || fgr[k] == 0) continue;
@@ -399,7 +487,7 @@ int grid_for(int64_t items, int per_block) {
 // rounds until no tile is active. Synchronises the stream (reads one flag per batch).
 int run_rounds(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s, int r0, int* rounds_out) {
   const int ntiles = b.ntz * b.nty * b.ntw;
-  const size_t smem = (size_t)(b.tz + 2) * (b.ty + 2) * (b.tw + 2) * sizeof(uint32_t);
+  const size_t smem = 2 * (size_t)(b.tz + 2) * (b.ty + 2) * (b.tw + 2) * sizeof(uint32_t);
   int r = r0, batch = 4, rc;
   B2V_REQUIRE(r0 >= 0 && r0 + batch < kMaxRounds, B2V_ERR_NOCONV, "floodfill: round counter exhausted (%d)", r0);
   while (true) {

@@ -186,8 +186,13 @@ __global__ void __launch_bounds__(kThreads) k_ws_round(const uint16_t* __restric
     uint32_t c = kInfC;
     unsigned long long k = kInfK;
     uint16_t v = 0;
-    if (z >= 0 && z < g.nz && y >= 0 && y < g.ny && x >= 0 && x < g.nx) {
-      int64_t p = (z * g.ny + y) * g.nx + x;
+    // MODE 0 reproduces scipy.ndimage.watershed_ift's neighbourhood: the volume is walked as
+    // a flat array, a neighbour is any flat index + structure offset inside [0, N), so rows
+    // and planes wrap into each other at the volume faces (verified against SciPy 1.18.1).
+    const int64_t p = (z * g.ny + y) * g.nx + x;
+    const bool valid = MODE == 0 ? (p >= 0 && p < g.nz * g.ny * g.nx)
+                                 : (z >= 0 && z < g.nz && y >= 0 && y < g.ny && x >= 0 && x < g.nx);
+    if (valid) {
       c = __ldcg(&cost[p]);
       v = img[p];
       if (PHASE == 2) k = __ldcg(&key[p]);
@@ -304,9 +309,9 @@ __global__ void __launch_bounds__(kThreads) k_ws_round(const uint16_t* __restric
     if (lz == 0) faces |= 1;
     if (lz == kT - 1) faces |= 2;
     if (ly == 0) faces |= 4;
-    if (ly == kT - 1) faces |= 8;
+    if (ly == kT - 1 || y0 + ly == g.ny - 1) faces |= 8;
     if (lx == 0) faces |= 16;
-    if (lx == kT - 1) faces |= 32;
+    if (lx == kT - 1 || x0 + lx == g.nx - 1) faces |= 32;
   }
   (void)any_own_changed;
   if (faces) atomicOr(&s_faces, faces);
@@ -318,6 +323,24 @@ __global__ void __launch_bounds__(kThreads) k_ws_round(const uint16_t* __restric
   }
   if ((faces & 63) == 0) return;
   __threadfence();
+  if (MODE == 0) {
+    // wrapped neighbours live in tiles on the opposite x / y border (a row end touches the
+    // next row's start, a plane's last row the next plane's first): wake those up too
+    const bool xb = ((faces & 16) && tx == 0) || ((faces & 32) && tx == g.ntx - 1);
+    const bool yb = ((faces & 4) && ty == 0) || ((faces & 8) && ty == g.nty - 1);
+    if (xb)
+      for (int i = tid; i < 2 * 5 * g.nty; i += kThreads) {
+        int side = i % 2, dzt = (i / 2) % 5 - 2, yy = i / 10;
+        int nz = tz + dzt, nx = side ? g.ntx - 1 : 0;
+        if (nz >= 0 && nz < g.ntz) { active_next[(nz * g.nty + yy) * g.ntx + nx] = 1; flags[round + 1] = 1; }
+      }
+    if (yb)
+      for (int i = tid; i < 2 * 5 * g.ntx; i += kThreads) {
+        int side = i % 2, dzt = (i / 2) % 5 - 2, xx = i / 10;
+        int nz = tz + dzt, ny = side ? g.nty - 1 : 0;
+        if (nz >= 0 && nz < g.ntz) { active_next[(nz * g.nty + ny) * g.ntx + xx] = 1; flags[round + 1] = 1; }
+      }
+  }
   if (tid < 27) {
     int oz = tid / 9 - 1, oy = (tid / 3) % 3 - 1, ox = tid % 3 - 1;
     if (oz == 0 && oy == 0 && ox == 0) return;

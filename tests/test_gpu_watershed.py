@@ -74,18 +74,27 @@ def _markers(shape, seed, k=4):
 
 @pytest.mark.parametrize("conn", [1, 3])
 def test_ift_matches_scipy_when_tie_free(wp, conn):
+    """Random full-range uint16 volumes: edge weights |dI| rarely collide, so SciPy's answer
+    is (almost) free of queue-order ties and must be reproduced — including its flat-array
+    neighbourhood that wraps rows and planes into each other at the volume faces."""
     st = generate_binary_structure(3, conn)
+    rng = np.random.default_rng(conn)
     agree_total, n_total = 0, 0
-    for seed, shape in enumerate([(6, 7, 8), (10, 12, 14), (5, 30, 31)]):
-        img = _tie_free_image(shape, seed)
+    for seed, shape in enumerate([(6, 7, 8), (10, 12, 14), (5, 30, 31), (20, 33, 47), (3, 70, 18)]):
+        img = rng.integers(0, 65536, shape).astype(np.uint16)
         mk = _markers(shape, seed + 10)
         want = ndimage.watershed_ift(img, mk, st)
         got = wp.flood(_t(img.view(np.int16)), _t(mk), st, "Watershed IFT").cpu().numpy()
         agree_total += int((got == want).sum()); n_total += want.size
         assert np.array_equal(got[mk != 0], mk[mk != 0])
         assert (got != 0).all()
-    # distinct values leave only a few genuine ties (equal max-edge from two labels)
-    assert agree_total / n_total >= 0.98, agree_total / n_total
+    assert agree_total / n_total >= 0.995, agree_total / n_total
+    # narrow value range: many equal edge weights, i.e. genuine queue-order ties
+    img = rng.integers(0, 300, (8, 20, 20)).astype(np.uint16)
+    mk = _markers(img.shape, 99)
+    want = ndimage.watershed_ift(img, mk, st)
+    got = wp.flood(_t(img.view(np.int16)), _t(mk), st, "Watershed IFT").cpu().numpy()
+    assert (got == want).mean() >= 0.9, (got == want).mean()
 
 
 def test_ift_simple_known_answers(wp):
