@@ -337,6 +337,8 @@ __global__ void __launch_bounds__(256) k_mc_emit(const T* __restrict__ vol, McGe
                                                  int foreign_base, float* __restrict__ verts,
                                                  int* __restrict__ tris) {
   __shared__ signed char s_tri[256][16];  // 15 edge ids + triangle count
+  __shared__ uint4 s_rec[8][8];           // per warp: owner records of the current word
+  __shared__ int s_base[8][8];
   for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
     int c = i >> 4, k = i & 15;
     s_tri[c][k] = k < 15 ? B2V_MC_TRI[c][k] : (signed char)B2V_MC_NTRI[c];
@@ -406,6 +408,25 @@ __global__ void __launch_bounds__(256) k_mc_emit(const T* __restrict__ vol, McGe
       }
       // ---- triangles of cell (z, y, x)
       if (y + 1 < g.ny && z + 1 < g.nz) {
+        // the 12 edges of the 32 cells of this word are owned by voxels of 4 rows x 2 words:
+        // fetch those 8 records once per warp instead of once per triangle corner
+        __syncwarp();
+        if (lane < 8) {
+          const int cz = lane >> 2, cy = (lane >> 1) & 1, cw = lane & 1;
+          uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+          int base = vbase;
+          if (w + cw < g.wx) {
+            if (skip_last && z + cz == g.nz - 1) {
+              rec = __ldg(foreign + (y + cy) * g.wx + (w + cw));
+              base = foreign_base;
+            } else {
+              rec = __ldg(info + ((z + cz) * g.ny + (y + cy)) * g.wx + (w + cw));
+            }
+          }
+          s_rec[threadIdx.x >> 5][lane] = rec;
+          s_base[threadIdx.x >> 5][lane] = base;
+        }
+        __syncwarp();
         Rows r = load_rows(bits, g, z, y, w);
         int c = (x + 1 < g.nx) ? cell_case(r, lane) : 0;
         int ntri = s_tri[c][15];
@@ -424,20 +445,13 @@ __global__ void __launch_bounds__(256) k_mc_emit(const T* __restrict__ vol, McGe
             for (int m = 0; m < 3; ++m) {
               int code = edge_code(s_tri[c][3 * t + m]);
               int a = code & 3;
-              int64_t qx = x + ((code >> 2) & 1), qy = y + ((code >> 3) & 1), qz = z + ((code >> 4) & 1);
-              int ob = (int)(qx & 31);
+              int qx = lane + ((code >> 2) & 1);            // 0..32 within the word pair
+              int slot = ((code >> 4) & 1) * 4 + ((code >> 3) & 1) * 2 + (qx >> 5);
+              int ob = qx & 31;
               uint32_t ol = (1u << ob) - 1u;
-              uint4 oi;
-              int v;
-              if (skip_last && qz == g.nz - 1) {
-                // owned by the next shard: its records of that plane, its numbering
-                oi = __ldg(foreign + qy * g.wx + (qx >> 5));
-                v = foreign_base;
-              } else {
-                oi = __ldg(info + (qz * g.ny + qy) * g.wx + (qx >> 5));
-                v = vbase;
-              }
-              v += (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
+              uint4 oi = s_rec[threadIdx.x >> 5][slot];
+              int v = s_base[threadIdx.x >> 5][slot] +
+                      (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
               if (a > 0) v += (oi.x >> ob) & 1;
               if (a > 1) v += (oi.y >> ob) & 1;
               id[m] = v;

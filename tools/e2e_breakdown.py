@@ -1,0 +1,50 @@
+"""Where does the numpy-in/numpy-out time go? Times each transfer / kernel piece of the
+three reference-shaped calls on a 512^3 volume with pinned host buffers."""
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from invesalius3_b200 import device as dev, phantom  # noqa: E402
+
+
+def t(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    return best * 1e3
+
+
+def main():
+    n = 512
+    vol = phantom.ct((n, n, n), seed=2)
+    h_vol = torch.from_numpy(vol).pin_memory().numpy()
+    h_mask = torch.zeros((n + 1, n + 1, n + 1), dtype=torch.uint8).pin_memory().numpy()
+    h_out = torch.zeros((n, n, n), dtype=torch.uint8).pin_memory().numpy()
+    pageable = np.zeros((n, n, n), np.uint8)
+    d_vol = dev.to_device(h_vol)
+    d_mask = dev.threshold(d_vol, 226, 3071)
+    gb = lambda nbytes, ms: nbytes / ms / 1e6
+    r = {}
+    ms = t(lambda: dev.to_device(h_vol)); r["H2D image 256MiB pinned dense"] = (ms, gb(vol.nbytes, ms))
+    ms = t(lambda: dev.to_device(vol)); r["H2D image 256MiB pageable"] = (ms, gb(vol.nbytes, ms))
+    ms = t(lambda: dev.to_host(d_mask, h_out)); r["D2H mask 128MiB pinned dense"] = (ms, gb(h_out.nbytes, ms))
+    ms = t(lambda: dev.to_host(d_mask, pageable)); r["D2H mask 128MiB pageable dense"] = (ms, gb(h_out.nbytes, ms))
+    ms = t(lambda: dev.to_host(d_mask, h_mask[1:, 1:, 1:])); r["D2H mask 128MiB pinned strided [1:,1:,1:]"] = (ms, gb(h_out.nbytes, ms))
+    ms = t(lambda: dev.to_device(h_mask[1:, 1:, 1:])); r["H2D mask 128MiB pinned strided"] = (ms, gb(h_out.nbytes, ms))
+    ms = t(lambda: h_out.fill(0)); r["host memset 128MiB"] = (ms, gb(h_out.nbytes, ms))
+    ms = t(lambda: d_mask.cpu().numpy()); r["tensor.cpu() 128MiB (pageable alloc)"] = (ms, gb(h_out.nbytes, ms))
+    for k, (ms, g) in r.items():
+        print(f"{k:48s} {ms:8.2f} ms  {g:7.1f} GB/s")
+
+
+if __name__ == "__main__":
+    main()
