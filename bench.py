@@ -213,7 +213,7 @@ def run_gpu(args):
     def step_e2e():
         if world == 1:
             slice_ops.set_mask_threshold(np_vol, np_mask, THR)
-            np_out[...] = 0
+            h_out.zero_()      # the reference allocates out_mask = np.zeros_like(mask) here (styles.py:3183)
             invesalius_rs.floodfill_threshold(np_vol, [seed], THR[0], THR[1], FILL, strct, np_out)
             v, f = surface_process.contour(np_out, [127], SPACING, 0, True)
             return v, f

@@ -275,75 +275,123 @@ __global__ void __launch_bounds__(kFloodThreads)
   do {
     changed = 0;
     // ---- directional sweeps: each carries reached bits across the whole tile along one
-    // axis in a single pass (a Jacobi step moves them by one row / one word only)
+    // axis in O(1) dependent steps (a Jacobi step moves them by one row / one word only)
     if (xfill) {
-      for (int r = tid; r < tz * ty; r += kFloodThreads) {
-        const int base = ((r / ty + 1) * py + (r % ty + 1)) * pw + 1;
-        uint32_t carry = sR[base - 1] >> 31;
-        for (int w = 0; w < tw; ++w) {
-          uint32_t f = sF[base + w], cur = sR[base + w];
-          uint32_t v = f ? run_fill((cur | carry) & f, f) : 0u;
-          if (v != cur) { sR[base + w] = v; changed = 1; }
-          carry = v >> 31;
+      // Along x a row is a chain of words. Per word: fill the runs that already hold a
+      // reached bit; g = "the fill reaches the word's last bit" (carry generate), p = "the
+      // word is all passable" (carry propagate). The carries into every word of the row
+      // are then one integer addition (carry-lookahead): (a + b + c0) ^ a ^ b with
+      // a = g | p, b = g. Same towards lower x on the bit-reversed masks.
+      const int lane = tid & 31;
+      const int grp = lane / tw;                       // tw is a power of two <= 16
+      const uint32_t gmask = (tw == 32) ? 0xffffffffu : ((1u << tw) - 1u);
+      for (int i0 = 0; i0 < nint || i0 == 0; i0 += kFloodThreads) {
+        const int i = i0 + tid;
+        const bool live = i < nint;
+        const int row = live ? i / tw : 0, w = live ? i % tw : 0;
+        const int base = ((row / ty + 1) * py + (row % ty + 1)) * pw + 1;
+        uint32_t f = 0, cur = 0, filled = 0;
+        if (live) {
+          f = sF[base + w];
+          cur = sR[base + w];
+          filled = (f && cur) ? run_fill(cur & f, f) : 0u;
         }
-        carry = sR[base + tw] & 1u;
-        for (int w = tw - 1; w >= 0; --w) {
-          uint32_t f = sF[base + w], cur = sR[base + w];
-          uint32_t v = f ? run_fill((cur | (carry << 31)) & f, f) : 0u;
+        const bool pfull = live && f == 0xffffffffu;
+        const uint32_t gu = (__ballot_sync(0xffffffffu, filled >> 31) >> (grp * tw)) & gmask;
+        const uint32_t gd = (__ballot_sync(0xffffffffu, filled & 1u) >> (grp * tw)) & gmask;
+        const uint32_t pm = (__ballot_sync(0xffffffffu, pfull) >> (grp * tw)) & gmask;
+        if (live) {
+          // up: carry into word k = bit k of the carry vector; the left halo word feeds bit 0
+          const uint32_t c0 = sR[base - 1] >> 31;
+          const uint32_t au = gu | pm, bu = gu;
+          const uint32_t cu = ((au + bu + c0) ^ au ^ bu);
+          // down: reverse the word order so that the same adder runs towards lower x
+          const uint32_t gdr = __brev(gd) >> (32 - tw), pmr = __brev(pm) >> (32 - tw);
+          const uint32_t c1 = sR[base + tw] & 1u;
+          const uint32_t ad = gdr | pmr, bd = gdr;
+          const uint32_t cd = ((ad + bd + c1) ^ ad ^ bd);
+          const uint32_t cin_lo = (cu >> w) & 1u;                 // enters at bit 0
+          const uint32_t cin_hi = (cd >> (tw - 1 - w)) & 1u;      // enters at bit 31
+          const uint32_t seed = (cur | cin_lo | (cin_hi << 31)) & f;
+          const uint32_t v = seed ? run_fill(seed, f) : 0u;
           if (v != cur) { sR[base + w] = v; changed = 1; }
-          carry = v & 1u;
         }
       }
       __syncthreads();
     }
     if (yfwd || ybwd) {
+      // one thread per (z, word) column: the ty rows live in registers, the chain is two
+      // logic ops per row
       for (int c = tid; c < tz * tw; c += kFloodThreads) {
-        const int base = ((c / tw + 1) * py) * pw + (c % tw + 1);  // row hy = 0 of this column
+        const int base = ((c / tw + 1) * py) * pw + (c % tw + 1);  // halo row hy = 0 of this column
+        uint32_t r[8], f[8];
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+          r[y] = y < ty ? sR[base + (y + 1) * pw] : 0u;
+          f[y] = y < ty ? sF[base + (y + 1) * pw] : 0u;
+        }
+        uint32_t v[8];
+#pragma unroll
+        for (int y = 0; y < 8; ++y) v[y] = r[y];
         if (yfwd) {
           uint32_t prev = sR[base];
-          for (int y = 1; y <= ty; ++y) {
-            uint32_t f = sF[base + y * pw], cur = sR[base + y * pw];
-            uint32_t v = (cur | prev) & f;
-            if (xfill && v) v = run_fill(v, f);
-            if (v != cur) { sR[base + y * pw] = v; changed = 1; }
-            prev = v;
-          }
+#pragma unroll
+          for (int y = 0; y < 8; ++y) { v[y] = (v[y] | prev) & f[y]; prev = v[y]; }
         }
         if (ybwd) {
           uint32_t prev = sR[base + (ty + 1) * pw];
-          for (int y = ty; y >= 1; --y) {
-            uint32_t f = sF[base + y * pw], cur = sR[base + y * pw];
-            uint32_t v = (cur | prev) & f;
-            if (xfill && v) v = run_fill(v, f);
-            if (v != cur) { sR[base + y * pw] = v; changed = 1; }
-            prev = v;
+#pragma unroll
+          for (int y = 7; y >= 0; --y) {
+            if (y < ty) { v[y] = (v[y] | prev) & f[y]; prev = v[y]; }
           }
         }
+#pragma unroll
+        for (int y = 0; y < 8; ++y)
+          if (y < ty && v[y] != r[y]) { sR[base + (y + 1) * pw] = v[y]; changed = 1; }
       }
       __syncthreads();
     }
     if (zfwd || zbwd) {
       const int pz = py * pw;
       for (int c = tid; c < ty * tw; c += kFloodThreads) {
-        const int base = (c / tw + 1) * pw + (c % tw + 1);  // plane hz = 0 of this column
+        const int base = (c / tw + 1) * pw + (c % tw + 1);  // halo plane hz = 0 of this column
+        // tz can exceed 8 for narrow volumes: chunks of 8 planes, the carry crosses chunks
         if (zfwd) {
           uint32_t prev = sR[base];
-          for (int z = 1; z <= tz; ++z) {
-            uint32_t f = sF[base + z * pz], cur = sR[base + z * pz];
-            uint32_t v = (cur | prev) & f;
-            if (xfill && v) v = run_fill(v, f);
-            if (v != cur) { sR[base + z * pz] = v; changed = 1; }
-            prev = v;
+          for (int z0c = 0; z0c < tz; z0c += 8) {
+            uint32_t r[8], f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              r[k] = z0c + k < tz ? sR[base + (z0c + k + 1) * pz] : 0u;
+              f[k] = z0c + k < tz ? sF[base + (z0c + k + 1) * pz] : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              uint32_t v = (r[k] | prev) & f[k];
+              if (z0c + k < tz) {
+                if (v != r[k]) { sR[base + (z0c + k + 1) * pz] = v; changed = 1; }
+                prev = v;
+              }
+            }
           }
         }
         if (zbwd) {
           uint32_t prev = sR[base + (tz + 1) * pz];
-          for (int z = tz; z >= 1; --z) {
-            uint32_t f = sF[base + z * pz], cur = sR[base + z * pz];
-            uint32_t v = (cur | prev) & f;
-            if (xfill && v) v = run_fill(v, f);
-            if (v != cur) { sR[base + z * pz] = v; changed = 1; }
-            prev = v;
+          for (int z1c = tz; z1c > 0; z1c -= 8) {
+            uint32_t r[8], f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              r[k] = z1c - 1 - k >= 0 ? sR[base + (z1c - k) * pz] : 0u;
+              f[k] = z1c - 1 - k >= 0 ? sF[base + (z1c - k) * pz] : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              uint32_t v = (r[k] | prev) & f[k];
+              if (z1c - 1 - k >= 0) {
+                if (v != r[k]) { sR[base + (z1c - k) * pz] = v; changed = 1; }
+                prev = v;
+              }
+            }
           }
         }
       }

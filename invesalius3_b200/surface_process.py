@@ -19,33 +19,37 @@ from .mesh import marching_cubes
 
 
 def contour(volume: np.ndarray, isovalues, spacing=(1.0, 1.0, 1.0), z0: int = 0, flip_y: bool = True,
-            padding=(0, 0, 0)):
+            padding=(0, 0, 0), index_dtype=np.int32):
     """Iso-surfaces of `volume` (uint8 or int16, [z][y][x]) at each value of `isovalues`.
 
     spacing = (sx, sy, sz); z0 = index of the first slice in the full volume; padding =
     (px, py, pz) voxels already added in front of the data (subtracted from the indices as
-    in converters.to_vtk). Returns (vertices float32 [V,3], faces int64 [T,3]); the
-    surfaces of successive isovalues are concatenated in order."""
+    in converters.to_vtk). Returns (vertices float32 [V,3], faces [T,3] of `index_dtype`);
+    the surfaces of successive isovalues are concatenated in order. int32 faces (what
+    `invesalius_rs.Mesh` takes as FaceArray::I32, types.rs:63-70) halve the device->host
+    traffic; pass index_dtype=np.int64 for vtkIdType-sized indices."""
     if not isinstance(volume, np.ndarray) or volume.ndim != 3:
         raise TypeError("contour: 3-D numpy volume expected")
     if volume.dtype not in (np.uint8, np.int16):
         raise TypeError("contour: volume must be uint8 or int16")
     isovalues = [float(v) for v in np.atleast_1d(isovalues)]
     t = dev.to_device(volume)
-    return _contour_device(t, isovalues, spacing, z0, flip_y, padding)
+    return _contour_device(t, isovalues, spacing, z0, flip_y, padding, index_dtype)
 
 
-def _contour_device(t: torch.Tensor, isovalues, spacing, z0, flip_y, padding):
+def _contour_device(t: torch.Tensor, isovalues, spacing, z0, flip_y, padding, index_dtype=np.int32):
     px, py, pz = padding
+    tdt = torch.int64 if np.dtype(index_dtype) == np.int64 else torch.int32
     vs, fs, base = [], [], 0
     for iso in isovalues:
         v, f = marching_cubes(t, iso, spacing, (-px, -py, z0 - pz), flip_y)
         vs.append(v)
-        fs.append(f.to(torch.int64) + base)
+        f = f.to(tdt)
+        fs.append(f + base if base else f)
         base += v.shape[0]
     verts = torch.cat(vs) if len(vs) > 1 else vs[0]
     faces = torch.cat(fs) if len(fs) > 1 else fs[0]
-    return verts.cpu().numpy(), faces.cpu().numpy()
+    return dev.to_numpy(verts), dev.to_numpy(faces)
 
 
 def _pad_device(t: torch.Tensor, pad_value: int, pad_bottom: bool, pad_top: bool) -> torch.Tensor:
@@ -59,7 +63,8 @@ def _pad_device(t: torch.Tensor, pad_value: int, pad_bottom: bool, pad_top: bool
 
 
 def contour_piece(image: np.ndarray | None, mask_matrix: np.ndarray | None, roi: slice, spacing, min_value=None,
-                  max_value=None, from_binary: bool = True, fill_border_holes: bool = True, flip_y: bool = True):
+                  max_value=None, from_binary: bool = True, fill_border_holes: bool = True, flip_y: bool = True,
+                  index_dtype=np.int32):
     """The contour part of create_surface_piece for one Z piece.
 
     image: int16 [dz][dy][dx] (needed unless from_binary); mask_matrix: the padded uint8
@@ -78,7 +83,7 @@ def contour_piece(image: np.ndarray | None, mask_matrix: np.ndarray | None, roi:
         piece = image[roi]
         pad_value, isovalues = int(np.iinfo(image.dtype).min), [float(min_value), float(max_value)]
     if piece.shape[0] == 0:
-        return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int64)
+        return np.zeros((0, 3), np.float32), np.zeros((0, 3), index_dtype)
     pad_bottom = roi.start == 0
     pad_top = roi.stop >= nz_full
     t = dev.to_device(piece)
@@ -87,4 +92,4 @@ def contour_piece(image: np.ndarray | None, mask_matrix: np.ndarray | None, roi:
         padding = (1, 1, int(pad_bottom))
     else:
         padding = (0, 0, 0)
-    return _contour_device(t, isovalues, spacing, roi.start, flip_y, padding)
+    return _contour_device(t, isovalues, spacing, roi.start, flip_y, padding, index_dtype)

@@ -100,7 +100,7 @@ def test_ift_matches_scipy_when_tie_free(wp, conn):
 
 def test_ift_simple_known_answers(wp):
     """SURVEY appendix B behaviours that do not depend on queue order."""
-    st = np.ones((1, 1, 3), np.uint8)
+    st = np.zeros((3, 3, 3), np.uint8); st[1, 1, :] = 1   # SciPy insists on 3 x 3 x 3 structures
     img = np.array([0, 0, 0, 0, 5, 0, 0, 0, 0], np.uint16).reshape(1, 1, 9)
     mk = np.zeros((1, 1, 9), np.int16); mk[0, 0, 0] = 1; mk[0, 0, 8] = 2
     want = ndimage.watershed_ift(img, mk, st)

@@ -38,6 +38,7 @@ def main():
     n = args.n
     g = torch.Generator(device="cuda").manual_seed(0)
     vol = torch.randint(-1024, 3072, (n, n, n), dtype=torch.int16, device="cuda", generator=g)
+    vol[0, 0, 0] = -1024; vol[0, 0, 1] = 3071
     flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
     N = vol.numel()
     res = {}
@@ -55,6 +56,25 @@ def main():
                 med, best = timeit(lambda: dev.mip(vol, axis, kind, out=o), flush=flush)
                 res[f"mip_{kind}_axis{axis}"] = dict(ms=med, best_ms=best, gbs=2 * N / med / 1e6,
                                                      frac=2 * N / med / 1e6 / PEAK)
+    if "mida" in ops:
+        from invesalius3_b200 import projection
+        for axis in (0, 1, 2):
+            o = projection.mida(vol, axis, 300, 300)
+            med, best = timeit(lambda: projection.mida(vol, axis, 300, 300, out=o), flush=flush)
+            res[f"mida_axis{axis}"] = dict(ms=med, best_ms=best, gbs=4 * N / med / 1e6, frac=4 * N / med / 1e6 / PEAK)
+            o = projection.lmip(vol, axis, 700, 3033)
+            med, best = timeit(lambda: projection.lmip(vol, axis, 700, 3033, out=o), flush=flush)
+            res[f"lmip_axis{axis}"] = dict(ms=med, best_ms=best, gbs=2 * N / med / 1e6, frac=2 * N / med / 1e6 / PEAK)
+    if "fcm" in ops:
+        from invesalius3_b200 import projection
+        for axis in (0, 2):
+            for tmip in (0, 2):
+                o = projection.fast_countour_mip(vol, 2.0, axis, 300, 300, tmip)
+                med, best = timeit(lambda: projection.fast_countour_mip(vol, 2.0, axis, 300, 300, tmip, out=o), iters=5,
+                                   flush=flush)
+                b = 2 if tmip == 0 else 4
+                res[f"fcm_tmip{tmip}_axis{axis}"] = dict(ms=med, best_ms=best, gbs=b * N / med / 1e6,
+                                                         frac=b * N / med / 1e6 / PEAK)
     if "minmax" in ops:
         med, best = timeit(lambda: dev.minmax(vol), flush=flush)
         res["minmax"] = dict(ms=med, best_ms=best, gbs=2 * N / med / 1e6, frac=2 * N / med / 1e6 / PEAK)
