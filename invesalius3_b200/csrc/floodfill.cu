@@ -57,6 +57,10 @@ struct Workspace {
   uint32_t* reach;
   uint8_t* active[2];
   int* flags;        // flags[r] != 0  <=>  some tile is active in round r
+  int* queue;        // async worklist ring (tile id + 1, 0 = empty slot)
+  int* queued;       // per tile: already in the ring
+  int* ctl;          // [0] head, [1] tail, [2] pending, [3] error, [4] tiles processed
+  int qcap;          // ring capacity (power of two)
   int64_t* seeds;    // device copy, 3 per seed
   int64_t bytes;
 };
@@ -73,6 +77,11 @@ Workspace carve(void* base, const BitVol& b, int64_t nseeds) {
   w.active[0] = (uint8_t*)(p + off); off += align(ntiles);
   w.active[1] = (uint8_t*)(p + off); off += align(ntiles);
   w.flags = (int*)(p + off); off += align((int64_t)(kMaxRounds + 2) * 4);
+  w.qcap = 1;
+  while (w.qcap < 2 * ntiles + 4096) w.qcap <<= 1;
+  w.queue = (int*)(p + off); off += align((int64_t)w.qcap * 4);
+  w.queued = (int*)(p + off); off += align(ntiles * 4);
+  w.ctl = (int*)(p + off); off += 256;
   w.seeds = (int64_t*)(p + off); off += align((nseeds > 0 ? nseeds : 1) * 24);
   w.bytes = off;
   return w;
@@ -203,27 +212,20 @@ __device__ __forceinline__ uint32_t run_fill(uint32_t s, uint32_t m) {
 
 // sb: 27 structuring-element bits, index (oz+1)*9 + (oy+1)*3 + (ox+1); the flood moves
 // from p to p + (oz, oy, ox).
-__global__ void __launch_bounds__(kFloodThreads)
-    k_ff_round(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b, uint32_t sb, uint8_t* active_cur,
-               uint8_t* active_next, int* flags, int round) {
-  if (flags[round] == 0) return;
-  const int tile = blockIdx.x;
-  // consistent decision for the whole block before thread 0 clears the entry
-  if (!__syncthreads_or(active_cur[tile] != 0)) return;
-  extern __shared__ uint32_t sR[];  // [(tz+2)][(ty+2)][(tw+2)]
-  __shared__ int s_faces;
+// One tile of the bit volume relaxed to local convergence in shared memory; grown words are
+// written back. Returns (uniformly over the block) the 27-bit mask of neighbour tiles that
+// can gain reached bits from this tile (bit (oz+1)*9 + (oy+1)*3 + (ow+1)).
+__device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, uint32_t* reach, const BitVol& b,
+                                               uint32_t sb, int tile, uint32_t* sR, int* s_faces) {
   const int tid = threadIdx.x;
   const int tw = b.tw, ty = b.ty, tz = b.tz;
   const int pw = tw + 2, py = ty + 2;
   const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
   const int64_t z0 = (int64_t)tzi * tz, y0 = (int64_t)tyi * ty;
   const int w0 = twi * tw;
-  if (tid == 0) {
-    active_cur[tile] = 0;  // this buffer becomes `next` of the following round
-    s_faces = 0;
-  }
-  // halo load (zero outside the volume); passable bits of the interior ride along for the
-  // directional sweeps (halo entries of sF stay 0: halo words are never written)
+  if (tid == 0) *s_faces = 0;
+  // halo load (zero outside the volume); the passable bits ride along (halo words are
+  // never written)
   const int nh = (tz + 2) * py * pw;
   uint32_t* sF = sR + nh;
   for (int i = tid; i < nh; i += kFloodThreads) {
@@ -234,8 +236,7 @@ __global__ void __launch_bounds__(kFloodThreads)
     if (z >= 0 && z < b.dz && y >= 0 && y < b.dy && w >= 0 && w < b.wx) {
       int64_t gi = (z * b.dy + y) * b.wx + w;
       v = __ldcg(&reach[gi]);
-      bool interior = hz >= 1 && hz <= tz && hy >= 1 && hy <= ty && hw >= 1 && hw <= tw;
-      if (interior) f = __ldg(&fg[gi]);
+      f = __ldg(&fg[gi]);  // halo words included: they decide which neighbour tiles can gain
     }
     sR[i] = v;
     sF[i] = f;
@@ -428,8 +429,8 @@ __global__ void __launch_bounds__(kFloodThreads)
     ++iters;
   } while (changed);
 
-  // write back what grew; collect which faces of the tile changed
-  int faces = 0;
+  // write back what grew
+  int grew = 0;
 #pragma unroll
   for (int k = 0; k < kOwn; ++k) {
     if (hidx[k] < 0) continue;
@@ -439,35 +440,155 @@ __global__ void __launch_bounds__(kFloodThreads)
       int iw = i % tw, iy = (i / tw) % ty, iz = i / (tw * ty);
       int64_t z = z0 + iz, y = y0 + iy;
       __stcg(&reach[(z * b.dy + y) * b.wx + (w0 + iw)], v);
-      faces |= 64;
-      if (iz == 0) faces |= 1;
-      if (iz == tz - 1) faces |= 2;
-      if (iy == 0) faces |= 4;
-      if (iy == ty - 1) faces |= 8;
-      if (iw == 0) faces |= 16;
-      if (iw == tw - 1) faces |= 32;
+      grew = 1;
     }
   }
-  if (faces) atomicOr(&s_faces, faces);
+  // Which neighbour tiles would gain a bit from this tile's state? For every halo word with
+  // passable-but-unreached bits, apply one hop of the structuring element from the tile
+  // box; a non-empty gain marks the tile that owns the word (bit (oz+1)*9+(oy+1)*3+(ow+1)).
+  int nbmask = 0;
+  (void)grew;  // checked even without growth: a lone seed on a tile face must still wake its neighbour
   __syncthreads();
-  faces = s_faces;
-  if ((faces & 63) == 0) return;
+  {
+    const int hzmax = tz + 1, hymax = ty + 1, hwmax = tw + 1;
+    for (int i = tid; i < nh; i += kFloodThreads) {
+      const int hw = i % pw, hy = (i / pw) % py, hz = i / (pw * py);
+      const int tz_o = hz == 0 ? -1 : (hz == hzmax ? 1 : 0);
+      const int ty_o = hy == 0 ? -1 : (hy == hymax ? 1 : 0);
+      const int tw_o = hw == 0 ? -1 : (hw == hwmax ? 1 : 0);
+      if (tz_o == 0 && ty_o == 0 && tw_o == 0) continue;  // interior
+      const uint32_t want = sF[i] & ~sR[i];
+      if (want == 0) continue;
+      uint32_t acc = 0;
+#pragma unroll
+      for (int oz = -1; oz <= 1; ++oz) {
+#pragma unroll
+        for (int oy = -1; oy <= 1; ++oy) {
+          uint32_t xm = (sb >> ((oz + 1) * 9 + (oy + 1) * 3)) & 7u;
+          if (xm == 0) continue;
+          const int sz = hz - oz, sy = hy - oy;  // source row (z - oz, y - oy)
+          if (sz < 0 || sz > hzmax || sy < 0 || sy > hymax) continue;
+          const int src = (sz * py + sy) * pw + hw;
+          const uint32_t c = sR[src];
+          if (xm & 2u) acc |= c;
+          if (xm & 4u) acc |= (c << 1) | (hw > 0 ? (sR[src - 1] >> 31) : 0u);
+          if (xm & 1u) acc |= (c >> 1) | (hw < hwmax ? (sR[src + 1] << 31) : 0u);
+        }
+      }
+      if (acc & want) nbmask |= 1 << ((tz_o + 1) * 9 + (ty_o + 1) * 3 + (tw_o + 1));
+    }
+  }
+  if (nbmask) atomicOr(s_faces, nbmask);
+  __syncthreads();
+  return *s_faces;
+}
+
+__global__ void __launch_bounds__(kFloodThreads)
+    k_ff_round(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b, uint32_t sb, uint8_t* active_cur,
+               uint8_t* active_next, int* flags, int round) {
+  if (flags[round] == 0) return;
+  const int tile = blockIdx.x;
+  // consistent decision for the whole block before thread 0 clears the entry
+  if (!__syncthreads_or(active_cur[tile] != 0)) return;
+  extern __shared__ uint32_t sR[];  // [(tz+2)][(ty+2)][(tw+2)] reached + same for passable
+  __shared__ int s_faces;
+  const int tid = threadIdx.x;
+  if (tid == 0) active_cur[tile] = 0;  // this buffer becomes `next` of the following round
+  const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
+  const int nbmask = ff_process_tile(fg, reach, b, sb, tile, sR, &s_faces);
+  if (nbmask == 0) return;
   __threadfence();
-  // activate the (up to 26) neighbour tiles that share a changed face / edge / corner
-  if (tid < 27) {
+  // activate the neighbour tiles that can gain from this one
+  if (tid < 27 && ((nbmask >> tid) & 1)) {
     int oz = tid / 9 - 1, oy = (tid / 3) % 3 - 1, ow = tid % 3 - 1;
-    if (oz == 0 && oy == 0 && ow == 0) return;
-    bool need = true;
-    if (oz == -1) need = need && (faces & 1);
-    if (oz == 1) need = need && (faces & 2);
-    if (oy == -1) need = need && (faces & 4);
-    if (oy == 1) need = need && (faces & 8);
-    if (ow == -1) need = need && (faces & 16);
-    if (ow == 1) need = need && (faces & 32);
     int nz = tzi + oz, ny = tyi + oy, nw = twi + ow;
-    if (need && nz >= 0 && nz < b.ntz && ny >= 0 && ny < b.nty && nw >= 0 && nw < b.ntw) {
+    if (nz >= 0 && nz < b.ntz && ny >= 0 && ny < b.nty && nw >= 0 && nw < b.ntw) {
       active_next[(nz * b.nty + ny) * b.ntw + nw] = 1;
       flags[round + 1] = 1;
+    }
+  }
+}
+
+// ---- asynchronous variant: one persistent grid, a global worklist of tiles ------------------
+// No round barrier: a block pops a tile, relaxes it, pushes the neighbours whose shared face
+// grew (at most once each: `queued`), and decrements `pending` only after its pushes, so
+// pending == 0 means the fixed point is reached. A tile clears its `queued` flag BEFORE it
+// reads its halo: any neighbour growing later re-queues it, so no update is lost.
+__global__ void k_ff_async_init(const uint8_t* __restrict__ active, uint8_t* active_clr, int ntiles, int* queue,
+                                int* queued, int* ctl) {
+  // single block: compact the active flags into the ring
+  __shared__ int s_tail;
+  if (threadIdx.x == 0) s_tail = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
+    queued[t] = 0;
+    if (active[t]) {
+      int slot = atomicAdd(&s_tail, 1);
+      queue[slot] = t + 1;
+      queued[t] = 1;
+      active_clr[t] = 0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ctl[0] = 0;
+    ctl[1] = s_tail;
+    ctl[2] = s_tail;
+    ctl[3] = 0;
+    ctl[4] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kFloodThreads)
+    k_ff_async(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b, uint32_t sb, int* queue, int qmask,
+               int* queued, int* ctl) {
+  extern __shared__ uint32_t sR[];
+  __shared__ int s_faces;
+  __shared__ int s_tile;
+  const int tid = threadIdx.x;
+  volatile int* vq = queue;
+  volatile int* vctl = ctl;
+  while (true) {
+    if (tid == 0) {
+      int t = 0;
+      const int idx = atomicAdd(&ctl[0], 1);
+      int spins = 0;
+      while ((t = vq[idx & qmask]) == 0) {
+        if (vctl[2] == 0 || vctl[3] != 0) { t = -1; break; }
+        __nanosleep(64);
+        if (++spins > (1 << 23)) { atomicExch(&ctl[3], 1); t = -1; break; }  // watchdog, ~1 s
+      }
+      if (t > 0) {
+        vq[idx & qmask] = 0;             // the slot is free for the ring's next lap
+        atomicExch(&queued[t - 1], 0);   // from now on a growing neighbour re-queues this tile
+        __threadfence();
+      }
+      s_tile = t;
+    }
+    __syncthreads();
+    const int tile = s_tile - 1;
+    if (tile < 0) return;
+    const int nbmask = ff_process_tile(fg, reach, b, sb, tile, sR, &s_faces);
+    __threadfence();   // the grown words are visible before any neighbour is queued
+    __syncthreads();
+    if (tid < 27 && ((nbmask >> tid) & 1)) {
+      const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
+      int oz = tid / 9 - 1, oy = (tid / 3) % 3 - 1, ow = tid % 3 - 1;
+      int nz = tzi + oz, ny = tyi + oy, nw = twi + ow;
+      if (nz >= 0 && nz < b.ntz && ny >= 0 && ny < b.nty && nw >= 0 && nw < b.ntw) {
+        int nb = (nz * b.nty + ny) * b.ntw + nw;
+        if (atomicExch(&queued[nb], 1) == 0) {
+          atomicAdd(&ctl[2], 1);
+          int slot = atomicAdd(&ctl[1], 1);
+          vq[slot & qmask] = nb + 1;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(&ctl[4], 1);
+      atomicSub(&ctl[2], 1);   // after the pushes: pending never reads 0 while work exists
     }
   }
 }
@@ -555,6 +676,34 @@ int run_rounds(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s,
   return B2V_OK;
 }
 
+// Asynchronous convergence: the tiles active for round *round_io (seeds, merged planes) seed
+// the worklist; one persistent launch runs to the fixed point. Synchronises the stream.
+static int g_flood_async = 1;
+
+int run_async(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s, int r0, int* rounds_out) {
+  const int ntiles = b.ntz * b.nty * b.ntw;
+  const size_t smem = 2 * (size_t)(b.tz + 2) * (b.ty + 2) * (b.tw + 2) * sizeof(uint32_t);
+  int rc;
+  k_ff_async_init<<<1, 1024, 0, s>>>(w.active[r0 & 1], w.active[r0 & 1], ntiles, w.queue, w.queued, w.ctl);
+  if ((rc = b2v_check_launch("k_ff_async_init"))) return rc;
+  int per_sm = 0;
+  B2V_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ff_async, kFloodThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  int grid = per_sm * b2v_sm_count();
+  if (grid > ntiles) grid = ntiles;
+  k_ff_async<<<grid, kFloodThreads, smem, s>>>(w.fg, w.reach, b, sb, w.queue, w.qcap - 1, w.queued, w.ctl);
+  if ((rc = b2v_check_launch("k_ff_async"))) return rc;
+  int ctl[5] = {0, 0, 0, 0, 0};
+  B2V_CUDA(cudaMemcpyAsync(ctl, w.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
+  B2V_CUDA(cudaStreamSynchronize(s));
+  B2V_REQUIRE(ctl[3] == 0 && ctl[2] == 0, B2V_ERR_NOCONV, "floodfill: asynchronous worklist stalled (pending %d)",
+              ctl[2]);
+  // the round flag of r0 was consumed; the next merge raises flags[r0 + 1]
+  B2V_CUDA(cudaMemsetAsync(w.flags + r0, 0, sizeof(int), s));
+  if (rounds_out) *rounds_out = r0 + 1;
+  return B2V_OK;
+}
+
 enum { STAGE_BEGIN = 1, STAGE_CONVERGE = 2, STAGE_FINISH = 4, STAGE_ALL = 7 };
 
 // stages: BEGIN builds the bit volumes and plants the seeds; CONVERGE runs rounds from
@@ -596,7 +745,7 @@ int flood(T* data, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64
   }
   if (stages & STAGE_CONVERGE) {
     int r0 = round_io ? *round_io : 0, r1 = r0;
-    if ((rc = run_rounds(b, w, sb, s, r0, &r1))) return rc;
+    if ((rc = g_flood_async ? run_async(b, w, sb, s, r0, &r1) : run_rounds(b, w, sb, s, r0, &r1))) return rc;
     if (round_io) *round_io = r1;
   }
   if (stages & STAGE_FINISH) {
@@ -656,6 +805,8 @@ int flood_dispatch(void* data, int dtype, uint8_t* out, int64_t dz, int64_t dy, 
 }
 
 }  // namespace
+
+extern "C" void b2v_floodfill_set_async(int on) { g_flood_async = on ? 1 : 0; }
 
 extern "C" int64_t b2v_floodfill_workspace_bytes(int64_t dz, int64_t dy, int64_t dx, int64_t nseeds) {
   if (dz <= 0 || dy <= 0 || dx <= 0) return 0;

@@ -17,6 +17,16 @@ def rs():
     return invesalius_rs
 
 
+@pytest.fixture(autouse=True, params=["async", "rounds"])
+def engine(request):
+    """Every test runs on both convergence engines (asynchronous worklist / synchronous rounds)."""
+    from invesalius3_b200 import _lib
+    lib = _lib.load()
+    lib.b2v_floodfill_set_async(1 if request.param == "async" else 0)
+    yield request.param
+    lib.b2v_floodfill_set_async(1)
+
+
 def test_region_growing_threshold(rs):
     image = np.array([[[1, 1, 1, 5, 5], [1, 2, 2, 5, 5], [1, 2, 3, 5, 5], [1, 2, 2, 5, 5], [1, 1, 1, 5, 5]]],
                      dtype=np.int16)

@@ -61,7 +61,12 @@ def main():
         for axis in (0, 1, 2):
             o = projection.mida(vol, axis, 300, 300)
             med, best = timeit(lambda: projection.mida(vol, axis, 300, 300, out=o), flush=flush)
-            res[f"mida_axis{axis}"] = dict(ms=med, best_ms=best, gbs=4 * N / med / 1e6, frac=4 * N / med / 1e6 / PEAK)
+            res[f"mida_axis{axis}_earlyexit"] = dict(ms=med, best_ms=best, gbs=4 * N / med / 1e6,
+                                                     frac=4 * N / med / 1e6 / PEAK)
+            # opacity 0 everywhere: no ray terminates, the whole volume is read twice (min/max + rays)
+            med, best = timeit(lambda: projection.mida(vol, axis, 32000, 2, out=o), flush=flush)
+            res[f"mida_axis{axis}_fullrays"] = dict(ms=med, best_ms=best, gbs=4 * N / med / 1e6,
+                                                    frac=4 * N / med / 1e6 / PEAK)
             o = projection.lmip(vol, axis, 700, 3033)
             med, best = timeit(lambda: projection.lmip(vol, axis, 700, 3033, out=o), flush=flush)
             res[f"lmip_axis{axis}"] = dict(ms=med, best_ms=best, gbs=2 * N / med / 1e6, frac=2 * N / med / 1e6 / PEAK)
