@@ -216,7 +216,7 @@ __device__ __forceinline__ uint32_t run_fill(uint32_t s, uint32_t m) {
 // written back. Returns (uniformly over the block) the 27-bit mask of neighbour tiles that
 // can gain reached bits from this tile (bit (oz+1)*9 + (oy+1)*3 + (ow+1)).
 __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, uint32_t* reach, const BitVol& b,
-                                               uint32_t sb, int tile, uint32_t* sR, int* s_faces) {
+                                               uint32_t sb, int tile, uint32_t* sR, int* s_faces, int* stats) {
   const int tid = threadIdx.x;
   const int tw = b.tw, ty = b.ty, tz = b.tz;
   const int pw = tw + 2, py = ty + 2;
@@ -447,8 +447,13 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
   // passable-but-unreached bits, apply one hop of the structuring element from the tile
   // box; a non-empty gain marks the tile that owns the word (bit (oz+1)*9+(oy+1)*3+(ow+1)).
   int nbmask = 0;
-  (void)grew;  // checked even without growth: a lone seed on a tile face must still wake its neighbour
-  __syncthreads();
+  // (checked even without growth: a lone seed on a tile face must still wake its neighbour)
+  grew = __syncthreads_or(grew);
+  if (tid == 0) {   // stats[4] tile visits, [5] visits that grew, [6] local iterations
+    atomicAdd(&stats[4], 1);
+    if (grew) atomicAdd(&stats[5], 1);
+    atomicAdd(&stats[6], iters);
+  }
   {
     const int hzmax = tz + 1, hymax = ty + 1, hwmax = tw + 1;
     for (int i = tid; i < nh; i += kFloodThreads) {
@@ -485,7 +490,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
 
 __global__ void __launch_bounds__(kFloodThreads)
     k_ff_round(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b, uint32_t sb, uint8_t* active_cur,
-               uint8_t* active_next, int* flags, int round) {
+               uint8_t* active_next, int* flags, int round, int* stats) {
   if (flags[round] == 0) return;
   const int tile = blockIdx.x;
   // consistent decision for the whole block before thread 0 clears the entry
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(kFloodThreads)
   const int tid = threadIdx.x;
   if (tid == 0) active_cur[tile] = 0;  // this buffer becomes `next` of the following round
   const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
-  const int nbmask = ff_process_tile(fg, reach, b, sb, tile, sR, &s_faces);
+  const int nbmask = ff_process_tile(fg, reach, b, sb, tile, sR, &s_faces, stats);
   if (nbmask == 0) return;
   __threadfence();
   // activate the neighbour tiles that can gain from this one
@@ -535,7 +540,6 @@ __global__ void k_ff_async_init(const uint8_t* __restrict__ active, uint8_t* act
     ctl[1] = s_tail;
     ctl[2] = s_tail;
     ctl[3] = 0;
-    ctl[4] = 0;
   }
 }
 
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(kFloodThreads)
     __syncthreads();
     const int tile = s_tile - 1;
     if (tile < 0) return;
-    const int nbmask = ff_process_tile(fg, reach, b, sb, tile, sR, &s_faces);
+    const int nbmask = ff_process_tile(fg, reach, b, sb, tile, sR, &s_faces, ctl);
     __threadfence();   // the grown words are visible before any neighbour is queued
     __syncthreads();
     if (tid < 27 && ((nbmask >> tid) & 1)) {
@@ -587,7 +591,6 @@ __global__ void __launch_bounds__(kFloodThreads)
     __syncthreads();
     if (tid == 0) {
       __threadfence();
-      atomicAdd(&ctl[4], 1);
       atomicSub(&ctl[2], 1);   // after the pushes: pending never reads 0 while work exists
     }
   }
@@ -662,7 +665,7 @@ int run_rounds(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s,
   while (true) {
     for (int k = 0; k < batch; ++k, ++r) {
       k_ff_round<<<ntiles, kFloodThreads, smem, s>>>(w.fg, w.reach, b, sb, w.active[r & 1], w.active[(r + 1) & 1],
-                                                     w.flags, r);
+                                                     w.flags, r, w.ctl);
       if ((rc = b2v_check_launch("k_ff_round"))) return rc;
     }
     int more = 0;
@@ -873,6 +876,7 @@ extern "C" int b2v_floodfill_layout(int64_t dz, int64_t dy, int64_t dx, int64_t 
   layout_out[3] = (int64_t)b.dy * b.wx * 4;  // bytes per z-plane of a bit volume
   layout_out[4] = (int64_t)b.ntz * b.nty * b.ntw;
   layout_out[5] = kMaxRounds;
+  layout_out[6] = (int64_t)((char*)w.ctl - (char*)nullptr);  // int32 ctl[]: [4] tile visits, [5] grew, [6] iterations
   return B2V_OK;
 }
 

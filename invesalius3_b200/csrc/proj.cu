@@ -80,7 +80,8 @@ struct FcmSampler {
       float base = __fsub_rn(1.0f, fabsf(__fdiv_rn(dd, gm)));
       // powf of the reference is libm's (<1 ulp); a double pow rounded once is within the
       // same ulp. See DESIGN.md (contour-MIP tolerance).
-      float sf = (float)pow((double)base, (double)n);
+      // n == 1 (InVesalius' default border size) and n == 2 are exact in any libm
+      float sf = n == 1.0f ? base : (n == 2.0f ? __fmul_rn(base, base) : (float)pow((double)base, (double)n));
       val = __fmul_rn(gm, sf);
     }
     T o = 0;

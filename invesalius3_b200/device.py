@@ -243,10 +243,12 @@ def _strct_array(strct) -> np.ndarray:
     return st
 
 
-def floodfill_threshold(data: torch.Tensor, seeds, t0, t1, fill: int, strct, out: torch.Tensor) -> int:
+def floodfill_threshold(data: torch.Tensor, seeds, t0, t1, fill: int, strct, out: torch.Tensor,
+                        stats: dict | None = None) -> int:
     """Region grow from `seeds` ((x, y, z) triples) through voxels with t0 <= data <= t1 that
     are not already `fill` in `out`; reached voxels get out = fill (floodfill.rs:96-166).
-    Returns the number of flood rounds. Synchronises the stream."""
+    Returns the number of flood rounds. Synchronises the stream. `stats` (optional dict)
+    receives tile_visits / visits_that_grew / local_iterations of the flood."""
     _dense(data, "data"); _dense(out, "out")
     if out.dtype != torch.uint8 or out.shape != data.shape or data.dim() != 3:
         raise TypeError("floodfill_threshold: out must be uint8 with data's 3-D shape")
@@ -260,6 +262,12 @@ def floodfill_threshold(data: torch.Tensor, seeds, t0, t1, fill: int, strct, out
         _lib.call("b2v_floodfill_threshold", _p(data), code, dz, dy, dx, C.c_void_p(s.ctypes.data), len(s),
                   float(t0), float(t1), int(fill), C.c_void_p(st.ctypes.data), *st.shape, _p(out), _p(ws), _stream(),
                   C.byref(rounds))
+    if stats is not None and ws is not None:
+        lay = (C.c_int64 * 8)()
+        _lib.call("b2v_floodfill_layout", dz, dy, dx, max(len(s), 1), lay)
+        ctl = ws[lay[6]: lay[6] + 32].view(torch.int32).cpu().tolist()
+        stats.update(tile_visits=ctl[4], visits_that_grew=ctl[5], local_iterations=ctl[6],
+                     tiles=int(lay[4]))
     return rounds.value
 
 

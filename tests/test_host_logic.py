@@ -1,0 +1,88 @@
+"""CPU-only checks of the host side: argument coercion / error behaviour of the
+invesalius_rs mirror (raised before any device work), stride analysis of the packer,
+Z-shard arithmetic, and that compute entry points fail loudly without a CUDA device."""
+import numpy as np
+import pytest
+
+
+def test_box_pitches_recognises_memmap_style_views():
+    from invesalius3_b200.device import _box_pitches
+    m = np.zeros((11, 12, 13), np.uint8)
+    assert _box_pitches(m) == (13, 12 * 13)
+    assert _box_pitches(m[1:, 1:, 1:]) == (13, 12 * 13)          # mask.matrix[1:,1:,1:]
+    assert _box_pitches(m[:, :, ::2]) is None                      # x not contiguous
+    assert _box_pitches(m[::2]) == (13, 2 * 12 * 13)
+    assert _box_pitches(m.transpose(2, 1, 0)) is None
+    i = np.zeros((5, 6, 7), np.int16)
+    assert _box_pitches(i[2:4]) == (14, 84)
+    assert _box_pitches(i[0:1, 1:3]) is not None
+
+
+def test_shim_type_and_range_errors_before_device_work():
+    from invesalius3_b200 import invesalius_rs as rs
+    st = np.ones((3, 3, 3), np.uint8)
+    d16 = np.zeros((3, 4, 5), np.int16)
+    out = np.zeros((3, 4, 5), np.uint8)
+    with pytest.raises(TypeError):
+        rs.floodfill_threshold(d16.astype(np.float32), [(0, 0, 0)], 0, 1, 1, st, out)
+    with pytest.raises(TypeError):
+        rs.floodfill_threshold(d16, [(0, 0, 0)], 0, 1, 1, st, out.astype(np.int16))
+    with pytest.raises(OverflowError):
+        rs.floodfill_threshold(d16, [(0, 0, 0)], 0, 70000, 1, st, out)      # t1 extracted as i16
+    with pytest.raises(OverflowError):
+        rs.floodfill_threshold(d16, [(0, 0, 0)], 0, 1, 300, st, out)        # fill: u8
+    with pytest.raises(TypeError):
+        rs.floodfill_threshold(np.zeros((3, 4, 5)), [(0, 0, 0)], 0, 1, 1, st, out)  # f64 data: fill becomes float
+    with pytest.raises(TypeError):
+        rs.floodfill_threshold_inplace(d16, [(0, 0, 0)], 0.5, 1, 1, st)
+    with pytest.raises(TypeError):
+        rs.fill_holes_automatically(out, np.zeros((3, 4, 5), np.int32), 1, 1)
+    with pytest.raises(TypeError):
+        rs.mida(d16, 0, 1, 1, np.zeros((4, 5), np.uint8))
+    with pytest.raises(OverflowError):
+        rs.mida(d16, 0, 40000, 1, np.zeros((4, 5), np.int16))
+    with pytest.raises(TypeError):
+        rs.lmip(d16, 0, 1, 2, np.zeros((4, 5), np.uint8))
+    with pytest.raises(TypeError):
+        rs.fast_countour_mip(d16, 1.0, 0, 1, 1, 0, np.zeros((4, 5), np.uint8))
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point must raise, never compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from invesalius3_b200 import invesalius_rs as rs, slice_ops, surface_process
+    d16 = np.zeros((3, 4, 5), np.int16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rs.floodfill_threshold(d16, [(0, 0, 0)], 0, 1, 1, np.ones((3, 3, 3), np.uint8), np.zeros((3, 4, 5), np.uint8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        slice_ops.set_mask_threshold_slice(d16[0], (0, 1))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        surface_process.contour(np.zeros((3, 4, 5), np.uint8), [127])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rs.mida(d16, 0, 1, 1, np.zeros((4, 5), np.int16))
+
+
+def test_zshard_arithmetic():
+    from invesalius3_b200.dist import ZShard
+    DZ, W = 23, 4
+    covered = []
+    for r in range(W):
+        s = ZShard(DZ, r, W)
+        covered += list(range(s.z0, s.z1))
+        assert s.ze0 == s.z0 - (1 if r > 0 else 0) and s.ze1 == s.z1 + (1 if r < W - 1 else 0)
+        assert s.nz_ext == s.ze1 - s.ze0
+        seeds = s.local_seeds([(1, 2, z) for z in range(DZ)])
+        assert [z for (_, _, z) in seeds] == list(range(s.nz_ext))
+    assert covered == list(range(DZ))
+    with pytest.raises(IndexError):
+        ZShard(DZ, 0, W).local_seeds([(0, 0, DZ)])
+
+
+def test_phantom_is_shard_consistent():
+    from invesalius3_b200 import phantom
+    a = phantom.ct((20, 24, 28), seed=5)
+    assert a.dtype == np.int16 and a.min() >= -1024 and a.max() <= 3071
+    assert np.array_equal(phantom.ct((20, 24, 28), seed=5, zrange=(7, 13)), a[7:13])
+    assert not np.array_equal(phantom.ct((20, 24, 28), seed=6), a)

@@ -42,6 +42,17 @@ def main():
     ms = t(lambda: dev.to_device(h_mask[1:, 1:, 1:])); r["H2D mask 128MiB pinned strided"] = (ms, gb(h_out.nbytes, ms))
     ms = t(lambda: h_out.fill(0)); r["host memset 128MiB"] = (ms, gb(h_out.nbytes, ms))
     ms = t(lambda: d_mask.cpu().numpy()); r["tensor.cpu() 128MiB (pageable alloc)"] = (ms, gb(h_out.nbytes, ms))
+    # the three reference-shaped calls of bench.py's e2e leg
+    from scipy.ndimage import generate_binary_structure
+    from invesalius3_b200 import invesalius_rs, slice_ops, surface_process
+    seed = phantom.first_seed_in_range(vol, n // 2, 226, 3071)
+    st = generate_binary_structure(3, 1)
+    th_out = torch.zeros((n, n, n), dtype=torch.uint8).pin_memory()
+    ms = t(lambda: slice_ops.set_mask_threshold(h_vol, h_mask, (226, 3071))); r["call: set_mask_threshold"] = (ms, 0)
+    ms = t(lambda: th_out.zero_()); r["call: zero the out mask (torch, pinned)"] = (ms, gb(h_out.nbytes, ms))
+    np_o = th_out.numpy()
+    ms = t(lambda: invesalius_rs.floodfill_threshold(h_vol, [seed], 226, 3071, 254, st, np_o)); r["call: floodfill_threshold"] = (ms, 0)
+    ms = t(lambda: surface_process.contour(np_o, [127], (1, 1, 1), 0, True)); r["call: contour"] = (ms, 0)
     for k, (ms, g) in r.items():
         print(f"{k:48s} {ms:8.2f} ms  {g:7.1f} GB/s")
 
