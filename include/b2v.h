@@ -102,9 +102,10 @@ int b2v_minmax_f32(const void* img, int dtype, int64_t n, float* minmax_out, voi
  * rounds_out (optional, host): number of flood rounds launched.
  * Algorithmic bytes: 4 B/voxel (int16 data 2 + out read 1 + out write 1). */
 int64_t b2v_floodfill_workspace_bytes(int64_t dz, int64_t dy, int64_t dx, int64_t nseeds);
-/* Convergence engine of the flood-fill family: 1 (default) = one persistent launch with an
- * asynchronous tile worklist, 0 = round-synchronous launches. Same result either way. */
-void b2v_floodfill_set_async(int on);
+/* Convergence engine of the flood-fill family: 1 (default) = every round inside ONE
+ * persistent cooperative launch (compact tile lists, grid-wide barrier per round),
+ * 0 = one launch per round driven from the host. Same result either way. */
+void b2v_floodfill_set_engine(int persistent);
 int b2v_floodfill_threshold(const void* data, int dtype, int64_t dz, int64_t dy, int64_t dx,
                             const int64_t* seeds_host, int64_t nseeds, double t0, double t1, uint8_t fill,
                             const uint8_t* strct_host, int64_t odz, int64_t ody, int64_t odx, uint8_t* out,

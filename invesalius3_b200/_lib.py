@@ -33,7 +33,7 @@ PROTOTYPES = {
     "b2v_minmax_workspace_bytes": (i64, [i64]),
     "b2v_minmax_f32": (cint, [vp, cint, i64, vp, vp, vp]),
     "b2v_floodfill_workspace_bytes": (i64, [i64, i64, i64, i64]),
-    "b2v_floodfill_set_async": (None, [cint]),
+    "b2v_floodfill_set_engine": (None, [cint]),
     "b2v_floodfill_threshold": (cint, [vp, cint, i64, i64, i64, vp, i64, dbl, dbl, u8, vp, i64, i64, i64, vp, vp, vp,
                                        C.POINTER(cint)]),
     "b2v_floodfill_threshold_inplace": (cint, [vp, cint, i64, i64, i64, vp, i64, dbl, dbl, dbl, vp, i64, i64, i64, vp,

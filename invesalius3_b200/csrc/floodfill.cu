@@ -16,9 +16,12 @@
 //              run fill along x; tiles whose neighbours changed are re-activated for the
 //              next round. Rounds ~ geodesic length measured in tiles, not voxels.
 //   3. write   (sparse): reached bits are expanded to `fill` stores into out.
+#include <cooperative_groups.h>
 #include <string.h>
 
 #include "b2v_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -57,10 +60,10 @@ struct Workspace {
   uint32_t* reach;
   uint8_t* active[2];
   int* flags;        // flags[r] != 0  <=>  some tile is active in round r
-  int* queue;        // async worklist ring (tile id + 1, 0 = empty slot)
-  int* queued;       // per tile: already in the ring
-  int* ctl;          // [0] head, [1] tail, [2] pending, [3] error, [4] tiles processed
-  int qcap;          // ring capacity (power of two)
+  int* lists;        // persistent engine: 3 rotating tile lists [3][ntiles]
+  int* lflags;       // one "already listed" flag array per list [3][ntiles]
+  int* counts;       // list lengths [3]
+  int* ctl;          // [3] error, [4] tile visits, [5] visits that grew, [6] local iterations, [7] rounds
   int64_t* seeds;    // device copy, 3 per seed
   int64_t bytes;
 };
@@ -77,10 +80,9 @@ Workspace carve(void* base, const BitVol& b, int64_t nseeds) {
   w.active[0] = (uint8_t*)(p + off); off += align(ntiles);
   w.active[1] = (uint8_t*)(p + off); off += align(ntiles);
   w.flags = (int*)(p + off); off += align((int64_t)(kMaxRounds + 2) * 4);
-  w.qcap = 1;
-  while (w.qcap < 2 * ntiles + 4096) w.qcap <<= 1;
-  w.queue = (int*)(p + off); off += align((int64_t)w.qcap * 4);
-  w.queued = (int*)(p + off); off += align(ntiles * 4);
+  w.lists = (int*)(p + off); off += align(3 * ntiles * 4);
+  w.lflags = (int*)(p + off); off += align(3 * ntiles * 4);
+  w.counts = (int*)(p + off); off += 256;
   w.ctl = (int*)(p + off); off += 256;
   w.seeds = (int64_t*)(p + off); off += align((nseeds > 0 ? nseeds : 1) * 24);
   w.bytes = off;
@@ -514,86 +516,64 @@ __global__ void __launch_bounds__(kFloodThreads)
   }
 }
 
-// ---- asynchronous variant: one persistent grid, a global worklist of tiles ------------------
-// No round barrier: a block pops a tile, relaxes it, pushes the neighbours whose shared face
-// grew (at most once each: `queued`), and decrements `pending` only after its pushes, so
-// pending == 0 means the fixed point is reached. A tile clears its `queued` flag BEFORE it
-// reads its halo: any neighbour growing later re-queues it, so no update is lost.
-__global__ void k_ff_async_init(const uint8_t* __restrict__ active, uint8_t* active_clr, int ntiles, int* queue,
-                                int* queued, int* ctl) {
-  // single block: compact the active flags into the ring
-  __shared__ int s_tail;
-  if (threadIdx.x == 0) s_tail = 0;
+// ---- persistent variant: all rounds in ONE cooperative launch ------------------------------
+// The host-driven rounds above pay for a launch of every tile's block per round although a
+// few dozen tiles are active. Here the active tiles of a round are a compact list; a
+// persistent grid walks it, appends the tiles that can gain to the next round's list (once
+// each: one flag array per list), and crosses a grid-wide barrier. Three lists rotate so
+// that the list being appended to was emptied a full round earlier.
+__global__ void k_ff_lists_init(const uint8_t* __restrict__ active, uint8_t* active_clr, int ntiles, int* lists,
+                                int* counts, int* lflags) {
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
-    queued[t] = 0;
+    lflags[t] = 0; lflags[ntiles + t] = 0; lflags[2 * ntiles + t] = 0;
     if (active[t]) {
-      int slot = atomicAdd(&s_tail, 1);
-      queue[slot] = t + 1;
-      queued[t] = 1;
+      lists[atomicAdd(&s_n, 1)] = t;
       active_clr[t] = 0;
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    ctl[0] = 0;
-    ctl[1] = s_tail;
-    ctl[2] = s_tail;
-    ctl[3] = 0;
-  }
+  if (threadIdx.x == 0) { counts[0] = s_n; counts[1] = 0; counts[2] = 0; }
 }
 
 __global__ void __launch_bounds__(kFloodThreads)
-    k_ff_async(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b, uint32_t sb, int* queue, int qmask,
-               int* queued, int* ctl) {
+    k_ff_persistent(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b, uint32_t sb, int* lists, int* counts,
+                    int* lflags, int* ctl, int max_rounds) {
+  cg::grid_group grid = cg::this_grid();
   extern __shared__ uint32_t sR[];
   __shared__ int s_faces;
-  __shared__ int s_tile;
   const int tid = threadIdx.x;
-  volatile int* vq = queue;
-  volatile int* vctl = ctl;
-  while (true) {
-    if (tid == 0) {
-      int t = 0;
-      const int idx = atomicAdd(&ctl[0], 1);
-      int spins = 0;
-      while ((t = vq[idx & qmask]) == 0) {
-        if (vctl[2] == 0 || vctl[3] != 0) { t = -1; break; }
-        __nanosleep(64);
-        if (++spins > (1 << 23)) { atomicExch(&ctl[3], 1); t = -1; break; }  // watchdog, ~1 s
-      }
-      if (t > 0) {
-        vq[idx & qmask] = 0;             // the slot is free for the ring's next lap
-        atomicExch(&queued[t - 1], 0);   // from now on a growing neighbour re-queues this tile
-        __threadfence();
-      }
-      s_tile = t;
-    }
-    __syncthreads();
-    const int tile = s_tile - 1;
-    if (tile < 0) return;
-    const int nbmask = ff_process_tile(fg, reach, b, sb, tile, sR, &s_faces, ctl);
-    __threadfence();   // the grown words are visible before any neighbour is queued
-    __syncthreads();
-    if (tid < 27 && ((nbmask >> tid) & 1)) {
-      const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
-      int oz = tid / 9 - 1, oy = (tid / 3) % 3 - 1, ow = tid % 3 - 1;
-      int nz = tzi + oz, ny = tyi + oy, nw = twi + ow;
-      if (nz >= 0 && nz < b.ntz && ny >= 0 && ny < b.nty && nw >= 0 && nw < b.ntw) {
-        int nb = (nz * b.nty + ny) * b.ntw + nw;
-        if (atomicExch(&queued[nb], 1) == 0) {
-          atomicAdd(&ctl[2], 1);
-          int slot = atomicAdd(&ctl[1], 1);
-          vq[slot & qmask] = nb + 1;
+  const int ntiles = b.ntz * b.nty * b.ntw;
+  int n_prev = 0, r = 0;
+  for (;; ++r) {
+    const int cur = r % 3, nxt = (r + 1) % 3, old = (r + 2) % 3;
+    const int n = *(volatile int*)&counts[cur];
+    if (n == 0) break;
+    if (r >= max_rounds) { if (blockIdx.x == 0 && tid == 0) ctl[3] = 1; break; }
+    if (blockIdx.x == 0 && tid == 0) counts[old] = 0;   // appended to from the next round on
+    for (int i = blockIdx.x * kFloodThreads + tid; i < n_prev; i += gridDim.x * kFloodThreads)
+      lflags[old * ntiles + lists[old * ntiles + i]] = 0;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+      const int tile = lists[cur * ntiles + i];
+      const int nbmask = ff_process_tile(fg, reach, b, sb, tile, sR, &s_faces, ctl);
+      if (tid < 27 && ((nbmask >> tid) & 1)) {
+        const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
+        int oz = tid / 9 - 1, oy = (tid / 3) % 3 - 1, ow = tid % 3 - 1;
+        int nz = tzi + oz, ny = tyi + oy, nw = twi + ow;
+        if (nz >= 0 && nz < b.ntz && ny >= 0 && ny < b.nty && nw >= 0 && nw < b.ntw) {
+          int nb = (nz * b.nty + ny) * b.ntw + nw;
+          if (atomicExch(&lflags[nxt * ntiles + nb], 1) == 0) lists[nxt * ntiles + atomicAdd(&counts[nxt], 1)] = nb;
         }
       }
+      __syncthreads();   // s_faces / shared tile are reused by the next tile of this block
     }
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      atomicSub(&ctl[2], 1);   // after the pushes: pending never reads 0 while work exists
-    }
+    n_prev = n;
+    __threadfence();
+    grid.sync();
   }
+  if (blockIdx.x == 0 && tid == 0) ctl[7] = r;
 }
 
 // ---- write back ----------------------------------------------------------------------------
@@ -679,31 +659,38 @@ int run_rounds(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s,
   return B2V_OK;
 }
 
-// Asynchronous convergence: the tiles active for round *round_io (seeds, merged planes) seed
-// the worklist; one persistent launch runs to the fixed point. Synchronises the stream.
-static int g_flood_async = 1;
+// Persistent convergence: the tiles active for round r0 (seeds, merged planes) seed the first
+// list; one cooperative launch runs every round to the fixed point. Synchronises the stream.
+static thread_local int g_last_rounds = 0;
+static int g_flood_engine = 1;   // 1 persistent (default), 0 host-driven rounds
 
-int run_async(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s, int r0, int* rounds_out) {
-  const int ntiles = b.ntz * b.nty * b.ntw;
+int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s, int r0, int* rounds_out) {
+  int ntiles = b.ntz * b.nty * b.ntw;
   const size_t smem = 2 * (size_t)(b.tz + 2) * (b.ty + 2) * (b.tw + 2) * sizeof(uint32_t);
   int rc;
-  k_ff_async_init<<<1, 1024, 0, s>>>(w.active[r0 & 1], w.active[r0 & 1], ntiles, w.queue, w.queued, w.ctl);
-  if ((rc = b2v_check_launch("k_ff_async_init"))) return rc;
+  k_ff_lists_init<<<1, 1024, 0, s>>>(w.active[r0 & 1], w.active[r0 & 1], ntiles, w.lists, w.counts, w.lflags);
+  if ((rc = b2v_check_launch("k_ff_lists_init"))) return rc;
   int per_sm = 0;
-  B2V_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ff_async, kFloodThreads, smem));
-  if (per_sm < 1) per_sm = 1;
-  int grid = per_sm * b2v_sm_count();
+  B2V_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ff_persistent, kFloodThreads, smem));
+  B2V_REQUIRE(per_sm >= 1, B2V_ERR_CUDA, "floodfill: persistent kernel does not fit on an SM");
+  int grid = b2v_sm_count();                 // one block per SM: a round has few active tiles
   if (grid > ntiles) grid = ntiles;
-  k_ff_async<<<grid, kFloodThreads, smem, s>>>(w.fg, w.reach, b, sb, w.queue, w.qcap - 1, w.queued, w.ctl);
-  if ((rc = b2v_check_launch("k_ff_async"))) return rc;
-  int ctl[5] = {0, 0, 0, 0, 0};
-  B2V_CUDA(cudaMemcpyAsync(ctl, w.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
+  const uint32_t* fg = w.fg;
+  uint32_t* reach = w.reach;
+  BitVol bb = b;
+  int* lists = w.lists; int* counts = w.counts; int* lflags = w.lflags; int* ctl = w.ctl;
+  int max_rounds = kMaxRounds;
+  void* args[] = {&fg, &reach, &bb, &sb, &lists, &counts, &lflags, &ctl, &max_rounds};
+  B2V_CUDA(cudaLaunchCooperativeKernel((void*)k_ff_persistent, dim3(grid), dim3(kFloodThreads), args, smem, s));
+  if ((rc = b2v_check_launch("k_ff_persistent"))) return rc;
+  int ctlh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  B2V_CUDA(cudaMemcpyAsync(ctlh, w.ctl, sizeof(ctlh), cudaMemcpyDeviceToHost, s));
   B2V_CUDA(cudaStreamSynchronize(s));
-  B2V_REQUIRE(ctl[3] == 0 && ctl[2] == 0, B2V_ERR_NOCONV, "floodfill: asynchronous worklist stalled (pending %d)",
-              ctl[2]);
+  B2V_REQUIRE(ctlh[3] == 0, B2V_ERR_NOCONV, "floodfill: no convergence after %d rounds", ctlh[7]);
   // the round flag of r0 was consumed; the next merge raises flags[r0 + 1]
   B2V_CUDA(cudaMemsetAsync(w.flags + r0, 0, sizeof(int), s));
   if (rounds_out) *rounds_out = r0 + 1;
+  g_last_rounds = ctlh[7];
   return B2V_OK;
 }
 
@@ -748,8 +735,8 @@ int flood(T* data, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64
   }
   if (stages & STAGE_CONVERGE) {
     int r0 = round_io ? *round_io : 0, r1 = r0;
-    if ((rc = g_flood_async ? run_async(b, w, sb, s, r0, &r1) : run_rounds(b, w, sb, s, r0, &r1))) return rc;
-    if (round_io) *round_io = r1;
+    if ((rc = g_flood_engine ? run_persistent(b, w, sb, s, r0, &r1) : run_rounds(b, w, sb, s, r0, &r1))) return rc;
+    if (round_io) *round_io = (stages == STAGE_ALL && g_flood_engine) ? g_last_rounds : r1;
   }
   if (stages & STAGE_FINISH) {
     if (MODE == MODE_INPLACE)
@@ -809,7 +796,7 @@ int flood_dispatch(void* data, int dtype, uint8_t* out, int64_t dz, int64_t dy, 
 
 }  // namespace
 
-extern "C" void b2v_floodfill_set_async(int on) { g_flood_async = on ? 1 : 0; }
+extern "C" void b2v_floodfill_set_engine(int persistent) { g_flood_engine = persistent ? 1 : 0; }
 
 extern "C" int64_t b2v_floodfill_workspace_bytes(int64_t dz, int64_t dy, int64_t dx, int64_t nseeds) {
   if (dz <= 0 || dy <= 0 || dx <= 0) return 0;

@@ -17,14 +17,14 @@ def rs():
     return invesalius_rs
 
 
-@pytest.fixture(autouse=True, params=["async", "rounds"])
+@pytest.fixture(autouse=True, params=["persistent", "host-rounds"])
 def engine(request):
-    """Every test runs on both convergence engines (asynchronous worklist / synchronous rounds)."""
+    """Every test runs on both convergence engines (one cooperative launch / a launch per round)."""
     from invesalius3_b200 import _lib
     lib = _lib.load()
-    lib.b2v_floodfill_set_async(1 if request.param == "async" else 0)
+    lib.b2v_floodfill_set_engine(1 if request.param == "persistent" else 0)
     yield request.param
-    lib.b2v_floodfill_set_async(1)
+    lib.b2v_floodfill_set_engine(1)
 
 
 def test_region_growing_threshold(rs):

@@ -7,7 +7,7 @@ vol=phantom.ct((512,512,512),seed=2); seed=phantom.first_seed_in_range(vol,256,2
 t=torch.from_numpy(vol).cuda(); st=generate_binary_structure(3,1)
 ref=None
 for eng in (0,1,0,1):
-    lib.b2v_floodfill_set_async(eng)
+    lib.b2v_floodfill_set_engine(eng)
     out=torch.zeros(vol.shape,dtype=torch.uint8,device='cuda')
     for _ in range(3): out.zero_(); dev.floodfill_threshold(t,[seed],226,3071,254,st,out)
     ts=[]
@@ -18,7 +18,7 @@ for eng in (0,1,0,1):
     print("engine",eng,"rounds",r,"median ms",sorted(ts)[5],"min",min(ts),"equal",bool(torch.equal(ref,out)),"filled",int((out==254).sum()),stt)
 st26=generate_binary_structure(3,3)
 for eng in (0,1):
-    lib.b2v_floodfill_set_async(eng)
+    lib.b2v_floodfill_set_engine(eng)
     out=torch.zeros(vol.shape,dtype=torch.uint8,device='cuda')
     ts=[]
     for _ in range(5):
