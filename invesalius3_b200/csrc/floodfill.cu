@@ -32,8 +32,10 @@ constexpr int kFloodThreads = 256;
 struct BitVol {
   int64_t dz, dy, dx;
   int wx;              // words per row
-  int tz, ty, tw;      // tile dims (rows, rows, words)
+  int tz, ty, tw;      // tile dims (rows, rows, words), powers of two
   int ntz, nty, ntw;   // tile grid
+  int ltw, lty;        // log2(tw), log2(ty)
+  uint32_t m_pw, m_pp; // ceil(2^24 / (tw+2)), ceil(2^24 / ((tw+2)(ty+2))): exact division for i < 2^12
 };
 
 int pow2ceil(int64_t v, int cap) {
@@ -52,6 +54,11 @@ BitVol make_bitvol(int64_t dz, int64_t dy, int64_t dx) {
   b.ntz = (int)ceil_div64(dz, b.tz);
   b.nty = (int)ceil_div64(dy, b.ty);
   b.ntw = (int)ceil_div64(b.wx, b.tw);
+  b.ltw = 0; while ((1 << b.ltw) < b.tw) ++b.ltw;
+  b.lty = 0; while ((1 << b.lty) < b.ty) ++b.lty;
+  const uint32_t pw = b.tw + 2, pp = (b.tw + 2) * (b.ty + 2);
+  b.m_pw = ((1u << 24) + pw - 1) / pw;
+  b.m_pp = ((1u << 24) + pp - 1) / pp;
   return b;
 }
 
@@ -230,18 +237,33 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
   // never written)
   const int nh = (tz + 2) * py * pw;
   uint32_t* sF = sR + nh;
-  for (int i = tid; i < nh; i += kFloodThreads) {
-    int hw = i % pw, hy = (i / pw) % py, hz = i / (pw * py);
-    int64_t z = z0 + hz - 1, y = y0 + hy - 1;
-    int w = w0 + hw - 1;
-    uint32_t v = 0, f = 0;
-    if (z >= 0 && z < b.dz && y >= 0 && y < b.dy && w >= 0 && w < b.wx) {
-      int64_t gi = (z * b.dy + y) * b.wx + w;
-      v = __ldcg(&reach[gi]);
-      f = __ldg(&fg[gi]);  // halo words included: they decide which neighbour tiles can gain
+  // all loads of a batch are issued before the first shared store: eight L2 round trips
+  // in flight per thread instead of one
+  for (int i0 = 0; i0 < nh; i0 += 8 * kFloodThreads) {
+    uint32_t v[8], f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * kFloodThreads + tid;
+      v[k] = 0; f[k] = 0;
+      if (i < nh) {
+        const int hz = (int)(((unsigned long long)i * b.m_pp) >> 24);
+        const int rem = i - hz * (pw * py);
+        const int hy = (int)(((unsigned long long)rem * b.m_pw) >> 24);
+        const int hw = rem - hy * pw;
+        const int64_t z = z0 + hz - 1, y = y0 + hy - 1;
+        const int w = w0 + hw - 1;
+        if (z >= 0 && z < b.dz && y >= 0 && y < b.dy && w >= 0 && w < b.wx) {
+          const int64_t gi = (z * b.dy + y) * b.wx + w;
+          v[k] = __ldcg(&reach[gi]);
+          f[k] = __ldg(&fg[gi]);   // halo words included: they decide which neighbour tiles can gain
+        }
+      }
     }
-    sR[i] = v;
-    sF[i] = f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * kFloodThreads + tid;
+      if (i < nh) { sR[i] = v[k]; sF[i] = f[k]; }
+    }
   }
   // owned words: fg and the initial reach value stay in registers
   constexpr int kOwn = kTileWords / kFloodThreads;
@@ -253,7 +275,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
     int i = tid + k * kFloodThreads;
     fgr[k] = 0; r0[k] = 0; hidx[k] = -1;
     if (i < nint) {
-      int iw = i % tw, iy = (i / tw) % ty, iz = i / (tw * ty);
+      int iw = i & (tw - 1), iy = (i >> b.ltw) & (ty - 1), iz = i >> (b.ltw + b.lty);
       int64_t z = z0 + iz, y = y0 + iy;
       int w = w0 + iw;
       if (z < b.dz && y < b.dy && w < b.wx) {
@@ -286,13 +308,13 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
       // are then one integer addition (carry-lookahead): (a + b + c0) ^ a ^ b with
       // a = g | p, b = g. Same towards lower x on the bit-reversed masks.
       const int lane = tid & 31;
-      const int grp = lane / tw;                       // tw is a power of two <= 16
+      const int grp = lane >> b.ltw;                   // tw is a power of two <= 16
       const uint32_t gmask = (tw == 32) ? 0xffffffffu : ((1u << tw) - 1u);
       for (int i0 = 0; i0 < nint || i0 == 0; i0 += kFloodThreads) {
         const int i = i0 + tid;
         const bool live = i < nint;
-        const int row = live ? i / tw : 0, w = live ? i % tw : 0;
-        const int base = ((row / ty + 1) * py + (row % ty + 1)) * pw + 1;
+        const int row = live ? i >> b.ltw : 0, w = live ? i & (tw - 1) : 0;
+        const int base = (((row >> b.lty) + 1) * py + ((row & (ty - 1)) + 1)) * pw + 1;
         uint32_t f = 0, cur = 0, filled = 0;
         if (live) {
           f = sF[base + w];
@@ -326,7 +348,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
       // one thread per (z, word) column: the ty rows live in registers, the chain is two
       // logic ops per row
       for (int c = tid; c < tz * tw; c += kFloodThreads) {
-        const int base = ((c / tw + 1) * py) * pw + (c % tw + 1);  // halo row hy = 0 of this column
+        const int base = (((c >> b.ltw) + 1) * py) * pw + ((c & (tw - 1)) + 1);  // halo row hy = 0 of this column
         uint32_t r[8], f[8];
 #pragma unroll
         for (int y = 0; y < 8; ++y) {
@@ -357,7 +379,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
     if (zfwd || zbwd) {
       const int pz = py * pw;
       for (int c = tid; c < ty * tw; c += kFloodThreads) {
-        const int base = (c / tw + 1) * pw + (c % tw + 1);  // halo plane hz = 0 of this column
+        const int base = ((c >> b.ltw) + 1) * pw + ((c & (tw - 1)) + 1);  // halo plane hz = 0 of this column
         // tz can exceed 8 for narrow volumes: chunks of 8 planes, the carry crosses chunks
         if (zfwd) {
           uint32_t prev = sR[base];
@@ -439,7 +461,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
     uint32_t v = sR[hidx[k]];
     if (v != r0[k]) {
       int i = tid + k * kFloodThreads;
-      int iw = i % tw, iy = (i / tw) % ty, iz = i / (tw * ty);
+      int iw = i & (tw - 1), iy = (i >> b.ltw) & (ty - 1), iz = i >> (b.ltw + b.lty);
       int64_t z = z0 + iz, y = y0 + iy;
       __stcg(&reach[(z * b.dy + y) * b.wx + (w0 + iw)], v);
       grew = 1;
@@ -459,7 +481,10 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
   {
     const int hzmax = tz + 1, hymax = ty + 1, hwmax = tw + 1;
     for (int i = tid; i < nh; i += kFloodThreads) {
-      const int hw = i % pw, hy = (i / pw) % py, hz = i / (pw * py);
+      const int hz = (int)(((unsigned long long)i * b.m_pp) >> 24);
+      const int rem = i - hz * (pw * py);
+      const int hy = (int)(((unsigned long long)rem * b.m_pw) >> 24);
+      const int hw = rem - hy * pw;
       const int tz_o = hz == 0 ? -1 : (hz == hzmax ? 1 : 0);
       const int ty_o = hy == 0 ? -1 : (hy == hymax ? 1 : 0);
       const int tw_o = hw == 0 ? -1 : (hw == hwmax ? 1 : 0);
@@ -547,7 +572,9 @@ __global__ void __launch_bounds__(kFloodThreads)
   const int tid = threadIdx.x;
   const int ntiles = b.ntz * b.nty * b.ntw;
   int n_prev = 0, r = 0;
+  long long c_proc = 0, c_sync = 0, c_all0 = clock64();
   for (;; ++r) {
+    const long long c0 = clock64();
     const int cur = r % 3, nxt = (r + 1) % 3, old = (r + 2) % 3;
     const int n = *(volatile int*)&counts[cur];
     if (n == 0) break;
@@ -570,10 +597,19 @@ __global__ void __launch_bounds__(kFloodThreads)
       __syncthreads();   // s_faces / shared tile are reused by the next tile of this block
     }
     n_prev = n;
+    const long long c1 = clock64();
     __threadfence();
     grid.sync();
+    const long long c2 = clock64();
+    c_proc += c1 - c0;
+    c_sync += c2 - c1;
   }
-  if (blockIdx.x == 0 && tid == 0) ctl[7] = r;
+  if (blockIdx.x == 0 && tid == 0) {
+    ctl[7] = r;
+    ctl[8] = (int)(c_proc >> 4);    // block 0: cycles/16 spent on its tiles ...
+    ctl[9] = (int)(c_sync >> 4);    // ... and in fence + grid barrier (incl. waiting for slower blocks)
+    ctl[10] = (int)((clock64() - c_all0) >> 4);
+  }
 }
 
 // ---- write back ----------------------------------------------------------------------------
@@ -673,7 +709,7 @@ int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_
   int per_sm = 0;
   B2V_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ff_persistent, kFloodThreads, smem));
   B2V_REQUIRE(per_sm >= 1, B2V_ERR_CUDA, "floodfill: persistent kernel does not fit on an SM");
-  int grid = b2v_sm_count();                 // one block per SM: a round has few active tiles
+  int grid = per_sm * b2v_sm_count();        // every co-resident slot: one tile per block per round
   if (grid > ntiles) grid = ntiles;
   const uint32_t* fg = w.fg;
   uint32_t* reach = w.reach;

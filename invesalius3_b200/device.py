@@ -283,9 +283,10 @@ def floodfill_threshold(data: torch.Tensor, seeds, t0, t1, fill: int, strct, out
     if stats is not None and ws is not None:
         lay = (C.c_int64 * 8)()
         _lib.call("b2v_floodfill_layout", dz, dy, dx, max(len(s), 1), lay)
-        ctl = ws[lay[6]: lay[6] + 32].view(torch.int32).cpu().tolist()
+        ctl = ws[lay[6]: lay[6] + 64].view(torch.int32).cpu().tolist()
         stats.update(tile_visits=ctl[4], visits_that_grew=ctl[5], local_iterations=ctl[6],
-                     tiles=int(lay[4]))
+                     tiles=int(lay[4]), rounds=ctl[7], block0_cycles_processing=ctl[8] * 16,
+                     block0_cycles_barrier=ctl[9] * 16, block0_cycles_total=ctl[10] * 16)
     return rounds.value
 
 
