@@ -27,7 +27,7 @@ namespace {
 
 constexpr int kTileWords = 1024;   // interior words per tile
 constexpr int kMaxRounds = 1 << 16;
-constexpr int kFloodThreads = 256;
+constexpr int kFloodThreads = 1024;  // one thread per tile word: short dependent chains, 32 warps to overlap them
 
 struct BitVol {
   int64_t dz, dy, dx;
@@ -224,8 +224,20 @@ __device__ __forceinline__ uint32_t run_fill(uint32_t s, uint32_t m) {
 // One tile of the bit volume relaxed to local convergence in shared memory; grown words are
 // written back. Returns (uniformly over the block) the 27-bit mask of neighbour tiles that
 // can gain reached bits from this tile (bit (oz+1)*9 + (oy+1)*3 + (ow+1)).
+// SBC != 0 fixes the structuring element at compile time (6-, 18-, 26-connectivity): the
+// stencil loops lose their dead rows and, for axis-only elements, the generic hop vanishes
+// (the three sweeps already cover every offset).
+constexpr uint32_t kSB6 = (1u << 12) | (1u << 14) | (1u << 10) | (1u << 16) | (1u << 4) | (1u << 22);
+constexpr uint32_t kSB26 = 0x7ffffffu & ~(1u << 13);
+constexpr uint32_t kSB18 = kSB26 & ~((1u << 0) | (1u << 2) | (1u << 6) | (1u << 8) | (1u << 18) | (1u << 20) |
+                                     (1u << 24) | (1u << 26));
+
+template <uint32_t SBC>
 __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, uint32_t* reach, const BitVol& b,
-                                               uint32_t sb, int tile, uint32_t* sR, int* s_faces, int* stats) {
+                                               uint32_t sb_rt, int tile, uint32_t* sR, int* s_faces, int* stats) {
+  const uint32_t sb = SBC ? SBC : sb_rt;
+  // the x sweep needs both x offsets; a one-sided x offset is left to the generic hop
+  const bool axis_only = (sb & ~kSB6) == 0 && (((sb >> 12) & 1u) == ((sb >> 14) & 1u));
   const int tid = threadIdx.x;
   const int tw = b.tw, ty = b.ty, tz = b.tz;
   const int pw = tw + 2, py = ty + 2;
@@ -233,16 +245,17 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
   const int64_t z0 = (int64_t)tzi * tz, y0 = (int64_t)tyi * ty;
   const int w0 = twi * tw;
   if (tid == 0) *s_faces = 0;
+  const long long pc0 = clock64();
   // halo load (zero outside the volume); the passable bits ride along (halo words are
   // never written)
   const int nh = (tz + 2) * py * pw;
   uint32_t* sF = sR + nh;
-  // all loads of a batch are issued before the first shared store: eight L2 round trips
-  // in flight per thread instead of one
-  for (int i0 = 0; i0 < nh; i0 += 8 * kFloodThreads) {
-    uint32_t v[8], f[8];
+  // all loads of a batch are issued before the first shared store: the L2 round trips of a
+  // thread overlap
+  for (int i0 = 0; i0 < nh; i0 += 4 * kFloodThreads) {
+    uint32_t v[4], f[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 4; ++k) {
       const int i = i0 + k * kFloodThreads + tid;
       v[k] = 0; f[k] = 0;
       if (i < nh) {
@@ -260,7 +273,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
       }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 4; ++k) {
       const int i = i0 + k * kFloodThreads + tid;
       if (i < nh) { sR[i] = v[k]; sF[i] = f[k]; }
     }
@@ -291,6 +304,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
       fgr[k] = sF[hidx[k]];
     }
 
+  const long long pc1 = clock64();
   const bool xfill = ((sb >> 12) & 1u) && ((sb >> 14) & 1u);  // (0,0,-1) and (0,0,+1)
   // axis-aligned offsets present in the structuring element (flood moves p -> p + off)
   const bool yfwd = (sb >> 16) & 1u, ybwd = (sb >> 10) & 1u;   // (0,+1,0), (0,-1,0)
@@ -355,9 +369,10 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
           r[y] = y < ty ? sR[base + (y + 1) * pw] : 0u;
           f[y] = y < ty ? sF[base + (y + 1) * pw] : 0u;
         }
-        uint32_t v[8];
+        uint32_t v[8], anyr = sR[base] | sR[base + (ty + 1) * pw];
 #pragma unroll
-        for (int y = 0; y < 8; ++y) v[y] = r[y];
+        for (int y = 0; y < 8; ++y) { v[y] = r[y]; anyr |= r[y]; }
+        if (anyr == 0) continue;   // nothing reached in or next to this column
         if (yfwd) {
           uint32_t prev = sR[base];
 #pragma unroll
@@ -423,6 +438,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
       __syncthreads();
     }
     // ---- generic step: every offset of the structuring element, one hop
+    if (!axis_only)
 #pragma unroll
     for (int k = 0; k < kOwn; ++k) {
       if (hidx[k] < 0 || fgr[k] == 0) continue;
@@ -453,6 +469,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
     ++iters;
   } while (changed);
 
+  const long long pc2 = clock64();
   // write back what grew
   int grew = 0;
 #pragma unroll
@@ -473,7 +490,11 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
   int nbmask = 0;
   // (checked even without growth: a lone seed on a tile face must still wake its neighbour)
   grew = __syncthreads_or(grew);
+  const long long pc3 = clock64();
   if (tid == 0) {   // stats[4] tile visits, [5] visits that grew, [6] local iterations
+    atomicAdd(&stats[11], (int)((pc1 - pc0) >> 4));   // cycles/16: halo load
+    atomicAdd(&stats[12], (int)((pc2 - pc1) >> 4));   //            local convergence
+    atomicAdd(&stats[13], (int)((pc3 - pc2) >> 4));   //            write back
     atomicAdd(&stats[4], 1);
     if (grew) atomicAdd(&stats[5], 1);
     atomicAdd(&stats[6], iters);
@@ -512,9 +533,11 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
   }
   if (nbmask) atomicOr(s_faces, nbmask);
   __syncthreads();
+  if (tid == 0) atomicAdd(&stats[14], (int)((clock64() - pc3) >> 4));   // neighbour gain test
   return *s_faces;
 }
 
+template <uint32_t SBC>
 __global__ void __launch_bounds__(kFloodThreads)
     k_ff_round(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b, uint32_t sb, uint8_t* active_cur,
                uint8_t* active_next, int* flags, int round, int* stats) {
@@ -527,7 +550,7 @@ __global__ void __launch_bounds__(kFloodThreads)
   const int tid = threadIdx.x;
   if (tid == 0) active_cur[tile] = 0;  // this buffer becomes `next` of the following round
   const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
-  const int nbmask = ff_process_tile(fg, reach, b, sb, tile, sR, &s_faces, stats);
+  const int nbmask = ff_process_tile<SBC>(fg, reach, b, sb, tile, sR, &s_faces, stats);
   if (nbmask == 0) return;
   __threadfence();
   // activate the neighbour tiles that can gain from this one
@@ -563,6 +586,7 @@ __global__ void k_ff_lists_init(const uint8_t* __restrict__ active, uint8_t* act
   if (threadIdx.x == 0) { counts[0] = s_n; counts[1] = 0; counts[2] = 0; }
 }
 
+template <uint32_t SBC>
 __global__ void __launch_bounds__(kFloodThreads)
     k_ff_persistent(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b, uint32_t sb, int* lists, int* counts,
                     int* lflags, int* ctl, int max_rounds) {
@@ -584,7 +608,7 @@ __global__ void __launch_bounds__(kFloodThreads)
       lflags[old * ntiles + lists[old * ntiles + i]] = 0;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
       const int tile = lists[cur * ntiles + i];
-      const int nbmask = ff_process_tile(fg, reach, b, sb, tile, sR, &s_faces, ctl);
+      const int nbmask = ff_process_tile<SBC>(fg, reach, b, sb, tile, sR, &s_faces, ctl);
       if (tid < 27 && ((nbmask >> tid) & 1)) {
         const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
         int oz = tid / 9 - 1, oy = (tid / 3) % 3 - 1, ow = tid % 3 - 1;
@@ -680,8 +704,14 @@ int run_rounds(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s,
   B2V_REQUIRE(r0 >= 0 && r0 + batch < kMaxRounds, B2V_ERR_NOCONV, "floodfill: round counter exhausted (%d)", r0);
   while (true) {
     for (int k = 0; k < batch; ++k, ++r) {
-      k_ff_round<<<ntiles, kFloodThreads, smem, s>>>(w.fg, w.reach, b, sb, w.active[r & 1], w.active[(r + 1) & 1],
-                                                     w.flags, r, w.ctl);
+#define B2V_FF_ROUND(SBC)                                                                                     \
+  k_ff_round<SBC><<<ntiles, kFloodThreads, smem, s>>>(w.fg, w.reach, b, sb, w.active[r & 1], w.active[(r + 1) & 1], \
+                                                      w.flags, r, w.ctl)
+      if (sb == kSB6) B2V_FF_ROUND(kSB6);
+      else if (sb == kSB26) B2V_FF_ROUND(kSB26);
+      else if (sb == kSB18) B2V_FF_ROUND(kSB18);
+      else B2V_FF_ROUND(0u);
+#undef B2V_FF_ROUND
       if ((rc = b2v_check_launch("k_ff_round"))) return rc;
     }
     int more = 0;
@@ -706,8 +736,11 @@ int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_
   int rc;
   k_ff_lists_init<<<1, 1024, 0, s>>>(w.active[r0 & 1], w.active[r0 & 1], ntiles, w.lists, w.counts, w.lflags);
   if ((rc = b2v_check_launch("k_ff_lists_init"))) return rc;
+  void* kern = sb == kSB6 ? (void*)k_ff_persistent<kSB6>
+             : sb == kSB26 ? (void*)k_ff_persistent<kSB26>
+             : sb == kSB18 ? (void*)k_ff_persistent<kSB18> : (void*)k_ff_persistent<0u>;
   int per_sm = 0;
-  B2V_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ff_persistent, kFloodThreads, smem));
+  B2V_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, kFloodThreads, smem));
   B2V_REQUIRE(per_sm >= 1, B2V_ERR_CUDA, "floodfill: persistent kernel does not fit on an SM");
   int grid = per_sm * b2v_sm_count();        // every co-resident slot: one tile per block per round
   if (grid > ntiles) grid = ntiles;
@@ -717,7 +750,7 @@ int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_
   int* lists = w.lists; int* counts = w.counts; int* lflags = w.lflags; int* ctl = w.ctl;
   int max_rounds = kMaxRounds;
   void* args[] = {&fg, &reach, &bb, &sb, &lists, &counts, &lflags, &ctl, &max_rounds};
-  B2V_CUDA(cudaLaunchCooperativeKernel((void*)k_ff_persistent, dim3(grid), dim3(kFloodThreads), args, smem, s));
+  B2V_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kFloodThreads), args, smem, s));
   if ((rc = b2v_check_launch("k_ff_persistent"))) return rc;
   int ctlh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   B2V_CUDA(cudaMemcpyAsync(ctlh, w.ctl, sizeof(ctlh), cudaMemcpyDeviceToHost, s));

@@ -286,7 +286,9 @@ def floodfill_threshold(data: torch.Tensor, seeds, t0, t1, fill: int, strct, out
         ctl = ws[lay[6]: lay[6] + 64].view(torch.int32).cpu().tolist()
         stats.update(tile_visits=ctl[4], visits_that_grew=ctl[5], local_iterations=ctl[6],
                      tiles=int(lay[4]), rounds=ctl[7], block0_cycles_processing=ctl[8] * 16,
-                     block0_cycles_barrier=ctl[9] * 16, block0_cycles_total=ctl[10] * 16)
+                     block0_cycles_barrier=ctl[9] * 16, block0_cycles_total=ctl[10] * 16,
+                     cycles_halo_load=ctl[11] * 16, cycles_converge=ctl[12] * 16, cycles_writeback=ctl[13] * 16,
+                     cycles_gain_test=ctl[14] * 16)
     return rounds.value
 
 

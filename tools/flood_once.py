@@ -8,3 +8,7 @@ out = torch.zeros(vol.shape, dtype=torch.uint8, device='cuda')
 for _ in range(3):
     out.zero_(); stt = {}; r = dev.floodfill_threshold(t, [seed], 226, 3071, 254, st, out, stats=stt)
 torch.cuda.synchronize(); print(r, stt)
+from invesalius3_b200 import _lib
+import ctypes as C
+lay=(C.c_int64*8)(); _lib.call('b2v_floodfill_layout',512,512,512,1,lay)
+
