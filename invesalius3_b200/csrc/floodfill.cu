@@ -25,7 +25,7 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kTileWords = 1024;   // interior words per tile
+constexpr int kTileWords = 4096;   // interior words per tile (16 x 16 rows x 16 words = 131 072 voxels)
 constexpr int kMaxRounds = 1 << 16;
 constexpr int kFloodThreads = 1024;  // one thread per tile word: short dependent chains, 32 warps to overlap them
 
@@ -49,8 +49,10 @@ BitVol make_bitvol(int64_t dz, int64_t dy, int64_t dx) {
   b.dz = dz; b.dy = dy; b.dx = dx;
   b.wx = (int)ceil_div64(dx, 32);
   b.tw = pow2ceil(b.wx, 16);
-  b.ty = pow2ceil(dy, 8);
+  b.ty = pow2ceil(dy, 16);
   b.tz = pow2ceil(dz, kTileWords / (b.tw * b.ty));
+  // reached + passable tiles with halo must fit the 48 KB of default shared memory
+  while (b.tz > 1 && (int64_t)(b.tz + 2) * (b.ty + 2) * (b.tw + 2) * 8 > 48 * 1024) b.tz >>= 1;
   b.ntz = (int)ceil_div64(dz, b.tz);
   b.nty = (int)ceil_div64(dy, b.ty);
   b.ntw = (int)ceil_div64(b.wx, b.tw);
@@ -224,6 +226,53 @@ __device__ __forceinline__ uint32_t run_fill(uint32_t s, uint32_t m) {
 // One tile of the bit volume relaxed to local convergence in shared memory; grown words are
 // written back. Returns (uniformly over the block) the 27-bit mask of neighbour tiles that
 // can gain reached bits from this tile (bit (oz+1)*9 + (oy+1)*3 + (ow+1)).
+// Axis sweep of one column of words: v[k] = (v[k] | v[k-1]) & f[k] along +axis (and the
+// mirror image along -axis), rows held in registers eight at a time; the ends are fed by
+// the read-only halo words. Returns whether anything changed.
+__device__ __forceinline__ int sweep_column(uint32_t* sR, const uint32_t* sF, int base, int stride, int n, bool fwd,
+                                            bool bwd) {
+  int changed = 0;
+  if (fwd) {
+    uint32_t prev = sR[base];
+    for (int c0 = 0; c0 < n; c0 += 8) {
+      uint32_t r[8], f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        r[k] = c0 + k < n ? sR[base + (c0 + k + 1) * stride] : 0u;
+        f[k] = c0 + k < n ? sF[base + (c0 + k + 1) * stride] : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        uint32_t v = (r[k] | prev) & f[k];
+        if (c0 + k < n) {
+          if (v != r[k]) { sR[base + (c0 + k + 1) * stride] = v; changed = 1; }
+          prev = v;
+        }
+      }
+    }
+  }
+  if (bwd) {
+    uint32_t prev = sR[base + (n + 1) * stride];
+    for (int c1 = n; c1 > 0; c1 -= 8) {
+      uint32_t r[8], f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        r[k] = c1 - 1 - k >= 0 ? sR[base + (c1 - k) * stride] : 0u;
+        f[k] = c1 - 1 - k >= 0 ? sF[base + (c1 - k) * stride] : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        uint32_t v = (r[k] | prev) & f[k];
+        if (c1 - 1 - k >= 0) {
+          if (v != r[k]) { sR[base + (c1 - k) * stride] = v; changed = 1; }
+          prev = v;
+        }
+      }
+    }
+  }
+  return changed;
+}
+
 // SBC != 0 fixes the structuring element at compile time (6-, 18-, 26-connectivity): the
 // stencil loops lose their dead rows and, for axis-only elements, the generic hop vanishes
 // (the three sweeps already cover every offset).
@@ -359,81 +408,18 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
       __syncthreads();
     }
     if (yfwd || ybwd) {
-      // one thread per (z, word) column: the ty rows live in registers, the chain is two
-      // logic ops per row
+      // one thread per (z, word) column
       for (int c = tid; c < tz * tw; c += kFloodThreads) {
-        const int base = (((c >> b.ltw) + 1) * py) * pw + ((c & (tw - 1)) + 1);  // halo row hy = 0 of this column
-        uint32_t r[8], f[8];
-#pragma unroll
-        for (int y = 0; y < 8; ++y) {
-          r[y] = y < ty ? sR[base + (y + 1) * pw] : 0u;
-          f[y] = y < ty ? sF[base + (y + 1) * pw] : 0u;
-        }
-        uint32_t v[8], anyr = sR[base] | sR[base + (ty + 1) * pw];
-#pragma unroll
-        for (int y = 0; y < 8; ++y) { v[y] = r[y]; anyr |= r[y]; }
-        if (anyr == 0) continue;   // nothing reached in or next to this column
-        if (yfwd) {
-          uint32_t prev = sR[base];
-#pragma unroll
-          for (int y = 0; y < 8; ++y) { v[y] = (v[y] | prev) & f[y]; prev = v[y]; }
-        }
-        if (ybwd) {
-          uint32_t prev = sR[base + (ty + 1) * pw];
-#pragma unroll
-          for (int y = 7; y >= 0; --y) {
-            if (y < ty) { v[y] = (v[y] | prev) & f[y]; prev = v[y]; }
-          }
-        }
-#pragma unroll
-        for (int y = 0; y < 8; ++y)
-          if (y < ty && v[y] != r[y]) { sR[base + (y + 1) * pw] = v[y]; changed = 1; }
+        const int base = (((c >> b.ltw) + 1) * py) * pw + ((c & (tw - 1)) + 1);  // halo row hy = 0
+        changed |= sweep_column(sR, sF, base, pw, ty, yfwd, ybwd);
       }
       __syncthreads();
     }
     if (zfwd || zbwd) {
-      const int pz = py * pw;
+      // one thread per (y, word) column
       for (int c = tid; c < ty * tw; c += kFloodThreads) {
-        const int base = ((c >> b.ltw) + 1) * pw + ((c & (tw - 1)) + 1);  // halo plane hz = 0 of this column
-        // tz can exceed 8 for narrow volumes: chunks of 8 planes, the carry crosses chunks
-        if (zfwd) {
-          uint32_t prev = sR[base];
-          for (int z0c = 0; z0c < tz; z0c += 8) {
-            uint32_t r[8], f[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              r[k] = z0c + k < tz ? sR[base + (z0c + k + 1) * pz] : 0u;
-              f[k] = z0c + k < tz ? sF[base + (z0c + k + 1) * pz] : 0u;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              uint32_t v = (r[k] | prev) & f[k];
-              if (z0c + k < tz) {
-                if (v != r[k]) { sR[base + (z0c + k + 1) * pz] = v; changed = 1; }
-                prev = v;
-              }
-            }
-          }
-        }
-        if (zbwd) {
-          uint32_t prev = sR[base + (tz + 1) * pz];
-          for (int z1c = tz; z1c > 0; z1c -= 8) {
-            uint32_t r[8], f[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              r[k] = z1c - 1 - k >= 0 ? sR[base + (z1c - k) * pz] : 0u;
-              f[k] = z1c - 1 - k >= 0 ? sF[base + (z1c - k) * pz] : 0u;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              uint32_t v = (r[k] | prev) & f[k];
-              if (z1c - 1 - k >= 0) {
-                if (v != r[k]) { sR[base + (z1c - k) * pz] = v; changed = 1; }
-                prev = v;
-              }
-            }
-          }
-        }
+        const int base = ((c >> b.ltw) + 1) * pw + ((c & (tw - 1)) + 1);         // halo plane hz = 0
+        changed |= sweep_column(sR, sF, base, py * pw, tz, zfwd, zbwd);
       }
       __syncthreads();
     }

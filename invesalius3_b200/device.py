@@ -95,6 +95,31 @@ def to_device(a: np.ndarray, device=None) -> torch.Tensor:
     return t
 
 
+def h2d_async(dst: torch.Tensor, a: np.ndarray) -> None:
+    """Enqueue host box view -> dense device tensor on the current stream, no synchronise
+    (the caller keeps `a` alive and untouched until the stream is synchronised)."""
+    pit = _box_pitches(a)
+    if pit is None or tuple(dst.shape) != tuple(a.shape) or not dst.is_contiguous():
+        raise ValueError("h2d_async needs an x-contiguous 3-D box view and a dense destination")
+    dz, dy, dx = a.shape
+    with torch.cuda.device(dst.device):
+        _lib.call("b2v_copy3d_h2d", _p(dst), C.c_void_p(a.ctypes.data), dz, dy, dx, a.itemsize, pit[0], pit[1],
+                  _stream())
+
+
+def d2h_async(src: torch.Tensor, out: np.ndarray) -> None:
+    """Enqueue dense device tensor -> host box view on the current stream, no synchronise."""
+    pit = _box_pitches(out)
+    if pit is None or tuple(src.shape) != tuple(out.shape) or not src.is_contiguous():
+        raise ValueError("d2h_async needs an x-contiguous 3-D box view and a dense source")
+    if not out.flags.writeable:
+        raise ValueError("output array is read-only")
+    dz, dy, dx = out.shape
+    with torch.cuda.device(src.device):
+        _lib.call("b2v_copy3d_d2h", C.c_void_p(out.ctypes.data), _p(src), dz, dy, dx, out.itemsize, pit[0], pit[1],
+                  _stream())
+
+
 class _PinnedPool:
     """Recycled page-locked host blocks for result arrays. `tensor.cpu()` into fresh pageable
     memory runs at ~2.6 GB/s (page faults + staged copies); a DMA into pinned memory runs at

@@ -58,9 +58,38 @@ def set_mask_threshold(matrix: np.ndarray, mask_matrix: np.ndarray, threshold_ra
     if mask_matrix.shape != (dz + 1, dy + 1, dx + 1) or mask_matrix.dtype != np.uint8:
         raise ValueError("mask_matrix must be uint8 of shape (dz+1, dy+1, dx+1)")
     tmin, tmax = threshold_range
-    out = dev.threshold(dev.to_device(matrix), tmin, tmax)
-    dev.to_host(out, mask_matrix[1:, 1:, 1:])
+    body = mask_matrix[1:, 1:, 1:]
+    if dz >= 32 and dev._box_pitches(matrix) is not None and dev._box_pitches(body) is not None:
+        _threshold_pipelined(matrix, body, tmin, tmax)
+    else:
+        out = dev.threshold(dev.to_device(matrix), tmin, tmax)
+        dev.to_host(out, body)
     mask_matrix[1:, 0, 0] = 1
+
+
+def _threshold_pipelined(matrix: np.ndarray, body: np.ndarray, tmin, tmax, nchunks: int = 4) -> None:
+    """Z slabs on two streams: slab k's device->host copy runs while slab k+1 travels host->
+    device (PCIe is full duplex), with the threshold kernel in between. Pays off with pinned
+    host memory; with pageable memory the copies are staged by the driver and merely
+    serialise, the result being the same."""
+    dev.require_cuda()
+    dz = matrix.shape[0]
+    img = torch.empty(matrix.shape, dtype=torch.int16, device="cuda")
+    out = torch.empty(matrix.shape, dtype=torch.uint8, device="cuda")
+    cur = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for s in streams:
+        s.wait_stream(cur)
+    bounds = [dz * k // nchunks for k in range(nchunks + 1)]
+    for k in range(nchunks):
+        z0, z1 = bounds[k], bounds[k + 1]
+        with torch.cuda.stream(streams[k % 2]):
+            dev.h2d_async(img[z0:z1], matrix[z0:z1])
+            dev.threshold(img[z0:z1], tmin, tmax, out=out[z0:z1])
+            dev.d2h_async(out[z0:z1], body[z0:z1])
+    for s in streams:
+        s.synchronize()
+        cur.wait_stream(s)
 
 
 def do_threshold_to_all_slices(matrix: np.ndarray, mask_matrix: np.ndarray, threshold_range) -> None:

@@ -133,3 +133,23 @@ def test_minmax(dev):
     f = np.random.default_rng(1).normal(size=(5, 6, 7))
     mm = dev.minmax(torch.from_numpy(f).cuda()).cpu().numpy()
     assert mm.tolist() == [float(np.float32(f.min())), float(np.float32(f.max()))]
+
+
+def test_set_mask_threshold_pipelined_path(dev, orc):
+    """dz >= 32 takes the two-stream slab pipeline; pinned and pageable hosts, odd shapes."""
+    import torch
+    from invesalius3_b200 import slice_ops
+    for shape, pinned in [((40, 33, 47), False), ((67, 16, 64), True)]:
+        vol = _rand_i16(shape, 21)
+        mm = np.zeros(tuple(s + 1 for s in shape), np.uint8)
+        mm[0, :, :] = 9          # flags of the other orientations must survive
+        mm[:, 0, 1:] = 7
+        want = mm.copy()
+        orc.set_mask_threshold_numpy(vol, want, (226, 3071))
+        if pinned:
+            hv = torch.from_numpy(vol).pin_memory().numpy()
+            hm = torch.from_numpy(mm).pin_memory().numpy()
+        else:
+            hv, hm = vol, mm.copy()
+        slice_ops.set_mask_threshold(hv, hm, (226, 3071))
+        assert np.array_equal(hm, want), shape
