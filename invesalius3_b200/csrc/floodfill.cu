@@ -25,7 +25,8 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kTileWords = 4096;   // interior words per tile (16 x 16 rows x 16 words = 131 072 voxels)
+constexpr int kTileWords = 1024;   // interior words per tile (8 x 8 rows x 16 words = 32 768 voxels; 4096-word
+                                   // tiles halve the rounds but triple the per-round critical path: measured slower)
 constexpr int kMaxRounds = 1 << 16;
 constexpr int kFloodThreads = 1024;  // one thread per tile word: short dependent chains, 32 warps to overlap them
 
@@ -49,7 +50,7 @@ BitVol make_bitvol(int64_t dz, int64_t dy, int64_t dx) {
   b.dz = dz; b.dy = dy; b.dx = dx;
   b.wx = (int)ceil_div64(dx, 32);
   b.tw = pow2ceil(b.wx, 16);
-  b.ty = pow2ceil(dy, 16);
+  b.ty = pow2ceil(dy, 8);
   b.tz = pow2ceil(dz, kTileWords / (b.tw * b.ty));
   // reached + passable tiles with halo must fit the 48 KB of default shared memory
   while (b.tz > 1 && (int64_t)(b.tz + 2) * (b.ty + 2) * (b.tw + 2) * 8 > 48 * 1024) b.tz >>= 1;
@@ -153,39 +154,52 @@ __global__ void __launch_bounds__(256) k_ff_build_i16_vec(const int16_t* __restr
                                                           uint32_t* __restrict__ reach) {
   const int gx = b.wx * 4;                      // 8-voxel groups per row (padded)
   const int64_t ngroups = b.dz * b.dy * gx;     // multiple of 4
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   const int lane = threadIdx.x & 31;
-  for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x; g0 < ngroups; g0 += stride) {
-    int64_t g = g0 + threadIdx.x;
-    uint32_t bits = 0;
-    int64_t row = 0;
-    int q = 0;
-    if (g < ngroups) {
-      row = g / gx;
-      q = (int)(g - row * gx);
-      int64_t x = (int64_t)q * 8;
-      if (x < b.dx) {
-        int64_t i = row * b.dx + x;
-        int4 v = ld_stream((const int4*)(data + i));
-        uint2 o = ld_stream((const uint2*)(out + i));
-        int vv[8] = {(int16_t)(v.x & 0xffff), v.x >> 16, (int16_t)(v.y & 0xffff), v.y >> 16,
-                     (int16_t)(v.z & 0xffff), v.z >> 16, (int16_t)(v.w & 0xffff), v.w >> 16};
+  // four groups per thread and iteration: 4 x (128-bit + 64-bit) loads in flight
+  for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x * 4; g0 < ngroups; g0 += stride) {
+    int4 v[4];
+    uint2 o[4];
+    int64_t row[4];
+    int q[4];
+    bool ok[4], in[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          uint8_t ob = (uint8_t)(((k < 4 ? o.x : o.y) >> (8 * (k & 3))) & 0xff);
-          bool p = (MODE == MODE_EQUAL) ? (vv[k] == t0 && ob != fill_o)
-                                        : (vv[k] >= t0 && vv[k] <= t1 && ob != fill_o);
-          bits |= (uint32_t)p << k;
-        }
+    for (int k = 0; k < 4; ++k) {
+      const int64_t g = g0 + k * blockDim.x + threadIdx.x;
+      ok[k] = g < ngroups;
+      row[k] = ok[k] ? g / gx : 0;
+      q[k] = ok[k] ? (int)(g - row[k] * gx) : 0;
+      in[k] = ok[k] && (int64_t)q[k] * 8 < b.dx;
+      v[k] = make_int4(0, 0, 0, 0);
+      o[k] = make_uint2(0u, 0u);
+      if (in[k]) {
+        const int64_t i = row[k] * b.dx + (int64_t)q[k] * 8;
+        v[k] = ld_stream((const int4*)(data + i));
+        o[k] = ld_stream((const uint2*)(out + i));
       }
     }
-    uint32_t word = bits << (8 * (lane & 3));
-    word |= __shfl_xor_sync(0xffffffffu, word, 1);
-    word |= __shfl_xor_sync(0xffffffffu, word, 2);
-    if ((lane & 3) == 0 && g < ngroups) {
-      int64_t wi = row * b.wx + (q >> 2);
-      fg[wi] = word;
-      reach[wi] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t bits = 0;
+      if (in[k]) {
+        int vv[8] = {(int16_t)(v[k].x & 0xffff), v[k].x >> 16, (int16_t)(v[k].y & 0xffff), v[k].y >> 16,
+                     (int16_t)(v[k].z & 0xffff), v[k].z >> 16, (int16_t)(v[k].w & 0xffff), v[k].w >> 16};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint8_t ob = (uint8_t)(((j < 4 ? o[k].x : o[k].y) >> (8 * (j & 3))) & 0xff);
+          bool p = (MODE == MODE_EQUAL) ? (vv[j] == t0 && ob != fill_o)
+                                        : (vv[j] >= t0 && vv[j] <= t1 && ob != fill_o);
+          bits |= (uint32_t)p << j;
+        }
+      }
+      uint32_t word = bits << (8 * (lane & 3));
+      word |= __shfl_xor_sync(0xffffffffu, word, 1);
+      word |= __shfl_xor_sync(0xffffffffu, word, 2);
+      if ((lane & 3) == 0 && ok[k]) {
+        int64_t wi = row[k] * b.wx + (q[k] >> 2);
+        fg[wi] = word;
+        reach[wi] = 0;
+      }
     }
   }
 }
@@ -775,7 +789,7 @@ int flood(T* data, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64
     bool vec = sizeof(T) == 2 && MODE != MODE_INPLACE && dx % 8 == 0 && b2v_aligned16(data) &&
                ((uintptr_t)out & 7u) == 0;
     if (vec) {
-      k_ff_build_i16_vec<MODE><<<grid_for(nwords * 4, 256), 256, 0, s>>>((const int16_t*)data, out, b, (int)t0,
+      k_ff_build_i16_vec<MODE><<<grid_for(nwords * 4, 1024), 256, 0, s>>>((const int16_t*)data, out, b, (int)t0,
                                                                          (int)t1, fill_o, w.fg, w.reach);
     } else {
       k_ff_build<T, MODE><<<grid_for(nwords, 8), 256, 0, s>>>(data, out, b, t0, t1, fill_t, fill_o, w.fg, w.reach);

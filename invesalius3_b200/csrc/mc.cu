@@ -80,27 +80,41 @@ __global__ void __launch_bounds__(256) k_mc_bits_u8_vec(const uint8_t* __restric
                                                         uint32_t* __restrict__ bits) {
   const int gx = g.wx * 2;  // 16-voxel groups per row (padded)
   const int64_t ngroups = g.nz * g.ny * gx;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   const int lane = threadIdx.x & 31;
-  for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x; g0 < ngroups; g0 += stride) {
-    int64_t gi = g0 + threadIdx.x;
-    uint32_t b = 0;
-    int64_t row = 0;
-    int q = 0;
-    if (gi < ngroups) {
-      row = gi / gx;
-      q = (int)(gi - row * gx);
-      int64_t x = (int64_t)q * 16;
-      if (x < g.nx) {
-        uint4 v = ld_stream((const uint4*)(vol + row * g.nx + x));
-        uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+  const uint32_t thr4 = (uint32_t)(ithr > 255 ? 255 : (ithr < 0 ? 0 : ithr)) * 0x01010101u;
+  const bool none = ithr > 255;
+  // four 128-bit loads in flight per thread; bytes are compared four at a time
+  for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x * 4; g0 < ngroups; g0 += stride) {
+    uint4 v[4];
+    int64_t row[4];
+    int q[4];
+    bool ok[4];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) b |= (uint32_t)((int)((wv[k >> 2] >> (8 * (k & 3))) & 0xff) >= ithr) << k;
-      }
+    for (int k = 0; k < 4; ++k) {
+      const int64_t gi = g0 + k * blockDim.x + threadIdx.x;
+      ok[k] = gi < ngroups;
+      row[k] = ok[k] ? gi / gx : 0;
+      q[k] = ok[k] ? (int)(gi - row[k] * gx) : 0;
+      v[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok[k] && (int64_t)q[k] * 16 < g.nx) v[k] = ld_stream((const uint4*)(vol + row[k] * g.nx + (int64_t)q[k] * 16));
+      else if (ok[k]) ok[k] = true;  // padded group: contributes zero bits (unless ithr <= 0, handled below)
     }
-    uint32_t word = b << (16 * (lane & 1));
-    word |= __shfl_xor_sync(0xffffffffu, word, 1);
-    if ((lane & 1) == 0 && gi < ngroups) bits[row * g.wx + (q >> 1)] = word;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t b = 0;
+      if (ok[k] && (int64_t)q[k] * 16 < g.nx && !none) {
+        const uint32_t wv[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t ge = __vcmpgeu4(wv[j], thr4);                     // 0xFF per byte >= threshold
+          b |= (((ge & 0x01010101u) * 0x01020408u) >> 24 & 0xfu) << (4 * j);
+        }
+      }
+      uint32_t word = b << (16 * (lane & 1));
+      word |= __shfl_xor_sync(0xffffffffu, word, 1);
+      if ((lane & 1) == 0 && ok[k]) bits[row[k] * g.wx + (q[k] >> 1)] = word;
+    }
   }
 }
 
@@ -368,18 +382,49 @@ __global__ void __launch_bounds__(256) k_mc_emit(const T* __restrict__ vol, McGe
       const int w = (int)(wi - row * g.wx);
       const int64_t z = row / g.ny, y = row - z * g.ny;
       const int64_t x = (int64_t)w * 32 + lane;
+      // Everything this word needs is addressed by (wi, lane) alone: issue all the loads up
+      // front so that their latencies overlap (one round trip per word instead of three).
+      const bool cells = y + 1 < g.ny && z + 1 < g.nz;
       const uint4 inf = info[wi];
+      const int64_t p = row * g.nx + x;
+      const bool inx = x < g.nx;
+      T v0 = 0, vx = 0, vy = 0, vz = 0;
+      if (inx) {
+        v0 = vol[p];
+        if (x + 1 < g.nx) vx = vol[p + 1];
+        if (y + 1 < g.ny) vy = vol[p + g.nx];
+        if (z + 1 < g.nz) vz = vol[p + g.nx * g.ny];
+      }
+      uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+      int rbase = vbase;
+      Rows r;
+      r.i00 = r.i01 = r.i10 = r.i11 = r.n00 = r.n01 = r.n10 = r.n11 = 0u;
+      if (cells) {
+        if (lane < 8) {
+          // the 12 edges of the 32 cells of this word are owned by voxels of 4 rows x 2 words:
+          // those 8 records are fetched once per warp, not once per triangle corner
+          const int cz = lane >> 2, cy = (lane >> 1) & 1, cw = lane & 1;
+          if (w + cw < g.wx) {
+            if (skip_last && z + cz == g.nz - 1) {
+              rec = __ldg(foreign + (y + cy) * g.wx + (w + cw));
+              rbase = foreign_base;
+            } else {
+              rec = __ldg(info + ((z + cz) * g.ny + (y + cy)) * g.wx + (w + cw));
+            }
+          }
+        }
+        r = load_rows(bits, g, z, y, w);
+      }
       // ---- vertices owned by voxel (z, y, x)
       {
         const int bx = (inf.x >> lane) & 1, by = (inf.y >> lane) & 1, bz = (inf.z >> lane) & 1;
         if ((bx | by | bz) && !(skip_last && z == g.nz - 1)) {
           uint32_t vid = inf.w + __popc(inf.x & low) + __popc(inf.y & low) + __popc(inf.z & low);
-          const int64_t p = row * g.nx + x;
-          const float s0 = (float)vol[p];
+          const float s0 = (float)v0;
           const float fx = (float)((int)x + xf.ox), fy = (float)((int)y + xf.oy), fz = (float)((int)z + xf.oz);
           const float num = __fsub_rn(xf.iso, s0);
           if (bx) {
-            float t = __fdiv_rn(num, __fsub_rn((float)vol[p + 1], s0));
+            float t = __fdiv_rn(num, __fsub_rn((float)vx, s0));
             float py = __fmul_rn(fy, xf.sy);
             float* o = verts + 3ll * vid;
             o[0] = __fmul_rn(__fadd_rn(fx, t), xf.sx);
@@ -388,7 +433,7 @@ __global__ void __launch_bounds__(256) k_mc_emit(const T* __restrict__ vol, McGe
             ++vid;
           }
           if (by) {
-            float t = __fdiv_rn(num, __fsub_rn((float)vol[p + g.nx], s0));
+            float t = __fdiv_rn(num, __fsub_rn((float)vy, s0));
             float py = __fmul_rn(__fadd_rn(fy, t), xf.sy);
             float* o = verts + 3ll * vid;
             o[0] = __fmul_rn(fx, xf.sx);
@@ -397,7 +442,7 @@ __global__ void __launch_bounds__(256) k_mc_emit(const T* __restrict__ vol, McGe
             ++vid;
           }
           if (bz) {
-            float t = __fdiv_rn(num, __fsub_rn((float)vol[p + g.nx * g.ny], s0));
+            float t = __fdiv_rn(num, __fsub_rn((float)vz, s0));
             float py = __fmul_rn(fy, xf.sy);
             float* o = verts + 3ll * vid;
             o[0] = __fmul_rn(fx, xf.sx);
@@ -407,27 +452,13 @@ __global__ void __launch_bounds__(256) k_mc_emit(const T* __restrict__ vol, McGe
         }
       }
       // ---- triangles of cell (z, y, x)
-      if (y + 1 < g.ny && z + 1 < g.nz) {
-        // the 12 edges of the 32 cells of this word are owned by voxels of 4 rows x 2 words:
-        // fetch those 8 records once per warp instead of once per triangle corner
+      if (cells) {
         __syncwarp();
         if (lane < 8) {
-          const int cz = lane >> 2, cy = (lane >> 1) & 1, cw = lane & 1;
-          uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-          int base = vbase;
-          if (w + cw < g.wx) {
-            if (skip_last && z + cz == g.nz - 1) {
-              rec = __ldg(foreign + (y + cy) * g.wx + (w + cw));
-              base = foreign_base;
-            } else {
-              rec = __ldg(info + ((z + cz) * g.ny + (y + cy)) * g.wx + (w + cw));
-            }
-          }
           s_rec[threadIdx.x >> 5][lane] = rec;
-          s_base[threadIdx.x >> 5][lane] = base;
+          s_base[threadIdx.x >> 5][lane] = rbase;
         }
         __syncwarp();
-        Rows r = load_rows(bits, g, z, y, w);
         int c = (x + 1 < g.nx) ? cell_case(r, lane) : 0;
         int ntri = s_tri[c][15];
         // exclusive prefix of ntri over the lanes
@@ -504,7 +535,7 @@ static int mc_count_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int
   if (dtype == B2V_U8) {
     int thr = int_threshold(iso, 0, 255);
     if (nx % 16 == 0 && b2v_aligned16(vol))
-      k_mc_bits_u8_vec<<<grid_for(g.nwords * 2, 256), 256, 0, s>>>((const uint8_t*)vol, g, thr, w.bits);
+      k_mc_bits_u8_vec<<<grid_for(g.nwords * 2, 1024), 256, 0, s>>>((const uint8_t*)vol, g, thr, w.bits);
     else
       k_mc_bits<uint8_t><<<grid_for(g.nwords, 8), 256, 0, s>>>((const uint8_t*)vol, g, thr, w.bits);
   } else {
