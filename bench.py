@@ -37,6 +37,11 @@ SEED_SLICE_FRAC = 0.5
 FILL = 254
 
 
+def workload_desc(n):
+    return (f"{n}^3 synthetic int16 CT phantom (seed 2) per GPU: threshold [226,3071] -> 6-connected flood fill "
+            f"from one seed per {n}^3 shard -> marching cubes iso 127 on the grown mask")
+
+
 def measured_peak():
     try:
         return float(json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"]), "measured"
@@ -46,14 +51,19 @@ def measured_peak():
 
 def make_volume(n, world=1, zrange=None):
     """The job's volume is (n*world) x n x n, Z-sharded; returns the planes `zrange` (default:
-    all) and the global seed (x, y, z) in the middle slice."""
+    all) and the global seeds (x, y, z): one per n^3 shard, in the shard's middle slice (the
+    first in-range voxel in raveled order). One connected region spans all shards, so the
+    waves started in different shards meet at the shard boundaries."""
     from invesalius3_b200 import phantom
     DZ = n * world
-    zmid = int(DZ * SEED_SLICE_FRAC)
-    mid = phantom.ct((DZ, n, n), seed=2, zrange=(zmid, zmid + 1))
-    sx, sy, _ = phantom.first_seed_in_range(mid, 0, *THR)
+    seeds = []
+    for r in range(world):
+        zmid = r * n + int(n * SEED_SLICE_FRAC)
+        mid = phantom.ct((DZ, n, n), seed=2, zrange=(zmid, zmid + 1))
+        sx, sy, _ = phantom.first_seed_in_range(mid, 0, *THR)
+        seeds.append((sx, sy, zmid))
     vol = phantom.ct((DZ, n, n), seed=2, zrange=zrange)
-    return vol, (sx, sy, zmid)
+    return vol, seeds
 
 
 # ------------------------------------------------------------------ CPU reference path
@@ -160,7 +170,8 @@ def run_gpu(args):
     n = args.size
     from invesalius3_b200 import dist as zd
     shard = zd.ZShard(n * world, rank, world)
-    ext_np, seed = make_volume(n, world, (shard.ze0, shard.ze1))   # own planes + halo planes
+    ext_np, seeds = make_volume(n, world, (shard.ze0, shard.ze1))   # own planes + halo planes
+    seed = seeds[0]
     vol = shard.interior(torch.from_numpy(ext_np)).numpy()          # this rank's n^3 shard
     strct = generate_binary_structure(3, 1)
     N = vol.size
@@ -179,13 +190,12 @@ def run_gpu(args):
     d_out = torch.empty((nz_ext, n, n), dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
     info = {}
-    local_seed = (seed[0], seed[1], seed[2] - shard.ze0)
 
     def do_flood(data_ext, out_ext):
         if world == 1:
             info["rounds"] = dev.floodfill_threshold(data_ext, [seed], THR[0], THR[1], FILL, strct, out_ext)
         else:
-            info["rounds"] = zd.floodfill_threshold(data_ext, [seed], THR[0], THR[1], FILL, strct, out_ext, shard)
+            info["rounds"] = zd.floodfill_threshold(data_ext, seeds, THR[0], THR[1], FILL, strct, out_ext, shard)
 
     def do_surface(out_ext):
         if world == 1:
@@ -320,8 +330,7 @@ def run_gpu(args):
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": f"{n}^3 synthetic int16 CT phantom (seed 2): threshold [226,3071] -> "
-                               "6-connected flood fill from one seed -> marching cubes iso 127 on the grown mask",
+        "config": {"workload": workload_desc(n),
                    "volume": f"{n * world}x{n}x{n} (Z-sharded, one halo plane per inner side)",
                    "shard": f"{n}^3 voxels per GPU", "l2": "inputs (256 MiB int16 + 128 MiB uint8) exceed the 126 MB L2",
                    "flood_rounds": info["rounds"], "vertices": info["V"], "triangles": info["T"],
@@ -352,7 +361,8 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.size
-    vol, seed = make_volume(n)
+    vol, seeds = make_volume(n)
+    seed = seeds[0]
     cores = os.cpu_count() or 1
     sub, sseed = cpu_sample(vol, seed, min(n, args.cpu_slices))
     for _ in range(min(args.warmup, 1)):
@@ -367,8 +377,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(s * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": f"{n}^3 synthetic int16 CT phantom (seed 2): threshold [226,3071] -> 6-connected "
-                               "flood fill from one seed -> marching cubes iso 127 on the grown mask"},
+        "config": {"workload": workload_desc(n)},
         "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
