@@ -17,6 +17,7 @@
 //              next round. Rounds ~ geodesic length measured in tiles, not voxels.
 //   3. write   (sparse): reached bits are expanded to `fill` stores into out.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "b2v_common.cuh"
@@ -37,6 +38,7 @@ struct BitVol {
   int ntz, nty, ntw;   // tile grid
   int ltw, lty;        // log2(tw), log2(ty)
   uint32_t m_pw, m_pp; // ceil(2^24 / (tw+2)), ceil(2^24 / ((tw+2)(ty+2))): exact division for i < 2^12
+  int max_trips;       // local sweeps per visit before the tile re-queues itself
 };
 
 int pow2ceil(int64_t v, int cap) {
@@ -62,6 +64,8 @@ BitVol make_bitvol(int64_t dz, int64_t dy, int64_t dx) {
   const uint32_t pw = b.tw + 2, pp = (b.tw + 2) * (b.ty + 2);
   b.m_pw = ((1u << 24) + pw - 1) / pw;
   b.m_pp = ((1u << 24) + pp - 1) / pp;
+  b.max_trips = 1;   // measured: one sweep set per visit, stragglers re-queue themselves (round time = one trip)
+  if (const char* e = getenv("B2V_FF_TRIPS")) { int v = atoi(e); if (v > 0) b.max_trips = v; }
   return b;
 }
 
@@ -467,7 +471,8 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
     }
     changed = __syncthreads_or(changed);
     ++iters;
-  } while (changed);
+  } while (changed && iters < b.max_trips);
+  const bool unfinished = changed != 0;   // trip cap hit: this tile must be visited again
 
   const long long pc2 = clock64();
   // write back what grew
@@ -531,6 +536,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
       if (acc & want) nbmask |= 1 << ((tz_o + 1) * 9 + (ty_o + 1) * 3 + (tw_o + 1));
     }
   }
+  if (unfinished && tid == 0) nbmask |= 1 << 13;   // (0,0,0): re-queue this tile itself
   if (nbmask) atomicOr(s_faces, nbmask);
   __syncthreads();
   if (tid == 0) atomicAdd(&stats[14], (int)((clock64() - pc3) >> 4));   // neighbour gain test
@@ -743,6 +749,10 @@ int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_
   B2V_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, kFloodThreads, smem));
   B2V_REQUIRE(per_sm >= 1, B2V_ERR_CUDA, "floodfill: persistent kernel does not fit on an SM");
   int grid = per_sm * b2v_sm_count();        // every co-resident slot: one tile per block per round
+  if (const char* e = getenv("B2V_FF_GRID")) {   // tuning knob (blocks of the persistent grid)
+    int v = atoi(e);
+    if (v > 0 && v < grid) grid = v;
+  }
   if (grid > ntiles) grid = ntiles;
   const uint32_t* fg = w.fg;
   uint32_t* reach = w.reach;
