@@ -151,6 +151,30 @@ class ClockSampler:
                 "samples": len(rows)}
 
 
+def bind_to_gpu_numa(local_rank):
+    """Best effort: run this process on the CPUs of the NUMA node the GPU hangs off, so that
+    first-touch puts the pinned host buffers next to the GPU's PCIe root (cross-socket DMA and
+    memset are several times slower). Returns a short description for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, ids)
+        return f"numa: bound to node {node} ({len(ids)} cpus)"
+    except Exception as e:   # noqa: BLE001
+        return f"numa: not bound ({type(e).__name__})"
+
+
 # ------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import torch
@@ -164,6 +188,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dev.require_cuda()
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
@@ -320,7 +345,7 @@ def run_gpu(args):
         traffic = json.load(open(ROOT / "profiles" / "r01_traffic.json"))["stages"][names[dom]]["traffic"]
     except Exception:
         pass
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cpu_baseline = None
     if world == 1:   # the CPU baseline is an N=1 figure (rank 0's host cores)
         cpu_v, cpu_sample_desc = time_cpu(vol, seed, min(n, args.cpu_slices), 1, cores)
@@ -333,7 +358,7 @@ def run_gpu(args):
         "config": {"workload": workload_desc(n),
                    "volume": f"{n * world}x{n}x{n} (Z-sharded, one halo plane per inner side)",
                    "shard": f"{n}^3 voxels per GPU", "l2": "inputs (256 MiB int16 + 128 MiB uint8) exceed the 126 MB L2",
-                   "flood_rounds": info["rounds"], "vertices": info["V"], "triangles": info["T"],
+                   "host": numa, "flood_rounds": info["rounds"], "vertices": info["V"], "triangles": info["T"],
                    "stage_ms": {k: round(float(m), 4) for k, m in zip(names, stage_ms)}},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
