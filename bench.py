@@ -189,6 +189,7 @@ def run_gpu(args):
     dev.require_cuda()
     torch.cuda.set_device(local)
     numa = bind_to_gpu_numa(local)
+    torch.set_num_threads(16)   # host memset of the out mask: 128 OpenMP threads make it erratic (0.3 .. 25 ms)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()

@@ -47,6 +47,10 @@ extern "C" void b2v_launch_count_reset(void) { g_launches = 0; }
 static int copy3d(void* dst, int64_t dpitch, int64_t dslice_rows, const void* src, int64_t spitch,
                   int64_t sslice_rows, int64_t dz, int64_t dy, int64_t dx_bytes, cudaMemcpyKind kind,
                   cudaStream_t s) {
+  if (dz == 1 && dy == 1) {  // flat run: plain async copy (no pitch limit, fastest DMA path)
+    B2V_CUDA(cudaMemcpyAsync(dst, src, (size_t)dx_bytes, kind, s));
+    return B2V_OK;
+  }
   cudaMemcpy3DParms p;
   memset(&p, 0, sizeof(p));
   p.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src), (size_t)spitch, (size_t)dx_bytes, (size_t)sslice_rows);

@@ -81,9 +81,13 @@ def to_device(a: np.ndarray, device=None) -> torch.Tensor:
     t = torch.empty(a.shape, dtype=tdt, device=device)
     if a.size == 0:
         return t
-    pit = _box_pitches(a)
+    pit = None if a.flags.c_contiguous else _box_pitches(a)
     with torch.cuda.device(device):
-        if pit is not None:
+        if a.flags.c_contiguous:
+            # one flat copy: the DMA engine is measurably slower on 3-D copies with short rows
+            _lib.call("b2v_copy3d_h2d", _p(t), C.c_void_p(a.ctypes.data), 1, 1, a.size, a.itemsize,
+                      a.size * a.itemsize, a.size * a.itemsize, _stream())
+        elif pit is not None:
             dz, dy, dx = a.shape
             _lib.call("b2v_copy3d_h2d", _p(t), C.c_void_p(a.ctypes.data), dz, dy, dx, a.itemsize, pit[0], pit[1],
                       _stream())
@@ -170,16 +174,16 @@ def to_host(t: torch.Tensor, out: np.ndarray) -> None:
         return
     if not out.flags.writeable:
         raise ValueError("output array is read-only")
-    pit = _box_pitches(out)
+    pit = None if out.flags.c_contiguous else _box_pitches(out)
     with torch.cuda.device(t.device):
-        if pit is not None:
+        if out.flags.c_contiguous:
+            _lib.call("b2v_copy3d_d2h", C.c_void_p(out.ctypes.data), _p(t), 1, 1, out.size, out.itemsize,
+                      out.size * out.itemsize, out.size * out.itemsize, _stream())
+            torch.cuda.current_stream().synchronize()
+        elif pit is not None:
             dz, dy, dx = out.shape
             _lib.call("b2v_copy3d_d2h", C.c_void_p(out.ctypes.data), _p(t), dz, dy, dx, out.itemsize, pit[0], pit[1],
                       _stream())
-            torch.cuda.current_stream().synchronize()
-        elif out.flags.c_contiguous:
-            _lib.call("b2v_copy3d_d2h", C.c_void_p(out.ctypes.data), _p(t), 1, 1, out.size, out.itemsize,
-                      out.size * out.itemsize, out.size * out.itemsize, _stream())
             torch.cuda.current_stream().synchronize()
         else:
             tmp = np.empty(out.shape, dtype=out.dtype)
