@@ -143,6 +143,10 @@ int b2v_fill_holes(uint8_t* mask, const uint32_t* labels, int64_t n, uint32_t nl
 int64_t b2v_proj_workspace_bytes(int64_t n);
 int b2v_mida(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double wl, double ww,
              void* out, int out_dtype, void* workspace, void* stream);
+/* same, with the (min, max) pair of mips.rs:113-122 supplied by the caller as float[2] on
+ * the device: a Z shard passes the all-reduced global pair (invesalius3_b200/dist.py). */
+int b2v_mida_minmax(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double wl, double ww,
+                    const float* minmax_dev, void* out, int out_dtype, void* workspace, void* stream);
 /* lmip(image, axis, tmin, tmax, out): mips.rs:7-86 (called as mips.lmip by slice_.py:892,
  * 980,1063 although the crate forgets to export it). out has the image dtype. */
 int b2v_lmip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double tmin, double tmax,

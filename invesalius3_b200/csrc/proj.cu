@@ -421,8 +421,8 @@ bool check_axis_dims(int64_t dz, int64_t dy, int64_t dx, int axis) {
 
 extern "C" int64_t b2v_proj_workspace_bytes(int64_t n) { return 256 + b2v_minmax_workspace_bytes(n); }
 
-extern "C" int b2v_mida(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double wl,
-                        double ww, void* out, int out_dtype, void* workspace, void* stream) {
+static int mida_impl(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double wl, double ww,
+                     const float* minmax_dev, void* out, int out_dtype, void* workspace, void* stream) {
   B2V_REQUIRE(img && out && workspace, B2V_ERR_ARG, "mida: null pointer");
   B2V_REQUIRE(check_axis_dims(dz, dy, dx, axis), B2V_ERR_ARG, "mida: bad shape or axis");
   cudaStream_t s = (cudaStream_t)stream;
@@ -431,7 +431,12 @@ extern "C" int b2v_mida(const void* img, int dtype, int64_t dz, int64_t dy, int6
   int rc;
   k_status_init<<<1, 1, 0, s>>>(w.status);
   if ((rc = b2v_check_launch("k_status_init"))) return rc;
-  if ((rc = b2v_minmax_f32(img, dtype, dz * dy * dx, w.mm_f, w.minmax_ws, stream))) return rc;
+  if (minmax_dev) {
+    // the caller already knows the (global) min / max: a Z shard after its all_reduce
+    B2V_CUDA(cudaMemcpyAsync(w.mm_f, minmax_dev, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else if ((rc = b2v_minmax_f32(img, dtype, dz * dy * dx, w.mm_f, w.minmax_ws, stream))) {
+    return rc;
+  }
   if (dtype == B2V_I16 && out_dtype == B2V_I16) {
     PlainSampler<int16_t> smp = {(const int16_t*)img, d};
     rc = launch_mida<int16_t, int16_t>(smp, axis, w.mm_f, (float)(int16_t)wl, (float)(int16_t)ww, (int16_t*)out,
@@ -448,6 +453,18 @@ extern "C" int b2v_mida(const void* img, int dtype, int64_t dz, int64_t dy, int6
   }
   if (rc) return rc;
   return finish_status(w.status, s, "mida");
+}
+
+extern "C" int b2v_mida(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double wl,
+                        double ww, void* out, int out_dtype, void* workspace, void* stream) {
+  return mida_impl(img, dtype, dz, dy, dx, axis, wl, ww, nullptr, out, out_dtype, workspace, stream);
+}
+
+extern "C" int b2v_mida_minmax(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double wl,
+                               double ww, const float* minmax_dev, void* out, int out_dtype, void* workspace,
+                               void* stream) {
+  B2V_REQUIRE(minmax_dev, B2V_ERR_ARG, "mida_minmax: null min/max pointer");
+  return mida_impl(img, dtype, dz, dy, dx, axis, wl, ww, minmax_dev, out, out_dtype, workspace, stream);
 }
 
 extern "C" int b2v_lmip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double tmin,

@@ -8,7 +8,8 @@ op of the path is sharded the same way:
   threshold            independent voxels: no communication
   MaxIP/MinIP/MeanIP   axis 1/2: rows stay with their shard (optional all_gather);
                        axis 0: partial planes, one all_reduce
-  MIDA axis 1/2        all_reduce of the global (min, max), then local rays
+  MIDA / LMIP axis 1/2 all_reduce of the global (min, max) for MIDA, then local rays (built);
+                       axis 0 needs a pipelined ray-state hand-off between shards (not built)
   flood fill           local convergence on slab + one halo plane per inner side, then the
                        reached bits of the two shared planes are swapped with each neighbour
                        (2 x dy x dx/8 bytes) and merged; repeat until no shard gains a bit
@@ -181,6 +182,17 @@ class DeviceBackend:
     def sum_axis0(self, img):
         return img.to(torch.int64).sum(dim=0)  # partial sums for MeanIP axis 0 (tiny plane op)
 
+    def minmax(self, img):
+        return self.dev.minmax(img)
+
+    def mida(self, img, axis, wl, ww, minmax):
+        from . import projection
+        return projection.mida(img, axis, wl, ww, minmax=minmax)
+
+    def lmip(self, img, axis, tmin, tmax):
+        from . import projection
+        return projection.lmip(img, axis, tmin, tmax)
+
     # -- flood fill
     def ff_begin(self, data, out, seeds, t0, t1, fill, strct):
         dev, lib = self.dev, self._lib.load()
@@ -298,6 +310,36 @@ def mip(img_slab, axis, kind, shard: ZShard, gather=True, backend=None):
         _all_reduce(shard, part, dist.ReduceOp.MAX if kind == "max" else dist.ReduceOp.MIN)
         return part.to(img_slab.dtype)
     rows = be.mip(img_slab, axis, kind)
+    if not gather:
+        return rows
+    sizes = [shard.bounds(r)[1] - shard.bounds(r)[0] for r in range(shard.world)]
+    return _all_gather_rows(shard, rows, sizes)
+
+
+def mida(img_slab, axis, wl, ww, shard: ZShard, gather=True, backend=None):
+    """MIDA of the whole volume from per-shard slabs, rays along y or x (axis 1 / 2): the only
+    global quantity is the (min, max) pair of mips.rs:113-122 — two 4-byte all_reduces — then
+    every shard walks its own rays. Rays along z (axis 0) cross the shards: that case needs the
+    per-ray state (fmax, alpha, colour) handed from shard to shard and is not built yet."""
+    if axis == 0:
+        raise NotImplementedError("MIDA along z over Z shards needs the pipelined ray-state hand-off (next)")
+    be = _backend(backend)
+    mm = be.minmax(img_slab).clone()
+    lo, hi = mm[0:1].clone(), mm[1:2].clone()
+    _all_reduce(shard, lo, dist.ReduceOp.MIN)
+    _all_reduce(shard, hi, dist.ReduceOp.MAX)
+    rows = be.mida(img_slab, axis, wl, ww, torch.cat([lo, hi]))
+    if not gather:
+        return rows
+    sizes = [shard.bounds(r)[1] - shard.bounds(r)[0] for r in range(shard.world)]
+    return _all_gather_rows(shard, rows, sizes)
+
+
+def lmip(img_slab, axis, tmin, tmax, shard: ZShard, gather=True, backend=None):
+    """LMIP with rays along y or x: purely local rows (mips.rs:7-86 keeps no global state)."""
+    if axis == 0:
+        raise NotImplementedError("LMIP along z over Z shards needs the pipelined ray-state hand-off (next)")
+    rows = _backend(backend).lmip(img_slab, axis, tmin, tmax)
     if not gather:
         return rows
     sizes = [shard.bounds(r)[1] - shard.bounds(r)[0] for r in range(shard.world)]

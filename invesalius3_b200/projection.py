@@ -26,8 +26,11 @@ def _prep(image: torch.Tensor, axis: int, out: torch.Tensor | None, out_dtype):
     return out, ws
 
 
-def mida(image: torch.Tensor, axis: int, wl, ww, out: torch.Tensor | None = None) -> torch.Tensor:
-    """mips.rs:102-168. wl/ww are interpreted as the image dtype, like the PyO3 layer."""
+def mida(image: torch.Tensor, axis: int, wl, ww, out: torch.Tensor | None = None,
+         minmax: torch.Tensor | None = None) -> torch.Tensor:
+    """mips.rs:102-168. wl/ww are interpreted as the image dtype, like the PyO3 layer.
+    `minmax` (float32 [2] on the device) replaces the pass over the volume that finds them —
+    a Z shard passes the all-reduced global pair."""
     odt = {torch.int16: torch.int16, torch.uint8: torch.uint8, torch.float64: torch.uint8}.get(image.dtype)
     if odt is None:
         raise TypeError("Invalid image or output type")
@@ -36,8 +39,14 @@ def mida(image: torch.Tensor, axis: int, wl, ww, out: torch.Tensor | None = None
         raise TypeError("Invalid image or output type")
     dz, dy, dx = image.shape
     with torch.cuda.device(image.device):
-        _lib.call("b2v_mida", _p(image), dtype_code(image), dz, dy, dx, axis, float(wl), float(ww), _p(out),
-                  dtype_code(out), _p(ws), _stream())
+        if minmax is None:
+            _lib.call("b2v_mida", _p(image), dtype_code(image), dz, dy, dx, axis, float(wl), float(ww), _p(out),
+                      dtype_code(out), _p(ws), _stream())
+        else:
+            if minmax.dtype != torch.float32 or minmax.numel() != 2 or not minmax.is_cuda:
+                raise TypeError("minmax must be a float32 CUDA tensor with 2 elements")
+            _lib.call("b2v_mida_minmax", _p(image), dtype_code(image), dz, dy, dx, axis, float(wl), float(ww),
+                      _p(minmax.contiguous()), _p(out), dtype_code(out), _p(ws), _stream())
     return out
 
 

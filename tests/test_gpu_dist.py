@@ -25,6 +25,9 @@ def rank_all(rank, world, device):
         for kind in ("max", "min", "mean"):
             res[("mip", axis, kind)] = d.mip(own, axis, kind, shard).cpu().numpy()
     res["thr"] = (shard.z0, shard.z1, d.threshold(own, *THR, shard).cpu().numpy())
+    for axis in (1, 2):
+        res[("mida", axis)] = d.mida(own, axis, 300, 600, shard).cpu().numpy()
+        res[("lmip", axis)] = d.lmip(own, axis, 700, 3033, shard).cpu().numpy()
     # flood fill
     for ci, (strct, seeds) in enumerate(ff_cases(g)):
         data = torch.from_numpy(ext_slab(g, shard)).to(_dev())
@@ -53,6 +56,12 @@ def _check(out, orc):
             for kind in ("max", "min", "mean"):
                 want = {"max": g.max, "min": g.min, "mean": g.mean}[kind](axis)
                 assert np.array_equal(out[rank][("mip", axis, kind)], want), (rank, axis, kind)
+        for axis in (1, 2):
+            want = np.zeros([(40, 96), (37, 96), (37, 40)][axis], np.int16)
+            orc.mida(g, axis, 300, 600, want)
+            assert np.array_equal(out[rank][("mida", axis)], want), ("mida", rank, axis)
+            orc.lmip(g, axis, 700, 3033, want)
+            assert np.array_equal(out[rank][("lmip", axis)], want), ("lmip", rank, axis)
         z0, z1, m = out[rank]["thr"]
         want = np.zeros(g.shape, np.uint8)
         orc.threshold(g, *THR, want, False)
