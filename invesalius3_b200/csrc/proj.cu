@@ -30,6 +30,7 @@ struct Dims {
 // ---- samplers -----------------------------------------------------------------------------
 template <typename T>
 struct PlainSampler {
+  static constexpr int kBatch = 8;   // samples fetched ahead of the recurrence (plain loads)
   const T* __restrict__ vol;
   Dims d;
   __device__ __forceinline__ T at(int64_t z, int64_t y, int64_t x, int* status) const {
@@ -60,6 +61,7 @@ template <> __device__ __forceinline__ bool cast_f32<uint8_t>(float f, uint8_t* 
 // calc_fcm_intensity (mips.rs:197-213) cast to T (mips.rs:241)
 template <typename T>
 struct FcmSampler {
+  static constexpr int kBatch = 1;   // a contour sample is expensive: never compute past the ray's end
   const T* __restrict__ vol;
   Dims d;
   float n;
@@ -183,9 +185,18 @@ __global__ void __launch_bounds__(128) k_rays_keepx(S smp, int axis, Op op0, U* 
     T v0 = axis == 0 ? smp.at(0, r, x, &st) : smp.at(r, 0, x, &st);
     op.first(v0);
   }
-  for (int64_t l = 0; l < n_l; ++l) {
-    T v = axis == 0 ? smp.at(l, r, x, &st) : smp.at(r, l, x, &st);
-    if (op.step(v)) break;
+  bool done = false;
+  constexpr int B = S::kBatch;
+  for (int64_t l0 = 0; l0 < n_l && !done; l0 += B) {
+    T v[B];
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      const int64_t l = l0 + k < n_l ? l0 + k : n_l - 1;
+      v[k] = axis == 0 ? smp.at(l, r, x, &st) : smp.at(r, l, x, &st);
+    }
+#pragma unroll
+    for (int k = 0; k < B; ++k)
+      if (!done && l0 + k < n_l && op.step(v[k])) done = true;
   }
   U o;
   if (op.result(&o)) out[r * d.nx + x] = o; else st = B2V_ERR_RANGE;
@@ -322,9 +333,20 @@ __global__ void __launch_bounds__(128) k_mida_keepx(S smp, int axis, const float
   MidaOp<T, U> op = make_mida<T, U>(mm, wl, ww);
   op.init();
   int st = 0;
-  for (int64_t l = 0; l < n_l; ++l) {
-    T v = axis == 0 ? smp.at(l, r, x, &st) : smp.at(r, l, x, &st);
-    if (op.step(v)) break;
+  // eight samples are fetched before any of them is consumed: the ray recurrence is a long
+  // dependent chain, the loads must not wait for it (8 x 2 B in flight per thread)
+  bool done = false;
+  constexpr int B = S::kBatch;
+  for (int64_t l0 = 0; l0 < n_l && !done; l0 += B) {
+    T v[B];
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      const int64_t l = l0 + k < n_l ? l0 + k : n_l - 1;
+      v[k] = axis == 0 ? smp.at(l, r, x, &st) : smp.at(r, l, x, &st);
+    }
+#pragma unroll
+    for (int k = 0; k < B; ++k)
+      if (!done && l0 + k < n_l && op.step(v[k])) done = true;
   }
   U o;
   if (op.result(&o)) out[r * d.nx + x] = o; else st = B2V_ERR_RANGE;

@@ -25,3 +25,16 @@ print("flood (device) ", T(lambda: (o.zero_(), dev.floodfill_threshold(d, [seed]
 print("to_host(out)   ", T(lambda: dev.to_host(o, np_out)))
 print("shares_memory  ", T(lambda: np.shares_memory(np_vol, np_out)))
 print("shim call      ", T(lambda: (h_out.zero_(), invesalius_rs.floodfill_threshold(np_vol, [seed], 226, 3071, 254, st, np_out))))
+def seq():
+    d = dev.to_device(np_vol); o = dev.to_device(np_out)
+    dev.floodfill_threshold(d, [seed], 226, 3071, 254, st, o)
+    dev.to_host(o, np_out)
+print("manual sequence", T(seq))
+def seq2():
+    d = dev.to_device(np_vol); torch.cuda.synchronize(); t1 = time.perf_counter()
+    o = dev.to_device(np_out); torch.cuda.synchronize(); t2 = time.perf_counter()
+    dev.floodfill_threshold(d, [seed], 226, 3071, 254, st, o); t3 = time.perf_counter()
+    dev.to_host(o, np_out); t4 = time.perf_counter()
+    return t2 - t1, t3 - t2, t4 - t3
+seq2(); r = [seq2() for _ in range(5)]
+print("in-sequence: to_device(out) %.2f flood %.2f to_host %.2f ms" % tuple(1e3 * min(x[i] for x in r) for i in range(3)))
