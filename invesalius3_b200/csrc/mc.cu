@@ -34,12 +34,13 @@ McGeom make_geom(int64_t nz, int64_t ny, int64_t nx) {
 constexpr int kScanBlock = 256;
 
 struct McWs {
-  uint32_t* bits;    // [nwords]
+  uint32_t* bits;    // [nwords] inside bits
   uint4* info;       // [nwords] (cx, cy, cz, vertex offset)
-  uint32_t* toff;    // [nwords] triangle offset
+  unsigned long long* toff;   // [nwords] (active-cell offset << 32) | triangle offset
+  uint32_t* amask;   // [nwords] cells of the word that produce triangles
   uint32_t* bsum_v;  // [nblocks]
-  uint32_t* bsum_t;  // [nblocks]
-  unsigned long long* totals;  // [2] V, T
+  unsigned long long* bsum_t;  // [nblocks] packed like toff
+  unsigned long long* totals;  // [0] V, [1] (C << 32) | T
   int64_t nblocks;
   int64_t bytes;
 };
@@ -52,9 +53,10 @@ McWs carve(void* base, const McGeom& g) {
   w.nblocks = ceil_div64(g.nwords, kScanBlock);
   w.bits = (uint32_t*)(p + off); off += align(g.nwords * 4 + 4);
   w.info = (uint4*)(p + off); off += align(g.nwords * 16);
-  w.toff = (uint32_t*)(p + off); off += align(g.nwords * 4);
+  w.toff = (unsigned long long*)(p + off); off += align(g.nwords * 8);
+  w.amask = (uint32_t*)(p + off); off += align(g.nwords * 4);
   w.bsum_v = (uint32_t*)(p + off); off += align(w.nblocks * 4);
-  w.bsum_t = (uint32_t*)(p + off); off += align(w.nblocks * 4);
+  w.bsum_t = (unsigned long long*)(p + off); off += align(w.nblocks * 8);
   w.totals = (unsigned long long*)(p + off); off += 256;
   w.bytes = off;
   return w;
@@ -190,15 +192,16 @@ __device__ __forceinline__ int cell_case(const Rows& r, int i) {
 }
 
 __global__ void __launch_bounds__(kScanBlock) k_mc_count(const uint32_t* __restrict__ bits, McGeom g, int skip_last,
-                                                         uint4* __restrict__ info, uint32_t* __restrict__ toff,
-                                                         uint32_t* __restrict__ bsum_v,
-                                                         uint32_t* __restrict__ bsum_t) {
+                                                         uint4* __restrict__ info,
+                                                         unsigned long long* __restrict__ toff,
+                                                         uint32_t* __restrict__ amask, uint32_t* __restrict__ bsum_v,
+                                                         unsigned long long* __restrict__ bsum_t) {
   __shared__ unsigned char s_ntri[256];
-  __shared__ uint32_t s_red[2][kScanBlock / 32];
+  __shared__ unsigned long long s_red[2][kScanBlock / 32];
   s_ntri[threadIdx.x] = B2V_MC_NTRI[threadIdx.x];
   __syncthreads();
   const int64_t wi = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
-  uint32_t nv = 0, nt = 0;
+  uint32_t nv = 0, nt = 0, nact = 0;
   if (wi < g.nwords) {
     int64_t row = wi / g.wx;
     int w = (int)(wi - row * g.wx);
@@ -211,23 +214,27 @@ __global__ void __launch_bounds__(kScanBlock) k_mc_count(const uint32_t* __restr
     uint32_t cz = hz ? (r.i00 ^ r.i10) : 0u;
     // a Z shard does not own the vertices of its last (shared) plane: the next shard does
     nv = (skip_last && z == g.nz - 1) ? 0 : __popc(cx) + __popc(cy) + __popc(cz);
+    uint32_t act = 0;
     if (hy && hz) {
       uint32_t s00 = shift_in(r.i00, r.n00), s01 = shift_in(r.i01, r.n01), s10 = shift_in(r.i10, r.n10),
                s11 = shift_in(r.i11, r.n11);
       uint32_t any = r.i00 | r.i01 | r.i10 | r.i11 | s00 | s01 | s10 | s11;
       uint32_t all = r.i00 & r.i01 & r.i10 & r.i11 & s00 & s01 & s10 & s11;
-      uint32_t act = any & ~all & vx;
-      while (act) {
-        int i = __ffs(act) - 1;
-        act &= act - 1;
+      act = any & ~all & vx;
+      nact = __popc(act);
+      uint32_t m = act;
+      while (m) {
+        int i = __ffs(m) - 1;
+        m &= m - 1;
         nt += s_ntri[cell_case(r, i)];
       }
     }
     info[wi] = make_uint4(cx, cy, cz, nv);
-    toff[wi] = nt;
+    toff[wi] = ((unsigned long long)nact << 32) | nt;
+    amask[wi] = act;
   }
-  // block sums
-  uint32_t a = nv, b = nt;
+  // block sums (cells and triangles travel packed: no carry can cross, totals < 2^31)
+  unsigned long long a = nv, b = ((unsigned long long)nact << 32) | nt;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -239,13 +246,13 @@ __global__ void __launch_bounds__(kScanBlock) k_mc_count(const uint32_t* __restr
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t sa = 0, sb = 0;
+    unsigned long long sa = 0, sb = 0;
 #pragma unroll
     for (int k = 0; k < kScanBlock / 32; ++k) {
       sa += s_red[0][k];
       sb += s_red[1][k];
     }
-    bsum_v[blockIdx.x] = sa;
+    bsum_v[blockIdx.x] = (uint32_t)sa;
     bsum_t[blockIdx.x] = sb;
   }
 }
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(kScanBlock) k_mc_count(const uint32_t* __restr
 // ---- 3. scan -------------------------------------------------------------------------------
 // one block: exclusive scan of the block sums (in place, as 64-bit running totals truncated
 // to 32 bits on store; the host rejects totals >= 2^32), totals[0..1] = V, T
-__global__ void __launch_bounds__(1024) k_mc_scan_bsums(uint32_t* bsum_v, uint32_t* bsum_t, int64_t nblocks,
+__global__ void __launch_bounds__(1024) k_mc_scan_bsums(uint32_t* bsum_v, unsigned long long* bsum_t, int64_t nblocks,
                                                         unsigned long long* totals) {
   __shared__ unsigned long long s_w[2][32];
   __shared__ unsigned long long s_carry[2];
@@ -287,7 +294,7 @@ __global__ void __launch_bounds__(1024) k_mc_scan_bsums(uint32_t* bsum_v, uint32
     unsigned long long et = s_carry[1] + s_w[1][wid] + it - t;
     if (i < nblocks) {
       bsum_v[i] = (uint32_t)ev;
-      bsum_t[i] = (uint32_t)et;
+      bsum_t[i] = et;
     }
     __syncthreads();
     if (threadIdx.x == 1023) {
@@ -302,30 +309,36 @@ __global__ void __launch_bounds__(1024) k_mc_scan_bsums(uint32_t* bsum_v, uint32
   }
 }
 
-__global__ void __launch_bounds__(kScanBlock) k_mc_scan_apply(uint4* __restrict__ info, uint32_t* __restrict__ toff,
-                                                              int64_t nwords, const uint32_t* __restrict__ bsum_v,
-                                                              const uint32_t* __restrict__ bsum_t) {
-  __shared__ uint32_t s_w[2][kScanBlock / 32];
+__global__ void __launch_bounds__(kScanBlock) k_mc_scan_apply(uint4* __restrict__ info,
+                                                              unsigned long long* __restrict__ toff, int64_t nwords,
+                                                              const uint32_t* __restrict__ bsum_v,
+                                                              const unsigned long long* __restrict__ bsum_t) {
+  __shared__ unsigned long long s_w[2][kScanBlock / 32];
   const int64_t wi = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t v = wi < nwords ? info[wi].w : 0u, t = wi < nwords ? toff[wi] : 0u;
-  uint32_t iv = v, it = t;
+  unsigned long long v = wi < nwords ? info[wi].w : 0u, t = wi < nwords ? toff[wi] : 0ull;
+  unsigned long long iv = v, it = t;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    uint32_t pv = __shfl_up_sync(0xffffffffu, iv, o), pt = __shfl_up_sync(0xffffffffu, it, o);
+    unsigned long long pv = __shfl_up_sync(0xffffffffu, iv, o), pt = __shfl_up_sync(0xffffffffu, it, o);
     if (lane >= o) { iv += pv; it += pt; }
   }
   if (lane == 31) { s_w[0][wid] = iv; s_w[1][wid] = it; }
   __syncthreads();
-  uint32_t ov = bsum_v[blockIdx.x], ot = bsum_t[blockIdx.x];
+  unsigned long long ov = bsum_v[blockIdx.x], ot = bsum_t[blockIdx.x];
   for (int k = 0; k < wid; ++k) { ov += s_w[0][k]; ot += s_w[1][k]; }
   if (wi < nwords) {
-    info[wi].w = ov + iv - v;
+    info[wi].w = (uint32_t)(ov + iv - v);
     toff[wi] = ot + it - t;
   }
 }
 
 // ---- 4. emit -------------------------------------------------------------------------------
+// The surface touches a few cells per word, so a warp-per-word emitter leaves most lanes idle
+// (measured: 510 us, instruction-issue bound). Instead: one thread per VERTEX and one thread
+// per ACTIVE CELL. A thread finds its word by a two-level binary search over the exclusive
+// offsets (block sums, then the 256 words of the block), then its voxel / cell inside the
+// word by popcounts. Outputs of consecutive threads are consecutive in memory.
 struct McXform {
   float sx, sy, sz;
   int ox, oy, oz;
@@ -343,157 +356,129 @@ __device__ __forceinline__ int edge_code(int e) {
   return a | (ox << 2) | (oy << 3) | (oz << 4);
 }
 
+// largest i in [0, n) with key(i) <= k; key is non-decreasing and key(0) <= k
+template <typename F>
+__device__ __forceinline__ int64_t last_le(int64_t n, uint32_t k, F key) {
+  int64_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (key(mid) <= k) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ uint32_t below(int i) { return i >= 32 ? 0xffffffffu : ((1u << i) - 1u); }
+
 template <typename T>
-__global__ void __launch_bounds__(256) k_mc_emit(const T* __restrict__ vol, McGeom g, const uint32_t* __restrict__ bits,
-                                                 const uint4* __restrict__ info, const uint32_t* __restrict__ toff,
-                                                 const unsigned long long* __restrict__ totals, McXform xf,
-                                                 int skip_last, int vbase, const uint4* __restrict__ foreign,
-                                                 int foreign_base, float* __restrict__ verts,
-                                                 int* __restrict__ tris) {
+__global__ void __launch_bounds__(256) k_mc_emit_verts(const T* __restrict__ vol, McGeom g,
+                                                       const uint4* __restrict__ info,
+                                                       const uint32_t* __restrict__ bsum_v, int64_t nblocks,
+                                                       const unsigned long long* __restrict__ totals, McXform xf,
+                                                       float* __restrict__ verts) {
+  const uint32_t V = (uint32_t)totals[0];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < V; k += stride) {
+    const int64_t blk = last_le(nblocks, k, [&](int64_t i) { return __ldg(bsum_v + i); });
+    const int64_t w0 = blk * kScanBlock;
+    const int64_t nw = g.nwords - w0 < kScanBlock ? g.nwords - w0 : kScanBlock;
+    const int64_t wi = w0 + last_le(nw, k, [&](int64_t i) { return __ldg(&info[w0 + i].w); });
+    const uint4 inf = __ldg(info + wi);
+    const uint32_t r = k - inf.w;
+    // voxel: largest i with (#vertices of voxels below i) <= r
+    int lo = 0, hi = 32;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      uint32_t m = below(mid);
+      if ((uint32_t)(__popc(inf.x & m) + __popc(inf.y & m) + __popc(inf.z & m)) <= r) lo = mid; else hi = mid;
+    }
+    const int i = lo;
+    const uint32_t m = below(i);
+    int rr = (int)(r - (uint32_t)(__popc(inf.x & m) + __popc(inf.y & m) + __popc(inf.z & m)));
+    const int bx = (inf.x >> i) & 1, by = (inf.y >> i) & 1;
+    // rr-th crossing edge of the voxel in x, y, z order
+    int axis;
+    if (bx && rr == 0) axis = 0;
+    else { rr -= bx; if (by && rr == 0) axis = 1; else axis = 2; }
+    const int64_t row = wi / g.wx;
+    const int w = (int)(wi - row * g.wx);
+    const int64_t z = row / g.ny, y = row - z * g.ny;
+    const int64_t x = (int64_t)w * 32 + i;
+    const int64_t p = row * g.nx + x;
+    const int64_t step = axis == 0 ? 1 : (axis == 1 ? g.nx : g.nx * g.ny);
+    const float s0 = (float)vol[p], s1 = (float)vol[p + step];
+    const float t = __fdiv_rn(__fsub_rn(xf.iso, s0), __fsub_rn(s1, s0));
+    float fx = (float)((int)x + xf.ox), fy = (float)((int)y + xf.oy), fz = (float)((int)z + xf.oz);
+    if (axis == 0) fx = __fadd_rn(fx, t); else if (axis == 1) fy = __fadd_rn(fy, t); else fz = __fadd_rn(fz, t);
+    const float py = __fmul_rn(fy, xf.sy);
+    float* o = verts + 3ll * k;
+    o[0] = __fmul_rn(fx, xf.sx);
+    o[1] = xf.flip_y ? -py : py;
+    o[2] = __fmul_rn(fz, xf.sz);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_mc_emit_tris(McGeom g, const uint32_t* __restrict__ bits,
+                                                      const uint4* __restrict__ info,
+                                                      const unsigned long long* __restrict__ toff,
+                                                      const uint32_t* __restrict__ amask,
+                                                      const unsigned long long* __restrict__ bsum_t, int64_t nblocks,
+                                                      const unsigned long long* __restrict__ totals, int flip_y,
+                                                      int skip_last, int vbase, const uint4* __restrict__ foreign,
+                                                      int foreign_base, int* __restrict__ tris) {
   __shared__ signed char s_tri[256][16];  // 15 edge ids + triangle count
-  __shared__ uint4 s_rec[8][8];           // per warp: owner records of the current word
-  __shared__ int s_base[8][8];
   for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
     int c = i >> 4, k = i & 15;
     s_tri[c][k] = k < 15 ? B2V_MC_TRI[c][k] : (signed char)B2V_MC_NTRI[c];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const uint32_t low = (1u << lane) - 1u;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const uint32_t totV = (uint32_t)totals[0], totT = (uint32_t)totals[1];
-  for (int64_t wi0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; wi0 < g.nwords;
-       wi0 += nwarps * 32) {
-    // lane j looks at word wi0 + j: does it own vertices or triangles?
-    int64_t mine = wi0 + lane;
-    bool work = false;
-    if (mine < g.nwords) {
-      uint32_t v0 = info[mine].w, t0 = toff[mine];
-      uint32_t v1 = mine + 1 < g.nwords ? info[mine + 1].w : totV;
-      uint32_t t1 = mine + 1 < g.nwords ? toff[mine + 1] : totT;
-      work = v1 != v0 || t1 != t0;
-    }
-    uint32_t todo = __ballot_sync(0xffffffffu, work);
-    while (todo) {
-      int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int64_t wi = wi0 + src;
-      const int64_t row = wi / g.wx;
-      const int w = (int)(wi - row * g.wx);
-      const int64_t z = row / g.ny, y = row - z * g.ny;
-      const int64_t x = (int64_t)w * 32 + lane;
-      // Everything this word needs is addressed by (wi, lane) alone: issue all the loads up
-      // front so that their latencies overlap (one round trip per word instead of three).
-      const bool cells = y + 1 < g.ny && z + 1 < g.nz;
-      const uint4 inf = info[wi];
-      const int64_t p = row * g.nx + x;
-      const bool inx = x < g.nx;
-      T v0 = 0, vx = 0, vy = 0, vz = 0;
-      if (inx) {
-        v0 = vol[p];
-        if (x + 1 < g.nx) vx = vol[p + 1];
-        if (y + 1 < g.ny) vy = vol[p + g.nx];
-        if (z + 1 < g.nz) vz = vol[p + g.nx * g.ny];
-      }
-      uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-      int rbase = vbase;
-      Rows r;
-      r.i00 = r.i01 = r.i10 = r.i11 = r.n00 = r.n01 = r.n10 = r.n11 = 0u;
-      if (cells) {
-        if (lane < 8) {
-          // the 12 edges of the 32 cells of this word are owned by voxels of 4 rows x 2 words:
-          // those 8 records are fetched once per warp, not once per triangle corner
-          const int cz = lane >> 2, cy = (lane >> 1) & 1, cw = lane & 1;
-          if (w + cw < g.wx) {
-            if (skip_last && z + cz == g.nz - 1) {
-              rec = __ldg(foreign + (y + cy) * g.wx + (w + cw));
-              rbase = foreign_base;
-            } else {
-              rec = __ldg(info + ((z + cz) * g.ny + (y + cy)) * g.wx + (w + cw));
-            }
-          }
-        }
-        r = load_rows(bits, g, z, y, w);
-      }
-      // ---- vertices owned by voxel (z, y, x)
-      {
-        const int bx = (inf.x >> lane) & 1, by = (inf.y >> lane) & 1, bz = (inf.z >> lane) & 1;
-        if ((bx | by | bz) && !(skip_last && z == g.nz - 1)) {
-          uint32_t vid = inf.w + __popc(inf.x & low) + __popc(inf.y & low) + __popc(inf.z & low);
-          const float s0 = (float)v0;
-          const float fx = (float)((int)x + xf.ox), fy = (float)((int)y + xf.oy), fz = (float)((int)z + xf.oz);
-          const float num = __fsub_rn(xf.iso, s0);
-          if (bx) {
-            float t = __fdiv_rn(num, __fsub_rn((float)vx, s0));
-            float py = __fmul_rn(fy, xf.sy);
-            float* o = verts + 3ll * vid;
-            o[0] = __fmul_rn(__fadd_rn(fx, t), xf.sx);
-            o[1] = xf.flip_y ? -py : py;
-            o[2] = __fmul_rn(fz, xf.sz);
-            ++vid;
-          }
-          if (by) {
-            float t = __fdiv_rn(num, __fsub_rn((float)vy, s0));
-            float py = __fmul_rn(__fadd_rn(fy, t), xf.sy);
-            float* o = verts + 3ll * vid;
-            o[0] = __fmul_rn(fx, xf.sx);
-            o[1] = xf.flip_y ? -py : py;
-            o[2] = __fmul_rn(fz, xf.sz);
-            ++vid;
-          }
-          if (bz) {
-            float t = __fdiv_rn(num, __fsub_rn((float)vz, s0));
-            float py = __fmul_rn(fy, xf.sy);
-            float* o = verts + 3ll * vid;
-            o[0] = __fmul_rn(fx, xf.sx);
-            o[1] = xf.flip_y ? -py : py;
-            o[2] = __fmul_rn(__fadd_rn(fz, t), xf.sz);
-          }
-        }
-      }
-      // ---- triangles of cell (z, y, x)
-      if (cells) {
-        __syncwarp();
-        if (lane < 8) {
-          s_rec[threadIdx.x >> 5][lane] = rec;
-          s_base[threadIdx.x >> 5][lane] = rbase;
-        }
-        __syncwarp();
-        int c = (x + 1 < g.nx) ? cell_case(r, lane) : 0;
-        int ntri = s_tri[c][15];
-        // exclusive prefix of ntri over the lanes
-        int inc = ntri;
+  const uint32_t C = (uint32_t)(totals[1] >> 32);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < C; k += stride) {
+    const int64_t blk = last_le(nblocks, k, [&](int64_t i) { return (uint32_t)(__ldg(bsum_t + i) >> 32); });
+    const int64_t w0 = blk * kScanBlock;
+    const int64_t nw = g.nwords - w0 < kScanBlock ? g.nwords - w0 : kScanBlock;
+    const int64_t wi = w0 + last_le(nw, k, [&](int64_t i) { return (uint32_t)(__ldg(toff + w0 + i) >> 32); });
+    const unsigned long long tq = __ldg(toff + wi);
+    const uint32_t act = __ldg(amask + wi);
+    const int i = (int)__fns(act, 0, (int)(k - (uint32_t)(tq >> 32)) + 1);   // this thread's cell bit
+    const int64_t row = wi / g.wx;
+    const int w = (int)(wi - row * g.wx);
+    const int64_t z = row / g.ny, y = row - z * g.ny;
+    const Rows r = load_rows(bits, g, z, y, w);
+    // triangles of the active cells before mine in this word
+    int64_t tbase = (uint32_t)tq;
+    for (uint32_t e = act & below(i); e; e &= e - 1) tbase += s_tri[cell_case(r, __ffs(e) - 1)][15];
+    const int c = cell_case(r, i);
+    const int ntri = s_tri[c][15];
+    for (int t = 0; t < ntri; ++t) {
+      int id[3];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          int pv = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += pv;
+      for (int m = 0; m < 3; ++m) {
+        const int code = edge_code(s_tri[c][3 * t + m]);
+        const int a = code & 3;
+        const int qx = i + ((code >> 2) & 1);                      // 0..32 within the word pair
+        const int64_t qy = y + ((code >> 3) & 1), qz = z + ((code >> 4) & 1);
+        const int ob = qx & 31;
+        const uint32_t ol = (1u << ob) - 1u;
+        uint4 oi;
+        int v;
+        if (skip_last && qz == g.nz - 1) {
+          // owned by the next shard: its records of that plane, its numbering
+          oi = __ldg(foreign + qy * g.wx + (w + (qx >> 5)));
+          v = foreign_base;
+        } else {
+          oi = __ldg(info + (qz * g.ny + qy) * g.wx + (w + (qx >> 5)));
+          v = vbase;
         }
-        if (ntri) {
-          int64_t tbase = (int64_t)toff[wi] + (inc - ntri);
-          for (int t = 0; t < ntri; ++t) {
-            int id[3];
-#pragma unroll
-            for (int m = 0; m < 3; ++m) {
-              int code = edge_code(s_tri[c][3 * t + m]);
-              int a = code & 3;
-              int qx = lane + ((code >> 2) & 1);            // 0..32 within the word pair
-              int slot = ((code >> 4) & 1) * 4 + ((code >> 3) & 1) * 2 + (qx >> 5);
-              int ob = qx & 31;
-              uint32_t ol = (1u << ob) - 1u;
-              uint4 oi = s_rec[threadIdx.x >> 5][slot];
-              int v = s_base[threadIdx.x >> 5][slot] +
-                      (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
-              if (a > 0) v += (oi.x >> ob) & 1;
-              if (a > 1) v += (oi.y >> ob) & 1;
-              id[m] = v;
-            }
-            int* o = tris + 3 * (tbase + t);
-            o[0] = id[0];
-            o[1] = xf.flip_y ? id[2] : id[1];
-            o[2] = xf.flip_y ? id[1] : id[2];
-          }
-        }
+        v += (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
+        if (a > 0) v += (oi.x >> ob) & 1;
+        if (a > 1) v += (oi.y >> ob) & 1;
+        id[m] = v;
       }
+      int* o = tris + 3 * (tbase + t);
+      o[0] = id[0];
+      o[1] = flip_y ? id[2] : id[1];
+      o[2] = flip_y ? id[1] : id[2];
     }
   }
 }
@@ -546,7 +531,8 @@ static int mc_count_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int
       k_mc_bits<int16_t><<<grid_for(g.nwords, 8), 256, 0, s>>>((const int16_t*)vol, g, thr, w.bits);
   }
   if ((rc = b2v_check_launch("k_mc_bits"))) return rc;
-  k_mc_count<<<(unsigned)w.nblocks, kScanBlock, 0, s>>>(w.bits, g, skip_last, w.info, w.toff, w.bsum_v, w.bsum_t);
+  k_mc_count<<<(unsigned)w.nblocks, kScanBlock, 0, s>>>(w.bits, g, skip_last, w.info, w.toff, w.amask, w.bsum_v,
+                                                        w.bsum_t);
   if ((rc = b2v_check_launch("k_mc_count"))) return rc;
   k_mc_scan_bsums<<<1, 1024, 0, s>>>(w.bsum_v, w.bsum_t, w.nblocks, w.totals);
   if ((rc = b2v_check_launch("k_mc_scan_bsums"))) return rc;
@@ -555,10 +541,11 @@ static int mc_count_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int
   unsigned long long tot[2] = {0, 0};
   B2V_CUDA(cudaMemcpyAsync(tot, w.totals, sizeof(tot), cudaMemcpyDeviceToHost, s));
   B2V_CUDA(cudaStreamSynchronize(s));
-  B2V_REQUIRE(tot[0] < (1ull << 31) && tot[1] < (1ull << 31), B2V_ERR_RANGE,
-              "mc_count: %llu vertices / %llu triangles exceed int32 indices; shard along z", tot[0], tot[1]);
+  const unsigned long long ntri = tot[1] & 0xffffffffull;
+  B2V_REQUIRE(tot[0] < (1ull << 31) && ntri < (1ull << 31) && (tot[1] >> 32) < (1ull << 31), B2V_ERR_RANGE,
+              "mc_count: %llu vertices / %llu triangles exceed int32 indices; shard along z", tot[0], ntri);
   *nverts_host = (int64_t)tot[0];
-  *ntris_host = (int64_t)tot[1];
+  *ntris_host = (int64_t)ntri;
   return B2V_OK;
 }
 
@@ -573,15 +560,23 @@ static int mc_emit_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int6
   McWs w = carve(const_cast<void*>(workspace), g);
   cudaStream_t s = (cudaStream_t)stream;
   McXform xf = {sx, sy, sz, ox, oy, oz, flip_y ? 1 : 0, (float)iso};
-  if (dtype == B2V_U8)
-    k_mc_emit<uint8_t><<<grid_for(g.nwords, 256), 256, 0, s>>>((const uint8_t*)vol, g, w.bits, w.info, w.toff,
-                                                                w.totals, xf, skip_last, vbase, (const uint4*)foreign,
-                                                                foreign_base, verts, tris);
-  else
-    k_mc_emit<int16_t><<<grid_for(g.nwords, 256), 256, 0, s>>>((const int16_t*)vol, g, w.bits, w.info, w.toff,
-                                                                w.totals, xf, skip_last, vbase, (const uint4*)foreign,
-                                                                foreign_base, verts, tris);
-  return b2v_check_launch("k_mc_emit");
+  const int grid = b2v_sm_count() * 8;   // grid-stride over the counts that live on the device
+  int rc;
+  if (verts) {
+    if (dtype == B2V_U8)
+      k_mc_emit_verts<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)vol, g, w.info, w.bsum_v, w.nblocks, w.totals, xf,
+                                                    verts);
+    else
+      k_mc_emit_verts<int16_t><<<grid, 256, 0, s>>>((const int16_t*)vol, g, w.info, w.bsum_v, w.nblocks, w.totals, xf,
+                                                    verts);
+    if ((rc = b2v_check_launch("k_mc_emit_verts"))) return rc;
+  }
+  if (tris) {
+    k_mc_emit_tris<<<grid, 256, 0, s>>>(g, w.bits, w.info, w.toff, w.amask, w.bsum_t, w.nblocks, w.totals,
+                                        flip_y ? 1 : 0, skip_last, vbase, (const uint4*)foreign, foreign_base, tris);
+    if ((rc = b2v_check_launch("k_mc_emit_tris"))) return rc;
+  }
+  return B2V_OK;
 }
 
 extern "C" int b2v_mc_count(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
