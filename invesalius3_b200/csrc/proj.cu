@@ -126,6 +126,22 @@ struct MidaOp {
     final_colour = colour;
     return cur >= 1.0f;
   }
+  // same recurrence with (fpi, alpha) taken from a table indexed by the integer sample value
+  __device__ __forceinline__ bool step_lut(float fpi, float alpha) {
+    float dl = 0.0f;
+    if (fpi > fmax) {
+      dl = __fsub_rn(fpi, fmax);
+      fmax = fpi;
+    }
+    float bt = __fsub_rn(1.0f, dl);
+    float one_m = __fsub_rn(1.0f, __fmul_rn(bt, alpha_p));
+    float colour = __fadd_rn(__fmul_rn(bt, colour_p), __fmul_rn(__fmul_rn(one_m, fpi), alpha));
+    float cur = __fadd_rn(__fmul_rn(bt, alpha_p), __fmul_rn(one_m, alpha));
+    colour_p = colour;
+    alpha_p = cur;
+    final_colour = colour;
+    return cur >= 1.0f;
+  }
   __device__ __forceinline__ bool result(U* o) const {
     return cast_result(__fadd_rn(__fmul_rn(range, final_colour), img_min), o);
   }
@@ -322,16 +338,42 @@ __device__ __forceinline__ MidaOp<T, U> make_mida(const float* mm, float wl, flo
   return op;
 }
 
+// The per-sample terms of MIDA (normalised intensity, opacity) depend on the sample value
+// only. For integer volumes whose value range fits kLut entries (any CT: <= 4096 values) a
+// block tabulates them once in shared memory with the reference's float32 operations, and
+// the ray walk becomes a table fetch plus the 10-flop recurrence (half the instructions).
+constexpr int kLut = 4096;
+
+template <typename T, typename U>
+__device__ __forceinline__ unsigned build_mida_lut(float2* lut, const MidaOp<T, U>& op, const float* mm, int* imin_out) {
+  // returns the table length (0 = no table); samples outside it take the direct path, so a
+  // caller-supplied (min, max) that does not bound the data cannot index out of range
+  if (sizeof(T) > 2) return 0u;
+  const int imin = (int)mm[0];
+  const int R = (int)mm[1] - imin + 1;
+  *imin_out = imin;
+  if (R <= 0 || R > kLut) return 0u;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    const float vl = (float)(imin + i);
+    lut[i] = make_float2(__fmul_rn(op.inv, __fsub_rn(vl, op.img_min)), opacity(vl, op.wl, op.ww));
+  }
+  __syncthreads();
+  return (unsigned)R;
+}
+
 template <typename T, typename U, typename S>
 __global__ void __launch_bounds__(128) k_mida_keepx(S smp, int axis, const float* __restrict__ mm, float wl, float ww,
                                                     U* __restrict__ out, int* status) {
+  __shared__ float2 s_lut[kLut];
   const Dims d = smp.d;
   const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t r = blockIdx.y;
-  if (x >= d.nx) return;
   const int64_t n_l = axis == 0 ? d.nz : d.ny;
   MidaOp<T, U> op = make_mida<T, U>(mm, wl, ww);
   op.init();
+  int imin = 0;
+  const unsigned lut = build_mida_lut<T, U>(s_lut, op, mm, &imin);
+  if (x >= d.nx) return;
   int st = 0;
   // eight samples are fetched before any of them is consumed: the ray recurrence is a long
   // dependent chain, the loads must not wait for it (8 x 2 B in flight per thread)
@@ -345,8 +387,18 @@ __global__ void __launch_bounds__(128) k_mida_keepx(S smp, int axis, const float
       v[k] = axis == 0 ? smp.at(l, r, x, &st) : smp.at(r, l, x, &st);
     }
 #pragma unroll
-    for (int k = 0; k < B; ++k)
-      if (!done && l0 + k < n_l && op.step(v[k])) done = true;
+    for (int k = 0; k < B; ++k) {
+      if (done || l0 + k >= n_l) continue;
+      bool fin;
+      const unsigned li = (unsigned)((int)v[k] - imin);
+      if (li < lut) {
+        const float2 e = s_lut[li];
+        fin = op.step_lut(e.x, e.y);
+      } else {
+        fin = op.step(v[k]);
+      }
+      if (fin) done = true;
+    }
   }
   U o;
   if (op.result(&o)) out[r * d.nx + x] = o; else st = B2V_ERR_RANGE;
@@ -357,6 +409,7 @@ template <typename T, typename U, typename S>
 __global__ void __launch_bounds__(kRays) k_mida_alongx(S smp, const float* __restrict__ mm, float wl, float ww,
                                                        U* __restrict__ out, int* status) {
   __shared__ T tile[kRays][Pitch<T>::value];
+  __shared__ float2 s_lut[kLut];
   const Dims d = smp.d;
   const int64_t nrows = d.nz * d.ny;
   const int64_t row0 = (int64_t)blockIdx.x * kRays;
@@ -365,6 +418,8 @@ __global__ void __launch_bounds__(kRays) k_mida_alongx(S smp, const float* __res
   const bool live = myrow < nrows;
   MidaOp<T, U> op = make_mida<T, U>(mm, wl, ww);
   op.init();
+  int imin = 0;
+  const unsigned lut = build_mida_lut<T, U>(s_lut, op, mm, &imin);
   int st = 0;
   bool done = !live;
   for (int64_t x0 = 0; x0 < d.nx; x0 += kChunk) {
@@ -381,11 +436,21 @@ __global__ void __launch_bounds__(kRays) k_mida_alongx(S smp, const float* __res
     __syncthreads();
     if (!done) {
       int lim = (int)((d.nx - x0) < kChunk ? (d.nx - x0) : kChunk);
-      for (int k = 0; k < lim; ++k)
-        if (op.step(tile[tid][k])) {
+      for (int k = 0; k < lim; ++k) {
+        bool fin;
+        const T tv = tile[tid][k];
+        const unsigned li = (unsigned)((int)tv - imin);
+        if (li < lut) {
+          const float2 e = s_lut[li];
+          fin = op.step_lut(e.x, e.y);
+        } else {
+          fin = op.step(tv);
+        }
+        if (fin) {
           done = true;
           break;
         }
+      }
     }
     if (__syncthreads_and(done)) break;
   }

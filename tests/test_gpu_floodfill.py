@@ -258,3 +258,18 @@ def test_floodfill_512_properties(rs):
     out2 = out.clone()
     dev.floodfill_threshold(t, [seed], 226, 3071, 1, st, out2)
     assert torch.equal(out, out2)
+
+
+def test_floodfill_wide_rows_many_x_tiles(rs, orc):
+    """2048-wide rows (BASELINE config 5 geometry): 64 words per row = 4 tiles along x."""
+    rng = np.random.default_rng(12)
+    shape = (5, 37, 2048)
+    data = (ndimage.gaussian_filter(rng.normal(size=shape), (1, 2, 6)) > -0.05).astype(np.int16) * 1000
+    seeds = [(3, 3, 0), (2040, 30, 4), (1024, 18, 2)]
+    for conn in (1, 3):
+        st = generate_binary_structure(3, conn)
+        want = np.zeros(shape, np.uint8); got = want.copy()
+        orc.floodfill_threshold(data, seeds, 500, 1500, 200, st, want)
+        rs.floodfill_threshold(data, seeds, 500, 1500, 200, st, got)
+        assert np.array_equal(got, want), conn
+        assert (want == 200).sum() > 1000

@@ -131,3 +131,42 @@ def test_mc_512_properties(sp):
     assert torch.unique(key).numel() == key.numel()
     assert torch.equal(torch.sort(key).values, torch.sort(rkey).values)
     assert bool((V[:, 1] <= 0).all()) and bool(torch.isfinite(V).all())
+
+
+def test_mc_wide_rows(sp, orc):
+    """2048-wide rows (BASELINE config 5 geometry), uint8 mask and int16 image."""
+    rng = np.random.default_rng(21)
+    shape = (4, 19, 2048)
+    f = ndimage.gaussian_filter(rng.normal(size=shape), (1, 2, 5))
+    _check(sp, orc, (f > 0).astype(np.uint8) * 255, 127, spacing=(1, 1, 1))
+    _check(sp, orc, (f / np.abs(f).max() * 3000).astype(np.int16), 226, spacing=(0.5, 0.5, 2.0), z0=100)
+
+
+def test_mc_config5_shard_properties(sp):
+    """One GPU's share of BASELINE config 5 (2048 x 2048 x 1024 over 8 GPUs = 128 slices):
+    threshold -> marching cubes on 2^29 voxels; closed oriented manifold, indices in range."""
+    import torch
+    from invesalius3_b200 import device as dev
+    from invesalius3_b200.mesh import marching_cubes
+    nz, ny, nx = 128, 2048, 2048
+    z = torch.arange(nz, device="cuda", dtype=torch.float32)[:, None, None]
+    y = torch.arange(ny, device="cuda", dtype=torch.float32)[None, :, None]
+    x = torch.arange(nx, device="cuda", dtype=torch.float32)[None, None, :]
+    img = (1500.0 * torch.sin(0.011 * x) * torch.sin(0.013 * y) * torch.cos(0.05 * z)).to(torch.int16)
+    del x, y, z
+    mask = dev.threshold(img, 226, 3071)
+    del img
+    mask[0] = 0; mask[-1] = 0; mask[:, 0] = 0; mask[:, -1] = 0; mask[:, :, 0] = 0; mask[:, :, -1] = 0
+    V, F = marching_cubes(mask, 127, (1, 1, 1), (0, 0, 0), True)
+    nv, nt = V.shape[0], F.shape[0]
+    assert nv > 10 ** 6 and nt > 2 * 10 ** 6
+    assert int(F.min()) == 0 and int(F.max()) == nv - 1
+    F64 = F.to(torch.int64)
+    del F
+    e = torch.cat([F64[:, [0, 1]], F64[:, [1, 2]], F64[:, [2, 0]]])
+    key = e[:, 0] * (nv + 1) + e[:, 1]
+    rkey = e[:, 1] * (nv + 1) + e[:, 0]
+    del e
+    assert torch.unique(key).numel() == key.numel()
+    assert torch.equal(torch.sort(key).values, torch.sort(rkey).values)
+    assert bool(torch.isfinite(V).all())
