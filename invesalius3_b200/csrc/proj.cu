@@ -31,6 +31,7 @@ struct Dims {
 template <typename T>
 struct PlainSampler {
   static constexpr int kBatch = 8;   // samples fetched ahead of the recurrence (plain loads)
+  static constexpr bool kLinear = true;   // a sample is vol[flat index]: rays advance a pointer
   const T* __restrict__ vol;
   Dims d;
   __device__ __forceinline__ T at(int64_t z, int64_t y, int64_t x, int* status) const {
@@ -62,6 +63,7 @@ template <> __device__ __forceinline__ bool cast_f32<uint8_t>(float f, uint8_t* 
 template <typename T>
 struct FcmSampler {
   static constexpr int kBatch = 1;   // a contour sample is expensive: never compute past the ray's end
+  static constexpr bool kLinear = false;
   const T* __restrict__ vol;
   Dims d;
   float n;
@@ -93,19 +95,32 @@ struct FcmSampler {
 };
 
 // ---- per-ray operators --------------------------------------------------------------------
-__device__ __forceinline__ float opacity(float vl, float wl, float ww) {
-  float half = __fdiv_rn(ww, 2.0f);
-  float mn = __fsub_rn(wl, half), mx = __fadd_rn(wl, half);
-  if (vl < mn) return 0.0f;
-  if (vl > mx) return 1.0f;
-  return __fdiv_rn(__fsub_rn(vl, mn), __fsub_rn(mx, mn));
-}
+// get_opacity (mips.rs:88-100). The window bounds are ray-invariant: computed once per thread
+// (same float32 operations, so the same values) instead of once per sample.
+struct Window {
+  float mn, mx, den;
+  __device__ __forceinline__ void set(float wl, float ww) {
+    float half = __fdiv_rn(ww, 2.0f);
+    mn = __fsub_rn(wl, half);
+    mx = __fadd_rn(wl, half);
+    den = __fsub_rn(mx, mn);
+  }
+  __device__ __forceinline__ float opacity(float vl) const {
+    if (vl < mn) return 0.0f;
+    if (vl > mx) return 1.0f;
+    return __fdiv_rn(__fsub_rn(vl, mn), den);
+  }
+};
 
 template <typename T, typename U>
 struct MidaOp {
   float img_min, range, inv, wl, ww;
   float fmax, alpha_p, colour_p, final_colour;
-  __device__ __forceinline__ void init() { fmax = alpha_p = colour_p = final_colour = 0.0f; }
+  Window win;
+  __device__ __forceinline__ void init() {
+    fmax = alpha_p = colour_p = final_colour = 0.0f;
+    win.set(wl, ww);
+  }
   __device__ __forceinline__ void first(T) {}
   // returns true when the ray is finished
   __device__ __forceinline__ bool step(T raw) {
@@ -117,23 +132,7 @@ struct MidaOp {
       fmax = fpi;
     }
     float bt = __fsub_rn(1.0f, dl);
-    float alpha = opacity(vl, wl, ww);
-    float one_m = __fsub_rn(1.0f, __fmul_rn(bt, alpha_p));
-    float colour = __fadd_rn(__fmul_rn(bt, colour_p), __fmul_rn(__fmul_rn(one_m, fpi), alpha));
-    float cur = __fadd_rn(__fmul_rn(bt, alpha_p), __fmul_rn(one_m, alpha));
-    colour_p = colour;
-    alpha_p = cur;
-    final_colour = colour;
-    return cur >= 1.0f;
-  }
-  // same recurrence with (fpi, alpha) taken from a table indexed by the integer sample value
-  __device__ __forceinline__ bool step_lut(float fpi, float alpha) {
-    float dl = 0.0f;
-    if (fpi > fmax) {
-      dl = __fsub_rn(fpi, fmax);
-      fmax = fpi;
-    }
-    float bt = __fsub_rn(1.0f, dl);
+    float alpha = win.opacity(vl);
     float one_m = __fsub_rn(1.0f, __fmul_rn(bt, alpha_p));
     float colour = __fadd_rn(__fmul_rn(bt, colour_p), __fmul_rn(__fmul_rn(one_m, fpi), alpha));
     float cur = __fadd_rn(__fmul_rn(bt, alpha_p), __fmul_rn(one_m, alpha));
@@ -186,6 +185,37 @@ struct MaxOp {  // fold_axis with Bounded::min_value() (mips.rs:250-254)
 };
 
 // ---- ray walkers ---------------------------------------------------------------------------
+// One ray of a keep-x kernel (axis 0: along z, axis 1: along y). For a plain volume the ray is
+// a pointer advanced by a constant stride; kBatch samples are fetched before any of them is
+// consumed, because the recurrence is a long dependent chain the loads must not wait for. The
+// walk stops at the first sample whose step() reports the ray finished.
+template <typename T, typename S, typename Op>
+__device__ __forceinline__ void walk_keepx(const S& smp, int axis, int64_t r, int64_t x, int64_t n_l, Op& op, int* st) {
+  if constexpr (S::kLinear) {
+    constexpr int B = S::kBatch;
+    const int64_t plane = smp.d.ny * smp.d.nx;
+    const int64_t stride = axis == 0 ? plane : smp.d.nx;
+    const T* __restrict__ p = smp.vol + (axis == 0 ? r * smp.d.nx + x : r * plane + x);
+    int64_t l0 = 0;
+    for (; l0 + B <= n_l; l0 += B) {
+      T v[B];
+#pragma unroll
+      for (int k = 0; k < B; ++k) v[k] = p[k * stride];
+      p += B * stride;
+#pragma unroll
+      for (int k = 0; k < B; ++k)
+        if (op.step(v[k])) return;
+    }
+    for (; l0 < n_l; ++l0, p += stride)
+      if (op.step(*p)) return;
+  } else {
+    for (int64_t l = 0; l < n_l; ++l) {
+      const T v = axis == 0 ? smp.at(l, r, x, st) : smp.at(r, l, x, st);
+      if (op.step(v)) return;
+    }
+  }
+}
+
 // axis 0: out[y][x], ray along z; axis 1: out[z][x], ray along y. One thread per (r, x).
 template <typename T, typename U, typename S, typename Op>
 __global__ void __launch_bounds__(128) k_rays_keepx(S smp, int axis, Op op0, U* __restrict__ out, int* status) {
@@ -201,19 +231,7 @@ __global__ void __launch_bounds__(128) k_rays_keepx(S smp, int axis, Op op0, U* 
     T v0 = axis == 0 ? smp.at(0, r, x, &st) : smp.at(r, 0, x, &st);
     op.first(v0);
   }
-  bool done = false;
-  constexpr int B = S::kBatch;
-  for (int64_t l0 = 0; l0 < n_l && !done; l0 += B) {
-    T v[B];
-#pragma unroll
-    for (int k = 0; k < B; ++k) {
-      const int64_t l = l0 + k < n_l ? l0 + k : n_l - 1;
-      v[k] = axis == 0 ? smp.at(l, r, x, &st) : smp.at(r, l, x, &st);
-    }
-#pragma unroll
-    for (int k = 0; k < B; ++k)
-      if (!done && l0 + k < n_l && op.step(v[k])) done = true;
-  }
+  walk_keepx<T>(smp, axis, r, x, n_l, op, &st);
   U o;
   if (op.result(&o)) out[r * d.nx + x] = o; else st = B2V_ERR_RANGE;
   if (st) *status = st;
@@ -226,9 +244,72 @@ template <> struct Pitch<int16_t> { static constexpr int value = kChunk + 2; }; 
 template <> struct Pitch<uint8_t> { static constexpr int value = kChunk + 4; };   // 9 words
 template <> struct Pitch<double> { static constexpr int value = kChunk + 1; };
 
+// Stage the 32-sample segments [x0, x0+32) of kRays consecutive rows in shared memory. A plain
+// int16 volume with even rows moves two samples per lane (half a warp per row, 64 B each);
+// otherwise one sample per lane (a warp per row), through the sampler.
+template <typename T, typename S>
+__device__ __forceinline__ void load_tile(const S& smp, T (*tile)[Pitch<T>::value], int64_t row0, int64_t nrows,
+                                          int64_t x0, int lane, int warp, int* st) {
+  const Dims d = smp.d;
+  if constexpr (S::kLinear && sizeof(T) == 2) {
+    if ((d.nx & 1) == 0 && (reinterpret_cast<uintptr_t>(smp.vol) & 3) == 0) {
+      const int half = lane >> 4, l16 = lane & 15;
+      const int64_t x = x0 + 2 * l16;
+      const bool xin = x < d.nx;
+      const T* p = smp.vol + (row0 + warp * 2 + half) * d.nx + x;
+      const int64_t step = (int64_t)(kRays / 16) * d.nx;
+#pragma unroll
+      for (int rr = warp * 2 + half; rr < kRays; rr += kRays / 16, p += step) {
+        uint32_t w = 0;
+        if (row0 + rr < nrows && xin) w = *reinterpret_cast<const uint32_t*>(p);
+        *reinterpret_cast<uint32_t*>(&tile[rr][2 * l16]) = w;
+      }
+      return;
+    }
+  }
+  for (int rr = warp; rr < kRays; rr += kRays / 32) {
+    const int64_t row = row0 + rr;
+    const int64_t x = x0 + lane;
+    T v = 0;
+    if (row < nrows && x < d.nx) {
+      if constexpr (S::kLinear) {
+        v = smp.vol[row * d.nx + x];
+      } else {
+        const int64_t z = row / d.ny, y = row - z * d.ny;
+        v = smp.at(z, y, x, st);
+      }
+    }
+    tile[rr][lane] = v;
+  }
+}
+
+// Feed one thread's staged samples to its operator; true when the ray is finished.
+template <typename T, typename Op>
+__device__ __forceinline__ bool consume_tile(const T* row, int lim, Op& op) {
+  if (lim == kChunk) {
+    if constexpr (sizeof(T) == 2) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(row);   // rows are 4-byte aligned
+#pragma unroll
+      for (int k = 0; k < kChunk / 2; ++k) {
+        const uint32_t pair = w[k];
+        if (op.step((T)(pair & 0xffffu))) return true;
+        if (op.step((T)(pair >> 16))) return true;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kChunk; ++k)
+        if (op.step(row[k])) return true;
+    }
+    return false;
+  }
+  for (int k = 0; k < lim; ++k)
+    if (op.step(row[k])) return true;
+  return false;
+}
+
 template <typename T, typename U, typename S, typename Op>
 __global__ void __launch_bounds__(kRays) k_rays_alongx(S smp, Op op0, U* __restrict__ out, int* status) {
-  __shared__ T tile[kRays][Pitch<T>::value];
+  __shared__ __align__(16) T tile[kRays][Pitch<T>::value];
   const Dims d = smp.d;
   const int64_t nrows = d.nz * d.ny;
   const int64_t row0 = (int64_t)blockIdx.x * kRays;
@@ -240,26 +321,12 @@ __global__ void __launch_bounds__(kRays) k_rays_alongx(S smp, Op op0, U* __restr
   int st = 0;
   bool done = !live;
   for (int64_t x0 = 0; x0 < d.nx; x0 += kChunk) {
-    // each warp loads whole 32-sample row segments: coalesced 64 B (int16) per instruction
-    for (int rr = warp; rr < kRays; rr += kRays / 32) {
-      int64_t row = row0 + rr;
-      int64_t x = x0 + lane;
-      T v = 0;
-      if (row < nrows && x < d.nx) {
-        int64_t z = row / d.ny, y = row - z * d.ny;
-        v = smp.at(z, y, x, &st);
-      }
-      tile[rr][lane] = v;
-    }
+    load_tile<T>(smp, tile, row0, nrows, x0, lane, warp, &st);
     __syncthreads();
     if (!done) {
       if (x0 == 0) op.first(tile[tid][0]);
       int lim = (int)((d.nx - x0) < kChunk ? (d.nx - x0) : kChunk);
-      for (int k = 0; k < lim; ++k)
-        if (op.step(tile[tid][k])) {
-          done = true;
-          break;
-        }
+      done = consume_tile<T>(tile[tid], lim, op);
     }
     if (__syncthreads_and(done)) break;
   }
@@ -338,68 +405,18 @@ __device__ __forceinline__ MidaOp<T, U> make_mida(const float* mm, float wl, flo
   return op;
 }
 
-// The per-sample terms of MIDA (normalised intensity, opacity) depend on the sample value
-// only. For integer volumes whose value range fits kLut entries (any CT: <= 4096 values) a
-// block tabulates them once in shared memory with the reference's float32 operations, and
-// the ray walk becomes a table fetch plus the 10-flop recurrence (half the instructions).
-constexpr int kLut = 4096;
-
-template <typename T, typename U>
-__device__ __forceinline__ unsigned build_mida_lut(float2* lut, const MidaOp<T, U>& op, const float* mm, int* imin_out) {
-  // returns the table length (0 = no table); samples outside it take the direct path, so a
-  // caller-supplied (min, max) that does not bound the data cannot index out of range
-  if (sizeof(T) > 2) return 0u;
-  const int imin = (int)mm[0];
-  const int R = (int)mm[1] - imin + 1;
-  *imin_out = imin;
-  if (R <= 0 || R > kLut) return 0u;
-  for (int i = threadIdx.x; i < R; i += blockDim.x) {
-    const float vl = (float)(imin + i);
-    lut[i] = make_float2(__fmul_rn(op.inv, __fsub_rn(vl, op.img_min)), opacity(vl, op.wl, op.ww));
-  }
-  __syncthreads();
-  return (unsigned)R;
-}
-
 template <typename T, typename U, typename S>
 __global__ void __launch_bounds__(128) k_mida_keepx(S smp, int axis, const float* __restrict__ mm, float wl, float ww,
                                                     U* __restrict__ out, int* status) {
-  __shared__ float2 s_lut[kLut];
   const Dims d = smp.d;
   const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t r = blockIdx.y;
+  if (x >= d.nx) return;
   const int64_t n_l = axis == 0 ? d.nz : d.ny;
   MidaOp<T, U> op = make_mida<T, U>(mm, wl, ww);
   op.init();
-  int imin = 0;
-  const unsigned lut = build_mida_lut<T, U>(s_lut, op, mm, &imin);
-  if (x >= d.nx) return;
   int st = 0;
-  // eight samples are fetched before any of them is consumed: the ray recurrence is a long
-  // dependent chain, the loads must not wait for it (8 x 2 B in flight per thread)
-  bool done = false;
-  constexpr int B = S::kBatch;
-  for (int64_t l0 = 0; l0 < n_l && !done; l0 += B) {
-    T v[B];
-#pragma unroll
-    for (int k = 0; k < B; ++k) {
-      const int64_t l = l0 + k < n_l ? l0 + k : n_l - 1;
-      v[k] = axis == 0 ? smp.at(l, r, x, &st) : smp.at(r, l, x, &st);
-    }
-#pragma unroll
-    for (int k = 0; k < B; ++k) {
-      if (done || l0 + k >= n_l) continue;
-      bool fin;
-      const unsigned li = (unsigned)((int)v[k] - imin);
-      if (li < lut) {
-        const float2 e = s_lut[li];
-        fin = op.step_lut(e.x, e.y);
-      } else {
-        fin = op.step(v[k]);
-      }
-      if (fin) done = true;
-    }
-  }
+  walk_keepx<T>(smp, axis, r, x, n_l, op, &st);
   U o;
   if (op.result(&o)) out[r * d.nx + x] = o; else st = B2V_ERR_RANGE;
   if (st) *status = st;
@@ -408,8 +425,7 @@ __global__ void __launch_bounds__(128) k_mida_keepx(S smp, int axis, const float
 template <typename T, typename U, typename S>
 __global__ void __launch_bounds__(kRays) k_mida_alongx(S smp, const float* __restrict__ mm, float wl, float ww,
                                                        U* __restrict__ out, int* status) {
-  __shared__ T tile[kRays][Pitch<T>::value];
-  __shared__ float2 s_lut[kLut];
+  __shared__ __align__(16) T tile[kRays][Pitch<T>::value];
   const Dims d = smp.d;
   const int64_t nrows = d.nz * d.ny;
   const int64_t row0 = (int64_t)blockIdx.x * kRays;
@@ -418,39 +434,14 @@ __global__ void __launch_bounds__(kRays) k_mida_alongx(S smp, const float* __res
   const bool live = myrow < nrows;
   MidaOp<T, U> op = make_mida<T, U>(mm, wl, ww);
   op.init();
-  int imin = 0;
-  const unsigned lut = build_mida_lut<T, U>(s_lut, op, mm, &imin);
   int st = 0;
   bool done = !live;
   for (int64_t x0 = 0; x0 < d.nx; x0 += kChunk) {
-    for (int rr = warp; rr < kRays; rr += kRays / 32) {
-      int64_t row = row0 + rr;
-      int64_t x = x0 + lane;
-      T v = 0;
-      if (row < nrows && x < d.nx) {
-        int64_t z = row / d.ny, y = row - z * d.ny;
-        v = smp.at(z, y, x, &st);
-      }
-      tile[rr][lane] = v;
-    }
+    load_tile<T>(smp, tile, row0, nrows, x0, lane, warp, &st);
     __syncthreads();
     if (!done) {
       int lim = (int)((d.nx - x0) < kChunk ? (d.nx - x0) : kChunk);
-      for (int k = 0; k < lim; ++k) {
-        bool fin;
-        const T tv = tile[tid][k];
-        const unsigned li = (unsigned)((int)tv - imin);
-        if (li < lut) {
-          const float2 e = s_lut[li];
-          fin = op.step_lut(e.x, e.y);
-        } else {
-          fin = op.step(tv);
-        }
-        if (fin) {
-          done = true;
-          break;
-        }
-      }
+      done = consume_tile<T>(tile[tid], lim, op);
     }
     if (__syncthreads_and(done)) break;
   }

@@ -141,3 +141,40 @@ def test_mida_1024_slab_properties():
         diff = (out.to(torch.int32) - first.to(torch.int32)).abs()
         diff[0, 0] = 0  # the ray through the planted -1000 voxel does not saturate at once
         assert int(diff.max()) <= 1, axis
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_mida_wide_value_range_and_foreign_minmax(rs, orc, axis):
+    """A volume spanning far more than a CT's ~4k values, and a caller-supplied (min, max) that
+    does not bound the data (integer and float64 inputs of equal values must then agree)."""
+    import torch
+    from invesalius3_b200 import projection
+    shape = (21, 34, 70)
+    wide = (_ct_like(shape, 9).astype(np.int32) * 9).clip(-32768, 32767).astype(np.int16)
+    assert int(wide.max()) - int(wide.min()) > 4096
+    want = np.zeros(_oshape(shape, axis), np.int16); got = want.copy()
+    orc.mida(wide, axis, 300, 2000, want); rs.mida(wide, axis, 300, 2000, got)
+    assert np.array_equal(got, want)
+    # supplying the true extrema is the same as letting the kernel find them
+    img = _ct_like(shape, 10)
+    lo, hi = int(img.min()), int(img.max())
+    t = torch.from_numpy(img).cuda()
+    full = projection.mida(t, axis, 300, 300)
+    mm = torch.tensor([float(lo), float(hi)], dtype=torch.float32, device="cuda")
+    assert torch.equal(projection.mida(t, axis, 300, 300, minmax=mm), full)
+    # forced extrema narrower than the data: integer and float64 inputs of the same values agree
+    u8 = np.random.default_rng(11).integers(0, 256, shape).astype(np.uint8)
+    t8 = torch.from_numpy(u8).cuda()
+    t64 = t8.to(torch.float64)
+    for pair in [(20.0, 235.0), (0.0, 255.0), (60.0, 61.0)]:
+        mm2 = torch.tensor(pair, dtype=torch.float32, device="cuda")
+        outcome = []
+        for vol in (t8, t64):
+            try:
+                outcome.append(projection.mida(vol, axis, 120, 80, minmax=mm2).cpu())
+            except ValueError:
+                outcome.append(None)
+        if outcome[0] is None or outcome[1] is None:
+            assert outcome[0] is None and outcome[1] is None, pair
+        else:
+            assert torch.equal(outcome[0], outcome[1]), pair
