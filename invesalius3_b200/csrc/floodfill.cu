@@ -39,6 +39,7 @@ struct BitVol {
   int ltw, lty;        // log2(tw), log2(ty)
   uint32_t m_pw, m_pp; // ceil(2^24 / (tw+2)), ceil(2^24 / ((tw+2)(ty+2))): exact division for i < 2^12
   int max_trips;       // local sweeps per visit before the tile re-queues itself
+  int defer;           // persistent engine: up to this many tiles beyond one per block wait a round
 };
 
 int pow2ceil(int64_t v, int cap) {
@@ -66,6 +67,8 @@ BitVol make_bitvol(int64_t dz, int64_t dy, int64_t dx) {
   b.m_pp = ((1u << 24) + pp - 1) / pp;
   b.max_trips = 1;   // measured: one sweep set per visit, stragglers re-queue themselves (round time = one trip)
   if (const char* e = getenv("B2V_FF_TRIPS")) { int v = atoi(e); if (v > 0) b.max_trips = v; }
+  b.defer = 1 << 30;   // measured: always cheaper than a second visit per block (any n <= 2 x blocks)
+  if (const char* e = getenv("B2V_FF_DEFER")) { int v = atoi(e); if (v >= 0) b.defer = v; }
   return b;
 }
 
@@ -299,9 +302,160 @@ constexpr uint32_t kSB26 = 0x7ffffffu & ~(1u << 13);
 constexpr uint32_t kSB18 = kSB26 & ~((1u << 0) | (1u << 2) | (1u << 6) | (1u << 8) | (1u << 18) | (1u << 20) |
                                      (1u << 24) | (1u << 26));
 
+// ---- 6-connected, canonical tile (8 x 8 rows x 16 words, one word per thread) ----------------
+// The common case (InVesalius floods with the 6-neighbourhood; any volume at least 8 x 8 x 512
+// gets this tile) with every index a compile-time constant and all 1024 threads busy in every
+// phase. The y and z sweeps re-map the threads so that the eight words of a column sit in
+// eight adjacent lanes and run a Kogge-Stone scan of (generate, propagate) word pairs with
+// shuffles: v[k] = g[k] | (p[k] & v[k-1]) in three steps per direction instead of an
+// eight-step serial chain on an eighth of the threads.
+constexpr int kPW = 18, kPY = 10, kNH = 10 * 10 * 18;
+
+// both directions of one axis sweep; idx = this thread's word, j = its position in the
+// column (0..7, the low three lane bits), stride = distance between column neighbours
+__device__ __forceinline__ void scan_column(uint32_t* sR, const uint32_t* sF, int idx, int j, int stride) {
+  const uint32_t f = sF[idx], orig = sR[idx];
+  uint32_t G = orig, P = f;
+  if (j == 0) G |= f & sR[idx - stride];        // carry in from the halo word before the column
+#pragma unroll
+  for (int d = 1; d < 8; d <<= 1) {
+    const uint32_t Gu = __shfl_up_sync(0xffffffffu, G, d, 8), Pu = __shfl_up_sync(0xffffffffu, P, d, 8);
+    if (j >= d) { G |= P & Gu; P &= Pu; }
+  }
+  P = f;
+  if (j == 7) G |= f & sR[idx + stride];        // ... and from the one after it
+#pragma unroll
+  for (int d = 1; d < 8; d <<= 1) {
+    const uint32_t Gd = __shfl_down_sync(0xffffffffu, G, d, 8), Pd = __shfl_down_sync(0xffffffffu, P, d, 8);
+    if (j + d < 8) { G |= P & Gd; P &= Pd; }
+  }
+  if (G != orig) sR[idx] = G;
+}
+
+__device__ __forceinline__ int ff_process_tile_sb6(const uint32_t* __restrict__ fg, uint32_t* reach, const BitVol& b,
+                                                   int tile, uint32_t* sR, int* s_faces, int* stats) {
+  const int tid = threadIdx.x;
+  const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
+  const int64_t z0 = (int64_t)tzi * 8, y0 = (int64_t)tyi * 8;
+  const int w0 = twi * 16;
+  uint32_t* sF = sR + kNH;
+  if (tid == 0) *s_faces = 0;
+  const long long pc0 = clock64();
+  {
+    uint32_t v[2], f[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = tid + k * kFloodThreads;
+      v[k] = 0; f[k] = 0;
+      if (i < kNH) {
+        const int hz = i / (kPW * kPY), rem = i - hz * (kPW * kPY), hy = rem / kPW, hw = rem - hy * kPW;
+        const int64_t z = z0 + hz - 1, y = y0 + hy - 1;
+        const int w = w0 + hw - 1;
+        if (z >= 0 && z < b.dz && y >= 0 && y < b.dy && w >= 0 && w < b.wx) {
+          const int64_t gi = (z * b.dy + y) * b.wx + w;
+          v[k] = __ldcg(&reach[gi]);
+          f[k] = __ldg(&fg[gi]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = tid + k * kFloodThreads;
+      if (i < kNH) { sR[i] = v[k]; sF[i] = f[k]; }
+    }
+  }
+  const int iw = tid & 15, iy = (tid >> 4) & 7, iz = tid >> 7;
+  const int hidx = ((iz + 1) * kPY + (iy + 1)) * kPW + (iw + 1);
+  // transposed roles for the column scans: the column index runs over the low three lane bits
+  const int j = tid & 7, jw = (tid >> 3) & 15, jo = tid >> 7;
+  const int yidx = ((jo + 1) * kPY + (j + 1)) * kPW + (jw + 1);   // column along y: (z = jo, w = jw)
+  const int zidx = ((j + 1) * kPY + (jo + 1)) * kPW + (jw + 1);   // column along z: (y = jo, w = jw)
+  __syncthreads();
+  const uint32_t f = sF[hidx], r0 = sR[hidx];
+  uint32_t r = r0;
+  const long long pc1 = clock64();
+  const int grp = (tid & 31) >> 4;
+  int changed, iters = 0;
+  do {
+    const uint32_t before = r;
+    {
+      // x: carry-lookahead over the 16 words of the row (see the generic path for the algebra)
+      const uint32_t filled = (f && r) ? run_fill(r, f) : 0u;
+      const uint32_t gu = (__ballot_sync(0xffffffffu, filled >> 31) >> (grp * 16)) & 0xffffu;
+      const uint32_t gd = (__ballot_sync(0xffffffffu, filled & 1u) >> (grp * 16)) & 0xffffu;
+      const uint32_t pm = (__ballot_sync(0xffffffffu, f == 0xffffffffu) >> (grp * 16)) & 0xffffu;
+      const uint32_t c0 = sR[hidx - iw - 1] >> 31;
+      const uint32_t c1 = sR[hidx - iw + 16] & 1u;
+      const uint32_t au = gu | pm;
+      const uint32_t cu = (au + gu + c0) ^ au ^ gu;
+      const uint32_t gdr = __brev(gd) >> 16, pmr = __brev(pm) >> 16;
+      const uint32_t ad = gdr | pmr;
+      const uint32_t cd = (ad + gdr + c1) ^ ad ^ gdr;
+      const uint32_t seed = (r | ((cu >> iw) & 1u) | (((cd >> (15 - iw)) & 1u) << 31)) & f;
+      const uint32_t v = seed ? run_fill(seed, f) : 0u;
+      if (v != r) sR[hidx] = v;
+    }
+    __syncthreads();
+    scan_column(sR, sF, yidx, j, kPW);
+    __syncthreads();
+    scan_column(sR, sF, zidx, j, kPY * kPW);
+    __syncthreads();
+    r = sR[hidx];
+    changed = __syncthreads_or(r != before);
+    ++iters;
+  } while (changed && iters < b.max_trips);
+  const bool unfinished = changed != 0;
+  const long long pc2 = clock64();
+  int grew = 0;
+  if (r != r0) {   // r != 0 only inside the volume: out-of-volume words have no passable bit
+    __stcg(&reach[((z0 + iz) * b.dy + (y0 + iy)) * b.wx + (w0 + iw)], r);
+    grew = 1;
+  }
+  grew = __syncthreads_or(grew);
+  const long long pc3 = clock64();
+  if (tid == 0) {
+    atomicAdd(&stats[11], (int)((pc1 - pc0) >> 4));
+    atomicAdd(&stats[12], (int)((pc2 - pc1) >> 4));
+    atomicAdd(&stats[13], (int)((pc3 - pc2) >> 4));
+    atomicAdd(&stats[4], 1);
+    if (grew) atomicAdd(&stats[5], 1);
+    atomicAdd(&stats[6], iters);
+  }
+  // which of the six face neighbours can gain a bit from this tile's interior? One face word
+  // per thread: passable-but-unreached bits of the halo word against the reached bits of the
+  // interior word next to it (same bit across y / z, the adjacent bit across a word boundary).
+  if (tid < 640) {
+    bool gain;
+    int bit;
+    if (tid < 512) {
+      const int face = tid >> 7, a = (tid >> 4) & 7, bw = tid & 15;
+      int h, src;
+      if (face == 0)      { h = ((a + 1) * kPY) * kPW + bw + 1;       src = h + kPW;       bit = 10; }
+      else if (face == 1) { h = ((a + 1) * kPY + 9) * kPW + bw + 1;   src = h - kPW;       bit = 16; }
+      else if (face == 2) { h = (a + 1) * kPW + bw + 1;               src = h + kPY * kPW; bit = 4; }
+      else                { h = (9 * kPY + a + 1) * kPW + bw + 1;     src = h - kPY * kPW; bit = 22; }
+      gain = (sF[h] & ~sR[h] & sR[src]) != 0;
+    } else {
+      const int t = tid - 512, hi = t >> 6, a = (t >> 3) & 7, b8 = t & 7;
+      const int row = ((a + 1) * kPY + (b8 + 1)) * kPW;
+      if (hi == 0) { gain = (((sF[row] & ~sR[row]) >> 31) & sR[row + 1] & 1u) != 0;            bit = 12; }
+      else         { gain = ((sF[row + 17] & ~sR[row + 17]) & (sR[row + 16] >> 31) & 1u) != 0; bit = 14; }
+    }
+    if (__any_sync(0xffffffffu, gain) && (tid & 31) == 0) atomicOr(s_faces, 1 << bit);
+  }
+  if (unfinished && tid == 0) atomicOr(s_faces, 1 << 13);   // (0,0,0): re-queue this tile itself
+  __syncthreads();
+  if (tid == 0) atomicAdd(&stats[14], (int)((clock64() - pc3) >> 4));
+  return *s_faces;
+}
+
 template <uint32_t SBC>
 __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, uint32_t* reach, const BitVol& b,
                                                uint32_t sb_rt, int tile, uint32_t* sR, int* s_faces, int* stats) {
+  if constexpr (SBC == kSB6) {
+    if (b.tw == 16 && b.ty == 8 && b.tz == 8 && kFloodThreads == kTileWords)
+      return ff_process_tile_sb6(fg, reach, b, tile, sR, s_faces, stats);
+  }
   const uint32_t sb = SBC ? SBC : sb_rt;
   // the x sweep needs both x offsets; a one-sided x offset is left to the generic hop
   const bool axis_only = (sb & ~kSB6) == 0 && (((sb >> 12) & 1u) == ((sb >> 14) & 1u));
@@ -572,64 +726,123 @@ __global__ void __launch_bounds__(kFloodThreads)
 
 // ---- persistent variant: all rounds in ONE cooperative launch ------------------------------
 // The host-driven rounds above pay for a launch of every tile's block per round although a
-// few dozen tiles are active. Here the active tiles of a round are a compact list; a
-// persistent grid walks it, appends the tiles that can gain to the next round's list (once
-// each: one flag array per list), and crosses a grid-wide barrier. Three lists rotate so
-// that the list being appended to was emptied a full round earlier.
-__global__ void k_ff_lists_init(const uint8_t* __restrict__ active, uint8_t* active_clr, int ntiles, int* lists,
-                                int* counts, int* lflags) {
-  __shared__ int s_n;
-  if (threadIdx.x == 0) s_n = 0;
-  __syncthreads();
-  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
-    lflags[t] = 0; lflags[ntiles + t] = 0; lflags[2 * ntiles + t] = 0;
-    if (active[t]) {
-      lists[atomicAdd(&s_n, 1)] = t;
-      active_clr[t] = 0;
+// few dozen tiles are active. Here the active tiles of a round are a bitmap (one bit per
+// tile); a persistent grid reads it after the grid-wide barrier, every block ranks the set
+// bits with a block scan and takes the tiles whose rank is congruent to its index, and a
+// tile that can gain is posted to the next round's bitmap with one fire-and-forget atomic OR
+// (no list slot to reserve, no duplicate to filter: the per-round critical path is one
+// bitmap read, one tile visit and the barrier). Three bitmaps rotate so that the one being
+// posted to was cleared a full round earlier.
+constexpr int kMaxMine = 1024;   // tiles one block may own in a round (host falls back to launches beyond)
+
+__global__ void k_ff_lists_init(const uint8_t* __restrict__ active, uint8_t* active_clr, int ntiles, uint32_t* bm,
+                                int nbw) {
+  for (int wi = threadIdx.x; wi < nbw; wi += blockDim.x) {
+    uint32_t w = 0;
+    for (int j = 0; j < 32; ++j) {
+      const int t = wi * 32 + j;
+      if (t < ntiles && active[t]) { w |= 1u << j; active_clr[t] = 0; }
     }
+    bm[wi] = w;
+    bm[nbw + wi] = 0;
+    bm[2 * nbw + wi] = 0;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) { counts[0] = s_n; counts[1] = 0; counts[2] = 0; }
 }
 
-template <uint32_t SBC>
+// Rank the set bits of the bitmap; the tiles of rank bid, bid + nblocks, ... go to mine[].
+// Returns the number of set bits (uniform over the block).
+__device__ __forceinline__ int ff_select_tiles(const uint32_t* bm, int nbw, int bid, int nblocks, int* mine,
+                                               int* s_wsum) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int base = 0;
+  for (int i0 = 0; i0 < nbw; i0 += kFloodThreads) {
+    const int i = i0 + tid;
+    uint32_t w = i < nbw ? __ldcg(&bm[i]) : 0u;
+    const int c = __popc(w);
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int ws = s_wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, ws, d);
+        if (lane >= d) ws += v;
+      }
+      s_wsum[lane] = ws;   // inclusive over warps
+    }
+    __syncthreads();
+    int rank = base + (warp ? s_wsum[warp - 1] : 0) + incl - c;
+    const int total = s_wsum[31];
+    // ranks [rank, rank + c) sit in this word: those of the form bid + slot * nblocks are mine
+    if (c) {
+      int slot = rank > bid ? (rank - bid + nblocks - 1) / nblocks : 0;
+      for (int q = bid + slot * nblocks; q < rank + c; q += nblocks, ++slot)
+        if (slot < kMaxMine) mine[slot] = i * 32 + (int)__fns(w, 0, q - rank + 1);
+    }
+    base += total;
+    __syncthreads();   // s_wsum is reused by the next chunk
+  }
+  return base;
+}
+
+// CANON: 6-connected flood on the canonical tile only (ff_process_tile_sb6, no generic path).
+// (Two co-resident blocks per SM at 32 registers were measured slower: the barrier doubles
+// and the visits of the two blocks contend.)
+template <uint32_t SBC, bool CANON>
 __global__ void __launch_bounds__(kFloodThreads)
-    k_ff_persistent(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b, uint32_t sb, int* lists, int* counts,
-                    int* lflags, int* ctl, int max_rounds) {
+    k_ff_persistent(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b, uint32_t sb, uint32_t* bm, int nbw,
+                    int* ctl, int max_rounds) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ uint32_t sR[];
   __shared__ int s_faces;
+  __shared__ int s_wsum[32];
+  __shared__ int s_mine[kMaxMine];
   const int tid = threadIdx.x;
-  const int ntiles = b.ntz * b.nty * b.ntw;
-  int n_prev = 0, r = 0;
+  int r = 0;
   long long c_proc = 0, c_sync = 0, c_all0 = clock64();
   for (;; ++r) {
     const long long c0 = clock64();
     const int cur = r % 3, nxt = (r + 1) % 3, old = (r + 2) % 3;
-    const int n = *(volatile int*)&counts[cur];
+    const int n = ff_select_tiles(bm + (size_t)cur * nbw, nbw, blockIdx.x, gridDim.x, s_mine, s_wsum);
     if (n == 0) break;
     if (r >= max_rounds) { if (blockIdx.x == 0 && tid == 0) ctl[3] = 1; break; }
-    if (blockIdx.x == 0 && tid == 0) counts[old] = 0;   // appended to from the next round on
-    for (int i = blockIdx.x * kFloodThreads + tid; i < n_prev; i += gridDim.x * kFloodThreads)
-      lflags[old * ntiles + lists[old * ntiles + i]] = 0;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
-      const int tile = lists[cur * ntiles + i];
-      const int nbmask = ff_process_tile<SBC>(fg, reach, b, sb, tile, sR, &s_faces, ctl);
+    // `old` was read by everyone before the last barrier and is posted to from the next round on
+    for (int i = blockIdx.x * kFloodThreads + tid; i < nbw; i += gridDim.x * kFloodThreads) bm[(size_t)old * nbw + i] = 0;
+    int nmine = n > (int)blockIdx.x ? (n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    int keep = -1;
+    if (b.defer && nmine == 2 && n - (int)gridDim.x <= b.defer) {
+      // a few tiles more than blocks: pass them on to the next round instead of making every
+      // block wait for a second visit
+      // (alternating which of the two waits, so that no tile waits twice in a row)
+      const int t = s_mine[(r & 1) ? 0 : 1];
+      keep = s_mine[(r & 1) ? 1 : 0];
+      if (tid == 0) atomicOr(&bm[(size_t)nxt * nbw + (t >> 5)], 1u << (t & 31));
+      nmine = 1;
+    }
+    for (int k = 0; k < nmine; ++k) {
+      const int tile = keep >= 0 ? keep : s_mine[k];
+      int nbmask;
+      if constexpr (CANON) nbmask = ff_process_tile_sb6(fg, reach, b, tile, sR, &s_faces, ctl);
+      else nbmask = ff_process_tile<SBC>(fg, reach, b, sb, tile, sR, &s_faces, ctl);
       if (tid < 27 && ((nbmask >> tid) & 1)) {
         const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
         int oz = tid / 9 - 1, oy = (tid / 3) % 3 - 1, ow = tid % 3 - 1;
         int nz = tzi + oz, ny = tyi + oy, nw = twi + ow;
         if (nz >= 0 && nz < b.ntz && ny >= 0 && ny < b.nty && nw >= 0 && nw < b.ntw) {
-          int nb = (nz * b.nty + ny) * b.ntw + nw;
-          if (atomicExch(&lflags[nxt * ntiles + nb], 1) == 0) lists[nxt * ntiles + atomicAdd(&counts[nxt], 1)] = nb;
+          const int nb = (nz * b.nty + ny) * b.ntw + nw;
+          atomicOr(&bm[(size_t)nxt * nbw + (nb >> 5)], 1u << (nb & 31));
         }
       }
       __syncthreads();   // s_faces / shared tile are reused by the next tile of this block
     }
-    n_prev = n;
     const long long c1 = clock64();
-    __threadfence();
-    grid.sync();
+    grid.sync();   // orders every thread's writes (reach words, next bitmap) before the next round's reads
     const long long c2 = clock64();
     c_proc += c1 - c0;
     c_sync += c2 - c1;
@@ -679,7 +892,8 @@ int strct_bits(const uint8_t* strct_host, int64_t odz, int64_t ody, int64_t odx,
           int oz = (int)(kk - odz / 2), oy = (int)(jj - ody / 2), ox = (int)(ii - odx / 2);
           bits |= 1u << ((oz + 1) * 9 + (oy + 1) * 3 + (ox + 1));
         }
-  *sb = bits;
+  *sb = bits & ~(1u << 13);   // the centre offset moves nothing: drop it so that the standard elements
+                              // match the compile-time specialisations
   return B2V_OK;
 }
 
@@ -740,11 +954,13 @@ int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_
   int ntiles = b.ntz * b.nty * b.ntw;
   const size_t smem = 2 * (size_t)(b.tz + 2) * (b.ty + 2) * (b.tw + 2) * sizeof(uint32_t);
   int rc;
-  k_ff_lists_init<<<1, 1024, 0, s>>>(w.active[r0 & 1], w.active[r0 & 1], ntiles, w.lists, w.counts, w.lflags);
-  if ((rc = b2v_check_launch("k_ff_lists_init"))) return rc;
-  void* kern = sb == kSB6 ? (void*)k_ff_persistent<kSB6>
-             : sb == kSB26 ? (void*)k_ff_persistent<kSB26>
-             : sb == kSB18 ? (void*)k_ff_persistent<kSB18> : (void*)k_ff_persistent<0u>;
+  const int nbw = (int)((ntiles + 31) / 32);
+  uint32_t* bm = (uint32_t*)w.lists;   // three rotating tile bitmaps [3][nbw]
+  const bool canon = sb == kSB6 && b.tw == 16 && b.ty == 8 && b.tz == 8 && kFloodThreads == kTileWords;
+  void* kern = canon ? (void*)k_ff_persistent<kSB6, true>
+             : sb == kSB6 ? (void*)k_ff_persistent<kSB6, false>
+             : sb == kSB26 ? (void*)k_ff_persistent<kSB26, false>
+             : sb == kSB18 ? (void*)k_ff_persistent<kSB18, false> : (void*)k_ff_persistent<0u, false>;
   int per_sm = 0;
   B2V_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, kFloodThreads, smem));
   B2V_REQUIRE(per_sm >= 1, B2V_ERR_CUDA, "floodfill: persistent kernel does not fit on an SM");
@@ -753,13 +969,18 @@ int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_
     int v = atoi(e);
     if (v > 0 && v < grid) grid = v;
   }
-  if (grid > ntiles) grid = ntiles;
+  if (grid > ntiles) grid = (int)ntiles;
+  // a block keeps at most kMaxMine tiles of a round in shared memory (5 G voxels at 148 blocks)
+  if ((int64_t)grid * kMaxMine < ntiles) return run_rounds(b, w, sb, s, r0, rounds_out);
+  k_ff_lists_init<<<1, 1024, 0, s>>>(w.active[r0 & 1], w.active[r0 & 1], (int)ntiles, bm, nbw);
+  if ((rc = b2v_check_launch("k_ff_lists_init"))) return rc;
   const uint32_t* fg = w.fg;
   uint32_t* reach = w.reach;
   BitVol bb = b;
-  int* lists = w.lists; int* counts = w.counts; int* lflags = w.lflags; int* ctl = w.ctl;
+  int* ctl = w.ctl;
   int max_rounds = kMaxRounds;
-  void* args[] = {&fg, &reach, &bb, &sb, &lists, &counts, &lflags, &ctl, &max_rounds};
+  int nbw_arg = nbw;
+  void* args[] = {&fg, &reach, &bb, &sb, &bm, &nbw_arg, &ctl, &max_rounds};
   B2V_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kFloodThreads), args, smem, s));
   if ((rc = b2v_check_launch("k_ff_persistent"))) return rc;
   int ctlh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
