@@ -950,7 +950,20 @@ int run_rounds(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s,
 static thread_local int g_last_rounds = 0;
 static int g_flood_engine = 1;   // 1 persistent (default), 0 host-driven rounds
 
-int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s, int r0, int* rounds_out) {
+// Fetch the persistent kernel's verdict (synchronises the stream).
+int persistent_verdict(const Workspace& w, cudaStream_t s) {
+  int ctlh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  B2V_CUDA(cudaMemcpyAsync(ctlh, w.ctl, sizeof(ctlh), cudaMemcpyDeviceToHost, s));
+  B2V_CUDA(cudaStreamSynchronize(s));
+  B2V_REQUIRE(ctlh[3] == 0, B2V_ERR_NOCONV, "floodfill: no convergence after %d rounds", ctlh[7]);
+  g_last_rounds = ctlh[7];
+  return B2V_OK;
+}
+
+// verdict_later: the caller queues more work behind the kernel and calls persistent_verdict()
+// itself (one host round trip per flood instead of two).
+int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s, int r0, int* rounds_out,
+                   bool verdict_later) {
   int ntiles = b.ntz * b.nty * b.ntw;
   const size_t smem = 2 * (size_t)(b.tz + 2) * (b.ty + 2) * (b.tw + 2) * sizeof(uint32_t);
   int rc;
@@ -983,15 +996,10 @@ int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_
   void* args[] = {&fg, &reach, &bb, &sb, &bm, &nbw_arg, &ctl, &max_rounds};
   B2V_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kFloodThreads), args, smem, s));
   if ((rc = b2v_check_launch("k_ff_persistent"))) return rc;
-  int ctlh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  B2V_CUDA(cudaMemcpyAsync(ctlh, w.ctl, sizeof(ctlh), cudaMemcpyDeviceToHost, s));
-  B2V_CUDA(cudaStreamSynchronize(s));
-  B2V_REQUIRE(ctlh[3] == 0, B2V_ERR_NOCONV, "floodfill: no convergence after %d rounds", ctlh[7]);
   // the round flag of r0 was consumed; the next merge raises flags[r0 + 1]
   B2V_CUDA(cudaMemsetAsync(w.flags + r0, 0, sizeof(int), s));
   if (rounds_out) *rounds_out = r0 + 1;
-  g_last_rounds = ctlh[7];
-  return B2V_OK;
+  return verdict_later ? B2V_OK : persistent_verdict(w, s);
 }
 
 enum { STAGE_BEGIN = 1, STAGE_CONVERGE = 2, STAGE_FINISH = 4, STAGE_ALL = 7 };
@@ -1007,6 +1015,7 @@ int flood(T* data, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64
   B2V_REQUIRE(dz > 0 && dy > 0 && dx > 0, B2V_ERR_ARG, "floodfill: empty volume");
   B2V_REQUIRE(dz * dy * ceil_div64(dx, 32) < (1ll << 31), B2V_ERR_ARG, "floodfill: volume too large");
   int rc;
+  bool verdict_due = false;
   BitVol b = make_bitvol(dz, dy, dx);
   Workspace w = carve(workspace, b, nseeds);
   const int64_t nwords = dz * dy * b.wx;
@@ -1035,8 +1044,10 @@ int flood(T* data, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64
   }
   if (stages & STAGE_CONVERGE) {
     int r0 = round_io ? *round_io : 0, r1 = r0;
-    if ((rc = g_flood_engine ? run_persistent(b, w, sb, s, r0, &r1) : run_rounds(b, w, sb, s, r0, &r1))) return rc;
-    if (round_io) *round_io = (stages == STAGE_ALL && g_flood_engine) ? g_last_rounds : r1;
+    verdict_due = g_flood_engine && (stages & STAGE_FINISH);
+    if ((rc = g_flood_engine ? run_persistent(b, w, sb, s, r0, &r1, verdict_due) : run_rounds(b, w, sb, s, r0, &r1)))
+      return rc;
+    if (round_io) *round_io = r1;
   }
   if (stages & STAGE_FINISH) {
     if (MODE == MODE_INPLACE)
@@ -1044,6 +1055,10 @@ int flood(T* data, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64
     else
       k_ff_write<uint8_t><<<grid_for(nwords, 8), 256, 0, s>>>(w.reach, b, fill_o, out);
     if ((rc = b2v_check_launch("k_ff_write"))) return rc;
+  }
+  if (verdict_due) {
+    if ((rc = persistent_verdict(w, s))) return rc;
+    if (round_io && stages == STAGE_ALL) *round_io = g_last_rounds;
   }
   return B2V_OK;
 }
