@@ -26,8 +26,7 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kTileWords = 1024;   // interior words per tile (8 x 8 rows x 16 words = 32 768 voxels; 4096-word
-                                   // tiles halve the rounds but triple the per-round critical path: measured slower)
+constexpr int kTileWords = 4096;   // interior words of the largest tile (16 x 16 rows x 16 words = 131 072 voxels)
 constexpr int kMaxRounds = 1 << 16;
 constexpr int kFloodThreads = 1024;  // one thread per tile word: short dependent chains, 32 warps to overlap them
 
@@ -52,9 +51,14 @@ BitVol make_bitvol(int64_t dz, int64_t dy, int64_t dx) {
   BitVol b;
   b.dz = dz; b.dy = dy; b.dx = dx;
   b.wx = (int)ceil_div64(dx, 32);
+  // Tile edge (rows): 16 halves the number of rounds of a flood (one tile hop per round)
+  // against 8 for about twice the work per visit; B2V_FF_TILE=8 selects the small tile.
+  int edge = 16;
+  if (const char* e = getenv("B2V_FF_TILE")) { if (atoi(e) == 8) edge = 8; }
+  const int words = edge == 16 ? kTileWords : 1024;
   b.tw = pow2ceil(b.wx, 16);
-  b.ty = pow2ceil(dy, 8);
-  b.tz = pow2ceil(dz, kTileWords / (b.tw * b.ty));
+  b.ty = pow2ceil(dy, edge);
+  b.tz = pow2ceil(dz, words / (b.tw * b.ty));
   // reached + passable tiles with halo must fit the 48 KB of default shared memory
   while (b.tz > 1 && (int64_t)(b.tz + 2) * (b.ty + 2) * (b.tw + 2) * 8 > 48 * 1024) b.tz >>= 1;
   b.ntz = (int)ceil_div64(dz, b.tz);
@@ -302,53 +306,77 @@ constexpr uint32_t kSB26 = 0x7ffffffu & ~(1u << 13);
 constexpr uint32_t kSB18 = kSB26 & ~((1u << 0) | (1u << 2) | (1u << 6) | (1u << 8) | (1u << 18) | (1u << 20) |
                                      (1u << 24) | (1u << 26));
 
-// ---- 6-connected, canonical tile (8 x 8 rows x 16 words, one word per thread) ----------------
-// The common case (InVesalius floods with the 6-neighbourhood; any volume at least 8 x 8 x 512
-// gets this tile) with every index a compile-time constant and all 1024 threads busy in every
-// phase. The y and z sweeps re-map the threads so that the eight words of a column sit in
-// eight adjacent lanes and run a Kogge-Stone scan of (generate, propagate) word pairs with
-// shuffles: v[k] = g[k] | (p[k] & v[k-1]) in three steps per direction instead of an
-// eight-step serial chain on an eighth of the threads.
-constexpr int kPW = 18, kPY = 10, kNH = 10 * 10 * 18;
+// ---- 6-connected, canonical tiles (2^LZ x 2^LY rows x 16 words) ------------------------------
+// The common case (InVesalius floods with the 6-neighbourhood) with every index a
+// compile-time constant: K = tile words / 1024 words per thread for the loads, the write-back
+// and the change detection; the three axis sweeps as register chains.
 
-// both directions of one axis sweep; idx = this thread's word, j = its position in the
-// column (0..7, the low three lane bits), stride = distance between column neighbours
-__device__ __forceinline__ void scan_column(uint32_t* sR, const uint32_t* sF, int idx, int j, int stride) {
-  const uint32_t f = sF[idx], orig = sR[idx];
-  uint32_t G = orig, P = f;
-  if (j == 0) G |= f & sR[idx - stride];        // carry in from the halo word before the column
+// One row of 16 words swept along x by one thread: the run fill of a word (carry trick of
+// run_fill) plus the carry into the next word, towards higher x and then towards lower x.
+// The filled words of the first pass seed the second, so every run that holds a reached bit
+// ends up full across word boundaries. first = the row's word 0 in the haloed tile.
+__device__ __forceinline__ void sweep_row_x(uint32_t* sR, const uint32_t* sF, int first) {
+  uint32_t m[16], v[16];
 #pragma unroll
-  for (int d = 1; d < 8; d <<= 1) {
-    const uint32_t Gu = __shfl_up_sync(0xffffffffu, G, d, 8), Pu = __shfl_up_sync(0xffffffffu, P, d, 8);
-    if (j >= d) { G |= P & Gu; P &= Pu; }
-  }
-  P = f;
-  if (j == 7) G |= f & sR[idx + stride];        // ... and from the one after it
+  for (int w = 0; w < 16; ++w) { m[w] = sF[first + w]; v[w] = sR[first + w]; }
+  uint32_t cin = sR[first - 1] >> 31;           // last bit of the word before the row (halo)
 #pragma unroll
-  for (int d = 1; d < 8; d <<= 1) {
-    const uint32_t Gd = __shfl_down_sync(0xffffffffu, G, d, 8), Pd = __shfl_down_sync(0xffffffffu, P, d, 8);
-    if (j + d < 8) { G |= P & Gd; P &= Pd; }
+  for (int w = 0; w < 16; ++w) {
+    const uint32_t sd = v[w] | (cin & m[w]);
+    v[w] = (((m[w] + sd) ^ m[w]) & m[w]) | sd;
+    cin = v[w] >> 31;
   }
-  if (G != orig) sR[idx] = G;
+  cin = sR[first + 16] & 1u;                    // first bit of the word after the row (halo)
+#pragma unroll
+  for (int w = 15; w >= 0; --w) {
+    const uint32_t sd = v[w] | ((cin << 31) & m[w]);
+    const uint32_t rm = __brev(m[w]), rs = __brev(sd);
+    v[w] = __brev(((rm + rs) ^ rm) & rm) | sd;
+    cin = v[w] & 1u;
+  }
+#pragma unroll
+  for (int w = 0; w < 16; ++w) sR[first + w] = v[w];
 }
 
+// One column of N words swept along y or z by one thread: v[j] |= v[j-1] & m[j] down the
+// column, then the mirror image up; the ends are fed by the read-only halo words.
+// halo0 = the halo word before the column, stride = distance between column neighbours.
+template <int N>
+__device__ __forceinline__ void sweep_col(uint32_t* sR, const uint32_t* sF, int halo0, int stride) {
+  uint32_t m[N], v[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) { m[j] = sF[halo0 + (j + 1) * stride]; v[j] = sR[halo0 + (j + 1) * stride]; }
+  uint32_t prev = sR[halo0];
+#pragma unroll
+  for (int j = 0; j < N; ++j) { v[j] |= prev & m[j]; prev = v[j]; }
+  prev = sR[halo0 + (N + 1) * stride];
+#pragma unroll
+  for (int j = N - 1; j >= 0; --j) { v[j] |= prev & m[j]; prev = v[j]; }
+#pragma unroll
+  for (int j = 0; j < N; ++j) sR[halo0 + (j + 1) * stride] = v[j];
+}
+
+template <int LZ, int LY>
 __device__ __forceinline__ int ff_process_tile_sb6(const uint32_t* __restrict__ fg, uint32_t* reach, const BitVol& b,
                                                    int tile, uint32_t* sR, int* s_faces, int* stats) {
+  constexpr int TZ = 1 << LZ, TY = 1 << LY, PW = 18, PY = TY + 2, NH = (TZ + 2) * PY * PW;
+  constexpr int K = TZ * TY * 16 / kFloodThreads;          // words per thread
+  constexpr int NL = (NH + kFloodThreads - 1) / kFloodThreads;
   const int tid = threadIdx.x;
   const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
-  const int64_t z0 = (int64_t)tzi * 8, y0 = (int64_t)tyi * 8;
+  const int64_t z0 = (int64_t)tzi * TZ, y0 = (int64_t)tyi * TY;
   const int w0 = twi * 16;
-  uint32_t* sF = sR + kNH;
+  uint32_t* sF = sR + NH;
   if (tid == 0) *s_faces = 0;
   const long long pc0 = clock64();
   {
-    uint32_t v[2], f[2];
+    uint32_t v[NL], f[NL];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < NL; ++k) {
       const int i = tid + k * kFloodThreads;
       v[k] = 0; f[k] = 0;
-      if (i < kNH) {
-        const int hz = i / (kPW * kPY), rem = i - hz * (kPW * kPY), hy = rem / kPW, hw = rem - hy * kPW;
+      if (i < NH) {
+        const int hz = i / (PW * PY), rem = i - hz * (PW * PY), hy = rem / PW, hw = rem - hy * PW;
         const int64_t z = z0 + hz - 1, y = y0 + hy - 1;
         const int w = w0 + hw - 1;
         if (z >= 0 && z < b.dz && y >= 0 && y < b.dy && w >= 0 && w < b.wx) {
@@ -359,58 +387,59 @@ __device__ __forceinline__ int ff_process_tile_sb6(const uint32_t* __restrict__ 
       }
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < NL; ++k) {
       const int i = tid + k * kFloodThreads;
-      if (i < kNH) { sR[i] = v[k]; sF[i] = f[k]; }
+      if (i < NH) { sR[i] = v[k]; sF[i] = f[k]; }
     }
   }
-  const int iw = tid & 15, iy = (tid >> 4) & 7, iz = tid >> 7;
-  const int hidx = ((iz + 1) * kPY + (iy + 1)) * kPW + (iw + 1);
-  // transposed roles for the column scans: the column index runs over the low three lane bits
-  const int j = tid & 7, jw = (tid >> 3) & 15, jo = tid >> 7;
-  const int yidx = ((jo + 1) * kPY + (j + 1)) * kPW + (jw + 1);   // column along y: (z = jo, w = jw)
-  const int zidx = ((j + 1) * kPY + (jo + 1)) * kPW + (jw + 1);   // column along z: (y = jo, w = jw)
   __syncthreads();
-  const uint32_t f = sF[hidx], r0 = sR[hidx];
-  uint32_t r = r0;
+  // owner role: word i = tid + k * 1024 -> (iz, iy, iw), iw fastest (a 16-lane group = a row)
+  uint32_t f[K], r0[K], r[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int i = tid + k * kFloodThreads;
+    const int h = (((i >> (4 + LY)) + 1) * PY + (((i >> 4) & (TY - 1)) + 1)) * PW + (i & 15) + 1;
+    f[k] = sF[h];
+    r0[k] = r[k] = sR[h];
+  }
   const long long pc1 = clock64();
-  const int grp = (tid & 31) >> 4;
+  const int iw = tid & 15;
   int changed, iters = 0;
   do {
-    const uint32_t before = r;
-    {
-      // x: carry-lookahead over the 16 words of the row (see the generic path for the algebra)
-      const uint32_t filled = (f && r) ? run_fill(r, f) : 0u;
-      const uint32_t gu = (__ballot_sync(0xffffffffu, filled >> 31) >> (grp * 16)) & 0xffffu;
-      const uint32_t gd = (__ballot_sync(0xffffffffu, filled & 1u) >> (grp * 16)) & 0xffffu;
-      const uint32_t pm = (__ballot_sync(0xffffffffu, f == 0xffffffffu) >> (grp * 16)) & 0xffffu;
-      const uint32_t c0 = sR[hidx - iw - 1] >> 31;
-      const uint32_t c1 = sR[hidx - iw + 16] & 1u;
-      const uint32_t au = gu | pm;
-      const uint32_t cu = (au + gu + c0) ^ au ^ gu;
-      const uint32_t gdr = __brev(gd) >> 16, pmr = __brev(pm) >> 16;
-      const uint32_t ad = gdr | pmr;
-      const uint32_t cd = (ad + gdr + c1) ^ ad ^ gdr;
-      const uint32_t seed = (r | ((cu >> iw) & 1u) | (((cd >> (15 - iw)) & 1u) << 31)) & f;
-      const uint32_t v = seed ? run_fill(seed, f) : 0u;
-      if (v != r) sR[hidx] = v;
+    int moved = 0;
+    // Each sweep is a serial chain in the registers of ONE thread per row / column (a few
+    // hundred threads busy, a few hundred cycles): far fewer instructions than a
+    // word-per-thread scan, and the block is latency-bound here, not width-bound.
+    if (tid < TZ * TY)        // x: row (z = tid >> LY, y = tid & (TY-1))
+      sweep_row_x(sR, sF, (((tid >> LY) + 1) * PY + ((tid & (TY - 1)) + 1)) * PW + 1);
+    __syncthreads();
+    if (tid < TZ * 16)        // y: column (z = tid >> 4, w = tid & 15), halo row y = -1 first
+      sweep_col<TY>(sR, sF, ((tid >> 4) + 1) * PY * PW + (tid & 15) + 1, PW);
+    __syncthreads();
+    if (tid < TY * 16)        // z: column (y = tid >> 4, w = tid & 15), halo plane z = -1 first
+      sweep_col<TZ>(sR, sF, ((tid >> 4) + 1) * PW + (tid & 15) + 1, PY * PW);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int i = tid + k * kFloodThreads;
+      const int h = (((i >> (4 + LY)) + 1) * PY + (((i >> 4) & (TY - 1)) + 1)) * PW + iw + 1;
+      const uint32_t v = sR[h];
+      moved |= v != r[k];
+      r[k] = v;
     }
-    __syncthreads();
-    scan_column(sR, sF, yidx, j, kPW);
-    __syncthreads();
-    scan_column(sR, sF, zidx, j, kPY * kPW);
-    __syncthreads();
-    r = sR[hidx];
-    changed = __syncthreads_or(r != before);
+    changed = __syncthreads_or(moved);
     ++iters;
   } while (changed && iters < b.max_trips);
   const bool unfinished = changed != 0;
   const long long pc2 = clock64();
   int grew = 0;
-  if (r != r0) {   // r != 0 only inside the volume: out-of-volume words have no passable bit
-    __stcg(&reach[((z0 + iz) * b.dy + (y0 + iy)) * b.wx + (w0 + iw)], r);
-    grew = 1;
-  }
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+    if (r[k] != r0[k]) {   // r != 0 only inside the volume: out-of-volume words have no passable bit
+      const int i = tid + k * kFloodThreads;
+      __stcg(&reach[((z0 + (i >> (4 + LY))) * b.dy + (y0 + ((i >> 4) & (TY - 1)))) * b.wx + (w0 + iw)], r[k]);
+      grew = 1;
+    }
   grew = __syncthreads_or(grew);
   const long long pc3 = clock64();
   if (tid == 0) {
@@ -424,22 +453,27 @@ __device__ __forceinline__ int ff_process_tile_sb6(const uint32_t* __restrict__ 
   // which of the six face neighbours can gain a bit from this tile's interior? One face word
   // per thread: passable-but-unreached bits of the halo word against the reached bits of the
   // interior word next to it (same bit across y / z, the adjacent bit across a word boundary).
-  if (tid < 640) {
+  // Every face is a multiple of 32 words, so a warp votes for one face.
+  constexpr int NYF = TZ * 16, NZF = TY * 16, NXF = TZ * TY, TOT = 2 * (NYF + NZF + NXF);
+  for (int t = tid; t < TOT; t += kFloodThreads) {
     bool gain;
     int bit;
-    if (tid < 512) {
-      const int face = tid >> 7, a = (tid >> 4) & 7, bw = tid & 15;
-      int h, src;
-      if (face == 0)      { h = ((a + 1) * kPY) * kPW + bw + 1;       src = h + kPW;       bit = 10; }
-      else if (face == 1) { h = ((a + 1) * kPY + 9) * kPW + bw + 1;   src = h - kPW;       bit = 16; }
-      else if (face == 2) { h = (a + 1) * kPW + bw + 1;               src = h + kPY * kPW; bit = 4; }
-      else                { h = (9 * kPY + a + 1) * kPW + bw + 1;     src = h - kPY * kPW; bit = 22; }
+    if (t < 2 * NYF) {
+      const int hi = t >= NYF, u = t - hi * NYF, a = u >> 4, bw = u & 15;
+      const int h = ((a + 1) * PY + (hi ? TY + 1 : 0)) * PW + bw + 1, src = hi ? h - PW : h + PW;
+      bit = hi ? 16 : 10;
+      gain = (sF[h] & ~sR[h] & sR[src]) != 0;
+    } else if (t < 2 * NYF + 2 * NZF) {
+      const int u0 = t - 2 * NYF, hi = u0 >= NZF, u = u0 - hi * NZF, a = u >> 4, bw = u & 15;
+      const int h = ((hi ? TZ + 1 : 0) * PY + a + 1) * PW + bw + 1, src = hi ? h - PY * PW : h + PY * PW;
+      bit = hi ? 22 : 4;
       gain = (sF[h] & ~sR[h] & sR[src]) != 0;
     } else {
-      const int t = tid - 512, hi = t >> 6, a = (t >> 3) & 7, b8 = t & 7;
-      const int row = ((a + 1) * kPY + (b8 + 1)) * kPW;
-      if (hi == 0) { gain = (((sF[row] & ~sR[row]) >> 31) & sR[row + 1] & 1u) != 0;            bit = 12; }
-      else         { gain = ((sF[row + 17] & ~sR[row + 17]) & (sR[row + 16] >> 31) & 1u) != 0; bit = 14; }
+      const int u0 = t - 2 * NYF - 2 * NZF, hi = u0 >= NXF, u = u0 - hi * NXF;
+      const int row = (((u >> LY) + 1) * PY + ((u & (TY - 1)) + 1)) * PW;
+      bit = hi ? 14 : 12;
+      gain = hi ? ((sF[row + 17] & ~sR[row + 17]) & (sR[row + 16] >> 31) & 1u) != 0
+                : (((sF[row] & ~sR[row]) >> 31) & sR[row + 1] & 1u) != 0;
     }
     if (__any_sync(0xffffffffu, gain) && (tid & 31) == 0) atomicOr(s_faces, 1 << bit);
   }
@@ -453,8 +487,8 @@ template <uint32_t SBC>
 __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, uint32_t* reach, const BitVol& b,
                                                uint32_t sb_rt, int tile, uint32_t* sR, int* s_faces, int* stats) {
   if constexpr (SBC == kSB6) {
-    if (b.tw == 16 && b.ty == 8 && b.tz == 8 && kFloodThreads == kTileWords)
-      return ff_process_tile_sb6(fg, reach, b, tile, sR, s_faces, stats);
+    if (b.tw == 16 && b.ty == 16 && b.tz == 16) return ff_process_tile_sb6<4, 4>(fg, reach, b, tile, sR, s_faces, stats);
+    if (b.tw == 16 && b.ty == 8 && b.tz == 8) return ff_process_tile_sb6<3, 3>(fg, reach, b, tile, sR, s_faces, stats);
   }
   const uint32_t sb = SBC ? SBC : sb_rt;
   // the x sweep needs both x offsets; a one-sided x offset is left to the generic hop
@@ -733,7 +767,7 @@ __global__ void __launch_bounds__(kFloodThreads)
 // (no list slot to reserve, no duplicate to filter: the per-round critical path is one
 // bitmap read, one tile visit and the barrier). Three bitmaps rotate so that the one being
 // posted to was cleared a full round earlier.
-constexpr int kMaxMine = 1024;   // tiles one block may own in a round (host falls back to launches beyond)
+constexpr int kMaxMine = 256;    // tiles one block may own in a round (host falls back to launches beyond)
 
 __global__ void k_ff_lists_init(const uint8_t* __restrict__ active, uint8_t* active_clr, int ntiles, uint32_t* bm,
                                 int nbw) {
@@ -791,10 +825,11 @@ __device__ __forceinline__ int ff_select_tiles(const uint32_t* bm, int nbw, int 
   return base;
 }
 
-// CANON: 6-connected flood on the canonical tile only (ff_process_tile_sb6, no generic path).
+// CANON = log2 of the tile edge (3, 4): 6-connected flood on that canonical tile only
+// (ff_process_tile_sb6, no generic path); 0 = any tile, any element.
 // (Two co-resident blocks per SM at 32 registers were measured slower: the barrier doubles
 // and the visits of the two blocks contend.)
-template <uint32_t SBC, bool CANON>
+template <uint32_t SBC, int CANON>
 __global__ void __launch_bounds__(kFloodThreads)
     k_ff_persistent(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b, uint32_t sb, uint32_t* bm, int nbw,
                     int* ctl, int max_rounds) {
@@ -828,7 +863,7 @@ __global__ void __launch_bounds__(kFloodThreads)
     for (int k = 0; k < nmine; ++k) {
       const int tile = keep >= 0 ? keep : s_mine[k];
       int nbmask;
-      if constexpr (CANON) nbmask = ff_process_tile_sb6(fg, reach, b, tile, sR, &s_faces, ctl);
+      if constexpr (CANON != 0) nbmask = ff_process_tile_sb6<CANON, CANON>(fg, reach, b, tile, sR, &s_faces, ctl);
       else nbmask = ff_process_tile<SBC>(fg, reach, b, sb, tile, sR, &s_faces, ctl);
       if (tid < 27 && ((nbmask >> tid) & 1)) {
         const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
@@ -922,6 +957,11 @@ int run_rounds(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s,
   const size_t smem = 2 * (size_t)(b.tz + 2) * (b.ty + 2) * (b.tw + 2) * sizeof(uint32_t);
   int r = r0, batch = 4, rc;
   B2V_REQUIRE(r0 >= 0 && r0 + batch < kMaxRounds, B2V_ERR_NOCONV, "floodfill: round counter exhausted (%d)", r0);
+  {
+    const void* kr = sb == kSB6 ? (const void*)k_ff_round<kSB6> : sb == kSB26 ? (const void*)k_ff_round<kSB26>
+                   : sb == kSB18 ? (const void*)k_ff_round<kSB18> : (const void*)k_ff_round<0u>;
+    B2V_CUDA(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   while (true) {
     for (int k = 0; k < batch; ++k, ++r) {
 #define B2V_FF_ROUND(SBC)                                                                                     \
@@ -969,11 +1009,13 @@ int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_
   int rc;
   const int nbw = (int)((ntiles + 31) / 32);
   uint32_t* bm = (uint32_t*)w.lists;   // three rotating tile bitmaps [3][nbw]
-  const bool canon = sb == kSB6 && b.tw == 16 && b.ty == 8 && b.tz == 8 && kFloodThreads == kTileWords;
-  void* kern = canon ? (void*)k_ff_persistent<kSB6, true>
-             : sb == kSB6 ? (void*)k_ff_persistent<kSB6, false>
-             : sb == kSB26 ? (void*)k_ff_persistent<kSB26, false>
-             : sb == kSB18 ? (void*)k_ff_persistent<kSB18, false> : (void*)k_ff_persistent<0u, false>;
+  const int canon = (sb == kSB6 && b.tw == 16 && b.ty == b.tz) ? (b.ty == 16 ? 4 : b.ty == 8 ? 3 : 0) : 0;
+  void* kern = canon == 4 ? (void*)k_ff_persistent<kSB6, 4>
+             : canon == 3 ? (void*)k_ff_persistent<kSB6, 3>
+             : sb == kSB6 ? (void*)k_ff_persistent<kSB6, 0>
+             : sb == kSB26 ? (void*)k_ff_persistent<kSB26, 0>
+             : sb == kSB18 ? (void*)k_ff_persistent<kSB18, 0> : (void*)k_ff_persistent<0u, 0>;
+  B2V_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   B2V_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, kFloodThreads, smem));
   B2V_REQUIRE(per_sm >= 1, B2V_ERR_CUDA, "floodfill: persistent kernel does not fit on an SM");
@@ -983,7 +1025,7 @@ int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_
     if (v > 0 && v < grid) grid = v;
   }
   if (grid > ntiles) grid = (int)ntiles;
-  // a block keeps at most kMaxMine tiles of a round in shared memory (5 G voxels at 148 blocks)
+  // a block keeps at most kMaxMine tiles of a round in shared memory (5 G voxels at 148 blocks and 16^3-word tiles)
   if ((int64_t)grid * kMaxMine < ntiles) return run_rounds(b, w, sb, s, r0, rounds_out);
   k_ff_lists_init<<<1, 1024, 0, s>>>(w.active[r0 & 1], w.active[r0 & 1], (int)ntiles, bm, nbw);
   if ((rc = b2v_check_launch("k_ff_lists_init"))) return rc;
