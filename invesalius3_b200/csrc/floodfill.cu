@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(256) k_ff_build(const T* __restrict__ data, co
 
 // int16 data + uint8 out, dx % 8 == 0, 16-byte aligned rows: each lane turns one 128-bit
 // load of data (8 voxels) and one 64-bit load of out into 8 bits; 4 lanes make a word.
-template <int MODE>
+// LINEAR: dx % 32 == 0, so a row holds no padding groups and group g is voxels [8g, 8g+8) and
+// byte g of the bit volume: no 64-bit division per group.
+template <int MODE, bool LINEAR>
 __global__ void __launch_bounds__(256) k_ff_build_i16_vec(const int16_t* __restrict__ data,
                                                           const uint8_t* __restrict__ out, BitVol b, int t0, int t1,
                                                           uint8_t fill_o, uint32_t* __restrict__ fg,
@@ -178,13 +180,19 @@ __global__ void __launch_bounds__(256) k_ff_build_i16_vec(const int16_t* __restr
     for (int k = 0; k < 4; ++k) {
       const int64_t g = g0 + k * blockDim.x + threadIdx.x;
       ok[k] = g < ngroups;
-      row[k] = ok[k] ? g / gx : 0;
-      q[k] = ok[k] ? (int)(g - row[k] * gx) : 0;
-      in[k] = ok[k] && (int64_t)q[k] * 8 < b.dx;
+      if (LINEAR) {
+        row[k] = 0;
+        q[k] = 0;
+        in[k] = ok[k];
+      } else {
+        row[k] = ok[k] ? g / gx : 0;
+        q[k] = ok[k] ? (int)(g - row[k] * gx) : 0;
+        in[k] = ok[k] && (int64_t)q[k] * 8 < b.dx;
+      }
       v[k] = make_int4(0, 0, 0, 0);
       o[k] = make_uint2(0u, 0u);
       if (in[k]) {
-        const int64_t i = row[k] * b.dx + (int64_t)q[k] * 8;
+        const int64_t i = LINEAR ? g * 8 : row[k] * b.dx + (int64_t)q[k] * 8;
         v[k] = ld_stream((const int4*)(data + i));
         o[k] = ld_stream((const uint2*)(out + i));
       }
@@ -207,7 +215,7 @@ __global__ void __launch_bounds__(256) k_ff_build_i16_vec(const int16_t* __restr
       word |= __shfl_xor_sync(0xffffffffu, word, 1);
       word |= __shfl_xor_sync(0xffffffffu, word, 2);
       if ((lane & 3) == 0 && ok[k]) {
-        int64_t wi = row[k] * b.wx + (q[k] >> 2);
+        const int64_t wi = LINEAR ? (g0 + k * blockDim.x + threadIdx.x) >> 2 : row[k] * b.wx + (q[k] >> 2);
         fg[wi] = word;
         reach[wi] = 0;
       }
@@ -364,8 +372,9 @@ __device__ __forceinline__ int ff_process_tile_sb6(const uint32_t* __restrict__ 
   constexpr int NL = (NH + kFloodThreads - 1) / kFloodThreads;
   const int tid = threadIdx.x;
   const int twi = tile % b.ntw, tyi = (tile / b.ntw) % b.nty, tzi = tile / (b.ntw * b.nty);
-  const int64_t z0 = (int64_t)tzi * TZ, y0 = (int64_t)tyi * TY;
-  const int w0 = twi * 16;
+  // 32-bit indices: the word count of a bit volume is below 2^31 (checked on entry)
+  const int z0 = tzi * TZ, y0 = tyi * TY, w0 = twi * 16;
+  const int dz = (int)b.dz, dy = (int)b.dy;
   uint32_t* sF = sR + NH;
   if (tid == 0) *s_faces = 0;
   const long long pc0 = clock64();
@@ -377,10 +386,9 @@ __device__ __forceinline__ int ff_process_tile_sb6(const uint32_t* __restrict__ 
       v[k] = 0; f[k] = 0;
       if (i < NH) {
         const int hz = i / (PW * PY), rem = i - hz * (PW * PY), hy = rem / PW, hw = rem - hy * PW;
-        const int64_t z = z0 + hz - 1, y = y0 + hy - 1;
-        const int w = w0 + hw - 1;
-        if (z >= 0 && z < b.dz && y >= 0 && y < b.dy && w >= 0 && w < b.wx) {
-          const int64_t gi = (z * b.dy + y) * b.wx + w;
+        const int z = z0 + hz - 1, y = y0 + hy - 1, w = w0 + hw - 1;
+        if ((unsigned)z < (unsigned)dz && (unsigned)y < (unsigned)dy && (unsigned)w < (unsigned)b.wx) {
+          const int gi = (z * dy + y) * b.wx + w;
           v[k] = __ldcg(&reach[gi]);
           f[k] = __ldg(&fg[gi]);
         }
@@ -437,7 +445,7 @@ __device__ __forceinline__ int ff_process_tile_sb6(const uint32_t* __restrict__ 
   for (int k = 0; k < K; ++k)
     if (r[k] != r0[k]) {   // r != 0 only inside the volume: out-of-volume words have no passable bit
       const int i = tid + k * kFloodThreads;
-      __stcg(&reach[((z0 + (i >> (4 + LY))) * b.dy + (y0 + ((i >> 4) & (TY - 1)))) * b.wx + (w0 + iw)], r[k]);
+      __stcg(&reach[((z0 + (i >> (4 + LY))) * dy + (y0 + ((i >> 4) & (TY - 1)))) * b.wx + (w0 + iw)], r[k]);
       grew = 1;
     }
   grew = __syncthreads_or(grew);
@@ -788,6 +796,27 @@ __global__ void k_ff_lists_init(const uint8_t* __restrict__ active, uint8_t* act
 __device__ __forceinline__ int ff_select_tiles(const uint32_t* bm, int nbw, int bid, int nblocks, int* mine,
                                                int* s_wsum) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (nbw <= 32) {   // up to 1024 tiles: one warp ranks the whole bitmap, one block barrier
+    if (warp == 0) {
+      const uint32_t w = lane < nbw ? __ldcg(&bm[lane]) : 0u;
+      const int c = __popc(w);
+      int incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int rank = incl - c;
+      if (c) {
+        int slot = rank > bid ? (rank - bid + nblocks - 1) / nblocks : 0;
+        for (int q = bid + slot * nblocks; q < rank + c; q += nblocks, ++slot)
+          if (slot < kMaxMine) mine[slot] = lane * 32 + (int)__fns(w, 0, q - rank + 1);
+      }
+      if (lane == 31) s_wsum[0] = incl;
+    }
+    __syncthreads();
+    return s_wsum[0];
+  }
   int base = 0;
   for (int i0 = 0; i0 < nbw; i0 += kFloodThreads) {
     const int i = i0 + tid;
@@ -1071,8 +1100,13 @@ int flood(T* data, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64
     bool vec = sizeof(T) == 2 && MODE != MODE_INPLACE && dx % 8 == 0 && b2v_aligned16(data) &&
                ((uintptr_t)out & 7u) == 0;
     if (vec) {
-      k_ff_build_i16_vec<MODE><<<grid_for(nwords * 4, 1024), 256, 0, s>>>((const int16_t*)data, out, b, (int)t0,
-                                                                         (int)t1, fill_o, w.fg, w.reach);
+      if (dx % 32 == 0)
+        k_ff_build_i16_vec<MODE, true><<<grid_for(nwords * 4, 1024), 256, 0, s>>>((const int16_t*)data, out, b, (int)t0,
+                                                                                 (int)t1, fill_o, w.fg, w.reach);
+      else
+        k_ff_build_i16_vec<MODE, false><<<grid_for(nwords * 4, 1024), 256, 0, s>>>((const int16_t*)data, out, b,
+                                                                                  (int)t0, (int)t1, fill_o, w.fg,
+                                                                                  w.reach);
     } else {
       k_ff_build<T, MODE><<<grid_for(nwords, 8), 256, 0, s>>>(data, out, b, t0, t1, fill_t, fill_o, w.fg, w.reach);
     }
