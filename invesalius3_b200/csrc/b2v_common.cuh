@@ -76,4 +76,25 @@ __device__ __forceinline__ uint32_t min_s16x2(uint32_t a, uint32_t b) {
   return r;
 }
 
+// four packed bytes -> 0x80 in every byte that is >= the (per-byte constant) threshold t4.
+// Low seven bits: (x | 0x80) - t7 keeps bit 7 exactly when x7 >= t7 and never borrows across
+// bytes; the top bit of x then decides alone (t >= 128: both needed, t < 128: either).
+__device__ __forceinline__ uint32_t ge_flags_u8x4(uint32_t x, uint32_t t7, bool t_high) {
+  const uint32_t d = (x | 0x80808080u) - t7;
+  return (t_high ? (x & d) : (x | d)) & 0x80808080u;
+}
+// 0x80-per-byte flags -> 4 bits (byte 0 -> bit 0)
+__device__ __forceinline__ uint32_t flags_to_nibble(uint32_t f) { return (((f >> 7) * 0x01020408u) >> 24) & 0xfu; }
+
+// two packed int16 -> 0x8000 in every half that lies in [lo, hi] (lo2 / hi2 = the bound in both halves)
+__device__ __forceinline__ uint32_t inrange_flags_s16x2(uint32_t w, uint32_t lo2, uint32_t hi2) {
+  const uint32_t d = max_s16x2(min_s16x2(w, hi2), lo2) ^ w;   // half == 0  <=>  in range
+  const uint32_t t = (d & 0x7fff7fffu) + 0x7fff7fffu;
+  return ~(t | d | 0x7fff7fffu);
+}
+// four packed bytes -> 0x80 in every non-zero byte
+__device__ __forceinline__ uint32_t nonzero_flags_u8x4(uint32_t x) {
+  return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+}
+
 __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -169,6 +169,12 @@ __global__ void __launch_bounds__(256) k_ff_build_i16_vec(const int16_t* __restr
   const int64_t ngroups = b.dz * b.dy * gx;     // multiple of 4
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   const int lane = threadIdx.x & 31;
+  // passable = lo <= v <= hi (MODE_EQUAL: lo = hi = t0) and out != fill, eight voxels at a time
+  const int lo = MODE == MODE_EQUAL ? t0 : (t0 < -32768 ? -32768 : t0);
+  const int hi = MODE == MODE_EQUAL ? t0 : (t1 > 32767 ? 32767 : t1);
+  const bool none = lo > hi || lo > 32767 || hi < -32768;
+  const uint32_t lo2 = ((uint32_t)lo & 0xffffu) * 0x00010001u, hi2 = ((uint32_t)hi & 0xffffu) * 0x00010001u;
+  const uint32_t fill4 = (uint32_t)fill_o * 0x01010101u;
   // four groups per thread and iteration: 4 x (128-bit + 64-bit) loads in flight
   for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x * 4; g0 < ngroups; g0 += stride) {
     int4 v[4];
@@ -200,16 +206,14 @@ __global__ void __launch_bounds__(256) k_ff_build_i16_vec(const int16_t* __restr
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       uint32_t bits = 0;
-      if (in[k]) {
-        int vv[8] = {(int16_t)(v[k].x & 0xffff), v[k].x >> 16, (int16_t)(v[k].y & 0xffff), v[k].y >> 16,
-                     (int16_t)(v[k].z & 0xffff), v[k].z >> 16, (int16_t)(v[k].w & 0xffff), v[k].w >> 16};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint8_t ob = (uint8_t)(((j < 4 ? o[k].x : o[k].y) >> (8 * (j & 3))) & 0xff);
-          bool p = (MODE == MODE_EQUAL) ? (vv[j] == t0 && ob != fill_o)
-                                        : (vv[j] >= t0 && vv[j] <= t1 && ob != fill_o);
-          bits |= (uint32_t)p << j;
-        }
+      if (in[k] && !none) {
+        // voxels 0..3 / 4..7 as 0x80-per-byte flags: in range AND out != fill
+        const uint32_t a = __byte_perm(inrange_flags_s16x2((uint32_t)v[k].x, lo2, hi2),
+                                       inrange_flags_s16x2((uint32_t)v[k].y, lo2, hi2), 0x7531);
+        const uint32_t c = __byte_perm(inrange_flags_s16x2((uint32_t)v[k].z, lo2, hi2),
+                                       inrange_flags_s16x2((uint32_t)v[k].w, lo2, hi2), 0x7531);
+        bits = flags_to_nibble(a & nonzero_flags_u8x4(o[k].x ^ fill4)) |
+               (flags_to_nibble(c & nonzero_flags_u8x4(o[k].y ^ fill4)) << 4);
       }
       uint32_t word = bits << (8 * (lane & 3));
       word |= __shfl_xor_sync(0xffffffffu, word, 1);

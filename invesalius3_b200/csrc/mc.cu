@@ -77,45 +77,55 @@ __global__ void __launch_bounds__(256) k_mc_bits(const T* __restrict__ vol, McGe
   }
 }
 
-// uint8, nx % 16 == 0, aligned: one 128-bit load = 16 voxels per lane, 2 lanes per word
+// uint8, nx % 16 == 0, aligned: one 128-bit load = 16 voxels per lane, 2 lanes per word.
+// LINEAR: nx % 32 == 0, rows hold no padding groups: group gi is voxels [16 gi, 16 gi + 16)
+// and half-word gi of the bit volume (no 64-bit division per group).
+template <bool LINEAR>
 __global__ void __launch_bounds__(256) k_mc_bits_u8_vec(const uint8_t* __restrict__ vol, McGeom g, int ithr,
                                                         uint32_t* __restrict__ bits) {
   const int gx = g.wx * 2;  // 16-voxel groups per row (padded)
   const int64_t ngroups = g.nz * g.ny * gx;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   const int lane = threadIdx.x & 31;
-  const uint32_t thr4 = (uint32_t)(ithr > 255 ? 255 : (ithr < 0 ? 0 : ithr)) * 0x01010101u;
+  const uint32_t thr = (uint32_t)(ithr > 255 ? 255 : (ithr < 0 ? 0 : ithr));
+  const uint32_t t7 = (thr & 0x7fu) * 0x01010101u;
+  const bool t_high = thr >= 128u;
   const bool none = ithr > 255;
   // four 128-bit loads in flight per thread; bytes are compared four at a time
   for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x * 4; g0 < ngroups; g0 += stride) {
     uint4 v[4];
     int64_t row[4];
     int q[4];
-    bool ok[4];
+    bool ok[4], in[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int64_t gi = g0 + k * blockDim.x + threadIdx.x;
       ok[k] = gi < ngroups;
-      row[k] = ok[k] ? gi / gx : 0;
-      q[k] = ok[k] ? (int)(gi - row[k] * gx) : 0;
+      if (LINEAR) {
+        row[k] = 0; q[k] = 0;
+        in[k] = ok[k];
+      } else {
+        row[k] = ok[k] ? gi / gx : 0;
+        q[k] = ok[k] ? (int)(gi - row[k] * gx) : 0;
+        in[k] = ok[k] && (int64_t)q[k] * 16 < g.nx;   // a padded group contributes zero bits
+      }
       v[k] = make_uint4(0u, 0u, 0u, 0u);
-      if (ok[k] && (int64_t)q[k] * 16 < g.nx) v[k] = ld_stream((const uint4*)(vol + row[k] * g.nx + (int64_t)q[k] * 16));
-      else if (ok[k]) ok[k] = true;  // padded group: contributes zero bits (unless ithr <= 0, handled below)
+      if (in[k]) v[k] = ld_stream((const uint4*)(vol + (LINEAR ? gi * 16 : row[k] * g.nx + (int64_t)q[k] * 16)));
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       uint32_t b = 0;
-      if (ok[k] && (int64_t)q[k] * 16 < g.nx && !none) {
-        const uint32_t wv[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t ge = __vcmpgeu4(wv[j], thr4);                     // 0xFF per byte >= threshold
-          b |= (((ge & 0x01010101u) * 0x01020408u) >> 24 & 0xfu) << (4 * j);
-        }
+      if (in[k] && !none) {
+        b = flags_to_nibble(ge_flags_u8x4(v[k].x, t7, t_high)) | (flags_to_nibble(ge_flags_u8x4(v[k].y, t7, t_high)) << 4) |
+            (flags_to_nibble(ge_flags_u8x4(v[k].z, t7, t_high)) << 8) |
+            (flags_to_nibble(ge_flags_u8x4(v[k].w, t7, t_high)) << 12);
       }
       uint32_t word = b << (16 * (lane & 1));
       word |= __shfl_xor_sync(0xffffffffu, word, 1);
-      if ((lane & 1) == 0 && ok[k]) bits[row[k] * g.wx + (q[k] >> 1)] = word;
+      if ((lane & 1) == 0 && ok[k]) {
+        const int64_t gi = g0 + k * blockDim.x + threadIdx.x;
+        bits[LINEAR ? gi >> 1 : row[k] * g.wx + (q[k] >> 1)] = word;
+      }
     }
   }
 }
@@ -367,6 +377,19 @@ __device__ __forceinline__ int64_t last_le(int64_t n, uint32_t k, F key) {
   return lo;
 }
 
+// the same, knowing key(start) <= k and expecting the answer near start: gallop, then bisect
+template <typename F>
+__device__ __forceinline__ int64_t last_le_from(int64_t start, int64_t n, uint32_t k, F key) {
+  int64_t lo = start, hi = start + 1, step = 1;
+  while (hi < n && key(hi) <= k) { lo = hi; step <<= 1; hi = lo + step; }
+  if (hi > n) hi = n;
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (key(mid) <= k) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 __device__ __forceinline__ uint32_t below(int i) { return i >= 32 ? 0xffffffffu : ((1u << i) - 1u); }
 
 template <typename T>
@@ -377,8 +400,16 @@ __global__ void __launch_bounds__(256) k_mc_emit_verts(const T* __restrict__ vol
                                                        float* __restrict__ verts) {
   const uint32_t V = (uint32_t)totals[0];
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < V; k += stride) {
-    const int64_t blk = last_le(nblocks, k, [&](int64_t i) { return __ldg(bsum_v + i); });
+  const int lane = threadIdx.x & 31;
+  // a warp's 32 consecutive outputs start in the same block of words or close to it: lane 0
+  // bisects the block sums once, the others gallop on from its answer
+  for (uint32_t kb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); kb < V; kb += stride) {
+    const uint32_t k = kb + lane;
+    auto bkey = [&](int64_t i) { return __ldg(bsum_v + i); };
+    int64_t blk = lane == 0 ? last_le(nblocks, kb, bkey) : 0;
+    blk = __shfl_sync(0xffffffffu, blk, 0);
+    if (k >= V) continue;
+    blk = last_le_from(blk, nblocks, k, bkey);
     const int64_t w0 = blk * kScanBlock;
     const int64_t nw = g.nwords - w0 < kScanBlock ? g.nwords - w0 : kScanBlock;
     const int64_t wi = w0 + last_le(nw, k, [&](int64_t i) { return __ldg(&info[w0 + i].w); });
@@ -433,8 +464,14 @@ __global__ void __launch_bounds__(256) k_mc_emit_tris(McGeom g, const uint32_t* 
   __syncthreads();
   const uint32_t C = (uint32_t)(totals[1] >> 32);
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < C; k += stride) {
-    const int64_t blk = last_le(nblocks, k, [&](int64_t i) { return (uint32_t)(__ldg(bsum_t + i) >> 32); });
+  const int lane = threadIdx.x & 31;
+  for (uint32_t kb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); kb < C; kb += stride) {
+    const uint32_t k = kb + lane;
+    auto bkey = [&](int64_t i) { return (uint32_t)(__ldg(bsum_t + i) >> 32); };
+    int64_t blk = lane == 0 ? last_le(nblocks, kb, bkey) : 0;
+    blk = __shfl_sync(0xffffffffu, blk, 0);
+    if (k >= C) continue;
+    blk = last_le_from(blk, nblocks, k, bkey);
     const int64_t w0 = blk * kScanBlock;
     const int64_t nw = g.nwords - w0 < kScanBlock ? g.nwords - w0 : kScanBlock;
     const int64_t wi = w0 + last_le(nw, k, [&](int64_t i) { return (uint32_t)(__ldg(toff + w0 + i) >> 32); });
@@ -520,7 +557,10 @@ static int mc_count_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int
   if (dtype == B2V_U8) {
     int thr = int_threshold(iso, 0, 255);
     if (nx % 16 == 0 && b2v_aligned16(vol))
-      k_mc_bits_u8_vec<<<grid_for(g.nwords * 2, 1024), 256, 0, s>>>((const uint8_t*)vol, g, thr, w.bits);
+      if (nx % 32 == 0)
+        k_mc_bits_u8_vec<true><<<grid_for(g.nwords * 2, 1024), 256, 0, s>>>((const uint8_t*)vol, g, thr, w.bits);
+      else
+        k_mc_bits_u8_vec<false><<<grid_for(g.nwords * 2, 1024), 256, 0, s>>>((const uint8_t*)vol, g, thr, w.bits);
     else
       k_mc_bits<uint8_t><<<grid_for(g.nwords, 8), 256, 0, s>>>((const uint8_t*)vol, g, thr, w.bits);
   } else {
