@@ -9,8 +9,9 @@
 //             number of owned vertices (popcounts) and of triangles (table lookups over
 //             the active cells only).
 //   3. scan   exclusive prefix sums of both counts (block sums -> one block -> apply).
-//   4. emit   one warp per word with work: lane = voxel (vertices) and lane = cell
-//             (triangles); a vertex id is  voff[owner word] + popcounts below the owner bit.
+//   4. emit   one thread per vertex and one thread per active cell, each finding its word by
+//             searching the offsets; a vertex id is  voff[owner word] + popcounts below the
+//             owner bit.
 #include "b2v_common.cuh"
 #define B2V_MC_QUAL __device__
 #include "mc_tables.h"
@@ -346,9 +347,12 @@ __global__ void __launch_bounds__(kScanBlock) k_mc_scan_apply(uint4* __restrict_
 // ---- 4. emit -------------------------------------------------------------------------------
 // The surface touches a few cells per word, so a warp-per-word emitter leaves most lanes idle
 // (measured: 510 us, instruction-issue bound). Instead: one thread per VERTEX and one thread
-// per ACTIVE CELL. A thread finds its word by a two-level binary search over the exclusive
-// offsets (block sums, then the 256 words of the block), then its voxel / cell inside the
-// word by popcounts. Outputs of consecutive threads are consecutive in memory.
+// per ACTIVE CELL. A thread finds its word by a two-level search over the exclusive offsets
+// (block sums: bisected once per warp, then a gallop from there; the 256 words of the block:
+// bisected), then its voxel / cell inside the word by popcounts. Outputs of consecutive
+// threads are consecutive in memory. (One thread per TRIANGLE was measured too: uniform
+// work, but every triangle repeats the search and the eight row loads: 144 us against
+// 128 us at 512^3.)
 struct McXform {
   float sx, sy, sz;
   int ox, oy, oz;
