@@ -103,8 +103,11 @@ int b2v_minmax_f32(const void* img, int dtype, int64_t n, float* minmax_out, voi
  * Algorithmic bytes: 4 B/voxel (int16 data 2 + out read 1 + out write 1). */
 int64_t b2v_floodfill_workspace_bytes(int64_t dz, int64_t dy, int64_t dx, int64_t nseeds);
 /* Convergence engine of the flood-fill family: 1 (default) = every round inside ONE
- * persistent cooperative launch (compact tile lists, grid-wide barrier per round),
- * 0 = one launch per round driven from the host. Same result either way. */
+ * persistent cooperative launch (rotating bitmaps of active tiles, grid-wide barrier per
+ * round), 0 = one launch per round driven from the host. Same result either way.
+ * Environment knobs read at call time (tuning only, results identical): B2V_FF_TILE=8
+ * (small tiles), B2V_FF_TRIPS=n (sweep sets per tile visit), B2V_FF_GRID=n (blocks of the
+ * persistent grid), B2V_FF_DEFER=n (surplus tiles a round may pass on). */
 void b2v_floodfill_set_engine(int persistent);
 int b2v_floodfill_threshold(const void* data, int dtype, int64_t dz, int64_t dy, int64_t dx,
                             const int64_t* seeds_host, int64_t nseeds, double t0, double t1, uint8_t fill,

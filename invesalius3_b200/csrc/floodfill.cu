@@ -11,10 +11,11 @@
 //   1. build   (HBM-bound, 3 B/voxel): one pass over data (+out) packs `passable` into a
 //              bit volume, 32 voxels per word along x. 512^3 voxels -> 16 MiB, i.e. the
 //              whole working set of step 2 lives in the B200's 126 MB L2.
-//   2. flood   (L2/SMEM-bound): tiles of the bit volume are pulled into shared memory and
-//              iterated to local convergence with word-parallel shifts plus a carry-chain
-//              run fill along x; tiles whose neighbours changed are re-activated for the
-//              next round. Rounds ~ geodesic length measured in tiles, not voxels.
+//   2. flood   (L2 / shared-memory latency-bound): tiles of the two bit volumes are pulled
+//              into shared memory, swept once along x (run fill by the carry trick), y and
+//              z, written back; the tiles that can gain from a grown tile are activated for
+//              the next round. Rounds ~ geodesic length measured in tiles, not voxels; all
+//              rounds run inside one persistent cooperative launch.
 //   3. write   (sparse): reached bits are expanded to `fill` stores into out.
 #include <cooperative_groups.h>
 #include <stdlib.h>
@@ -81,9 +82,9 @@ struct Workspace {
   uint32_t* reach;
   uint8_t* active[2];
   int* flags;        // flags[r] != 0  <=>  some tile is active in round r
-  int* lists;        // persistent engine: 3 rotating tile lists [3][ntiles]
-  int* lflags;       // one "already listed" flag array per list [3][ntiles]
-  int* counts;       // list lengths [3]
+  int* lists;        // persistent engine: three rotating bitmaps of active tiles [3][ceil(ntiles / 32)]
+  int* lflags;       // (unused since the bitmaps replaced the compact lists; kept so that the
+  int* counts;       //  offsets reported by b2v_floodfill_layout do not move)
   int* ctl;          // [3] error, [4] tile visits, [5] visits that grew, [6] local iterations, [7] rounds
   int64_t* seeds;    // device copy, 3 per seed
   int64_t bytes;
