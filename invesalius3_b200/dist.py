@@ -193,6 +193,10 @@ class DeviceBackend:
         from . import projection
         return projection.lmip(img, axis, tmin, tmax)
 
+    def fcm(self, img, n, axis, wl, ww, tmip):
+        from . import projection
+        return projection.fast_countour_mip(img, n, axis, wl, ww, tmip)
+
     # -- flood fill
     def ff_begin(self, data, out, seeds, t0, t1, fill, strct):
         dev, lib = self.dev, self._lib.load()
@@ -340,6 +344,28 @@ def lmip(img_slab, axis, tmin, tmax, shard: ZShard, gather=True, backend=None):
     if axis == 0:
         raise NotImplementedError("LMIP along z over Z shards needs the pipelined ray-state hand-off (next)")
     rows = _backend(backend).lmip(img_slab, axis, tmin, tmax)
+    if not gather:
+        return rows
+    sizes = [shard.bounds(r)[1] - shard.bounds(r)[0] for r in range(shard.world)]
+    return _all_gather_rows(shard, rows, sizes)
+
+
+def fast_countour_mip(img_ext, n, axis, wl, ww, tmip, shard: ZShard, gather=True, backend=None):
+    """Contour-enhanced projection (mips.rs:215-279) of the Z-sharded volume, rays along y or
+    x (axis 1 / 2), tmip 0 (maximum) or 1 (LMIP). img_ext is the extended slab with valid halo
+    planes (exchange_halo): the central differences of a shard's first and last own plane
+    read the neighbour's plane there, and clamp only at the true ends of the volume
+    (mips.rs:170-195). Every output row depends on its own plane and the two next to it, so
+    the rows of the halo planes are simply dropped. Not built yet: rays along z (they cross
+    the shards) and tmip 2, whose MIDA needs the extrema of the contour volume over own
+    planes only."""
+    if axis == 0:
+        raise NotImplementedError("contour-MIP along z over Z shards needs the ray-state hand-off (next)")
+    if tmip not in (0, 1):
+        raise NotImplementedError("contour-MIDA over Z shards needs a min/max restricted to the own planes (next)")
+    rows = _backend(backend).fcm(img_ext, n, axis, wl, ww, tmip)
+    lo, hi = int(shard.has_lo), int(shard.has_hi)
+    rows = rows[lo:rows.shape[0] - hi].contiguous()
     if not gather:
         return rows
     sizes = [shard.bounds(r)[1] - shard.bounds(r)[0] for r in range(shard.world)]

@@ -32,6 +32,12 @@ class CpuBackend:
     def sum_axis0(self, img):
         return torch.from_numpy(img.numpy().astype(np.int64).sum(axis=0))
 
+    def fcm(self, img, n, axis, wl, ww, tmip):
+        a = img.numpy()
+        out = np.zeros([(a.shape[1], a.shape[2]), (a.shape[0], a.shape[2]), (a.shape[0], a.shape[1])][axis], a.dtype)
+        self.o.fast_countour_mip(a, n, axis, wl, ww, tmip, out)
+        return torch.from_numpy(out)
+
     # ---- flood fill
     def ff_begin(self, data, out, seeds, t0, t1, fill, strct):
         d, o = data.numpy(), out.numpy()
@@ -152,6 +158,28 @@ def test_halo_mip_threshold_two_ranks(orc):
         want = np.zeros(g.shape, np.uint8)
         orc.threshold(g, *THR, want, False)
         assert np.array_equal(m, want[z0:z1])
+
+
+def rank_contour_mip(rank, world, device):
+    d, g, shard = _setup(rank, world)
+    be = CpuBackend()
+    ext = torch.from_numpy(ext_slab(g, shard).copy())
+    res = {}
+    for axis in (1, 2):
+        for tmip in (0, 1):
+            res[(axis, tmip)] = d.fast_countour_mip(ext, 2.0, axis, 300, 600, tmip, shard, backend=be).numpy()
+    return res
+
+
+def test_contour_mip_two_ranks(orc):
+    """Sharded contour-MIP (halo planes feed the central differences) = the whole-volume one."""
+    out = run_ranks("rank_contour_mip", "test_dist_gloo")
+    g = global_volume()
+    for (axis, tmip), got in out[0].items():
+        want = np.zeros([None, (g.shape[0], g.shape[2]), (g.shape[0], g.shape[1])][axis], np.int16)
+        orc.fast_countour_mip(g, 2.0, axis, 300, 600, tmip, want)
+        assert np.array_equal(got, want), (axis, tmip)
+        assert np.array_equal(out[1][(axis, tmip)], want), (axis, tmip)
 
 
 def ff_cases(g):

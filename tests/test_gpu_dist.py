@@ -28,6 +28,11 @@ def rank_all(rank, world, device):
     for axis in (1, 2):
         res[("mida", axis)] = d.mida(own, axis, 300, 600, shard).cpu().numpy()
         res[("lmip", axis)] = d.lmip(own, axis, 700, 3033, shard).cpu().numpy()
+    # contour-MIP on the extended slab (n = 1: the power is exact, so the result is bit-exact)
+    ext = torch.from_numpy(ext_slab(g, shard).copy()).to(_dev())
+    for axis in (1, 2):
+        for tmip in (0, 1):
+            res[("fcm", axis, tmip)] = d.fast_countour_mip(ext, 1.0, axis, 300, 600, tmip, shard).cpu().numpy()
     # flood fill
     for ci, (strct, seeds) in enumerate(ff_cases(g)):
         data = torch.from_numpy(ext_slab(g, shard)).to(_dev())
@@ -62,6 +67,9 @@ def _check(out, orc):
             assert np.array_equal(out[rank][("mida", axis)], want), ("mida", rank, axis)
             orc.lmip(g, axis, 700, 3033, want)
             assert np.array_equal(out[rank][("lmip", axis)], want), ("lmip", rank, axis)
+            for tmip in (0, 1):
+                orc.fast_countour_mip(g, 1.0, axis, 300, 600, tmip, want)
+                assert np.array_equal(out[rank][("fcm", axis, tmip)], want), ("fcm", rank, axis, tmip)
         z0, z1, m = out[rank]["thr"]
         want = np.zeros(g.shape, np.uint8)
         orc.threshold(g, *THR, want, False)
