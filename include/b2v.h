@@ -237,6 +237,19 @@ int b2v_mc_emit_shard(const void* vol, int dtype, int64_t nz, int64_t ny, int64_
                       int flip_y, int skip_last_plane, int32_t vertex_base, const void* next_shard_plane0_records,
                       int32_t next_shard_vertex_base, float* verts, int32_t* tris, void* stream);
 int b2v_mc_layout(int64_t nz, int64_t ny, int64_t nx, int64_t* layout_out);
+/* MIDA (mips.rs:102-168) / LMIP (mips.rs:7-86) with rays along z over ONE Z shard: the rays
+ * cross the shards, so each shard continues from the per-ray state its predecessor left and
+ * hands its own on (the per-ray operation order is that of the whole-volume walk: bit-exact).
+ * state: device uint32 [3][dy][dx] — MIDA: (fmax, alpha, colour) as float bits; LMIP: running
+ * maximum (two words), then bit 0 "inside [tmin, tmax] seen", bit 1 "ray finished".
+ * first != 0: this slab starts the rays (state is written, not read); last != 0: it ends
+ * them and writes out [dy][dx] (otherwise out may be NULL). minmax_dev: device float[2], the
+ * GLOBAL (min, max) of the volume. b2v_mida_z_partial synchronises the stream (range check). */
+int b2v_mida_z_partial(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, double wl, double ww,
+                       const float* minmax_dev, uint32_t* state, int first, int last, void* out, int out_dtype,
+                       void* workspace, void* stream);
+int b2v_lmip_z_partial(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, double tmin, double tmax,
+                       uint32_t* state, int first, int last, void* out, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,8 @@ PROTOTYPES = {
     "b2v_mc_emit_shard": (cint, [vp, cint, i64, i64, i64, dbl, vp, f32, f32, f32, i32, i32, i32, cint, cint, i32, vp,
                                  i32, vp, vp, vp]),
     "b2v_mc_layout": (cint, [i64, i64, i64, C.POINTER(i64)]),
+    "b2v_mida_z_partial": (cint, [vp, cint, i64, i64, i64, dbl, dbl, vp, vp, cint, cint, vp, cint, vp, vp]),
+    "b2v_lmip_z_partial": (cint, [vp, cint, i64, i64, i64, dbl, dbl, vp, cint, cint, vp, vp, vp]),
 }
 
 _lib = None

@@ -144,6 +144,20 @@ struct MidaOp {
   __device__ __forceinline__ bool result(U* o) const {
     return cast_result(__fadd_rn(__fmul_rn(range, final_colour), img_min), o);
   }
+  // ray state handed from one Z shard to the next: (fmax, alpha, colour) as three planes of
+  // 32-bit words; final_colour always equals colour_p, and the ray is finished exactly when
+  // the accumulated alpha reached 1 (the value step() tested)
+  __device__ __forceinline__ void load(const uint32_t* st, int64_t i, int64_t plane, bool* done) {
+    fmax = __uint_as_float(st[i]);
+    alpha_p = __uint_as_float(st[plane + i]);
+    colour_p = final_colour = __uint_as_float(st[2 * plane + i]);
+    *done = alpha_p >= 1.0f;
+  }
+  __device__ __forceinline__ void store(uint32_t* st, int64_t i, int64_t plane, bool) const {
+    st[i] = __float_as_uint(fmax);
+    st[plane + i] = __float_as_uint(alpha_p);
+    st[2 * plane + i] = __float_as_uint(colour_p);
+  }
   __device__ __forceinline__ static bool cast_result(float f, int16_t* o) { return cast_f32<int16_t>(f, o); }
   __device__ __forceinline__ static bool cast_result(float f, uint8_t* o) { return cast_f32<uint8_t>(f, o); }
 };
@@ -166,6 +180,30 @@ struct LmipOp {
   __device__ __forceinline__ bool result(T* o) const {
     *o = max_val;
     return true;
+  }
+  // ray state across Z shards: the running maximum (two words: a double needs both), then
+  // bit 0 = inside [tmin, tmax] seen, bit 1 = ray finished
+  __device__ __forceinline__ void load(const uint32_t* st, int64_t i, int64_t plane, bool* done) {
+    if (sizeof(T) == 8) {
+      const unsigned long long b = (unsigned long long)st[i] | ((unsigned long long)st[plane + i] << 32);
+      max_val = (T)__longlong_as_double((long long)b);
+    } else {
+      max_val = (T)(int)st[i];
+    }
+    const uint32_t f = st[2 * plane + i];
+    start = f & 1u;
+    *done = (f & 2u) != 0;
+  }
+  __device__ __forceinline__ void store(uint32_t* st, int64_t i, int64_t plane, bool done) const {
+    if (sizeof(T) == 8) {
+      const unsigned long long b = (unsigned long long)__double_as_longlong((double)max_val);
+      st[i] = (uint32_t)b;
+      st[plane + i] = (uint32_t)(b >> 32);
+    } else {
+      st[i] = (uint32_t)(int)max_val;
+      st[plane + i] = 0u;
+    }
+    st[2 * plane + i] = (start ? 1u : 0u) | (done ? 2u : 0u);
   }
 };
 
@@ -190,7 +228,7 @@ struct MaxOp {  // fold_axis with Bounded::min_value() (mips.rs:250-254)
 // consumed, because the recurrence is a long dependent chain the loads must not wait for. The
 // walk stops at the first sample whose step() reports the ray finished.
 template <typename T, typename S, typename Op>
-__device__ __forceinline__ void walk_keepx(const S& smp, int axis, int64_t r, int64_t x, int64_t n_l, Op& op, int* st) {
+__device__ __forceinline__ bool walk_keepx(const S& smp, int axis, int64_t r, int64_t x, int64_t n_l, Op& op, int* st) {
   if constexpr (S::kLinear) {
     constexpr int B = S::kBatch;
     const int64_t plane = smp.d.ny * smp.d.nx;
@@ -204,16 +242,17 @@ __device__ __forceinline__ void walk_keepx(const S& smp, int axis, int64_t r, in
       p += B * stride;
 #pragma unroll
       for (int k = 0; k < B; ++k)
-        if (op.step(v[k])) return;
+        if (op.step(v[k])) return true;
     }
     for (; l0 < n_l; ++l0, p += stride)
-      if (op.step(*p)) return;
+      if (op.step(*p)) return true;
   } else {
     for (int64_t l = 0; l < n_l; ++l) {
       const T v = axis == 0 ? smp.at(l, r, x, st) : smp.at(r, l, x, st);
-      if (op.step(v)) return;
+      if (op.step(v)) return true;
     }
   }
+  return false;
 }
 
 // axis 0: out[y][x], ray along z; axis 1: out[z][x], ray along y. One thread per (r, x).
@@ -495,6 +534,47 @@ bool check_axis_dims(int64_t dz, int64_t dy, int64_t dx, int axis) {
   return dz > 0 && dy > 0 && dx > 0 && axis >= 0 && axis <= 2;
 }
 
+// ---- rays along z over ONE Z shard (dist: MIDA / LMIP with rays that cross the shards) ------
+// The ray of pixel (y, x) starts from the state the previous shard left (or is started here),
+// walks this slab and leaves its state for the next shard; the last shard writes the pixel.
+// The per-ray operation order is that of the whole-volume walk, so the result is bit-exact.
+template <typename T, typename U, typename Op>
+__device__ __forceinline__ void ray_z_partial(const PlainSampler<T>& smp, Op& op, uint32_t* state, int first, int last,
+                                              U* out, int* status) {
+  const Dims d = smp.d;
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t y = blockIdx.y;
+  if (x >= d.nx) return;
+  const int64_t plane = d.ny * d.nx, i = y * d.nx + x;
+  int st = 0;
+  bool done = false;
+  op.init();
+  if (first) op.first(smp.vol[i]);
+  else op.load(state, i, plane, &done);
+  if (!done) done = walk_keepx<T>(smp, 0, y, x, d.nz, op, &st);
+  op.store(state, i, plane, done);
+  if (last) {
+    U o;
+    if (op.result(&o)) out[i] = o; else st = B2V_ERR_RANGE;
+  }
+  if (st) *status = st;
+}
+
+template <typename T, typename U>
+__global__ void __launch_bounds__(128) k_mida_z_partial(PlainSampler<T> smp, const float* __restrict__ mm, float wl,
+                                                        float ww, uint32_t* state, int first, int last,
+                                                        U* __restrict__ out, int* status) {
+  MidaOp<T, U> op = make_mida<T, U>(mm, wl, ww);
+  ray_z_partial<T, U>(smp, op, state, first, last, out, status);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_lmip_z_partial(PlainSampler<T> smp, LmipOp<T> op0, uint32_t* state, int first,
+                                                        int last, T* __restrict__ out, int* status) {
+  LmipOp<T> op = op0;
+  ray_z_partial<T, T>(smp, op, state, first, last, out, status);
+}
+
 }  // namespace
 
 extern "C" int64_t b2v_proj_workspace_bytes(int64_t n) { return 256 + b2v_minmax_workspace_bytes(n); }
@@ -625,4 +705,71 @@ extern "C" int b2v_fast_countour_mip(const void* img, int dtype, int64_t dz, int
   else B2V_REQUIRE(false, B2V_ERR_ARG, "fast_countour_mip: only int16 and uint8 volumes are supported on the device");
   if (rc) return rc;
   return finish_status(w.status, s, "fast_countour_mip");
+}
+
+extern "C" int b2v_mida_z_partial(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, double wl, double ww,
+                                  const float* minmax_dev, uint32_t* state, int first, int last, void* out,
+                                  int out_dtype, void* workspace, void* stream) {
+  B2V_REQUIRE(img && workspace && minmax_dev && state && (out || !last), B2V_ERR_ARG, "mida_z_partial: null pointer");
+  B2V_REQUIRE(dz > 0 && dy > 0 && dx > 0, B2V_ERR_ARG, "mida_z_partial: empty slab");
+  B2V_REQUIRE(dy <= 65535, B2V_ERR_ARG, "mida_z_partial: more than 65535 output rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  ProjWs w = carve(workspace);
+  Dims d = {dz, dy, dx};
+  int rc;
+  k_status_init<<<1, 1, 0, s>>>(w.status);
+  if ((rc = b2v_check_launch("k_status_init"))) return rc;
+  B2V_CUDA(cudaMemcpyAsync(w.mm_f, minmax_dev, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  const dim3 grid((unsigned)ceil_div64(dx, 128), (unsigned)dy);
+  if (dtype == B2V_I16 && out_dtype == B2V_I16) {
+    PlainSampler<int16_t> smp = {(const int16_t*)img, d};
+    k_mida_z_partial<int16_t, int16_t><<<grid, 128, 0, s>>>(smp, w.mm_f, (float)(int16_t)wl, (float)(int16_t)ww, state,
+                                                            first, last, (int16_t*)out, w.status);
+  } else if (dtype == B2V_U8 && out_dtype == B2V_U8) {
+    PlainSampler<uint8_t> smp = {(const uint8_t*)img, d};
+    k_mida_z_partial<uint8_t, uint8_t><<<grid, 128, 0, s>>>(smp, w.mm_f, (float)(uint8_t)wl, (float)(uint8_t)ww, state,
+                                                          first, last, (uint8_t*)out, w.status);
+  } else if (dtype == B2V_F64 && out_dtype == B2V_U8) {
+    PlainSampler<double> smp = {(const double*)img, d};
+    k_mida_z_partial<double, uint8_t><<<grid, 128, 0, s>>>(smp, w.mm_f, (float)wl, (float)ww, state, first, last,
+                                                         (uint8_t*)out, w.status);
+  } else {
+    B2V_REQUIRE(false, B2V_ERR_ARG, "Invalid image or output type");
+  }
+  if ((rc = b2v_check_launch("k_mida_z_partial"))) return rc;
+  return finish_status(w.status, s, "mida_z_partial");
+}
+
+extern "C" int b2v_lmip_z_partial(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, double tmin,
+                                  double tmax, uint32_t* state, int first, int last, void* out, void* workspace,
+                                  void* stream) {
+  B2V_REQUIRE(img && workspace && state && (out || !last), B2V_ERR_ARG, "lmip_z_partial: null pointer");
+  B2V_REQUIRE(dz > 0 && dy > 0 && dx > 0, B2V_ERR_ARG, "lmip_z_partial: empty slab");
+  B2V_REQUIRE(dy <= 65535, B2V_ERR_ARG, "lmip_z_partial: more than 65535 output rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  ProjWs w = carve(workspace);
+  Dims d = {dz, dy, dx};
+  int rc;
+  k_status_init<<<1, 1, 0, s>>>(w.status);
+  if ((rc = b2v_check_launch("k_status_init"))) return rc;
+  const dim3 grid((unsigned)ceil_div64(dx, 128), (unsigned)dy);
+  if (dtype == B2V_I16) {
+    PlainSampler<int16_t> smp = {(const int16_t*)img, d};
+    LmipOp<int16_t> op;
+    op.tmin = (int16_t)tmin; op.tmax = (int16_t)tmax;
+    k_lmip_z_partial<int16_t><<<grid, 128, 0, s>>>(smp, op, state, first, last, (int16_t*)out, w.status);
+  } else if (dtype == B2V_U8) {
+    PlainSampler<uint8_t> smp = {(const uint8_t*)img, d};
+    LmipOp<uint8_t> op;
+    op.tmin = (uint8_t)tmin; op.tmax = (uint8_t)tmax;
+    k_lmip_z_partial<uint8_t><<<grid, 128, 0, s>>>(smp, op, state, first, last, (uint8_t*)out, w.status);
+  } else if (dtype == B2V_F64) {
+    PlainSampler<double> smp = {(const double*)img, d};
+    LmipOp<double> op;
+    op.tmin = tmin; op.tmax = tmax;
+    k_lmip_z_partial<double><<<grid, 128, 0, s>>>(smp, op, state, first, last, (double*)out, w.status);
+  } else {
+    B2V_REQUIRE(false, B2V_ERR_ARG, "Invalid image or output type");
+  }
+  return b2v_check_launch("k_lmip_z_partial");
 }

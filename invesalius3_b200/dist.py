@@ -136,6 +136,44 @@ def _swap(shard: ZShard, send_lo, send_hi, like_lo=None, like_hi=None):
     return recv_lo, recv_hi
 
 
+def _send_up(shard: ZShard, t: torch.Tensor):
+    """Blocking send of `t` to the next shard."""
+    dist.send(_stage(shard, _bytes(t)), shard.rank + 1, group=shard.group)
+
+
+def _recv_from_below(shard: ZShard, like: torch.Tensor) -> torch.Tensor:
+    """Blocking receive, from the previous shard, of a tensor shaped like `like`."""
+    buf = torch.empty_like(_stage(shard, _bytes(like)))
+    dist.recv(buf, shard.rank - 1, group=shard.group)
+    return buf.to(like.device).view(like.dtype).view(like.shape)
+
+
+def _broadcast_from_last(shard: ZShard, t: torch.Tensor) -> torch.Tensor:
+    h = _stage(shard, _bytes(t))
+    dist.broadcast(h, shard.world - 1, group=shard.group)
+    return h.to(t.device).view(t.dtype).view(t.shape)
+
+
+def _rays_along_z(shard: ZShard, new_state, walk, out_like, gather):
+    """Rays that cross the shards (MIDA / LMIP along z): the per-ray state travels up the chain
+    of shards, every shard walking its own planes in turn — the operation order per ray is the
+    whole-volume one, so the image is bit-exact. The last shard holds the image; with
+    gather=True it is broadcast. (The chain is sequential; pipelining pixel tiles through it
+    is the next step.)"""
+    state = new_state()
+    first, last = not shard.has_lo, not shard.has_hi
+    if not first:
+        state.copy_(_recv_from_below(shard, state))
+    out = walk(state, first, last)
+    if not last:
+        _send_up(shard, state)
+    if not gather:
+        return out
+    if out is None:
+        out = out_like()
+    return _broadcast_from_last(shard, out)
+
+
 def _all_gather_rows(shard: ZShard, rows: torch.Tensor, sizes):
     """all_gather of per-shard row blocks of unequal height (padded to the tallest)."""
     m = max(sizes)
@@ -196,6 +234,18 @@ class DeviceBackend:
     def fcm(self, img, n, axis, wl, ww, tmip):
         from . import projection
         return projection.fast_countour_mip(img, n, axis, wl, ww, tmip)
+
+    def ray_state(self, img):
+        from . import projection
+        return projection.ray_state(img)
+
+    def mida_z(self, img, wl, ww, minmax, state, first, last):
+        from . import projection
+        return projection.mida_z_partial(img, wl, ww, minmax, state, first, last)
+
+    def lmip_z(self, img, tmin, tmax, state, first, last):
+        from . import projection
+        return projection.lmip_z_partial(img, tmin, tmax, state, first, last)
 
     # -- flood fill
     def ff_begin(self, data, out, seeds, t0, t1, fill, strct):
@@ -321,18 +371,23 @@ def mip(img_slab, axis, kind, shard: ZShard, gather=True, backend=None):
 
 
 def mida(img_slab, axis, wl, ww, shard: ZShard, gather=True, backend=None):
-    """MIDA of the whole volume from per-shard slabs, rays along y or x (axis 1 / 2): the only
-    global quantity is the (min, max) pair of mips.rs:113-122 — two 4-byte all_reduces — then
-    every shard walks its own rays. Rays along z (axis 0) cross the shards: that case needs the
-    per-ray state (fmax, alpha, colour) handed from shard to shard and is not built yet."""
-    if axis == 0:
-        raise NotImplementedError("MIDA along z over Z shards needs the pipelined ray-state hand-off (next)")
+    """MIDA of the whole volume from per-shard slabs. The only global quantity is the (min,
+    max) pair of mips.rs:113-122 — two 4-byte all_reduces. Rays along y or x (axis 1 / 2) stay
+    inside a shard; rays along z (axis 0) cross the shards and hand their state (fmax, alpha,
+    colour) from shard to shard (with gather=False only the last shard returns the image)."""
     be = _backend(backend)
     mm = be.minmax(img_slab).clone()
     lo, hi = mm[0:1].clone(), mm[1:2].clone()
     _all_reduce(shard, lo, dist.ReduceOp.MIN)
     _all_reduce(shard, hi, dist.ReduceOp.MAX)
-    rows = be.mida(img_slab, axis, wl, ww, torch.cat([lo, hi]))
+    mm = torch.cat([lo, hi])
+    if axis == 0:
+        odt = {torch.int16: torch.int16, torch.uint8: torch.uint8, torch.float64: torch.uint8}[img_slab.dtype]
+        return _rays_along_z(
+            shard, lambda: be.ray_state(img_slab),
+            lambda state, first, last: be.mida_z(img_slab, wl, ww, mm, state, first, last),
+            lambda: torch.empty(img_slab.shape[1:], dtype=odt, device=img_slab.device), gather)
+    rows = be.mida(img_slab, axis, wl, ww, mm)
     if not gather:
         return rows
     sizes = [shard.bounds(r)[1] - shard.bounds(r)[0] for r in range(shard.world)]
@@ -340,10 +395,15 @@ def mida(img_slab, axis, wl, ww, shard: ZShard, gather=True, backend=None):
 
 
 def lmip(img_slab, axis, tmin, tmax, shard: ZShard, gather=True, backend=None):
-    """LMIP with rays along y or x: purely local rows (mips.rs:7-86 keeps no global state)."""
+    """LMIP (mips.rs:7-86): rays along y or x are purely local rows; rays along z hand (running
+    maximum, inside-range seen, finished) from shard to shard."""
+    be = _backend(backend)
     if axis == 0:
-        raise NotImplementedError("LMIP along z over Z shards needs the pipelined ray-state hand-off (next)")
-    rows = _backend(backend).lmip(img_slab, axis, tmin, tmax)
+        return _rays_along_z(
+            shard, lambda: be.ray_state(img_slab),
+            lambda state, first, last: be.lmip_z(img_slab, tmin, tmax, state, first, last),
+            lambda: torch.empty(img_slab.shape[1:], dtype=img_slab.dtype, device=img_slab.device), gather)
+    rows = be.lmip(img_slab, axis, tmin, tmax)
     if not gather:
         return rows
     sizes = [shard.bounds(r)[1] - shard.bounds(r)[0] for r in range(shard.world)]
@@ -356,11 +416,11 @@ def fast_countour_mip(img_ext, n, axis, wl, ww, tmip, shard: ZShard, gather=True
     planes (exchange_halo): the central differences of a shard's first and last own plane
     read the neighbour's plane there, and clamp only at the true ends of the volume
     (mips.rs:170-195). Every output row depends on its own plane and the two next to it, so
-    the rows of the halo planes are simply dropped. Not built yet: rays along z (they cross
-    the shards) and tmip 2, whose MIDA needs the extrema of the contour volume over own
-    planes only."""
+    the rows of the halo planes are simply dropped. Not built yet: rays along z (the contour
+    sampler would have to skip the halo planes) and tmip 2, whose MIDA needs the extrema of
+    the contour volume over own planes only."""
     if axis == 0:
-        raise NotImplementedError("contour-MIP along z over Z shards needs the ray-state hand-off (next)")
+        raise NotImplementedError("contour-MIP along z over Z shards: the sampler cannot skip halo planes yet (next)")
     if tmip not in (0, 1):
         raise NotImplementedError("contour-MIDA over Z shards needs a min/max restricted to the own planes (next)")
     rows = _backend(backend).fcm(img_ext, n, axis, wl, ww, tmip)

@@ -73,3 +73,52 @@ def fast_countour_mip(image: torch.Tensor, n: float, axis: int, wl, ww, tmip: in
         _lib.call("b2v_fast_countour_mip", _p(image), dtype_code(image), dz, dy, dx, float(n), axis, float(wl),
                   float(ww), int(tmip), _p(out), _p(ws), _stream())
     return out
+
+
+# ---- rays along z over one Z shard (dist.mida / dist.lmip, axis 0) ---------------------------
+def ray_state(image: torch.Tensor) -> torch.Tensor:
+    """Per-ray state handed from shard to shard: uint32 words [3][dy][dx] (b2v.h)."""
+    return torch.zeros((3, image.shape[1], image.shape[2]), dtype=torch.int32, device=image.device)
+
+
+def _z_partial_prep(image, state, last, out_dtype):
+    _dense(image, "image")
+    if image.dim() != 3:
+        raise TypeError("image must be 3-dimensional")
+    if state.dtype != torch.int32 or tuple(state.shape) != (3, image.shape[1], image.shape[2]) or not state.is_cuda:
+        raise TypeError("state must be an int32 CUDA tensor of shape (3, dy, dx)")
+    _dense(state, "state")
+    out = torch.empty((image.shape[1], image.shape[2]), dtype=out_dtype, device=image.device) if last else None
+    ws = _workspace(_lib.load().b2v_proj_workspace_bytes(image.numel()), image.device)
+    return out, ws
+
+
+def mida_z_partial(image: torch.Tensor, wl, ww, minmax: torch.Tensor, state: torch.Tensor, first: bool,
+                   last: bool) -> torch.Tensor | None:
+    """One shard's stretch of the MIDA rays along z (b2v_mida_z_partial). Returns the image on
+    the last shard, None elsewhere; `state` is updated in place."""
+    odt = {torch.int16: torch.int16, torch.uint8: torch.uint8, torch.float64: torch.uint8}.get(image.dtype)
+    if odt is None:
+        raise TypeError("Invalid image or output type")
+    if minmax.dtype != torch.float32 or minmax.numel() != 2 or not minmax.is_cuda:
+        raise TypeError("minmax must be a float32 CUDA tensor with 2 elements")
+    out, ws = _z_partial_prep(image, state, last, odt)
+    dz, dy, dx = image.shape
+    with torch.cuda.device(image.device):
+        _lib.call("b2v_mida_z_partial", _p(image), dtype_code(image), dz, dy, dx, float(wl), float(ww),
+                  _p(minmax.contiguous()), _p(state), int(bool(first)), int(bool(last)),
+                  _p(out) if out is not None else None, _lib.I16 if odt == torch.int16 else _lib.U8, _p(ws),
+                  _stream())
+    return out
+
+
+def lmip_z_partial(image: torch.Tensor, tmin, tmax, state: torch.Tensor, first: bool, last: bool):
+    """One shard's stretch of the LMIP rays along z (b2v_lmip_z_partial)."""
+    out, ws = _z_partial_prep(image, state, last, image.dtype)
+    dz, dy, dx = image.shape
+    with torch.cuda.device(image.device):
+        _lib.call("b2v_lmip_z_partial", _p(image), dtype_code(image), dz, dy, dx, float(tmin), float(tmax),
+                  _p(state), int(bool(first)), int(bool(last)), _p(out) if out is not None else None, _p(ws),
+                  _stream())
+    return out
+

@@ -32,6 +32,73 @@ class CpuBackend:
     def sum_axis0(self, img):
         return torch.from_numpy(img.numpy().astype(np.int64).sum(axis=0))
 
+    # ---- rays along z with the state handed from shard to shard (float32 arithmetic in the
+    # order of mips.rs:102-168 / :7-86, vectorised over the pixels of a plane)
+    def minmax(self, img):
+        a = img.numpy()
+        return torch.tensor([float(a.min()), float(a.max())], dtype=torch.float32)
+
+    def ray_state(self, img):
+        return torch.zeros((3, img.shape[1], img.shape[2]), dtype=torch.int32)
+
+    def mida_z(self, img, wl, ww, minmax, state, first, last):
+        a = img.numpy()
+        f32 = np.float32
+        st = state.numpy().view(np.float32)
+        fmax, alpha_p, colour_p = st[0], st[1], st[2]
+        mn, mx = f32(minmax[0].item()), f32(minmax[1].item())
+        rng = f32(mx - mn)
+        inv = f32(1.0) / rng
+        wl, ww = f32(a.dtype.type(wl)), f32(a.dtype.type(ww))
+        half = ww / f32(2.0)
+        wmn, wmx = f32(wl - half), f32(wl + half)
+        with np.errstate(all="ignore"):
+            for z in range(a.shape[0]):
+                act = ~(alpha_p >= f32(1.0))
+                vl = a[z].astype(f32)
+                fpi = inv * (vl - mn)
+                gt = fpi > fmax
+                dl = np.where(gt, fpi - fmax, f32(0.0)).astype(f32)
+                nfmax = np.where(gt, fpi, fmax).astype(f32)
+                bt = f32(1.0) - dl
+                alpha = np.where(vl < wmn, f32(0.0), np.where(vl > wmx, f32(1.0), (vl - wmn) / (wmx - wmn))).astype(f32)
+                one_m = f32(1.0) - bt * alpha_p
+                colour = bt * colour_p + (one_m * fpi) * alpha
+                cur = bt * alpha_p + one_m * alpha
+                fmax[act] = nfmax[act]
+                colour_p[act] = colour[act]
+                alpha_p[act] = cur[act]
+        if not last:
+            return None
+        val = rng * colour_p + mn
+        odt = np.uint8 if a.dtype == np.float64 else a.dtype
+        return torch.from_numpy(np.trunc(val).astype(odt))
+
+    def lmip_z(self, img, tmin, tmax, state, first, last):
+        a = img.numpy()
+        st = state.numpy()
+        tmin, tmax = a.dtype.type(tmin), a.dtype.type(tmax)
+        if first:
+            mv = a[0].copy()
+            start = (a[0] >= tmin) & (a[0] <= tmax)
+            done = np.zeros(mv.shape, bool)
+        else:
+            mv = st[0].astype(a.dtype)
+            start = (st[2] & 1).astype(bool)
+            done = (st[2] & 2).astype(bool)
+        for z in range(a.shape[0]):
+            v = a[z]
+            act = ~done
+            gt = v > mv
+            stop = act & ~gt & (v < mv) & start
+            mv = np.where(act & gt, v, mv)
+            done |= stop
+            start |= act & ~stop & (v >= tmin) & (v <= tmax)
+        st[0] = mv.astype(np.int32)
+        st[1] = 0
+        st[2] = start.astype(np.int32) | (done.astype(np.int32) << 1)
+        return torch.from_numpy(np.ascontiguousarray(mv)) if last else None
+
     def fcm(self, img, n, axis, wl, ww, tmip):
         a = img.numpy()
         out = np.zeros([(a.shape[1], a.shape[2]), (a.shape[0], a.shape[2]), (a.shape[0], a.shape[1])][axis], a.dtype)
@@ -180,6 +247,32 @@ def test_contour_mip_two_ranks(orc):
         orc.fast_countour_mip(g, 2.0, axis, 300, 600, tmip, want)
         assert np.array_equal(got, want), (axis, tmip)
         assert np.array_equal(out[1][(axis, tmip)], want), (axis, tmip)
+
+
+def rank_rays_along_z(rank, world, device):
+    d, g, shard = _setup(rank, world)
+    be = CpuBackend()
+    own = torch.from_numpy(np.ascontiguousarray(g[shard.z0:shard.z1]))
+    res = {}
+    for wl, ww in ((300, 600), (40, 1), (3000, 30000)):
+        res[("mida", wl, ww)] = d.mida(own, 0, wl, ww, shard, backend=be).numpy()
+    for tmin, tmax in ((700, 3033), (-200, 100)):
+        res[("lmip", tmin, tmax)] = d.lmip(own, 0, tmin, tmax, shard, backend=be).numpy()
+    return res
+
+
+def test_mida_lmip_along_z_two_ranks(orc):
+    """Rays that cross the shards: the state hand-off reproduces the whole-volume walk."""
+    out = run_ranks("rank_rays_along_z", "test_dist_gloo")
+    g = global_volume()
+    for key, got in out[0].items():
+        want = np.zeros(g.shape[1:], np.int16)
+        if key[0] == "mida":
+            orc.mida(g, 0, key[1], key[2], want)
+        else:
+            orc.lmip(g, 0, key[1], key[2], want)
+        assert np.array_equal(got, want), key
+        assert np.array_equal(out[1][key], want), key
 
 
 def ff_cases(g):

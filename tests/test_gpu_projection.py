@@ -178,3 +178,51 @@ def test_mida_wide_value_range_and_foreign_minmax(rs, orc, axis):
             assert outcome[0] is None and outcome[1] is None, pair
         else:
             assert torch.equal(outcome[0], outcome[1]), pair
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.uint8, np.float64])
+def test_rays_along_z_in_stretches(rs, orc, dtype):
+    """b2v_mida_z_partial / b2v_lmip_z_partial: a ray walked slab by slab with its state handed
+    on equals the whole-volume walk bit for bit (the Z-sharded axis-0 projections, here on one
+    device, cut at uneven planes including a one-plane slab)."""
+    import torch
+    from invesalius3_b200 import device as dev, projection
+    shape = (23, 19, 150)
+    if dtype == np.int16:
+        vol = _ct_like(shape, 21)
+        windows, ranges = [(300, 600), (40, 1), (3000, 30000)], [(700, 3033), (-200, 100)]
+    elif dtype == np.uint8:
+        vol = np.random.default_rng(22).integers(0, 256, shape).astype(np.uint8)
+        windows, ranges = [(120, 80), (10, 250)], [(100, 200), (0, 255)]
+    else:
+        vol = np.random.default_rng(23).random(shape) * 255.0
+        windows, ranges = [(120, 80)], [(100.5, 200.25)]
+    t = torch.from_numpy(vol).cuda()
+    cuts = [0, 5, 6, 17, 23]
+    bad = []
+    mm = dev.minmax(t)
+    for wl, ww in windows:
+        odt = np.uint8 if dtype == np.float64 else dtype
+        want = np.zeros(shape[1:], odt)
+        orc.mida(vol, 0, wl, ww, want)
+        state = projection.ray_state(t)
+        got = None
+        for i in range(len(cuts) - 1):
+            got = projection.mida_z_partial(t[cuts[i]:cuts[i + 1]].contiguous(), wl, ww, mm, state, i == 0,
+                                            i == len(cuts) - 2)
+        if not np.array_equal(got.cpu().numpy(), want):
+            bad.append(("mida", wl, ww, int((got.cpu().numpy() != want).sum())))
+        whole = projection.mida_z_partial(t, wl, ww, mm, projection.ray_state(t), True, True)
+        if not np.array_equal(whole.cpu().numpy(), want):
+            bad.append(("mida-one-stretch", wl, ww))
+    for tmin, tmax in ranges:
+        want = np.zeros(shape[1:], dtype)
+        orc.lmip(vol, 0, tmin, tmax, want)
+        state = projection.ray_state(t)
+        got = None
+        for i in range(len(cuts) - 1):
+            got = projection.lmip_z_partial(t[cuts[i]:cuts[i + 1]].contiguous(), tmin, tmax, state, i == 0,
+                                            i == len(cuts) - 2)
+        if not np.array_equal(got.cpu().numpy(), want):
+            bad.append(("lmip", tmin, tmax, int((got.cpu().numpy() != want).sum())))
+    assert not bad, bad
