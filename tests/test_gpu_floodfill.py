@@ -273,3 +273,33 @@ def test_floodfill_wide_rows_many_x_tiles(rs, orc):
         rs.floodfill_threshold(data, seeds, 500, 1500, 200, st, got)
         assert np.array_equal(got, want), conn
         assert (want == 200).sum() > 1000
+
+
+@pytest.mark.parametrize("shape", [(37, 45, 1100), (16, 16, 544), (33, 17, 2048)])
+def test_floodfill_canonical_tiles_across_x(rs, orc, shape):
+    """The 6-connected fast path on 16 x 16 x 16-word tiles with several tiles along x (rows
+    wider than 512 voxels), partial tiles on every side: the run fill has to cross word and
+    tile boundaries through the halo words. Also in place and with the small-tile knob."""
+    import os
+    rng = np.random.default_rng(31)
+    # long thin structures along x so that the flood travels through many x tiles
+    data = (ndimage.gaussian_filter(rng.normal(size=shape), (1.5, 1.5, 12)) > 0.0).astype(np.int16) * 1000
+    dz, dy, dx = shape
+    seeds = [(1, 1, 0), (dx - 2, dy - 2, dz - 1), (dx // 2, dy // 2, dz // 2), (515, 3, 5)]
+    st = generate_binary_structure(3, 1)
+    want = np.zeros(shape, np.uint8)
+    orc.floodfill_threshold(data, seeds, 500, 1500, 200, st, want)
+    assert (want == 200).sum() > 5000
+    for knob in (None, "8"):
+        if knob: os.environ["B2V_FF_TILE"] = knob
+        try:
+            got = np.zeros(shape, np.uint8)
+            rs.floodfill_threshold(data, seeds, 500, 1500, 200, st, got)
+        finally:
+            os.environ.pop("B2V_FF_TILE", None)
+        assert np.array_equal(got, want), knob
+    mask = (data > 0).astype(np.uint8) * 255
+    want_ip = mask.copy(); got_ip = mask.copy()
+    orc.floodfill_threshold_inplace(want_ip, seeds, 255, 255, 7, st)
+    rs.floodfill_threshold_inplace(got_ip, seeds, 255, 255, 7, st)
+    assert np.array_equal(got_ip, want_ip)
