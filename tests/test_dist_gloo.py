@@ -275,6 +275,32 @@ def test_mida_lmip_along_z_two_ranks(orc):
         assert np.array_equal(out[1][key], want), key
 
 
+def test_mida_lmip_along_z_three_ranks(orc):
+    """World size 3: the middle shard both receives and forwards the ray state."""
+    out = run_ranks("rank_rays_along_z", "test_dist_gloo", world=3)
+    g = global_volume()
+    for key, got in out[0].items():
+        want = np.zeros(g.shape[1:], np.int16)
+        (orc.mida if key[0] == "mida" else orc.lmip)(g, 0, key[1], key[2], want)
+        for r in range(3):
+            assert np.array_equal(out[r][key], want), (key, r)
+
+
+def test_contour_mip_three_ranks_and_unsupported_modes(orc):
+    out = run_ranks("rank_contour_mip", "test_dist_gloo", world=3)
+    g = global_volume()
+    for (axis, tmip), got in out[1].items():   # the middle shard has a halo plane on both sides
+        want = np.zeros([None, (g.shape[0], g.shape[2]), (g.shape[0], g.shape[1])][axis], np.int16)
+        orc.fast_countour_mip(g, 2.0, axis, 300, 600, tmip, want)
+        assert np.array_equal(got, want), (axis, tmip)
+    from invesalius3_b200 import dist as d
+    shard = d.ZShard(g.shape[0], 0, 1)
+    with pytest.raises(NotImplementedError):
+        d.fast_countour_mip(torch.zeros((4, 4, 4), dtype=torch.int16), 2.0, 0, 300, 600, 0, shard, backend=CpuBackend())
+    with pytest.raises(NotImplementedError):
+        d.fast_countour_mip(torch.zeros((4, 4, 4), dtype=torch.int16), 2.0, 1, 300, 600, 2, shard, backend=CpuBackend())
+
+
 def ff_cases(g):
     from scipy.ndimage import generate_binary_structure
     def first(z):
