@@ -4,13 +4,27 @@ threshold -> seeded flood-fill region grow -> marching cubes on a 512^3 int16 CT
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-One JSON line on stdout (rank 0). `value` = Mvoxel/s of the whole job with inputs resident in
-HBM (CUDA-event timed, max over ranks); `e2e` = the same three ops called through the
-reference-shaped numpy API (slice_ops / invesalius_rs / surface_process) on pinned HOST
-buffers, host<->device copies inside the timed region; `roofline` = the dominant kernel
-against the measured HBM peak; `cpu_baseline` = the CPU restatement of the reference path
-timed on this box's host cores on a bounded sample (a reported baseline, not the target).
-`--impl reference` times that CPU path alone.
+One JSON line on stdout (rank 0).
+
+`value`     Mvoxel/s of the whole job with inputs resident in HBM (CUDA-event timed, max over
+            ranks). At N > 1 the job is ONE (N*512) x 512 x 512 volume, Z-sharded (weak scaling),
+            region-grown from ONE seed in its middle slice: the wave has to cross every shard —
+            the honest multi-GPU version of "the user clicks once". The easier workload (one
+            seed per shard, waves meet at the boundaries) is timed too and reported in
+            `config.seeding`.
+`e2e`       N = 1: the same three ops through the reference-shaped numpy API (slice_ops /
+            invesalius_rs / surface_process) on pinned HOST buffers, copies inside the timed
+            region. N > 1: the sharded pipeline fed from / drained to pinned host buffers (image
+            uploaded once per step; stated in `e2e.api`).
+`verified`  the GPU results are checked in this run: N = 1 against the CPU restatement of the
+            reference on the same 512^3 volume (reached-voxel count, mask equality, V, T, the
+            triangle array and the vertices); N > 1 against a single-GPU run of the whole
+            gathered volume on rank 0 (count, V, T, order-independent checksums of both arrays).
+`roofline`  the dominant stage against the measured HBM peak.
+`cpu_baseline` / `--impl reference`  the CPU restatement of the reference path timed on this
+            box's host cores on the SAME 512^3 volume (full, not a slab).
+`extra`     (N = 1) driver-visible secondary results: 1024^3 threshold / MaxIP x3 / MIDA with
+            their roofline fractions, 512^3 watershed times + agreement with the CPU checker.
 """
 from __future__ import annotations
 
@@ -20,7 +34,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 from pathlib import Path
 
@@ -33,13 +46,14 @@ METRIC = "Mvoxels/s threshold+floodfill+MC on 512^3 int16"
 UNIT = "Mvoxel/s"
 THR = (226, 3071)          # presets.py "Bone"
 SPACING = (1.0, 1.0, 1.0)
-SEED_SLICE_FRAC = 0.5
 FILL = 254
 
 
-def workload_desc(n):
-    return (f"{n}^3 synthetic int16 CT phantom (seed 2) per GPU: threshold [226,3071] -> 6-connected flood fill "
-            f"from one seed per {n}^3 shard -> marching cubes iso 127 on the grown mask")
+def workload_desc(n, world):
+    vol = f"{n}^3" if world == 1 else f"{n * world}x{n}x{n}"
+    return (f"{vol} synthetic int16 CT phantom (seed 2){'' if world == 1 else f', Z-sharded {n}^3 per GPU'}: "
+            f"threshold [226,3071] -> 6-connected flood fill from ONE seed in the middle slice -> marching cubes "
+            f"iso 127 on the grown mask")
 
 
 def measured_peak():
@@ -49,28 +63,36 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def make_volume(n, world=1, zrange=None):
-    """The job's volume is (n*world) x n x n, Z-sharded; returns the planes `zrange` (default:
-    all) and the global seeds (x, y, z): one per n^3 shard, in the shard's middle slice (the
-    first in-range voxel in raveled order). One connected region spans all shards, so the
-    waves started in different shards meet at the shard boundaries."""
+def global_seed(n, world):
+    """(x, y, z) of the first in-range voxel (raveled order) of the volume's middle slice."""
     from invesalius3_b200 import phantom
     DZ = n * world
-    seeds = []
-    for r in range(world):
-        zmid = r * n + int(n * SEED_SLICE_FRAC)
-        mid = phantom.ct((DZ, n, n), seed=2, zrange=(zmid, zmid + 1))
-        sx, sy, _ = phantom.first_seed_in_range(mid, 0, *THR)
-        seeds.append((sx, sy, zmid))
-    vol = phantom.ct((DZ, n, n), seed=2, zrange=zrange)
-    return vol, seeds
+    zmid = DZ // 2
+    mid = phantom.ct((DZ, n, n), seed=2, zrange=(zmid, zmid + 1))
+    sx, sy, _ = phantom.first_seed_in_range(mid, 0, *THR)
+    return (sx, sy, zmid)
+
+
+def shard_seed(own, z0):
+    """One seed inside this shard: the first in-range voxel of the plane closest to the shard's
+    middle that has one (the shards at the ends of a long volume hold mostly air). None if the
+    shard has no in-range voxel at all."""
+    nz = own.shape[0]
+    order = sorted(range(nz), key=lambda z: abs(z - nz // 2))
+    for z in order:
+        idx = np.flatnonzero((own[z] >= THR[0]) & (own[z] <= THR[1]))
+        if idx.size:
+            yy, xx = divmod(int(idx[0]), own.shape[2])
+            return (xx, yy, z0 + z)
+    return None
 
 
 # ------------------------------------------------------------------ CPU reference path
-def cpu_step(vol, seed, threads):
+def cpu_step(vol, seed, threads, want_arrays=False):
     """The reference's CPU path restated (oracle/): NumPy threshold statements verbatim
     (single thread, as in the reference), serial stack flood fill, marching cubes over
-    20(+1)-slice Z pieces on a thread pool (surface.py:1360-1381 uses a process pool)."""
+    20(+1)-slice Z pieces on a thread pool (surface.py:1360-1381 uses a process pool).
+    Returns (reached voxels, triangles[, mask, out])."""
     import oracle
     from concurrent.futures import ThreadPoolExecutor
     from scipy.ndimage import generate_binary_structure
@@ -91,25 +113,18 @@ def cpu_step(vol, seed, threads):
 
     with ThreadPoolExecutor(max_workers=max(1, min(threads, len(rois)))) as ex:
         ntri = sum(ex.map(piece, rois))
-    return ntri
+    count = int(np.count_nonzero(out == FILL))
+    if want_arrays:
+        return count, ntri, mm, out
+    return count, ntri
 
 
-def cpu_sample(vol, seed, nslices):
-    """A slab of the workload around the seed slice (bounded CPU time)."""
-    dz = vol.shape[0]
-    z0 = max(0, min(dz - nslices, seed[2] - nslices // 2))
-    return np.ascontiguousarray(vol[z0:z0 + nslices]), (seed[0], seed[1], seed[2] - z0)
-
-
-def time_cpu(vol, seed, nslices, reps, threads):
-    sub, sseed = cpu_sample(vol, seed, nslices)
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        cpu_step(sub, sseed, threads)
-        ts.append(time.perf_counter() - t0)
-    t = min(ts)
-    return sub.size / t / 1e6, f"{sub.shape[0]}x{sub.shape[1]}x{sub.shape[2]} slab around the seed, best of {reps}"
+def crossing_edges(mask_u8, iso=127):
+    """Number of iso-crossing grid edges = number of marching-cubes vertices (independent of any
+    case table)."""
+    ins = mask_u8 >= iso
+    return int(np.count_nonzero(ins[:, :, 1:] != ins[:, :, :-1]) + np.count_nonzero(ins[:, 1:] != ins[:, :-1]) +
+               np.count_nonzero(ins[1:] != ins[:-1]))
 
 
 # ------------------------------------------------------------------ clocks
@@ -175,13 +190,127 @@ def bind_to_gpu_numa(local_rank):
         return f"numa: not bound ({type(e).__name__})"
 
 
+def checksums(verts, tris):
+    """Order-independent exact checksums of a mesh on the device: int64 sums of the triangle
+    indices and of the vertex coordinates' bit patterns."""
+    import torch
+    tsum = int(tris.to(torch.int64).sum().item()) if tris.numel() else 0
+    vsum = int(verts.contiguous().view(torch.int32).to(torch.int64).sum().item()) if verts.numel() else 0
+    return tsum, vsum
+
+
+# ------------------------------------------------------------------ secondary results (N = 1)
+def extra_results(peak):
+    """1024^3 threshold / MaxIP on three axes / MIDA, and the 512^3 watershed (BASELINE configs
+    [2], [3]) — device-timed like the headline (CUDA events, median of 5, inputs >> L2)."""
+    import torch
+    from invesalius3_b200 import device as dev, projection
+    res = {}
+
+    def timeit(fn, iters=5, warmup=2):
+        for _ in range(warmup):
+            fn()
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    n = 1024
+    try:
+        g = torch.Generator(device="cuda").manual_seed(0)
+        vol = torch.randint(-1024, 3072, (n, n, n), dtype=torch.int16, device="cuda", generator=g)
+        N = vol.numel()
+        out = torch.empty((n, n, n), dtype=torch.uint8, device="cuda")
+        ms = timeit(lambda: dev.threshold(vol, 226, 3071, out=out))
+        res["threshold_1024"] = {"ms": round(ms, 4), "GBs": round(3 * N / ms / 1e6, 1), "frac": round(3 * N / ms / 1e6 / peak, 4)}
+        del out
+        tot = 0.0
+        for axis in (0, 1, 2):
+            o = dev.mip(vol, axis, "max")
+            ms = timeit(lambda: dev.mip(vol, axis, "max", out=o))
+            tot += ms
+            res[f"maxip_1024_axis{axis}"] = {"ms": round(ms, 4), "GBs": round(2 * N / ms / 1e6, 1),
+                                             "frac": round(2 * N / ms / 1e6 / peak, 4)}
+        t = res["threshold_1024"]["ms"] + tot
+        res["threshold_plus_3mip_1024"] = {"ms": round(t, 4), "alg_bytes_per_voxel": 9,
+                                           "frac": round(9 * N / t / 1e6 / peak, 4)}
+        for axis in (0, 1, 2):
+            o = projection.mida(vol, axis, 32000, 2)    # opacity 0 everywhere: no ray terminates early
+            ms = timeit(lambda: projection.mida(vol, axis, 32000, 2, out=o), iters=3)
+            res[f"mida_fullrays_1024_axis{axis}"] = {"ms": round(ms, 4), "GBs": round(4 * N / ms / 1e6, 1),
+                                                      "frac": round(4 * N / ms / 1e6 / peak, 4)}
+        del vol
+        torch.cuda.empty_cache()
+    except Exception as e:   # noqa: BLE001
+        res["error_1024"] = f"{type(e).__name__}: {e}"
+    try:
+        res["watershed_512"] = watershed_results()
+    except Exception as e:   # noqa: BLE001
+        res["watershed_512"] = {"error": f"{type(e).__name__}: {e}"}
+    return res
+
+
+def ws_markers(vol, seed):
+    rng = np.random.default_rng(seed)
+    m = np.zeros(vol.shape, np.uint8)
+    zz, yy, xx = np.ogrid[:vol.shape[0], :vol.shape[1], :vol.shape[2]]
+    ins, outs = np.argwhere(vol > 600), np.argwhere(vol < -900)
+    for lab, pool in ((1, ins), (2, outs)):
+        for _ in range(4):
+            c = pool[rng.integers(len(pool))]
+            m[(zz - c[0]) ** 2 + (yy - c[1]) ** 2 + (xx - c[2]) ** 2 <= 16] = lab
+    return m
+
+
+def watershed_results():
+    """BASELINE configs[3]: 512^3, 8 marker balls, ww 406 / wl -18, mg_size 3, 6-connected, both
+    algorithms; agreement with the CPU checker (SciPy itself for IFT) on a 96^3 phantom, overall
+    and on the voxels whose label does not depend on the queue order."""
+    import torch
+    from scipy.ndimage import generate_binary_structure
+    from invesalius3_b200 import phantom, watershed_process as wp
+    from oracle import watershed as W
+    st = generate_binary_structure(3, 1)
+    n = 512
+    vol = phantom.ct((n, n, n), seed=4)
+    mk = ws_markers(vol, 4)
+    t_vol, t_mk = torch.from_numpy(vol).cuda(), torch.from_numpy(mk).cuda()
+    res = {}
+    for alg in ("Watershed", "Watershed IFT"):
+        wp.watershed_device(t_vol, t_mk, st, alg, 3, True, -18, 406)
+        ts = []
+        for _ in range(2):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); wp.watershed_device(t_vol, t_mk, st, alg, 3, True, -18, 406); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        res[alg] = {"ms": round(min(ts), 2), "Mvoxel/s": round(vol.size / min(ts) / 1e3, 1)}
+    del t_vol, t_mk
+    m = 96
+    v2 = phantom.ct((m, m, m), seed=4)
+    mk2 = ws_markers(v2, 4)
+    for alg in ("Watershed", "Watershed IFT"):
+        want = W.do_watershed_array(v2, mk2, st, alg, 3, True, -18, 406)
+        r = wp.watershed_device(torch.from_numpy(v2).cuda(), torch.from_numpy(mk2).cuda(), st, alg, 3, True, -18, 406,
+                                return_ambiguous=True)
+        got, amb = r[0].cpu().numpy(), r[1].cpu().numpy().astype(bool)
+        res[alg].update(agreement_96=round(float((got == want).mean()), 5),
+                        order_independent_fraction_96=round(float((~amb).mean()), 5),
+                        exact_on_order_independent_96=bool(np.array_equal(got[~amb], want[~amb])))
+    return res
+
+
 # ------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     from scipy.ndimage import generate_binary_structure
-    from invesalius3_b200 import _lib, device as dev, invesalius_rs, slice_ops, surface_process
+    from invesalius3_b200 import _lib, device as dev, invesalius_rs, phantom, slice_ops, surface_process
     from invesalius3_b200.mesh import marching_cubes
+    from invesalius3_b200 import dist as zd
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,14 +323,21 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     n = args.size
-    from invesalius3_b200 import dist as zd
     shard = zd.ZShard(n * world, rank, world)
-    ext_np, seeds = make_volume(n, world, (shard.ze0, shard.ze1))   # own planes + halo planes
-    seed = seeds[0]
+    ext_np = phantom.ct((n * world, n, n), seed=2, zrange=(shard.ze0, shard.ze1))   # own planes + halo planes
     vol = shard.interior(torch.from_numpy(ext_np)).numpy()          # this rank's n^3 shard
+    gseed = global_seed(n, world)
+    if world > 1:
+        got = [None] * world
+        dist.all_gather_object(got, shard_seed(vol, shard.z0))
+        pseeds = [s for s in got if s is not None]
+    else:
+        pseeds = [gseed]
+    seedings = {"global": [gseed], "per_shard": pseeds}
     strct = generate_binary_structure(3, 1)
     N = vol.size
     nz_ext = ext_np.shape[0]
+    link = zd.peer_link(shard, n, n) if world > 1 else None   # NVLink peer mappings for the fused exchange kernels
 
     # pinned host buffers for the e2e leg (numpy views of torch pinned tensors)
     h_ext = torch.from_numpy(ext_np).pin_memory()
@@ -217,11 +353,12 @@ def run_gpu(args):
     torch.cuda.synchronize()
     info = {}
 
-    def do_flood(data_ext, out_ext):
+    def do_flood(data_ext, out_ext, seeds):
         if world == 1:
-            info["rounds"] = dev.floodfill_threshold(data_ext, [seed], THR[0], THR[1], FILL, strct, out_ext)
+            info["rounds"] = dev.floodfill_threshold(data_ext, seeds, THR[0], THR[1], FILL, strct, out_ext)
         else:
-            info["rounds"] = zd.floodfill_threshold(data_ext, seeds, THR[0], THR[1], FILL, strct, out_ext, shard)
+            info["rounds"] = zd.floodfill_threshold(data_ext, seeds, THR[0], THR[1], FILL, strct, out_ext, shard,
+                                                    link=link)
 
     def do_surface(out_ext):
         if world == 1:
@@ -229,22 +366,19 @@ def run_gpu(args):
             info["V"], info["T"] = int(v.shape[0]), int(f.shape[0])
         else:
             v, f, _, info["V"], info["T"] = zd.marching_cubes(out_ext[int(shard.has_lo):], 127, SPACING, (0, 0, 0),
-                                                              True, shard)
+                                                              True, shard, link=link)
         return v, f
 
-    def flood_and_surface(data_ext, out_ext):
-        do_flood(data_ext, out_ext)
-        return do_surface(out_ext)
-
-    def step_device(ev=None):
+    def step_device(seeds, ev=None):
         if ev: ev[0].record()
         dev.threshold(d_vol, THR[0], THR[1], out=d_mask)
         if ev: ev[1].record()
         d_out.zero_()
-        do_flood(d_ext, d_out)
+        do_flood(d_ext, d_out, seeds)
         if ev: ev[2].record()
-        do_surface(d_out)
+        v, f = do_surface(d_out)
         if ev: ev[3].record()
+        return v, f
 
     e2e_min = {}
     e2e_calls = {"set_mask_threshold": 0.0, "zero_out_mask": 0.0, "floodfill_threshold": 0.0, "contour": 0.0}
@@ -256,7 +390,7 @@ def run_gpu(args):
             t1 = time.perf_counter()
             h_out.zero_()      # the reference allocates out_mask = np.zeros_like(mask) here (styles.py:3183)
             t2 = time.perf_counter()
-            invesalius_rs.floodfill_threshold(np_vol, [seed], THR[0], THR[1], FILL, strct, np_out)
+            invesalius_rs.floodfill_threshold(np_vol, [gseed], THR[0], THR[1], FILL, strct, np_out)
             t3 = time.perf_counter()
             v, f = surface_process.contour(np_out, [127], SPACING, 0, True)
             t4 = time.perf_counter()
@@ -264,15 +398,16 @@ def run_gpu(args):
                 e2e_calls[k] += dt
                 e2e_min[k] = min(e2e_min.get(k, 1e9), dt)
             return v, f
-        # N > 1: the sharded pipeline fed from / drained to pinned host memory
+        # N > 1: the sharded pipeline fed from / drained to pinned host memory (image uploaded once)
         t_ext = dev.to_device(h_ext.numpy())
         m = dev.threshold(shard.interior(t_ext), THR[0], THR[1])
         dev.to_host(m, np_mask[1:, 1:, 1:])
         np_mask[1:, 0, 0] = 1
         o_ext = torch.zeros((nz_ext, n, n), dtype=torch.uint8, device="cuda")
-        v, f = flood_and_surface(t_ext, o_ext)
+        do_flood(t_ext, o_ext, seedings["global"])
+        v, f = do_surface(o_ext)
         dev.to_host(shard.interior(o_ext), shard.interior(h_out).numpy())
-        return v.cpu().numpy(), f.cpu().numpy()
+        return dev.to_numpy(v), dev.to_numpy(f)
 
     def barrier():
         if world > 1:
@@ -286,29 +421,111 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident leg
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    lib.b2v_launch_count_reset()
-    stage_ms = np.zeros(3)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step_device(ev)
-        torch.cuda.synchronize()
-        stage_ms += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
-    e1.record()
-    barrier()
-    launches = int(lib.b2v_launch_count())
-    total_ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if sampler else None
-    ms_per_step = total_ms / args.steps
+    def sum_over_ranks(*xs):
+        t = torch.tensor(list(xs), dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [int(v) for v in t.tolist()]
+
+    # ---- device-resident leg, both seedings (the headline is the single global seed)
+    timed = {}
+    clocks = None
+    launches = 0
+    for name in ("per_shard", "global") if world > 1 else ("global",):
+        seeds = seedings[name]
+        for _ in range(max(args.warmup, 3)):
+            step_device(seeds)
+        barrier()
+        head = name == "global"
+        sampler = ClockSampler(local) if (rank == 0 and head) else None
+        lib.b2v_launch_count_reset()
+        stage_ms = np.zeros(3)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            v, f = step_device(seeds, ev)
+            torch.cuda.synchronize()
+            stage_ms += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+        e1.record()
+        barrier()
+        if head:
+            launches = int(lib.b2v_launch_count())
+        total_ms = max_over_ranks(e0.elapsed_time(e1))
+        if sampler:
+            clocks = sampler.stop()
+        count = int((shard.interior(d_out) == FILL).sum().item())
+        tsum, vsum = checksums(v, f)
+        gc, gt, gv = sum_over_ranks(count, tsum, vsum)
+        timed[name] = {"ms_per_step": total_ms / args.steps, "stage_ms": stage_ms / args.steps,
+                       "rounds": info["rounds"], "V": info["V"], "T": info["T"], "reached": gc, "tsum": gt, "vsum": gv,
+                       "nseeds": len(seeds)}
+    head = timed["global"]
+    ms_per_step = head["ms_per_step"]
     value = world * N / (ms_per_step * 1e-3) / 1e6
-    stage_ms /= args.steps
+    stage_ms = head["stage_ms"]
+    info.update(V=head["V"], T=head["T"], rounds=head["rounds"])
+
+    # ---- verification (outside every timed region)
+    verified = {"ok": False}
+    if world == 1:
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        c_count, c_tri, c_mm, c_out = cpu_step(vol, gseed, cores, want_arrays=True)
+        cpu_s = time.perf_counter() - t0
+        import oracle
+        ov, of = oracle.marching_cubes(c_out, 127, SPACING, (0, 0, 0), True)
+        v, f = step_device(seedings["global"])
+        g_mask, g_out = d_mask.cpu().numpy(), d_out.cpu().numpy()
+        gv, gf = v.cpu().numpy(), f.cpu().numpy()
+        checks = {
+            "threshold_mask_equal": bool(np.array_equal(g_mask, c_mm[1:, 1:, 1:])),
+            "flood_mask_equal": bool(np.array_equal(g_out, c_out)),
+            "reached_voxels": [head["reached"], c_count],
+            "triangles": [head["T"], c_tri, int(of.shape[0])],
+            "vertices": [head["V"], int(ov.shape[0]), crossing_edges(c_out)],
+            "triangle_array_equal": bool(gf.shape == of.shape and np.array_equal(gf, of)),
+            "vertex_max_abs_diff": float(np.abs(gv - ov).max()) if gv.shape == ov.shape and gv.size else None,
+        }
+        ok = (checks["threshold_mask_equal"] and checks["flood_mask_equal"] and head["reached"] == c_count and
+              head["T"] == c_tri == of.shape[0] and head["V"] == ov.shape[0] == checks["vertices"][2] and
+              checks["triangle_array_equal"] and checks["vertex_max_abs_diff"] is not None and
+              checks["vertex_max_abs_diff"] <= 1e-5)
+        verified = {"ok": bool(ok), "against": "CPU restatement of the reference (oracle/) on the same 512^3 volume",
+                    **checks}
+        cpu_baseline = {"value": round(vol.size / cpu_s / 1e6, 2), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"the full {n}^3 volume, one step ({cpu_s:.2f} s): NumPy threshold (1 thread) + serial "
+                                  f"flood fill (1 thread) + marching cubes over 21-slice pieces on {cores} threads"}
+        del c_mm, c_out, g_mask, g_out
+    else:
+        cpu_baseline = None
+        # gather the whole volume on rank 0 and run the single-GPU path there
+        own = d_vol.contiguous()
+        if rank == 0:
+            whole = torch.empty((n * world, n, n), dtype=torch.int16, device="cuda")
+            whole[:n].copy_(own)
+            for r in range(1, world):
+                dist.recv(whole[r * n:(r + 1) * n].view(torch.uint8), src=r)
+        else:
+            dist.send(own.view(torch.uint8), dst=0)
+        if rank == 0:
+            res = {}
+            for name, seeds in seedings.items():
+                o = torch.zeros((n * world, n, n), dtype=torch.uint8, device="cuda")
+                dev.floodfill_threshold(whole, seeds, THR[0], THR[1], FILL, strct, o)
+                v1, f1 = marching_cubes(o, 127, SPACING, (0, 0, 0), True)
+                ts, vs = checksums(v1, f1)
+                one = {"reached": int((o == FILL).sum().item()), "V": int(v1.shape[0]), "T": int(f1.shape[0]),
+                       "tsum": ts, "vsum": vs}
+                shd = {k: timed[name][k] for k in one}
+                res[name] = {"sharded": shd, "single_gpu": one, "equal": shd == one}
+                del o, v1, f1
+            del whole
+            verified = {"ok": all(r["equal"] for r in res.values()),
+                        "against": "single-GPU run of the whole gathered volume on rank 0 (reached count, V, T, "
+                                   "int64 checksums of the triangle indices and of the vertex bit patterns)", **res}
+        barrier()
 
     # ---- e2e leg: reference-shaped numpy API on pinned host buffers
     e2e_steps = max(1, min(args.steps, 5))
@@ -341,41 +558,53 @@ def run_gpu(args):
     names = list(alg)
     dom = int(np.argmax(stage_ms))
     achieved = alg[names[dom]] / (stage_ms[dom] * 1e-3) / 1e9
-    traffic = None
-    try:   # DRAM bytes per launch of that stage from the committed ncu capture (profiles/)
-        traffic = json.load(open(ROOT / "profiles" / "r01_traffic.json"))["stages"][names[dom]]["traffic"]
-    except Exception:
-        pass
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    cpu_baseline = None
-    if world == 1:   # the CPU baseline is an N=1 figure (rank 0's host cores)
-        cpu_v, cpu_sample_desc = time_cpu(vol, seed, min(n, args.cpu_slices), 1, cores)
-        cpu_baseline = {"value": round(cpu_v, 2), "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": cpu_sample_desc}
+    traffic, traffic_src = None, None
+    for cand in ("r02_traffic.json", "r01_traffic.json"):
+        try:   # DRAM bytes per launch of that stage from the committed ncu capture (profiles/)
+            traffic = json.load(open(ROOT / "profiles" / cand))["stages"][names[dom]]["traffic"]
+            traffic_src = f"profiles/{cand}"
+            break
+        except Exception:
+            pass
+    seeding = {}
+    for name, t in timed.items():
+        seeding[name] = {"ms_per_step": round(t["ms_per_step"], 4),
+                         "Mvoxel/s": round(world * N / (t["ms_per_step"] * 1e-3) / 1e6, 1), "seeds": t["nseeds"],
+                         "flood_rounds": t["rounds"],
+                         "stage_ms": {k: round(float(m), 4) for k, m in zip(names, t["stage_ms"])}}
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": workload_desc(n),
+        "config": {"workload": workload_desc(n, world),
                    "volume": f"{n * world}x{n}x{n} (Z-sharded, one halo plane per inner side)",
                    "shard": f"{n}^3 voxels per GPU", "l2": "inputs (256 MiB int16 + 128 MiB uint8) exceed the 126 MB L2",
                    "host": numa, "flood_rounds": info["rounds"], "vertices": info["V"], "triangles": info["T"],
-                   "stage_ms": {k: round(float(m), 4) for k, m in zip(names, stage_ms)}},
+                   "stage_ms": {k: round(float(m), 4) for k, m in zip(names, stage_ms)},
+                   "seeding": seeding, "exchange": (link.describe() if link is not None else
+                                                    ("none (one GPU)" if world == 1 else "NCCL send/recv + all_reduce"))},
+        "verified": verified,
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_s * 1e3, 3),
-                "ms_per_call": {k: round(v / e2e_steps * 1e3, 3) for k, v in e2e_calls.items()},
-                "ms_per_call_min": {k: round(v * 1e3, 3) for k, v in e2e_min.items()},
+                "ms_per_call": {k: round(v / e2e_steps * 1e3, 3) for k, v in e2e_calls.items()} if world == 1 else None,
+                "ms_per_call_min": {k: round(v * 1e3, 3) for k, v in e2e_min.items()} if world == 1 else None,
                 "api": ("slice_ops.set_mask_threshold + invesalius_rs.floodfill_threshold + surface_process.contour "
-                        "on pinned numpy buffers") if world == 1 else
-                       "dist.* sharded pipeline fed from / drained to pinned host buffers"},
+                        "on pinned numpy buffers (image uploaded by each call, as the numpy API implies)") if world == 1 else
+                       "dist.* sharded pipeline fed from / drained to pinned host buffers (image uploaded once per step)"},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak,
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
-                     "note": "the dominant stage is the flood fill: 4 B/voxel over the whole op (build + rounds + "
-                             "write); its rounds are L2/latency-bound, see DESIGN.md",
-                     "per_stage_GBs": {k: round(alg[k] / (m * 1e-3) / 1e9, 1) for k, m in zip(names, stage_ms)}},
+                     "traffic_source": traffic_src,
+                     "note": "stage-level: algorithmic bytes of the dominant stage / its CUDA-event time; the flood's "
+                             "rounds are L2/latency-bound, see DESIGN.md",
+                     "per_stage_GBs": {k: round(alg[k] / (m * 1e-3) / 1e9, 1) for k, m in zip(names, stage_ms)},
+                     "per_stage_frac": {k: round(alg[k] / (m * 1e-3) / 1e9 / peak, 4) for k, m in zip(names, stage_ms)}},
         "cpu_baseline": cpu_baseline,
     }
+    if world == 1 and not args.no_extra:
+        del d_ext, d_mask, d_out
+        torch.cuda.empty_cache()
+        line["extra"] = extra_results(peak)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -386,24 +615,28 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from invesalius3_b200 import phantom
     n = args.size
-    vol, seeds = make_volume(n)
-    seed = seeds[0]
+    vol = phantom.ct((n, n, n), seed=2)
+    seed = global_seed(n, 1)
     cores = os.cpu_count() or 1
-    sub, sseed = cpu_sample(vol, seed, min(n, args.cpu_slices))
+    if args.cpu_slices and args.cpu_slices < n:     # optional bounded slab (not the default)
+        z0 = max(0, min(n - args.cpu_slices, seed[2] - args.cpu_slices // 2))
+        vol, seed = np.ascontiguousarray(vol[z0:z0 + args.cpu_slices]), (seed[0], seed[1], seed[2] - z0)
     for _ in range(min(args.warmup, 1)):
-        cpu_step(sub, sseed, cores)
+        cpu_step(vol, seed, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(sub, sseed, cores)
+        count, ntri = cpu_step(vol, seed, cores)
     s = (time.perf_counter() - t0) / args.steps
-    v = sub.size / s / 1e6
-    sample = f"{sub.shape[0]}x{sub.shape[1]}x{sub.shape[2]} slab of the {n}^3 workload around the seed, per step"
+    v = vol.size / s / 1e6
+    sample = (f"the full {vol.shape[0]}x{vol.shape[1]}x{vol.shape[2]} volume per step: NumPy threshold (1 thread) + serial "
+              f"flood fill (1 thread) + marching cubes over 21-slice pieces on {cores} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(s * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": workload_desc(n)},
+        "config": {"workload": workload_desc(n, 1), "reached_voxels": count, "triangles": ntri},
         "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -416,7 +649,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--cpu-slices", type=int, default=128)
+    ap.add_argument("--cpu-slices", type=int, default=0, help="reference arm: time a slab of this many slices instead "
+                                                              "of the full volume (0 = full volume, the default)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary 1024^3 / watershed measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

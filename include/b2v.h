@@ -105,7 +105,7 @@ int64_t b2v_floodfill_workspace_bytes(int64_t dz, int64_t dy, int64_t dx, int64_
 /* Convergence engine of the flood-fill family: 1 (default) = every round inside ONE
  * persistent cooperative launch (rotating bitmaps of active tiles, grid-wide barrier per
  * round), 0 = one launch per round driven from the host. Same result either way.
- * Environment knobs read at call time (tuning only, results identical): B2V_FF_TILE=8
+ * Environment knobs read once per process (tuning only, results identical): B2V_FF_TILE=8
  * (small tiles), B2V_FF_TRIPS=n (sweep sets per tile visit), B2V_FF_GRID=n (blocks of the
  * persistent grid), B2V_FF_DEFER=n (surplus tiles a round may pass on). */
 void b2v_floodfill_set_engine(int persistent);
@@ -224,9 +224,10 @@ int b2v_floodfill_layout(int64_t dz, int64_t dy, int64_t dx, int64_t nseeds, int
 int b2v_floodfill_merge_plane(int64_t dz, int64_t dy, int64_t dx, int64_t nseeds, void* workspace, int64_t z,
                               const uint32_t* plane_bits, int round, void* stream);
 /* Marching cubes on a slab whose last plane is shared with the next shard: that plane's
- * vertices are owned (numbered, emitted) by the next shard. b2v_mc_layout: [0] byte offset
- * of the per-word records {cx, cy, cz, vertex offset} in the workspace, [1] bytes of records
- * per z-plane. The emitting shard receives the next shard's plane-0 records and global
+ * vertices are owned (numbered, emitted) by the next shard. b2v_mc_layout (layout_out[4]): [0]
+ * byte offset of the dense plane-0 records {cx, cy, cz, vertex offset} in the workspace (filled
+ * by b2v_mc_count_shard), [1] their size in bytes, [2] byte offset of the uint64 totals (V, T).
+ * The emitting shard receives the next shard's plane-0 records and global
  * vertex base; concatenating the shards' outputs in rank order reproduces the single-GPU
  * output bit for bit (the boundary stitch). */
 int b2v_mc_count_shard(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
@@ -237,6 +238,50 @@ int b2v_mc_emit_shard(const void* vol, int dtype, int64_t nz, int64_t ny, int64_
                       int flip_y, int skip_last_plane, int32_t vertex_base, const void* next_shard_plane0_records,
                       int32_t next_shard_vertex_base, float* verts, int32_t* tris, void* stream);
 int b2v_mc_layout(int64_t nz, int64_t ny, int64_t nx, int64_t* layout_out);
+
+/* ---- peer mailboxes: the NVLink exchange layer of the Z-sharded ops ------------------------------
+ * Replaces the temp-file exchange between the reference's worker processes
+ * (invesalius/data/surface.py:1360-1430 pieces -> surface_process.py:229-268 stitch;
+ * invesalius/data/styles.py:2083-2108 watershed child). One process per GPU; every rank owns one
+ * MAILBOX in its HBM (b2v_peer_alloc: cudaMalloc + cudaIpc export), maps every other rank's
+ * (b2v_peer_open) and hands the array of the `world` base pointers (its own included, index =
+ * rank) to the *_peer entry points. Ranks only WRITE into peers (stores over NVLink + a release
+ * store of a signal word) and poll their own mailbox, with a time-out (B2V_ERR_NOCONV), so a
+ * mismatched call sequence cannot hang a GPU. `epoch` is a job-wide counter >= 1 that every rank
+ * advances identically: b2v_floodfill_threshold_peer reports how many epochs it consumed, the
+ * other calls consume one. Layout and protocol: invesalius3_b200/csrc/peer.cuh.
+ * b2v_peer_mailbox_bytes(dy, dx): size for shards whose planes are dy x dx voxels; the
+ * `mailbox_plane_bytes` argument of the calls below is dy * ceil(dx / 32) * 4 of that link. */
+int64_t b2v_peer_mailbox_bytes(int64_t dy, int64_t dx);
+int b2v_peer_alloc(int64_t bytes, void** dev_ptr_out, uint8_t* handle_out /* [64] */);
+int b2v_peer_open(const uint8_t* handle /* [64] */, void** dev_ptr_out);
+int b2v_peer_close(void* mapped_ptr);
+int b2v_peer_free(void* dev_ptr);
+/* all ranks meet (consumes one epoch); the self-check of a new link. Synchronises the stream. */
+int b2v_peer_barrier(int rank, int world, const void* const* mailboxes_host, int64_t mailbox_plane_bytes,
+                     uint32_t epoch, void* stream);
+/* invesalius_rs.floodfill_threshold over one Z shard with the boundary exchange FUSED into the
+ * persistent flood kernel: data / out are the extended slab (own planes + one halo plane per
+ * inner side, halo planes of data valid), seeds are local to it (a shard without seeds passes
+ * nseeds = 0 and still takes part). After local convergence the kernel pushes the reached bits
+ * of the two planes around each inner boundary into the neighbours' mailboxes, merges what they
+ * pushed, all ranks agree whether anyone gained a bit, and the rounds resume — ONE launch per
+ * GPU for the whole sharded flood, no host round trip. Synchronises the stream (verdict). */
+int b2v_floodfill_threshold_peer(const void* data, int dtype, int64_t dz, int64_t dy, int64_t dx,
+                                 const int64_t* seeds_host, int64_t nseeds, double t0, double t1, uint8_t fill,
+                                 const uint8_t* strct_host, int64_t odz, int64_t ody, int64_t odx, uint8_t* out,
+                                 void* workspace, void* stream, int rank, int world,
+                                 const void* const* mailboxes_host, int64_t mailbox_plane_bytes, uint32_t epoch,
+                                 int* rounds_out, int* epochs_used_out);
+/* b2v_mc_count_shard + the exchange the stitch needs, in one stream-ordered sequence: every
+ * rank's (V, T) lands in counts_host [world][2], and the upper neighbour's plane-0 records land
+ * in this rank's mailbox at byte offset b2v_peer_mc_inbox_offset(plane_bytes, epoch) — pass that
+ * device address as next_shard_plane0_records to b2v_mc_emit_shard. Synchronises the stream. */
+int b2v_mc_count_shard_peer(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
+                            int skip_last_plane, void* workspace, void* stream, int rank, int world,
+                            const void* const* mailboxes_host, int64_t mailbox_plane_bytes, uint32_t epoch,
+                            int64_t* counts_host);
+int64_t b2v_peer_mc_inbox_offset(int64_t mailbox_plane_bytes, uint32_t epoch);
 /* MIDA (mips.rs:102-168) / LMIP (mips.rs:7-86) with rays along z over ONE Z shard: the rays
  * cross the shards, so each shard continues from the per-ray state its predecessor left and
  * hands its own on (the per-ray operation order is that of the whole-volume walk: bit-exact).

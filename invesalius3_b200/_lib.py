@@ -62,6 +62,16 @@ PROTOTYPES = {
     "b2v_mc_emit_shard": (cint, [vp, cint, i64, i64, i64, dbl, vp, f32, f32, f32, i32, i32, i32, cint, cint, i32, vp,
                                  i32, vp, vp, vp]),
     "b2v_mc_layout": (cint, [i64, i64, i64, C.POINTER(i64)]),
+    "b2v_peer_mailbox_bytes": (i64, [i64, i64]),
+    "b2v_peer_alloc": (cint, [i64, C.POINTER(vp), vp]),
+    "b2v_peer_open": (cint, [vp, C.POINTER(vp)]),
+    "b2v_peer_close": (cint, [vp]),
+    "b2v_peer_free": (cint, [vp]),
+    "b2v_peer_barrier": (cint, [cint, cint, vp, i64, u32, vp]),
+    "b2v_floodfill_threshold_peer": (cint, [vp, cint, i64, i64, i64, vp, i64, dbl, dbl, u8, vp, i64, i64, i64, vp, vp,
+                                            vp, cint, cint, vp, i64, u32, C.POINTER(cint), C.POINTER(cint)]),
+    "b2v_mc_count_shard_peer": (cint, [vp, cint, i64, i64, i64, dbl, cint, vp, vp, cint, cint, vp, i64, u32, vp]),
+    "b2v_peer_mc_inbox_offset": (i64, [i64, u32]),
     "b2v_mida_z_partial": (cint, [vp, cint, i64, i64, i64, dbl, dbl, vp, vp, cint, cint, vp, cint, vp, vp]),
     "b2v_lmip_z_partial": (cint, [vp, cint, i64, i64, i64, dbl, dbl, vp, cint, cint, vp, vp, vp]),
 }

@@ -22,8 +22,23 @@
 #include <string.h>
 
 #include "b2v_common.cuh"
+#include "peer.cuh"
 
 namespace cg = cooperative_groups;
+
+// Profiling counters of the flood engine (cycles per visit phase, tile visits) are compiled in
+// only with -DB2V_FF_STATS=1 (tools/flood_once.py builds read them through
+// b2v_floodfill_layout()[6]); the production kernels carry no clock reads or counter atomics.
+#ifndef B2V_FF_STATS
+#define B2V_FF_STATS 0
+#endif
+#if B2V_FF_STATS
+#define FF_CLK() clock64()
+#define FF_STAT(...) do { __VA_ARGS__; } while (0)
+#else
+#define FF_CLK() 0ll
+#define FF_STAT(...) do { } while (0)
+#endif
 
 namespace {
 
@@ -48,14 +63,28 @@ int pow2ceil(int64_t v, int cap) {
   return p;
 }
 
+// Tuning knobs (results identical either way), read from the environment ONCE per process.
+struct FloodKnobs {
+  int edge = 16, trips = 1, defer = 1 << 30, grid = 0;
+  FloodKnobs() {
+    if (const char* e = getenv("B2V_FF_TILE")) { if (atoi(e) == 8) edge = 8; }
+    if (const char* e = getenv("B2V_FF_TRIPS")) { int v = atoi(e); if (v > 0) trips = v; }
+    if (const char* e = getenv("B2V_FF_DEFER")) { int v = atoi(e); if (v >= 0) defer = v; }
+    if (const char* e = getenv("B2V_FF_GRID")) { int v = atoi(e); if (v > 0) grid = v; }
+  }
+};
+const FloodKnobs& knobs() {
+  static const FloodKnobs k;
+  return k;
+}
+
 BitVol make_bitvol(int64_t dz, int64_t dy, int64_t dx) {
   BitVol b;
   b.dz = dz; b.dy = dy; b.dx = dx;
   b.wx = (int)ceil_div64(dx, 32);
   // Tile edge (rows): 16 halves the number of rounds of a flood (one tile hop per round)
   // against 8 for about twice the work per visit; B2V_FF_TILE=8 selects the small tile.
-  int edge = 16;
-  if (const char* e = getenv("B2V_FF_TILE")) { if (atoi(e) == 8) edge = 8; }
+  const int edge = knobs().edge;
   const int words = edge == 16 ? kTileWords : 1024;
   b.tw = pow2ceil(b.wx, 16);
   b.ty = pow2ceil(dy, edge);
@@ -70,10 +99,8 @@ BitVol make_bitvol(int64_t dz, int64_t dy, int64_t dx) {
   const uint32_t pw = b.tw + 2, pp = (b.tw + 2) * (b.ty + 2);
   b.m_pw = ((1u << 24) + pw - 1) / pw;
   b.m_pp = ((1u << 24) + pp - 1) / pp;
-  b.max_trips = 1;   // measured: one sweep set per visit, stragglers re-queue themselves (round time = one trip)
-  if (const char* e = getenv("B2V_FF_TRIPS")) { int v = atoi(e); if (v > 0) b.max_trips = v; }
-  b.defer = 1 << 30;   // measured: always cheaper than a second visit per block (any n <= 2 x blocks)
-  if (const char* e = getenv("B2V_FF_DEFER")) { int v = atoi(e); if (v >= 0) b.defer = v; }
+  b.max_trips = knobs().trips;   // default 1: one sweep set per visit, stragglers re-queue themselves
+  b.defer = knobs().defer;       // default: always cheaper than a second visit per block (any n <= 2 x blocks)
   return b;
 }
 
@@ -83,8 +110,6 @@ struct Workspace {
   uint8_t* active[2];
   int* flags;        // flags[r] != 0  <=>  some tile is active in round r
   int* lists;        // persistent engine: three rotating bitmaps of active tiles [3][ceil(ntiles / 32)]
-  int* lflags;       // (unused since the bitmaps replaced the compact lists; kept so that the
-  int* counts;       //  offsets reported by b2v_floodfill_layout do not move)
   int* ctl;          // [3] error, [4] tile visits, [5] visits that grew, [6] local iterations, [7] rounds
   int64_t* seeds;    // device copy, 3 per seed
   int64_t bytes;
@@ -102,9 +127,7 @@ Workspace carve(void* base, const BitVol& b, int64_t nseeds) {
   w.active[0] = (uint8_t*)(p + off); off += align(ntiles);
   w.active[1] = (uint8_t*)(p + off); off += align(ntiles);
   w.flags = (int*)(p + off); off += align((int64_t)(kMaxRounds + 2) * 4);
-  w.lists = (int*)(p + off); off += align(3 * ntiles * 4);
-  w.lflags = (int*)(p + off); off += align(3 * ntiles * 4);
-  w.counts = (int*)(p + off); off += 256;
+  w.lists = (int*)(p + off); off += align(3 * ((ntiles + 31) / 32) * 4);
   w.ctl = (int*)(p + off); off += 256;
   w.seeds = (int64_t*)(p + off); off += align((nseeds > 0 ? nseeds : 1) * 24);
   w.bytes = off;
@@ -382,7 +405,7 @@ __device__ __forceinline__ int ff_process_tile_sb6(const uint32_t* __restrict__ 
   const int dz = (int)b.dz, dy = (int)b.dy;
   uint32_t* sF = sR + NH;
   if (tid == 0) *s_faces = 0;
-  const long long pc0 = clock64();
+  const long long pc0 = FF_CLK();
   {
     uint32_t v[NL], f[NL];
 #pragma unroll
@@ -415,7 +438,7 @@ __device__ __forceinline__ int ff_process_tile_sb6(const uint32_t* __restrict__ 
     f[k] = sF[h];
     r0[k] = r[k] = sR[h];
   }
-  const long long pc1 = clock64();
+  const long long pc1 = FF_CLK();
   const int iw = tid & 15;
   int changed, iters = 0;
   do {
@@ -444,7 +467,7 @@ __device__ __forceinline__ int ff_process_tile_sb6(const uint32_t* __restrict__ 
     ++iters;
   } while (changed && iters < b.max_trips);
   const bool unfinished = changed != 0;
-  const long long pc2 = clock64();
+  const long long pc2 = FF_CLK();
   int grew = 0;
 #pragma unroll
   for (int k = 0; k < K; ++k)
@@ -454,15 +477,16 @@ __device__ __forceinline__ int ff_process_tile_sb6(const uint32_t* __restrict__ 
       grew = 1;
     }
   grew = __syncthreads_or(grew);
-  const long long pc3 = clock64();
-  if (tid == 0) {
+  const long long pc3 = FF_CLK();
+  FF_STAT(if (tid == 0) {
     atomicAdd(&stats[11], (int)((pc1 - pc0) >> 4));
     atomicAdd(&stats[12], (int)((pc2 - pc1) >> 4));
     atomicAdd(&stats[13], (int)((pc3 - pc2) >> 4));
     atomicAdd(&stats[4], 1);
     if (grew) atomicAdd(&stats[5], 1);
     atomicAdd(&stats[6], iters);
-  }
+  });
+  (void)pc0; (void)pc1; (void)pc2; (void)pc3; (void)stats;
   // which of the six face neighbours can gain a bit from this tile's interior? One face word
   // per thread: passable-but-unreached bits of the halo word against the reached bits of the
   // interior word next to it (same bit across y / z, the adjacent bit across a word boundary).
@@ -492,7 +516,7 @@ __device__ __forceinline__ int ff_process_tile_sb6(const uint32_t* __restrict__ 
   }
   if (unfinished && tid == 0) atomicOr(s_faces, 1 << 13);   // (0,0,0): re-queue this tile itself
   __syncthreads();
-  if (tid == 0) atomicAdd(&stats[14], (int)((clock64() - pc3) >> 4));
+  FF_STAT(if (tid == 0) atomicAdd(&stats[14], (int)((clock64() - pc3) >> 4)));
   return *s_faces;
 }
 
@@ -513,7 +537,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
   const int64_t z0 = (int64_t)tzi * tz, y0 = (int64_t)tyi * ty;
   const int w0 = twi * tw;
   if (tid == 0) *s_faces = 0;
-  const long long pc0 = clock64();
+  const long long pc0 = FF_CLK();
   // halo load (zero outside the volume); the passable bits ride along (halo words are
   // never written)
   const int nh = (tz + 2) * py * pw;
@@ -572,7 +596,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
       fgr[k] = sF[hidx[k]];
     }
 
-  const long long pc1 = clock64();
+  const long long pc1 = FF_CLK();
   const bool xfill = ((sb >> 12) & 1u) && ((sb >> 14) & 1u);  // (0,0,-1) and (0,0,+1)
   // axis-aligned offsets present in the structuring element (flood moves p -> p + off)
   const bool yfwd = (sb >> 16) & 1u, ybwd = (sb >> 10) & 1u;   // (0,+1,0), (0,-1,0)
@@ -675,7 +699,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
   } while (changed && iters < b.max_trips);
   const bool unfinished = changed != 0;   // trip cap hit: this tile must be visited again
 
-  const long long pc2 = clock64();
+  const long long pc2 = FF_CLK();
   // write back what grew
   int grew = 0;
 #pragma unroll
@@ -696,15 +720,16 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
   int nbmask = 0;
   // (checked even without growth: a lone seed on a tile face must still wake its neighbour)
   grew = __syncthreads_or(grew);
-  const long long pc3 = clock64();
-  if (tid == 0) {   // stats[4] tile visits, [5] visits that grew, [6] local iterations
+  const long long pc3 = FF_CLK();
+  FF_STAT(if (tid == 0) {   // stats[4] tile visits, [5] visits that grew, [6] local iterations
     atomicAdd(&stats[11], (int)((pc1 - pc0) >> 4));   // cycles/16: halo load
     atomicAdd(&stats[12], (int)((pc2 - pc1) >> 4));   //            local convergence
     atomicAdd(&stats[13], (int)((pc3 - pc2) >> 4));   //            write back
     atomicAdd(&stats[4], 1);
     if (grew) atomicAdd(&stats[5], 1);
     atomicAdd(&stats[6], iters);
-  }
+  });
+  (void)pc0; (void)pc1; (void)pc2; (void)pc3; (void)stats;
   {
     const int hzmax = tz + 1, hymax = ty + 1, hwmax = tw + 1;
     for (int i = tid; i < nh; i += kFloodThreads) {
@@ -740,7 +765,7 @@ __device__ __forceinline__ int ff_process_tile(const uint32_t* __restrict__ fg, 
   if (unfinished && tid == 0) nbmask |= 1 << 13;   // (0,0,0): re-queue this tile itself
   if (nbmask) atomicOr(s_faces, nbmask);
   __syncthreads();
-  if (tid == 0) atomicAdd(&stats[14], (int)((clock64() - pc3) >> 4));   // neighbour gain test
+  FF_STAT(if (tid == 0) atomicAdd(&stats[14], (int)((clock64() - pc3) >> 4)));   // neighbour gain test
   return *s_faces;
 }
 
@@ -863,20 +888,27 @@ __device__ __forceinline__ int ff_select_tiles(const uint32_t* bm, int nbw, int 
 // (ff_process_tile_sb6, no generic path); 0 = any tile, any element.
 // (Two co-resident blocks per SM at 32 registers were measured slower: the barrier doubles
 // and the visits of the two blocks contend.)
-template <uint32_t SBC, int CANON>
+// PEER: the slab is one Z shard of a larger volume (extended by one halo plane per inner side).
+// After local convergence the shard pushes the reached bits of the two planes around each inner
+// boundary into its neighbours' mailboxes over NVLink, merges what the neighbours pushed, and all
+// ranks agree (flag words written into every mailbox) whether anyone gained a bit; if so the
+// rounds resume. The whole sharded flood is this ONE launch per GPU: no host round trip, no
+// NCCL call. ctl[3] error (1 round cap, 2 peer timeout), ctl[7] rounds, ctl[18] exchanges.
+template <uint32_t SBC, int CANON, bool PEER>
 __global__ void __launch_bounds__(kFloodThreads)
     k_ff_persistent(const uint32_t* __restrict__ fg, uint32_t* reach, BitVol b, uint32_t sb, uint32_t* bm, int nbw,
-                    int* ctl, int max_rounds) {
+                    int* ctl, int max_rounds, PeerSet ps) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ uint32_t sR[];
   __shared__ int s_faces;
   __shared__ int s_wsum[32];
   __shared__ int s_mine[kMaxMine];
   const int tid = threadIdx.x;
-  int r = 0;
-  long long c_proc = 0, c_sync = 0, c_all0 = clock64();
+  int r = 0, outer = 0;
+  long long c_proc = 0, c_sync = 0, c_all0 = FF_CLK();
+  for (;;) {
   for (;; ++r) {
-    const long long c0 = clock64();
+    const long long c0 = FF_CLK();
     const int cur = r % 3, nxt = (r + 1) % 3, old = (r + 2) % 3;
     const int n = ff_select_tiles(bm + (size_t)cur * nbw, nbw, blockIdx.x, gridDim.x, s_mine, s_wsum);
     if (n == 0) break;
@@ -910,17 +942,105 @@ __global__ void __launch_bounds__(kFloodThreads)
       }
       __syncthreads();   // s_faces / shared tile are reused by the next tile of this block
     }
-    const long long c1 = clock64();
+    const long long c1 = FF_CLK();
     grid.sync();   // orders every thread's writes (reach words, next bitmap) before the next round's reads
-    const long long c2 = clock64();
+    const long long c2 = FF_CLK();
     c_proc += c1 - c0;
     c_sync += c2 - c1;
   }
+  if constexpr (!PEER) {
+    break;
+  } else {
+    // ---- exchange with the neighbour shards (every rank takes part in every exchange, in lockstep)
+    const uint32_t ep = ps.epoch + (uint32_t)outer;
+    const int par = (int)(ep & 1u);
+    const bool has_lo = ps.rank > 0, has_hi = ps.rank + 1 < ps.world;
+    const int pw = (int)b.dy * b.wx;                    // words per plane (checked on the host: fits the mailbox)
+    const int gt = blockIdx.x * kFloodThreads + tid, gs = gridDim.x * kFloodThreads;
+    // 1. push [halo, first own] down and [last own, halo] up
+    if (has_lo) {
+      uint32_t* dst = ps.of(ps.rank - 1).ff_from_hi();
+      for (int i = gt; i < 2 * pw; i += gs) dst[i] = __ldcg(reach + i);
+    }
+    if (has_hi) {
+      uint32_t* dst = ps.of(ps.rank + 1).ff_from_lo();
+      const uint32_t* src = reach + (size_t)(b.dz - 2) * pw;
+      for (int i = gt; i < 2 * pw; i += gs) dst[i] = __ldcg(src + i);
+    }
+    __threadfence_system();
+    grid.sync();
+    if (blockIdx.x == 0 && tid == 0) {
+      if (has_lo) st_release_sys(ps.of(ps.rank - 1).sig(PB_SIG_FF_FROM_HI), ep);
+      if (has_hi) st_release_sys(ps.of(ps.rank + 1).sig(PB_SIG_FF_FROM_LO), ep);
+      bool ok = true;
+      if (has_lo) ok = peer_wait_eq(ps.mine().sig(PB_SIG_FF_FROM_LO), ep, ps.timeout) && ok;
+      if (has_hi) ok = peer_wait_eq(ps.mine().sig(PB_SIG_FF_FROM_HI), ep, ps.timeout) && ok;
+      if (!ok) ctl[3] = 2;
+      ctl[16] = 0;
+      __threadfence();
+    }
+    grid.sync();
+    // 2. merge what the neighbours pushed; a word that gains bits re-activates its tile for round r
+    {
+      int changed = 0;
+      uint32_t* bmr = bm + (size_t)(r % 3) * nbw;
+      for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? !has_lo : !has_hi) continue;
+        const uint32_t* in = side == 0 ? ps.mine().ff_from_lo() : ps.mine().ff_from_hi();
+        const int z0 = side == 0 ? 0 : (int)b.dz - 2;
+        for (int i = gt; i < 2 * pw; i += gs) {
+          const size_t wi = (size_t)z0 * pw + i;
+          const uint32_t c = __ldcg(reach + wi);
+          const uint32_t nwv = c | (ld_relaxed_sys_u32(in + i) & __ldg(fg + wi));
+          if (nwv != c) {
+            __stcg(reach + wi, nwv);
+            const int z = z0 + i / pw, rem = i % pw, y = rem / b.wx, w = rem - y * b.wx;
+            const int tile = ((z / b.tz) * b.nty + y / b.ty) * b.ntw + w / b.tw;
+            atomicOr(&bmr[tile >> 5], 1u << (tile & 31));
+            changed = 1;
+          }
+        }
+      }
+      if (__syncthreads_or(changed) && tid == 0) atomicOr(&ctl[16], 1);
+    }
+    __threadfence();
+    grid.sync();
+    // 3. did any shard gain a bit? every rank writes its flag into every mailbox
+    if (blockIdx.x == 0) {
+      bool ok = true;
+      uint32_t got = 0;
+      if (tid < ps.world) {
+        const uint32_t tag = ep * 2u + (uint32_t)(__ldcg(&ctl[16]) != 0);
+        st_release_sys(ps.of(tid).flags(par) + ps.rank, tag);
+        const uint32_t* mine = ps.mine().flags(par) + tid;
+        const long long t0 = clock64();
+        uint32_t v;
+        while (((v = ld_acquire_sys(mine)) >> 1) != ep) {
+          if (clock64() - t0 > ps.timeout) { ok = false; break; }
+          __nanosleep(64);
+        }
+        got = ok ? (v & 1u) : 0u;
+      }
+      const int any = __syncthreads_or((int)got);
+      ok = __syncthreads_and(ok);
+      if (tid == 0) {
+        if (!ok) ctl[3] = 2;
+        ctl[17] = (ok && any && __ldcg(&ctl[3]) == 0) ? 1 : 0;
+        __threadfence();
+      }
+    }
+    grid.sync();
+    ++outer;
+    if (__ldcg(&ctl[17]) != 1) break;
+  }
+  }
   if (blockIdx.x == 0 && tid == 0) {
     ctl[7] = r;
-    ctl[8] = (int)(c_proc >> 4);    // block 0: cycles/16 spent on its tiles ...
-    ctl[9] = (int)(c_sync >> 4);    // ... and in fence + grid barrier (incl. waiting for slower blocks)
-    ctl[10] = (int)((clock64() - c_all0) >> 4);
+    ctl[18] = outer;
+    FF_STAT(ctl[8] = (int)(c_proc >> 4);    // block 0: cycles/16 spent on its tiles ...
+            ctl[9] = (int)(c_sync >> 4);    // ... and in fence + grid barrier (incl. waiting for slower blocks)
+            ctl[10] = (int)((clock64() - c_all0) >> 4));
+    (void)c_proc; (void)c_sync; (void)c_all0;
   }
 }
 
@@ -1022,45 +1142,56 @@ int run_rounds(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s,
 // Persistent convergence: the tiles active for round r0 (seeds, merged planes) seed the first
 // list; one cooperative launch runs every round to the fixed point. Synchronises the stream.
 static thread_local int g_last_rounds = 0;
+static thread_local int g_last_exchanges = 0;
 static int g_flood_engine = 1;   // 1 persistent (default), 0 host-driven rounds
 
 // Fetch the persistent kernel's verdict (synchronises the stream).
 int persistent_verdict(const Workspace& w, cudaStream_t s) {
-  int ctlh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int ctlh[20];
+  memset(ctlh, 0, sizeof(ctlh));
   B2V_CUDA(cudaMemcpyAsync(ctlh, w.ctl, sizeof(ctlh), cudaMemcpyDeviceToHost, s));
   B2V_CUDA(cudaStreamSynchronize(s));
-  B2V_REQUIRE(ctlh[3] == 0, B2V_ERR_NOCONV, "floodfill: no convergence after %d rounds", ctlh[7]);
   g_last_rounds = ctlh[7];
+  g_last_exchanges = ctlh[18];
+  B2V_REQUIRE(ctlh[3] != 2, B2V_ERR_NOCONV,
+              "floodfill: a neighbour shard did not answer within the time-out (exchange %d): ranks out of step?",
+              ctlh[18]);
+  B2V_REQUIRE(ctlh[3] == 0, B2V_ERR_NOCONV, "floodfill: no convergence after %d rounds", ctlh[7]);
   return B2V_OK;
 }
 
 // verdict_later: the caller queues more work behind the kernel and calls persistent_verdict()
 // itself (one host round trip per flood instead of two).
 int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_t s, int r0, int* rounds_out,
-                   bool verdict_later) {
+                   bool verdict_later, const PeerSet* peer = nullptr) {
   int ntiles = b.ntz * b.nty * b.ntw;
   const size_t smem = 2 * (size_t)(b.tz + 2) * (b.ty + 2) * (b.tw + 2) * sizeof(uint32_t);
   int rc;
   const int nbw = (int)((ntiles + 31) / 32);
   uint32_t* bm = (uint32_t*)w.lists;   // three rotating tile bitmaps [3][nbw]
   const int canon = (sb == kSB6 && b.tw == 16 && b.ty == b.tz) ? (b.ty == 16 ? 4 : b.ty == 8 ? 3 : 0) : 0;
-  void* kern = canon == 4 ? (void*)k_ff_persistent<kSB6, 4>
-             : canon == 3 ? (void*)k_ff_persistent<kSB6, 3>
-             : sb == kSB6 ? (void*)k_ff_persistent<kSB6, 0>
-             : sb == kSB26 ? (void*)k_ff_persistent<kSB26, 0>
-             : sb == kSB18 ? (void*)k_ff_persistent<kSB18, 0> : (void*)k_ff_persistent<0u, 0>;
+  void* kern = peer ? (canon == 4 ? (void*)k_ff_persistent<kSB6, 4, true>
+                      : canon == 3 ? (void*)k_ff_persistent<kSB6, 3, true>
+                      : sb == kSB6 ? (void*)k_ff_persistent<kSB6, 0, true>
+                      : sb == kSB26 ? (void*)k_ff_persistent<kSB26, 0, true>
+                      : sb == kSB18 ? (void*)k_ff_persistent<kSB18, 0, true> : (void*)k_ff_persistent<0u, 0, true>)
+                    : (canon == 4 ? (void*)k_ff_persistent<kSB6, 4, false>
+                      : canon == 3 ? (void*)k_ff_persistent<kSB6, 3, false>
+                      : sb == kSB6 ? (void*)k_ff_persistent<kSB6, 0, false>
+                      : sb == kSB26 ? (void*)k_ff_persistent<kSB26, 0, false>
+                      : sb == kSB18 ? (void*)k_ff_persistent<kSB18, 0, false> : (void*)k_ff_persistent<0u, 0, false>);
   B2V_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   B2V_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, kFloodThreads, smem));
   B2V_REQUIRE(per_sm >= 1, B2V_ERR_CUDA, "floodfill: persistent kernel does not fit on an SM");
   int grid = per_sm * b2v_sm_count();        // every co-resident slot: one tile per block per round
-  if (const char* e = getenv("B2V_FF_GRID")) {   // tuning knob (blocks of the persistent grid)
-    int v = atoi(e);
-    if (v > 0 && v < grid) grid = v;
-  }
+  if (knobs().grid > 0 && knobs().grid < grid) grid = knobs().grid;   // tuning knob
   if (grid > ntiles) grid = (int)ntiles;
   // a block keeps at most kMaxMine tiles of a round in shared memory (5 G voxels at 148 blocks and 16^3-word tiles)
-  if ((int64_t)grid * kMaxMine < ntiles) return run_rounds(b, w, sb, s, r0, rounds_out);
+  if ((int64_t)grid * kMaxMine < ntiles) {
+    B2V_REQUIRE(!peer, B2V_ERR_ARG, "floodfill: shard too large for the fused peer exchange (%d tiles)", ntiles);
+    return run_rounds(b, w, sb, s, r0, rounds_out);
+  }
   k_ff_lists_init<<<1, 1024, 0, s>>>(w.active[r0 & 1], w.active[r0 & 1], (int)ntiles, bm, nbw);
   if ((rc = b2v_check_launch("k_ff_lists_init"))) return rc;
   const uint32_t* fg = w.fg;
@@ -1069,7 +1200,9 @@ int run_persistent(const BitVol& b, const Workspace& w, uint32_t sb, cudaStream_
   int* ctl = w.ctl;
   int max_rounds = kMaxRounds;
   int nbw_arg = nbw;
-  void* args[] = {&fg, &reach, &bb, &sb, &bm, &nbw_arg, &ctl, &max_rounds};
+  PeerSet pset;
+  if (peer) pset = *peer; else memset(&pset, 0, sizeof(pset));
+  void* args[] = {&fg, &reach, &bb, &sb, &bm, &nbw_arg, &ctl, &max_rounds, &pset};
   B2V_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kFloodThreads), args, smem, s));
   if ((rc = b2v_check_launch("k_ff_persistent"))) return rc;
   // the round flag of r0 was consumed; the next merge raises flags[r0 + 1]
@@ -1086,7 +1219,7 @@ enum { STAGE_BEGIN = 1, STAGE_CONVERGE = 2, STAGE_FINISH = 4, STAGE_ALL = 7 };
 template <typename T, int MODE>
 int flood(T* data, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64_t* seeds_host, int64_t nseeds,
           typename Thr<T>::type t0, typename Thr<T>::type t1, typename Thr<T>::type fill_t, uint8_t fill_o,
-          uint32_t sb, void* workspace, cudaStream_t s, int stages, int* round_io) {
+          uint32_t sb, void* workspace, cudaStream_t s, int stages, int* round_io, const PeerSet* peer = nullptr) {
   B2V_REQUIRE(data && workspace && (MODE == MODE_INPLACE || out), B2V_ERR_ARG, "floodfill: null pointer");
   B2V_REQUIRE(dz > 0 && dy > 0 && dx > 0, B2V_ERR_ARG, "floodfill: empty volume");
   B2V_REQUIRE(dz * dy * ceil_div64(dx, 32) < (1ll << 31), B2V_ERR_ARG, "floodfill: volume too large");
@@ -1098,7 +1231,7 @@ int flood(T* data, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64
   if (stages & STAGE_BEGIN) {
     if ((rc = check_seeds(seeds_host, nseeds, dz, dy, dx))) return rc;
     if (round_io) *round_io = 0;
-    if (nseeds == 0 && stages == STAGE_ALL) return B2V_OK;
+    if (nseeds == 0 && stages == STAGE_ALL && !peer) return B2V_OK;
     // control region (active flags, round flags) starts clean
     B2V_CUDA(cudaMemsetAsync(w.active[0], 0, (size_t)((char*)w.seeds - (char*)w.active[0]), s));
     if (nseeds) B2V_CUDA(cudaMemcpyAsync(w.seeds, seeds_host, (size_t)nseeds * 24, cudaMemcpyHostToDevice, s));
@@ -1125,8 +1258,13 @@ int flood(T* data, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64
   }
   if (stages & STAGE_CONVERGE) {
     int r0 = round_io ? *round_io : 0, r1 = r0;
-    verdict_due = g_flood_engine && (stages & STAGE_FINISH);
-    if ((rc = g_flood_engine ? run_persistent(b, w, sb, s, r0, &r1, verdict_due) : run_rounds(b, w, sb, s, r0, &r1)))
+    verdict_due = (g_flood_engine || peer) && (stages & STAGE_FINISH);
+    if (peer) {
+      B2V_REQUIRE(b.dz >= 2 && b.dy * (int64_t)b.wx * 4 <= peer->pc, B2V_ERR_ARG,
+                  "floodfill: the shard's planes do not fit the peer mailboxes (or the slab has < 2 planes)");
+    }
+    if ((rc = (g_flood_engine || peer) ? run_persistent(b, w, sb, s, r0, &r1, verdict_due, peer)
+                                       : run_rounds(b, w, sb, s, r0, &r1)))
       return rc;
     if (round_io) *round_io = r1;
   }
@@ -1177,16 +1315,27 @@ __global__ void __launch_bounds__(256) k_ff_merge_plane(const uint32_t* __restri
 template <int MODE>
 int flood_dispatch(void* data, int dtype, uint8_t* out, int64_t dz, int64_t dy, int64_t dx, const int64_t* seeds_host,
                    int64_t nseeds, double t0, double t1, double fill_t, uint8_t fill_o, uint32_t sb, void* workspace,
-                   cudaStream_t s, int stages, int* round_io) {
-  if (dtype == B2V_I16)
-    return flood<int16_t, MODE>((int16_t*)data, out, dz, dy, dx, seeds_host, nseeds, (int)t0, (int)t1, (int)fill_t,
-                                fill_o, sb, workspace, s, stages, round_io);
-  if (dtype == B2V_U8)
-    return flood<uint8_t, MODE>((uint8_t*)data, out, dz, dy, dx, seeds_host, nseeds, (int)t0, (int)t1, (int)fill_t,
-                                fill_o, sb, workspace, s, stages, round_io);
+                   cudaStream_t s, int stages, int* round_io, const PeerSet* peer = nullptr) {
+  B2V_REQUIRE(t0 == t0 && t1 == t1 && fill_t == fill_t, B2V_ERR_ARG, "floodfill: NaN threshold");
+  if (dtype == B2V_I16 || dtype == B2V_U8) {
+    // Inclusive bounds on integer data: a fractional bound is equivalent to ceil(t0) / floor(t1)
+    // (MODE_EQUAL: a non-integer value matches nothing); clamped well inside int32 so the casts
+    // are defined for +-inf and huge values.
+    const double lim = 1073741824.0;   // 2^30
+    double a = MODE == MODE_EQUAL ? t0 : ceil(t0), b = MODE == MODE_EQUAL ? t0 : floor(t1);
+    if (MODE == MODE_EQUAL && t0 != floor(t0)) { a = lim; b = lim; }   // matches no integer voxel
+    a = a < -lim ? -lim : (a > lim ? lim : a);
+    b = b < -lim ? -lim : (b > lim ? lim : b);
+    const double f = fill_t < -lim ? -lim : (fill_t > lim ? lim : fill_t);
+    if (dtype == B2V_I16)
+      return flood<int16_t, MODE>((int16_t*)data, out, dz, dy, dx, seeds_host, nseeds, (int)a, (int)b, (int)f,
+                                  fill_o, sb, workspace, s, stages, round_io, peer);
+    return flood<uint8_t, MODE>((uint8_t*)data, out, dz, dy, dx, seeds_host, nseeds, (int)a, (int)b, (int)f,
+                                fill_o, sb, workspace, s, stages, round_io, peer);
+  }
   if (dtype == B2V_F64)
     return flood<double, MODE>((double*)data, out, dz, dy, dx, seeds_host, nseeds, t0, t1, fill_t, fill_o, sb,
-                               workspace, s, stages, round_io);
+                               workspace, s, stages, round_io, peer);
   B2V_REQUIRE(false, B2V_ERR_ARG, "floodfill: unknown dtype code %d", dtype);
 }
 
@@ -1249,6 +1398,32 @@ extern "C" int b2v_floodfill_threshold_staged(int stages, const void* data, int 
                                         0.0, fill, sb, workspace, (cudaStream_t)stream, stages, round_io);
 }
 
+// One Z shard of a sharded flood with the boundary exchange fused into the persistent kernel
+// (peer mailboxes over NVLink, csrc/peer.cuh). data / out are the EXTENDED slab (own planes plus
+// one halo plane per inner side, halo planes of `data` valid), seeds are local to it. Every rank
+// of the job must make this call with the same `epoch`; *epochs_used_out tells how many
+// exchanges (epochs) the call consumed — the same number on every rank. Synchronises the stream.
+extern "C" int b2v_floodfill_threshold_peer(const void* data, int dtype, int64_t dz, int64_t dy, int64_t dx,
+                                            const int64_t* seeds_host, int64_t nseeds, double t0, double t1,
+                                            uint8_t fill, const uint8_t* strct_host, int64_t odz, int64_t ody,
+                                            int64_t odx, uint8_t* out, void* workspace, void* stream, int rank,
+                                            int world, const void* const* mailboxes_host, int64_t mailbox_plane_bytes,
+                                            uint32_t epoch, int* rounds_out, int* epochs_used_out) {
+  uint32_t sb;
+  int rc;
+  if ((rc = strct_bits(strct_host, odz, ody, odx, &sb))) return rc;
+  B2V_REQUIRE(epoch >= 1 && epochs_used_out, B2V_ERR_ARG, "floodfill_peer: epochs start at 1");
+  PeerSet ps;
+  if ((rc = peer_make_set(rank, world, mailboxes_host, mailbox_plane_bytes, epoch, &ps))) return rc;
+  int rounds = 0;
+  *epochs_used_out = 0;
+  rc = flood_dispatch<MODE_THRESHOLD>(const_cast<void*>(data), dtype, out, dz, dy, dx, seeds_host, nseeds, t0, t1, 0.0,
+                                      fill, sb, workspace, (cudaStream_t)stream, STAGE_ALL, &rounds, &ps);
+  *epochs_used_out = g_last_exchanges;
+  if (rounds_out) *rounds_out = rounds;
+  return rc;
+}
+
 extern "C" int b2v_floodfill_layout(int64_t dz, int64_t dy, int64_t dx, int64_t nseeds, int64_t* layout_out) {
   B2V_REQUIRE(dz > 0 && dy > 0 && dx > 0 && layout_out, B2V_ERR_ARG, "floodfill_layout: bad arguments");
   BitVol b = make_bitvol(dz, dy, dx);
@@ -1307,12 +1482,17 @@ __global__ void __launch_bounds__(256) k_fh_any(const uint32_t* __restrict__ siz
 }
 
 __global__ void __launch_bounds__(256) k_fh_apply(const uint32_t* __restrict__ labels, int64_t n,
-                                                  const uint32_t* __restrict__ sizes, uint32_t max_size,
-                                                  const int* __restrict__ modified, uint8_t* __restrict__ mask) {
-  if (*modified == 0) return;
+                                                  const uint32_t* __restrict__ sizes, uint32_t nlabels,
+                                                  uint32_t max_size, const int* __restrict__ ctrl,
+                                                  uint8_t* __restrict__ mask) {
+  // ctrl[0] = something qualifies, ctrl[1] = a label exceeded nlabels (reported as B2V_ERR_RANGE:
+  // the mask is left untouched and no size is read out of bounds)
+  if (ctrl[0] == 0 || ctrl[1] != 0) return;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    if (__ldg(&sizes[labels[i]]) <= max_size) mask[i] = 254;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t l = labels[i];
+    if (l <= nlabels && __ldg(&sizes[l]) <= max_size) mask[i] = 254;
+  }
 }
 
 }  // namespace
@@ -1335,7 +1515,7 @@ extern "C" int b2v_fill_holes(uint8_t* mask, const uint32_t* labels, int64_t n, 
   if ((rc = b2v_check_launch("k_fh_hist"))) return rc;
   k_fh_any<<<(unsigned)ceil_div64(nbins, 256), 256, 0, s>>>(sizes, nbins, max_size, ctrl);
   if ((rc = b2v_check_launch("k_fh_any"))) return rc;
-  k_fh_apply<<<grid_for(n, 256), 256, 0, s>>>(labels, n, sizes, max_size, ctrl, mask);
+  k_fh_apply<<<grid_for(n, 256), 256, 0, s>>>(labels, n, sizes, nlabels, max_size, ctrl, mask);
   if ((rc = b2v_check_launch("k_fh_apply"))) return rc;
   int host[2] = {0, 0};
   B2V_CUDA(cudaMemcpyAsync(host, ctrl, sizeof(host), cudaMemcpyDeviceToHost, s));

@@ -5,14 +5,15 @@
 //
 //   1. bits   (HBM-bound, the only pass over the volume: 1 B/voxel uint8, 2 B/voxel int16):
 //             inside(p) = S[p] >= iso packed 32 voxels per word along x.
-//   2. count  (on bits, L2 resident): per word the crossing masks towards +x/+y/+z, the
-//             number of owned vertices (popcounts) and of triangles (table lookups over
-//             the active cells only).
-//   3. scan   exclusive prefix sums of both counts (block sums -> one block -> apply).
-//   4. emit   one thread per vertex and one thread per active cell, each finding its word by
-//             searching the offsets; a vertex id is  voff[owner word] + popcounts below the
-//             owner bit.
+//   2. classify + compact (on bits, L2 resident, ONE pass): per word the crossing masks towards
+//             +x/+y/+z, the owned vertices (popcounts) and the triangles of its active cells;
+//             non-empty words are appended in word order to two compact lists, the running
+//             offsets carried from tile to tile by a chained (decoupled look-back) scan.
+//   3. emit   one thread per vertex and one thread per active cell over the compact lists; a
+//             vertex id is  voff[owner word] + popcounts below the owner bit, each owner
+//             record fetched once per cell.
 #include "b2v_common.cuh"
+#include "peer.cuh"
 #define B2V_MC_QUAL __device__
 #include "mc_tables.h"
 
@@ -32,17 +33,27 @@ McGeom make_geom(int64_t nz, int64_t ny, int64_t nx) {
   return g;
 }
 
-constexpr int kScanBlock = 256;
+constexpr int kClsThreads = 256;
+enum { Q_VW = 0, Q_V = 1, Q_CW = 2, Q_C = 3, Q_T = 4, Q_N = 5 };   // listed words (verts), vertices, listed
+                                                                    // words (cells), active cells, triangles
+struct TileState {     // chained-scan state of one classify tile
+  uint32_t agg[Q_N];
+  uint32_t incl[Q_N];
+  uint32_t pad;
+  int flag;            // 0 nothing yet, 1 aggregate valid, 2 inclusive prefix valid
+};
 
 struct McWs {
   uint32_t* bits;    // [nwords] inside bits
-  uint4* info;       // [nwords] (cx, cy, cz, vertex offset)
-  unsigned long long* toff;   // [nwords] (active-cell offset << 32) | triangle offset
-  uint32_t* amask;   // [nwords] cells of the word that produce triangles
-  uint32_t* bsum_v;  // [nblocks]
-  unsigned long long* bsum_t;  // [nblocks] packed like toff
-  unsigned long long* totals;  // [0] V, [1] (C << 32) | T
-  int64_t nblocks;
+  uint32_t* vslot;   // [nwords] dense map word -> slot in the vertex list (written for listed words only)
+  uint4* vinfo;      // [<= nwords] listed words that own vertices: (cx, cy, cz, exclusive vertex offset)
+  uint32_t* vword;   // [<= nwords] their word indices
+  uint4* cinfo;      // [<= nwords] listed words with active cells: (word, cell mask, triangle offset, cell offset)
+  uint4* plane0;     // [ny * wx] dense records of plane 0 (Z-sharded volumes)
+  TileState* tiles;  // [ntiles4 or ntiles1]
+  unsigned long long* totals;  // [0] V, [1] T, [2] active cells, [3] listed v-words, [4] listed c-words, [5] overflow
+  unsigned int* ticket;
+  int64_t ctl_bytes; // tiles + totals + ticket: zeroed before every classify
   int64_t bytes;
 };
 
@@ -51,14 +62,18 @@ McWs carve(void* base, const McGeom& g) {
   auto align = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
   char* p = (char*)base;
   int64_t off = 0;
-  w.nblocks = ceil_div64(g.nwords, kScanBlock);
-  w.bits = (uint32_t*)(p + off); off += align(g.nwords * 4 + 4);
-  w.info = (uint4*)(p + off); off += align(g.nwords * 16);
-  w.toff = (unsigned long long*)(p + off); off += align(g.nwords * 8);
-  w.amask = (uint32_t*)(p + off); off += align(g.nwords * 4);
-  w.bsum_v = (uint32_t*)(p + off); off += align(w.nblocks * 4);
-  w.bsum_t = (unsigned long long*)(p + off); off += align(w.nblocks * 8);
+  const int64_t ntiles = ceil_div64(g.nwords, kClsThreads);   // capacity for one word per thread
+  w.bits = (uint32_t*)(p + off); off += align(g.nwords * 4 + 64);
+  w.vslot = (uint32_t*)(p + off); off += align(g.nwords * 4);
+  w.vinfo = (uint4*)(p + off); off += align(g.nwords * 16);
+  w.vword = (uint32_t*)(p + off); off += align(g.nwords * 4);
+  w.cinfo = (uint4*)(p + off); off += align(g.nwords * 16);
+  w.plane0 = (uint4*)(p + off); off += align(g.ny * g.wx * 16);
+  const int64_t ctl0 = off;
+  w.tiles = (TileState*)(p + off); off += align(ntiles * (int64_t)sizeof(TileState));
   w.totals = (unsigned long long*)(p + off); off += 256;
+  w.ticket = (unsigned int*)(p + off); off += 256;
+  w.ctl_bytes = off - ctl0;
   w.bytes = off;
   return w;
 }
@@ -162,28 +177,24 @@ __global__ void __launch_bounds__(256) k_mc_bits_i16_vec(const int16_t* __restri
   }
 }
 
-// ---- 2. count -------------------------------------------------------------------------------
+// ---- 2. classify + compact (one pass, decoupled look-back) -----------------------------------
+// The surface touches a few per cent of the words. One pass over the bit volume classifies every
+// word (crossing masks towards +x/+y/+z, active cells, triangle count) and appends the non-empty
+// ones, IN WORD ORDER, to two compact lists:
+//   vertex list   words that own vertices:   vinfo[slot] = (cx, cy, cz, exclusive vertex offset),
+//                 vword[slot] = word index, and the dense map vslot[word] = slot (written only
+//                 for listed words: a crossing edge's owner is always listed);
+//   cell list     words with active cells:   cinfo[slot] = (word index, active-cell mask,
+//                 exclusive triangle offset, exclusive active-cell offset).
+// The five running totals (listed words x2, vertices, cells, triangles) are carried from tile to
+// tile by a chained scan: a tile publishes its aggregate, looks back over its predecessors until
+// it meets an inclusive prefix, then publishes its own. Tiles are numbered by an atomic ticket,
+// so every predecessor of a running tile is itself running (no deadlock). Nothing is written for
+// empty words and no second pass re-reads per-word records.
 struct Rows {       // the four bit rows a cell row touches, word w and bit 0 of word w+1
   uint32_t i00, i01, i10, i11;  // [cz][cy]
   uint32_t n00, n01, n10, n11;  // next word in x (0 past the row end)
 };
-
-__device__ __forceinline__ Rows load_rows(const uint32_t* __restrict__ bits, const McGeom& g, int64_t z, int64_t y,
-                                          int w) {
-  Rows r;
-  const bool hy = y + 1 < g.ny, hz = z + 1 < g.nz, hn = w + 1 < g.wx;
-  const int64_t b00 = (z * g.ny + y) * g.wx + w;
-  const int64_t b01 = b00 + g.wx, b10 = b00 + (int64_t)g.ny * g.wx, b11 = b10 + g.wx;
-  r.i00 = __ldg(bits + b00);
-  r.i01 = hy ? __ldg(bits + b01) : 0u;
-  r.i10 = hz ? __ldg(bits + b10) : 0u;
-  r.i11 = (hy && hz) ? __ldg(bits + b11) : 0u;
-  r.n00 = hn ? __ldg(bits + b00 + 1) : 0u;
-  r.n01 = (hn && hy) ? __ldg(bits + b01 + 1) : 0u;
-  r.n10 = (hn && hz) ? __ldg(bits + b10 + 1) : 0u;
-  r.n11 = (hn && hy && hz) ? __ldg(bits + b11 + 1) : 0u;
-  return r;
-}
 
 // bit i of the result = bit i+1 of the 64-bit (hi:lo)
 __device__ __forceinline__ uint32_t shift_in(uint32_t lo, uint32_t hi) { return (lo >> 1) | (hi << 31); }
@@ -202,173 +213,251 @@ __device__ __forceinline__ int cell_case(const Rows& r, int i) {
   return (int)(a | (b << 2) | (c << 4) | (d << 6));
 }
 
-__global__ void __launch_bounds__(kScanBlock) k_mc_count(const uint32_t* __restrict__ bits, McGeom g, int skip_last,
-                                                         uint4* __restrict__ info,
-                                                         unsigned long long* __restrict__ toff,
-                                                         uint32_t* __restrict__ amask, uint32_t* __restrict__ bsum_v,
-                                                         unsigned long long* __restrict__ bsum_t) {
+__device__ __forceinline__ Rows load_rows(const uint32_t* __restrict__ bits, const McGeom& g, int64_t z, int64_t y,
+                                          int w) {
+  Rows r;
+  const bool hy = y + 1 < g.ny, hz = z + 1 < g.nz, hn = w + 1 < g.wx;
+  const int64_t b00 = (z * g.ny + y) * g.wx + w;
+  const int64_t b01 = b00 + g.wx, b10 = b00 + (int64_t)g.ny * g.wx, b11 = b10 + g.wx;
+  r.i00 = __ldg(bits + b00);
+  r.i01 = hy ? __ldg(bits + b01) : 0u;
+  r.i10 = hz ? __ldg(bits + b10) : 0u;
+  r.i11 = (hy && hz) ? __ldg(bits + b11) : 0u;
+  r.n00 = hn ? __ldg(bits + b00 + 1) : 0u;
+  r.n01 = (hn && hy) ? __ldg(bits + b01 + 1) : 0u;
+  r.n10 = (hn && hz) ? __ldg(bits + b10 + 1) : 0u;
+  r.n11 = (hn && hy && hz) ? __ldg(bits + b11 + 1) : 0u;
+  return r;
+}
+
+struct WordClass {
+  uint32_t cx, cy, cz, act;
+  uint32_t nv, nt;
+};
+
+__device__ __forceinline__ WordClass classify_word(const Rows& r, uint32_t vx, bool hy, bool hz, bool own_verts,
+                                                   const unsigned char* s_ntri) {
+  WordClass c;
+  const uint32_t s00 = shift_in(r.i00, r.n00);
+  c.cx = (r.i00 ^ s00) & vx;
+  c.cy = hy ? (r.i00 ^ r.i01) : 0u;
+  c.cz = hz ? (r.i00 ^ r.i10) : 0u;
+  // a Z shard does not own the vertices of its last (shared) plane: the next shard does
+  c.nv = own_verts ? __popc(c.cx) + __popc(c.cy) + __popc(c.cz) : 0;
+  c.act = 0;
+  c.nt = 0;
+  if (hy && hz) {
+    const uint32_t s01 = shift_in(r.i01, r.n01), s10 = shift_in(r.i10, r.n10), s11 = shift_in(r.i11, r.n11);
+    const uint32_t any = r.i00 | r.i01 | r.i10 | r.i11 | s00 | s01 | s10 | s11;
+    const uint32_t all = r.i00 & r.i01 & r.i10 & r.i11 & s00 & s01 & s10 & s11;
+    c.act = any & ~all & vx;
+    for (uint32_t m = c.act; m; m &= m - 1) c.nt += s_ntri[cell_case(r, __ffs(m) - 1)];
+  }
+  return c;
+}
+
+__device__ __forceinline__ int ld_flag(const int* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+template <int WPT>
+__global__ void __launch_bounds__(kClsThreads) k_mc_classify(const uint32_t* __restrict__ bits, McGeom g,
+                                                             int skip_last, uint32_t* __restrict__ vslot,
+                                                             uint4* __restrict__ vinfo, uint32_t* __restrict__ vword,
+                                                             uint4* __restrict__ cinfo, TileState* tiles,
+                                                             unsigned int* ticket, unsigned long long* totals,
+                                                             int ntiles) {
   __shared__ unsigned char s_ntri[256];
-  __shared__ unsigned long long s_red[2][kScanBlock / 32];
-  s_ntri[threadIdx.x] = B2V_MC_NTRI[threadIdx.x];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_wx[kClsThreads / 32];
+  __shared__ uint32_t s_wy[kClsThreads / 32];
+  __shared__ uint32_t s_base[Q_N];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  s_ntri[tid] = B2V_MC_NTRI[tid];
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
-  const int64_t wi = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
-  uint32_t nv = 0, nt = 0, nact = 0;
-  if (wi < g.nwords) {
-    int64_t row = wi / g.wx;
-    int w = (int)(wi - row * g.wx);
-    int64_t z = row / g.ny, y = row - z * g.ny;
-    Rows r = load_rows(bits, g, z, y, w);
-    const uint32_t vx = valid_x1(g, w);
+  const int tile = (int)s_tile;
+  const int64_t wi0 = ((int64_t)tile * kClsThreads + tid) * WPT;
+  WordClass wc[WPT];
+  // packed thread sums: X = nv (20) | listed-v (12) | cells (20) | listed-c (12), Y = triangles
+  unsigned long long X = 0;
+  uint32_t Y = 0;
+  if (wi0 < g.nwords) {
+    const int64_t row = wi0 / g.wx;
+    const int w0 = (int)(wi0 - row * g.wx);
+    const int64_t z = row / g.ny, y = row - z * g.ny;
     const bool hy = y + 1 < g.ny, hz = z + 1 < g.nz;
-    uint32_t cx = (r.i00 ^ shift_in(r.i00, r.n00)) & vx;
-    uint32_t cy = hy ? (r.i00 ^ r.i01) : 0u;
-    uint32_t cz = hz ? (r.i00 ^ r.i10) : 0u;
-    // a Z shard does not own the vertices of its last (shared) plane: the next shard does
-    nv = (skip_last && z == g.nz - 1) ? 0 : __popc(cx) + __popc(cy) + __popc(cz);
-    uint32_t act = 0;
-    if (hy && hz) {
-      uint32_t s00 = shift_in(r.i00, r.n00), s01 = shift_in(r.i01, r.n01), s10 = shift_in(r.i10, r.n10),
-               s11 = shift_in(r.i11, r.n11);
-      uint32_t any = r.i00 | r.i01 | r.i10 | r.i11 | s00 | s01 | s10 | s11;
-      uint32_t all = r.i00 & r.i01 & r.i10 & r.i11 & s00 & s01 & s10 & s11;
-      act = any & ~all & vx;
-      nact = __popc(act);
-      uint32_t m = act;
-      while (m) {
-        int i = __ffs(m) - 1;
-        m &= m - 1;
-        nt += s_ntri[cell_case(r, i)];
-      }
+    const bool own = !(skip_last && z == g.nz - 1);
+    uint32_t a00[WPT + 1], a01[WPT + 1], a10[WPT + 1], a11[WPT + 1];
+    const int64_t b00 = wi0, b01 = b00 + g.wx, b10 = b00 + (int64_t)g.ny * g.wx, b11 = b10 + g.wx;
+    if (WPT == 4) {   // wx % 4 == 0: the four words of a thread are one aligned 128-bit load per row
+      const uint4 q00 = __ldg((const uint4*)(bits + b00));
+      const uint4 q01 = hy ? __ldg((const uint4*)(bits + b01)) : make_uint4(0, 0, 0, 0);
+      const uint4 q10 = hz ? __ldg((const uint4*)(bits + b10)) : make_uint4(0, 0, 0, 0);
+      const uint4 q11 = (hy && hz) ? __ldg((const uint4*)(bits + b11)) : make_uint4(0, 0, 0, 0);
+      a00[0] = q00.x; a00[1] = q00.y; a00[2] = q00.z; a00[3] = q00.w;
+      a01[0] = q01.x; a01[1] = q01.y; a01[2] = q01.z; a01[3] = q01.w;
+      a10[0] = q10.x; a10[1] = q10.y; a10[2] = q10.z; a10[3] = q10.w;
+      a11[0] = q11.x; a11[1] = q11.y; a11[2] = q11.z; a11[3] = q11.w;
+    } else {
+      a00[0] = __ldg(bits + b00);
+      a01[0] = hy ? __ldg(bits + b01) : 0u;
+      a10[0] = hz ? __ldg(bits + b10) : 0u;
+      a11[0] = (hy && hz) ? __ldg(bits + b11) : 0u;
     }
-    info[wi] = make_uint4(cx, cy, cz, nv);
-    toff[wi] = ((unsigned long long)nact << 32) | nt;
-    amask[wi] = act;
-  }
-  // block sums (cells and triangles travel packed: no carry can cross, totals < 2^31)
-  unsigned long long a = nv, b = ((unsigned long long)nact << 32) | nt;
+    const bool hn = w0 + WPT < g.wx;
+    a00[WPT] = hn ? __ldg(bits + b00 + WPT) : 0u;
+    a01[WPT] = (hn && hy) ? __ldg(bits + b01 + WPT) : 0u;
+    a10[WPT] = (hn && hz) ? __ldg(bits + b10 + WPT) : 0u;
+    a11[WPT] = (hn && hy && hz) ? __ldg(bits + b11 + WPT) : 0u;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    s_red[0][threadIdx.x >> 5] = a;
-    s_red[1][threadIdx.x >> 5] = b;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long sa = 0, sb = 0;
+    for (int j = 0; j < WPT; ++j) {
+      Rows r = {a00[j], a01[j], a10[j], a11[j], a00[j + 1], a01[j + 1], a10[j + 1], a11[j + 1]};
+      wc[j] = classify_word(r, valid_x1(g, w0 + j), hy, hz, own, s_ntri);
+      X += (unsigned long long)wc[j].nv | ((unsigned long long)(wc[j].nv != 0) << 20) |
+           ((unsigned long long)__popc(wc[j].act) << 32) | ((unsigned long long)(wc[j].act != 0) << 52);
+      Y += wc[j].nt;
+    }
+  } else {
 #pragma unroll
-    for (int k = 0; k < kScanBlock / 32; ++k) {
-      sa += s_red[0][k];
-      sb += s_red[1][k];
-    }
-    bsum_v[blockIdx.x] = (uint32_t)sa;
-    bsum_t[blockIdx.x] = sb;
+    for (int j = 0; j < WPT; ++j) wc[j] = WordClass{0u, 0u, 0u, 0u, 0u, 0u};
   }
-}
-
-// ---- 3. scan -------------------------------------------------------------------------------
-// one block: exclusive scan of the block sums (in place, as 64-bit running totals truncated
-// to 32 bits on store; the host rejects totals >= 2^32), totals[0..1] = V, T
-__global__ void __launch_bounds__(1024) k_mc_scan_bsums(uint32_t* bsum_v, unsigned long long* bsum_t, int64_t nblocks,
-                                                        unsigned long long* totals) {
-  __shared__ unsigned long long s_w[2][32];
-  __shared__ unsigned long long s_carry[2];
-  if (threadIdx.x == 0) s_carry[0] = s_carry[1] = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int64_t base = 0; base < nblocks; base += 1024) {
-    int64_t i = base + threadIdx.x;
-    unsigned long long v = i < nblocks ? bsum_v[i] : 0ull, t = i < nblocks ? bsum_t[i] : 0ull;
-    unsigned long long iv = v, it = t;  // inclusive warp scan
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned long long pv = __shfl_up_sync(0xffffffffu, iv, o), pt = __shfl_up_sync(0xffffffffu, it, o);
-      if (lane >= o) { iv += pv; it += pt; }
-    }
-    if (lane == 31) { s_w[0][wid] = iv; s_w[1][wid] = it; }
-    __syncthreads();
-    if (wid == 0) {
-      unsigned long long a = s_w[0][lane], b = s_w[1][lane];
-      unsigned long long ia = a, ib = b;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long pa = __shfl_up_sync(0xffffffffu, ia, o), pb = __shfl_up_sync(0xffffffffu, ib, o);
-        if (lane >= o) { ia += pa; ib += pb; }
-      }
-      s_w[0][lane] = ia - a;  // exclusive over warps
-      s_w[1][lane] = ib - b;
-    }
-    __syncthreads();
-    unsigned long long ev = s_carry[0] + s_w[0][wid] + iv - v;
-    unsigned long long et = s_carry[1] + s_w[1][wid] + it - t;
-    if (i < nblocks) {
-      bsum_v[i] = (uint32_t)ev;
-      bsum_t[i] = et;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) {
-      s_carry[0] = ev + v;
-      s_carry[1] = et + t;
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    totals[0] = s_carry[0];
-    totals[1] = s_carry[1];
-  }
-}
-
-__global__ void __launch_bounds__(kScanBlock) k_mc_scan_apply(uint4* __restrict__ info,
-                                                              unsigned long long* __restrict__ toff, int64_t nwords,
-                                                              const uint32_t* __restrict__ bsum_v,
-                                                              const unsigned long long* __restrict__ bsum_t) {
-  __shared__ unsigned long long s_w[2][kScanBlock / 32];
-  const int64_t wi = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  unsigned long long v = wi < nwords ? info[wi].w : 0u, t = wi < nwords ? toff[wi] : 0ull;
-  unsigned long long iv = v, it = t;
+  // block exclusive scan of (X, Y)
+  unsigned long long ix = X;
+  uint32_t iy = Y;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    unsigned long long pv = __shfl_up_sync(0xffffffffu, iv, o), pt = __shfl_up_sync(0xffffffffu, it, o);
-    if (lane >= o) { iv += pv; it += pt; }
+    const unsigned long long px = __shfl_up_sync(0xffffffffu, ix, o);
+    const uint32_t py = __shfl_up_sync(0xffffffffu, iy, o);
+    if (lane >= o) { ix += px; iy += py; }
   }
-  if (lane == 31) { s_w[0][wid] = iv; s_w[1][wid] = it; }
+  if (lane == 31) { s_wx[warp] = ix; s_wy[warp] = iy; }
   __syncthreads();
-  unsigned long long ov = bsum_v[blockIdx.x], ot = bsum_t[blockIdx.x];
-  for (int k = 0; k < wid; ++k) { ov += s_w[0][k]; ot += s_w[1][k]; }
-  if (wi < nwords) {
-    info[wi].w = (uint32_t)(ov + iv - v);
-    toff[wi] = ot + it - t;
+  unsigned long long ox = 0, tx = 0;
+  uint32_t oy = 0, ty = 0;
+#pragma unroll
+  for (int k = 0; k < kClsThreads / 32; ++k) {
+    if (k < warp) { ox += s_wx[k]; oy += s_wy[k]; }
+    tx += s_wx[k]; ty += s_wy[k];
+  }
+  const unsigned long long ex = ox + ix - X;     // exclusive within the block
+  const uint32_t ey = oy + iy - Y;
+  // tile totals -> look-back (warp 0)
+  if (warp == 0) {
+    uint32_t tot[Q_N];
+    tot[Q_V] = (uint32_t)(tx & 0xfffffu); tot[Q_VW] = (uint32_t)((tx >> 20) & 0xfffu);
+    tot[Q_C] = (uint32_t)((tx >> 32) & 0xfffffu); tot[Q_CW] = (uint32_t)((tx >> 52) & 0xfffu);
+    tot[Q_T] = ty;
+    TileState* me = tiles + tile;
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < Q_N; ++q) { me->agg[q] = tot[q]; if (tile == 0) me->incl[q] = tot[q]; }
+      __threadfence();
+      *(volatile int*)&me->flag = tile == 0 ? 2 : 1;
+    }
+    uint32_t pre[Q_N];
+#pragma unroll
+    for (int q = 0; q < Q_N; ++q) pre[q] = 0;
+    for (int look = tile - 1; look >= 0; look -= 32) {
+      const int idx = look - lane;
+      int f = 2;
+      uint32_t v[Q_N];
+#pragma unroll
+      for (int q = 0; q < Q_N; ++q) v[q] = 0;
+      if (idx >= 0) {
+        const TileState* t = tiles + idx;
+        do { f = ld_flag(&t->flag); } while (f == 0);
+        __threadfence();
+#pragma unroll
+        for (int q = 0; q < Q_N; ++q) v[q] = __ldcg(f == 2 ? &t->incl[q] : &t->agg[q]);
+      }
+      // lanes up to (and including) the nearest inclusive prefix contribute
+      const unsigned m2 = __ballot_sync(0xffffffffu, idx < 0 || f == 2);
+      const int stop = __ffs(m2) - 1;     // m2 != 0: tile 0 or the lanes past it always qualify
+#pragma unroll
+      for (int q = 0; q < Q_N; ++q) {
+        uint32_t c = (lane <= stop && idx >= 0) ? v[q] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        pre[q] += c;
+      }
+      if (m2) break;
+    }
+    if (lane == 0) {
+      if (tile > 0) {
+#pragma unroll
+        for (int q = 0; q < Q_N; ++q) {
+          me->incl[q] = pre[q] + tot[q];
+          if (pre[q] + tot[q] < pre[q]) totals[5] = 1;   // a 32-bit running total wrapped: reported by the host
+        }
+        __threadfence();
+        *(volatile int*)&me->flag = 2;
+      }
+#pragma unroll
+      for (int q = 0; q < Q_N; ++q) s_base[q] = pre[q];
+      if (tile == ntiles - 1) {
+        totals[0] = pre[Q_V] + tot[Q_V];
+        totals[1] = pre[Q_T] + tot[Q_T];
+        totals[2] = pre[Q_C] + tot[Q_C];
+        totals[3] = pre[Q_VW] + tot[Q_VW];
+        totals[4] = pre[Q_CW] + tot[Q_CW];
+      }
+    }
+  }
+  __syncthreads();
+  if (wi0 >= g.nwords) return;
+  uint32_t rv = s_base[Q_V] + (uint32_t)(ex & 0xfffffu), rvw = s_base[Q_VW] + (uint32_t)((ex >> 20) & 0xfffu);
+  uint32_t rc = s_base[Q_C] + (uint32_t)((ex >> 32) & 0xfffffu), rcw = s_base[Q_CW] + (uint32_t)((ex >> 52) & 0xfffu);
+  uint32_t rt = s_base[Q_T] + ey;
+#pragma unroll
+  for (int j = 0; j < WPT; ++j) {
+    if (wc[j].nv) {
+      vinfo[rvw] = make_uint4(wc[j].cx, wc[j].cy, wc[j].cz, rv);
+      vword[rvw] = (uint32_t)(wi0 + j);
+      vslot[wi0 + j] = rvw;
+      ++rvw;
+      rv += wc[j].nv;
+    }
+    if (wc[j].act) {
+      cinfo[rcw] = make_uint4((uint32_t)(wi0 + j), wc[j].act, rt, rc);
+      ++rcw;
+      rc += __popc(wc[j].act);
+      rt += wc[j].nt;
+    }
   }
 }
 
-// ---- 4. emit -------------------------------------------------------------------------------
-// The surface touches a few cells per word, so a warp-per-word emitter leaves most lanes idle
-// (measured: 510 us, instruction-issue bound). Instead: one thread per VERTEX and one thread
-// per ACTIVE CELL. A thread finds its word by a two-level search over the exclusive offsets
-// (block sums: bisected once per warp, then a gallop from there; the 256 words of the block:
-// bisected), then its voxel / cell inside the word by popcounts. Outputs of consecutive
-// threads are consecutive in memory. (One thread per TRIANGLE was measured too: uniform
-// work, but every triangle repeats the search and the eight row loads: 144 us against
-// 128 us at 512^3.)
+// dense per-word records (cx, cy, cz, exclusive vertex offset) of plane 0: what the shard BELOW
+// needs to number the vertices of the plane it shares with this one (b2v_mc_emit_shard)
+__global__ void __launch_bounds__(256) k_mc_plane0(const uint32_t* __restrict__ bits, McGeom g,
+                                                   const uint32_t* __restrict__ vslot,
+                                                   const uint4* __restrict__ vinfo, uint4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.ny * g.wx) return;
+  const int64_t y = i / g.wx;
+  const int w = (int)(i - y * g.wx);
+  const Rows r = load_rows(bits, g, 0, y, w);
+  const uint32_t cx = (r.i00 ^ shift_in(r.i00, r.n00)) & valid_x1(g, w);
+  const uint32_t cy = y + 1 < g.ny ? (r.i00 ^ r.i01) : 0u;
+  const uint32_t cz = g.nz > 1 ? (r.i00 ^ r.i10) : 0u;
+  const uint32_t voff = (cx | cy | cz) ? __ldg(&vinfo[__ldg(&vslot[i])].w) : 0u;
+  out[i] = make_uint4(cx, cy, cz, voff);
+}
+
+// ---- 3. emit ---------------------------------------------------------------------------------
+// One thread per VERTEX and one thread per ACTIVE CELL (the surface touches a few cells per word:
+// a warp-per-word emitter leaves most lanes idle). A warp's 32 consecutive outputs live in at
+// most 32 consecutive list entries (every entry holds at least one): lane 0 bisects the compact
+// list once, the lanes load 32 entries together, and each lane finds its own with five shuffles.
+// Outputs of consecutive threads are consecutive in memory.
 struct McXform {
   float sx, sy, sz;
   int ox, oy, oz;
   int flip_y;
   float iso;
 };
-
-// per edge id: axis and owner offset, packed (a | ox<<2 | oy<<3 | oz<<4)
-__device__ __forceinline__ int edge_code(int e) {
-  int a = e >> 2, cu = e & 1, cv = (e >> 1) & 1;
-  int ox = 0, oy = 0, oz = 0;
-  if (a == 0) { oy = cu; oz = cv; }
-  else if (a == 1) { ox = cu; oz = cv; }
-  else { ox = cu; oy = cv; }
-  return a | (ox << 2) | (oy << 3) | (oz << 4);
-}
 
 // largest i in [0, n) with key(i) <= k; key is non-decreasing and key(0) <= k
 template <typename F>
@@ -381,43 +470,45 @@ __device__ __forceinline__ int64_t last_le(int64_t n, uint32_t k, F key) {
   return lo;
 }
 
-// the same, knowing key(start) <= k and expecting the answer near start: gallop, then bisect
-template <typename F>
-__device__ __forceinline__ int64_t last_le_from(int64_t start, int64_t n, uint32_t k, F key) {
-  int64_t lo = start, hi = start + 1, step = 1;
-  while (hi < n && key(hi) <= k) { lo = hi; step <<= 1; hi = lo + step; }
-  if (hi > n) hi = n;
-  while (hi - lo > 1) {
-    int64_t mid = (lo + hi) >> 1;
-    if (key(mid) <= k) lo = mid; else hi = mid;
+__device__ __forceinline__ uint32_t below(int i) { return i >= 32 ? 0xffffffffu : ((1u << i) - 1u); }
+
+// the lane's entry among the warp's 32 loaded ones: the last j <= lane with key_j <= k
+__device__ __forceinline__ int warp_locate(uint32_t my_key, uint32_t k, int lane) {
+  int lo = 0, hi = lane + 1;
+#pragma unroll
+  for (int it = 0; it < 5; ++it) {
+    const int mid = (lo + hi) >> 1;
+    const uint32_t v = __shfl_sync(0xffffffffu, my_key, mid);
+    if (hi - lo > 1) { if (v <= k) lo = mid; else hi = mid; }
   }
   return lo;
 }
 
-__device__ __forceinline__ uint32_t below(int i) { return i >= 32 ? 0xffffffffu : ((1u << i) - 1u); }
-
 template <typename T>
 __global__ void __launch_bounds__(256) k_mc_emit_verts(const T* __restrict__ vol, McGeom g,
-                                                       const uint4* __restrict__ info,
-                                                       const uint32_t* __restrict__ bsum_v, int64_t nblocks,
+                                                       const uint4* __restrict__ vinfo,
+                                                       const uint32_t* __restrict__ vword,
                                                        const unsigned long long* __restrict__ totals, McXform xf,
                                                        float* __restrict__ verts) {
   const uint32_t V = (uint32_t)totals[0];
+  const int64_t nlist = (int64_t)totals[3];
   const uint32_t stride = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
-  // a warp's 32 consecutive outputs start in the same block of words or close to it: lane 0
-  // bisects the block sums once, the others gallop on from its answer
   for (uint32_t kb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); kb < V; kb += stride) {
     const uint32_t k = kb + lane;
-    auto bkey = [&](int64_t i) { return __ldg(bsum_v + i); };
-    int64_t blk = lane == 0 ? last_le(nblocks, kb, bkey) : 0;
-    blk = __shfl_sync(0xffffffffu, blk, 0);
+    int64_t e0 = lane == 0 ? last_le(nlist, kb, [&](int64_t i) { return __ldg(&vinfo[i].w); }) : 0;
+    e0 = __shfl_sync(0xffffffffu, e0, 0);
+    uint4 ent = make_uint4(0u, 0u, 0u, 0xffffffffu);
+    uint32_t wd = 0;
+    if (e0 + lane < nlist) { ent = __ldg(vinfo + e0 + lane); wd = __ldg(vword + e0 + lane); }
+    const int j = warp_locate(ent.w, k, lane);
+    uint4 inf;
+    inf.x = __shfl_sync(0xffffffffu, ent.x, j);
+    inf.y = __shfl_sync(0xffffffffu, ent.y, j);
+    inf.z = __shfl_sync(0xffffffffu, ent.z, j);
+    inf.w = __shfl_sync(0xffffffffu, ent.w, j);
+    const int64_t wi = __shfl_sync(0xffffffffu, wd, j);
     if (k >= V) continue;
-    blk = last_le_from(blk, nblocks, k, bkey);
-    const int64_t w0 = blk * kScanBlock;
-    const int64_t nw = g.nwords - w0 < kScanBlock ? g.nwords - w0 : kScanBlock;
-    const int64_t wi = w0 + last_le(nw, k, [&](int64_t i) { return __ldg(&info[w0 + i].w); });
-    const uint4 inf = __ldg(info + wi);
     const uint32_t r = k - inf.w;
     // voxel: largest i with (#vertices of voxels below i) <= r
     int lo = 0, hi = 32;
@@ -452,74 +543,97 @@ __global__ void __launch_bounds__(256) k_mc_emit_verts(const T* __restrict__ vol
   }
 }
 
+// Crossing edges of a cell are owned by seven of its corner voxels: slot s = oz*4 + oy*2 + ox
+// owns the cell edges kSlotEdges[s] (edge id = axis*4 + cu + 2*cv as in mc_tables.h). A cell
+// resolves each NEEDED slot once (one record: exclusive vertex offset + popcounts below the
+// owner bit) and every triangle corner is then a shared-memory lookup by edge id.
+__constant__ unsigned short kSlotEdges[8] = {
+    (1u << 0) | (1u << 4) | (1u << 8),   // (0,0,0): x, y, z edges at the origin
+    (1u << 5) | (1u << 9),               // ox = 1
+    (1u << 1) | (1u << 10),              // oy = 1
+    (1u << 11),                          // ox = oy = 1
+    (1u << 2) | (1u << 6),               // oz = 1
+    (1u << 7),                           // ox = oz = 1
+    (1u << 3),                           // oy = oz = 1
+    0};
+
 __global__ void __launch_bounds__(256) k_mc_emit_tris(McGeom g, const uint32_t* __restrict__ bits,
-                                                      const uint4* __restrict__ info,
-                                                      const unsigned long long* __restrict__ toff,
-                                                      const uint32_t* __restrict__ amask,
-                                                      const unsigned long long* __restrict__ bsum_t, int64_t nblocks,
+                                                      const uint32_t* __restrict__ vslot,
+                                                      const uint4* __restrict__ vinfo,
+                                                      const uint4* __restrict__ cinfo,
                                                       const unsigned long long* __restrict__ totals, int flip_y,
                                                       int skip_last, int vbase, const uint4* __restrict__ foreign,
                                                       int foreign_base, int* __restrict__ tris) {
   __shared__ signed char s_tri[256][16];  // 15 edge ids + triangle count
+  __shared__ unsigned short s_emask[256];
+  __shared__ int s_id[12 * 256];          // [edge][thread]
   for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
     int c = i >> 4, k = i & 15;
     s_tri[c][k] = k < 15 ? B2V_MC_TRI[c][k] : (signed char)B2V_MC_NTRI[c];
   }
+  s_emask[threadIdx.x] = B2V_MC_EDGEMASK[threadIdx.x];
   __syncthreads();
-  const uint32_t C = (uint32_t)(totals[1] >> 32);
+  const uint32_t C = (uint32_t)totals[2];
+  const int64_t nlist = (int64_t)totals[4];
   const uint32_t stride = gridDim.x * blockDim.x;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, tid = threadIdx.x;
   for (uint32_t kb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); kb < C; kb += stride) {
     const uint32_t k = kb + lane;
-    auto bkey = [&](int64_t i) { return (uint32_t)(__ldg(bsum_t + i) >> 32); };
-    int64_t blk = lane == 0 ? last_le(nblocks, kb, bkey) : 0;
-    blk = __shfl_sync(0xffffffffu, blk, 0);
+    int64_t e0 = lane == 0 ? last_le(nlist, kb, [&](int64_t i) { return __ldg(&cinfo[i].w); }) : 0;
+    e0 = __shfl_sync(0xffffffffu, e0, 0);
+    uint4 ent = make_uint4(0u, 0u, 0u, 0xffffffffu);
+    if (e0 + lane < nlist) ent = __ldg(cinfo + e0 + lane);
+    const int j = warp_locate(ent.w, k, lane);
+    const int64_t wi = __shfl_sync(0xffffffffu, ent.x, j);
+    const uint32_t act = __shfl_sync(0xffffffffu, ent.y, j);
+    int64_t tbase = __shfl_sync(0xffffffffu, ent.z, j);
+    const uint32_t coff = __shfl_sync(0xffffffffu, ent.w, j);
     if (k >= C) continue;
-    blk = last_le_from(blk, nblocks, k, bkey);
-    const int64_t w0 = blk * kScanBlock;
-    const int64_t nw = g.nwords - w0 < kScanBlock ? g.nwords - w0 : kScanBlock;
-    const int64_t wi = w0 + last_le(nw, k, [&](int64_t i) { return (uint32_t)(__ldg(toff + w0 + i) >> 32); });
-    const unsigned long long tq = __ldg(toff + wi);
-    const uint32_t act = __ldg(amask + wi);
-    const int i = (int)__fns(act, 0, (int)(k - (uint32_t)(tq >> 32)) + 1);   // this thread's cell bit
+    const int i = (int)__fns(act, 0, (int)(k - coff) + 1);   // this thread's cell bit
     const int64_t row = wi / g.wx;
     const int w = (int)(wi - row * g.wx);
     const int64_t z = row / g.ny, y = row - z * g.ny;
     const Rows r = load_rows(bits, g, z, y, w);
     // triangles of the active cells before mine in this word
-    int64_t tbase = (uint32_t)tq;
     for (uint32_t e = act & below(i); e; e &= e - 1) tbase += s_tri[cell_case(r, __ffs(e) - 1)][15];
     const int c = cell_case(r, i);
     const int ntri = s_tri[c][15];
-    for (int t = 0; t < ntri; ++t) {
-      int id[3];
+    const uint32_t em = s_emask[c];
 #pragma unroll
-      for (int m = 0; m < 3; ++m) {
-        const int code = edge_code(s_tri[c][3 * t + m]);
-        const int a = code & 3;
-        const int qx = i + ((code >> 2) & 1);                      // 0..32 within the word pair
-        const int64_t qy = y + ((code >> 3) & 1), qz = z + ((code >> 4) & 1);
-        const int ob = qx & 31;
-        const uint32_t ol = (1u << ob) - 1u;
-        uint4 oi;
-        int v;
-        if (skip_last && qz == g.nz - 1) {
-          // owned by the next shard: its records of that plane, its numbering
-          oi = __ldg(foreign + qy * g.wx + (w + (qx >> 5)));
-          v = foreign_base;
-        } else {
-          oi = __ldg(info + (qz * g.ny + qy) * g.wx + (w + (qx >> 5)));
-          v = vbase;
-        }
-        v += (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
-        if (a > 0) v += (oi.x >> ob) & 1;
-        if (a > 1) v += (oi.y >> ob) & 1;
-        id[m] = v;
+    for (int s = 0; s < 7; ++s) {
+      const uint32_t need = em & kSlotEdges[s];
+      if (!need) continue;
+      const int ox = s & 1, oy = (s >> 1) & 1, oz = s >> 2;
+      const int qx = i + ox;                                   // 0..32 within the word pair
+      const int64_t qy = y + oy, qz = z + oz;
+      const int ob = qx & 31;
+      const uint32_t ol = (1u << ob) - 1u;
+      uint4 oi;
+      int v;
+      if (skip_last && qz == g.nz - 1) {
+        // owned by the next shard: its records of that plane, its numbering
+        oi = __ldg(foreign + qy * g.wx + (w + (qx >> 5)));
+        v = foreign_base;
+      } else {
+        oi = __ldg(vinfo + __ldg(vslot + (qz * g.ny + qy) * g.wx + (w + (qx >> 5))));
+        v = vbase;
       }
+      v += (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
+      const int bx = (oi.x >> ob) & 1, by = (oi.y >> ob) & 1;
+      // the slot's edges: at most one per axis; ids in x, y, z order among the owner's crossing edges
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const uint32_t ea = need & (0xfu << (4 * a));
+        if (ea) s_id[(__ffs(ea) - 1) * 256 + tid] = v + (a > 0 ? bx : 0) + (a > 1 ? by : 0);
+      }
+    }
+    for (int t = 0; t < ntri; ++t) {
+      const int i0 = s_id[s_tri[c][3 * t] * 256 + tid], i1 = s_id[s_tri[c][3 * t + 1] * 256 + tid],
+                i2 = s_id[s_tri[c][3 * t + 2] * 256 + tid];
       int* o = tris + 3 * (tbase + t);
-      o[0] = id[0];
-      o[1] = flip_y ? id[2] : id[1];
-      o[2] = flip_y ? id[1] : id[2];
+      o[0] = i0;
+      o[1] = flip_y ? i2 : i1;
+      o[2] = flip_y ? i1 : i2;
     }
   }
 }
@@ -548,7 +662,8 @@ extern "C" int64_t b2v_mc_workspace_bytes(int64_t nz, int64_t ny, int64_t nx) {
 }
 
 static int mc_count_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso, int skip_last,
-                         void* workspace, void* stream, int64_t* nverts_host, int64_t* ntris_host) {
+                         int shard, void* workspace, void* stream, int64_t* nverts_host, int64_t* ntris_host,
+                         bool no_sync = false) {
   B2V_REQUIRE(vol && workspace && nverts_host && ntris_host, B2V_ERR_ARG, "mc_count: null pointer");
   B2V_REQUIRE(nz > 0 && ny > 0 && nx > 0, B2V_ERR_ARG, "mc_count: empty volume");
   B2V_REQUIRE(dtype == B2V_U8 || dtype == B2V_I16, B2V_ERR_ARG, "mc_count: dtype must be uint8 or int16");
@@ -558,6 +673,7 @@ static int mc_count_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int
   McWs w = carve(workspace, g);
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
+  B2V_CUDA(cudaMemsetAsync(w.tiles, 0, (size_t)w.ctl_bytes, s));
   if (dtype == B2V_U8) {
     int thr = int_threshold(iso, 0, 255);
     if (nx % 16 == 0 && b2v_aligned16(vol))
@@ -575,21 +691,28 @@ static int mc_count_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int
       k_mc_bits<int16_t><<<grid_for(g.nwords, 8), 256, 0, s>>>((const int16_t*)vol, g, thr, w.bits);
   }
   if ((rc = b2v_check_launch("k_mc_bits"))) return rc;
-  k_mc_count<<<(unsigned)w.nblocks, kScanBlock, 0, s>>>(w.bits, g, skip_last, w.info, w.toff, w.amask, w.bsum_v,
-                                                        w.bsum_t);
-  if ((rc = b2v_check_launch("k_mc_count"))) return rc;
-  k_mc_scan_bsums<<<1, 1024, 0, s>>>(w.bsum_v, w.bsum_t, w.nblocks, w.totals);
-  if ((rc = b2v_check_launch("k_mc_scan_bsums"))) return rc;
-  k_mc_scan_apply<<<(unsigned)w.nblocks, kScanBlock, 0, s>>>(w.info, w.toff, g.nwords, w.bsum_v, w.bsum_t);
-  if ((rc = b2v_check_launch("k_mc_scan_apply"))) return rc;
-  unsigned long long tot[2] = {0, 0};
+  if (g.wx % 4 == 0) {
+    const int ntiles = (int)ceil_div64(g.nwords, kClsThreads * 4);
+    k_mc_classify<4><<<ntiles, kClsThreads, 0, s>>>(w.bits, g, skip_last, w.vslot, w.vinfo, w.vword, w.cinfo, w.tiles,
+                                                    w.ticket, w.totals, ntiles);
+  } else {
+    const int ntiles = (int)ceil_div64(g.nwords, kClsThreads);
+    k_mc_classify<1><<<ntiles, kClsThreads, 0, s>>>(w.bits, g, skip_last, w.vslot, w.vinfo, w.vword, w.cinfo, w.tiles,
+                                                    w.ticket, w.totals, ntiles);
+  }
+  if ((rc = b2v_check_launch("k_mc_classify"))) return rc;
+  if (shard) {
+    k_mc_plane0<<<(unsigned)ceil_div64(g.ny * g.wx, 256), 256, 0, s>>>(w.bits, g, w.vslot, w.vinfo, w.plane0);
+    if ((rc = b2v_check_launch("k_mc_plane0"))) return rc;
+  }
+  if (no_sync) return B2V_OK;   // the caller queues the peer exchange behind and reads everything at once
+  unsigned long long tot[6] = {0, 0, 0, 0, 0, 0};
   B2V_CUDA(cudaMemcpyAsync(tot, w.totals, sizeof(tot), cudaMemcpyDeviceToHost, s));
   B2V_CUDA(cudaStreamSynchronize(s));
-  const unsigned long long ntri = tot[1] & 0xffffffffull;
-  B2V_REQUIRE(tot[0] < (1ull << 31) && ntri < (1ull << 31) && (tot[1] >> 32) < (1ull << 31), B2V_ERR_RANGE,
-              "mc_count: %llu vertices / %llu triangles exceed int32 indices; shard along z", tot[0], ntri);
+  B2V_REQUIRE(tot[5] == 0 && tot[0] < (1ull << 31) && tot[1] < (1ull << 31) && tot[2] < (1ull << 31), B2V_ERR_RANGE,
+              "mc_count: %llu vertices / %llu triangles exceed int32 indices; shard along z", tot[0], tot[1]);
   *nverts_host = (int64_t)tot[0];
-  *ntris_host = (int64_t)ntri;
+  *ntris_host = (int64_t)tot[1];
   return B2V_OK;
 }
 
@@ -608,24 +731,83 @@ static int mc_emit_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int6
   int rc;
   if (verts) {
     if (dtype == B2V_U8)
-      k_mc_emit_verts<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)vol, g, w.info, w.bsum_v, w.nblocks, w.totals, xf,
-                                                    verts);
+      k_mc_emit_verts<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)vol, g, w.vinfo, w.vword, w.totals, xf, verts);
     else
-      k_mc_emit_verts<int16_t><<<grid, 256, 0, s>>>((const int16_t*)vol, g, w.info, w.bsum_v, w.nblocks, w.totals, xf,
-                                                    verts);
+      k_mc_emit_verts<int16_t><<<grid, 256, 0, s>>>((const int16_t*)vol, g, w.vinfo, w.vword, w.totals, xf, verts);
     if ((rc = b2v_check_launch("k_mc_emit_verts"))) return rc;
   }
   if (tris) {
-    k_mc_emit_tris<<<grid, 256, 0, s>>>(g, w.bits, w.info, w.toff, w.amask, w.bsum_t, w.nblocks, w.totals,
-                                        flip_y ? 1 : 0, skip_last, vbase, (const uint4*)foreign, foreign_base, tris);
+    k_mc_emit_tris<<<grid, 256, 0, s>>>(g, w.bits, w.vslot, w.vinfo, w.cinfo, w.totals, flip_y ? 1 : 0, skip_last,
+                                        vbase, (const uint4*)foreign, foreign_base, tris);
     if ((rc = b2v_check_launch("k_mc_emit_tris"))) return rc;
   }
   return B2V_OK;
 }
 
+// ---- Z shards over peer mailboxes (csrc/peer.cuh) ----------------------------------------------
+// After classify: publish this shard's (V, T) into every rank's mailbox, push the dense plane-0
+// records into the LOWER neighbour's (it numbers the vertices of the shared plane from them), and
+// wait until every rank's counts (and with them the upper neighbour's records) have arrived. One
+// small launch replaces an all_gather, a device->host copy and a send/recv pair.
+__global__ void __launch_bounds__(1024) k_mc_peer_exchange(PeerSet ps, const unsigned long long* __restrict__ totals,
+                                                           const uint4* __restrict__ plane0, int nrec, int* ok_dev) {
+  const int tid = threadIdx.x, par = (int)(ps.epoch & 1u);
+  if (ps.rank > 0) {
+    uint4* dst = ps.of(ps.rank - 1).mc_from_hi(par);
+    for (int i = tid; i < nrec; i += blockDim.x) dst[i] = plane0[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  bool ok = true;
+  if (tid < ps.world) {
+    PeerBox box = ps.of(tid);
+    st_relaxed_sys_s64(box.counts(par) + 2 * ps.rank, (long long)totals[0]);
+    st_relaxed_sys_s64(box.counts(par) + 2 * ps.rank + 1, (long long)totals[1]);
+    __threadfence_system();
+    st_release_sys(box.cnt_tag(par) + ps.rank, ps.epoch);
+    ok = peer_wait_eq(ps.mine().cnt_tag(par) + tid, ps.epoch, ps.timeout);
+  }
+  ok = __syncthreads_and(ok);
+  if (tid == 0) *ok_dev = ok ? 1 : 0;
+}
+
+extern "C" int64_t b2v_peer_mc_inbox_offset(int64_t plane_bytes, uint32_t epoch) {
+  return kPbData + 4 * plane_bytes + (int64_t)(epoch & 1u) * 4 * plane_bytes;
+}
+
+extern "C" int b2v_mc_count_shard_peer(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
+                                       int skip_last_plane, void* workspace, void* stream, int rank, int world,
+                                       const void* const* mailboxes_host, int64_t mailbox_plane_bytes, uint32_t epoch,
+                                       int64_t* counts_host /*[world][2]: (V, T) of every rank*/) {
+  B2V_REQUIRE(counts_host && epoch >= 1, B2V_ERR_ARG, "mc_count_shard_peer: bad arguments");
+  PeerSet ps;
+  int rc = peer_make_set(rank, world, mailboxes_host, mailbox_plane_bytes, epoch, &ps);
+  if (rc) return rc;
+  McGeom g = make_geom(nz, ny, nx);
+  B2V_REQUIRE(g.ny * g.wx * 16 <= 4 * ps.pc, B2V_ERR_ARG, "mc_count_shard_peer: plane records do not fit the mailbox");
+  int64_t nv = 0, nt = 0;
+  if ((rc = mc_count_impl(vol, dtype, nz, ny, nx, iso, skip_last_plane ? 1 : 0, 1, workspace, stream, &nv, &nt, true)))
+    return rc;
+  McWs w = carve(workspace, g);
+  cudaStream_t s = (cudaStream_t)stream;
+  int* ok_dev = (int*)(w.totals + 8);
+  k_mc_peer_exchange<<<1, 1024, 0, s>>>(ps, w.totals, w.plane0, (int)(g.ny * g.wx), ok_dev);
+  if ((rc = b2v_check_launch("k_mc_peer_exchange"))) return rc;
+  int ok = 0;
+  unsigned long long tot[6] = {0, 0, 0, 0, 0, 0};
+  B2V_CUDA(cudaMemcpyAsync(counts_host, ps.mine().counts((int)(epoch & 1u)), (size_t)world * 16, cudaMemcpyDeviceToHost, s));
+  B2V_CUDA(cudaMemcpyAsync(&ok, ok_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+  B2V_CUDA(cudaMemcpyAsync(tot, w.totals, sizeof(tot), cudaMemcpyDeviceToHost, s));
+  B2V_CUDA(cudaStreamSynchronize(s));
+  B2V_REQUIRE(ok == 1, B2V_ERR_NOCONV, "mc_count_shard_peer: a rank did not publish its counts in time (epoch %u)", epoch);
+  B2V_REQUIRE(tot[5] == 0 && tot[0] < (1ull << 31) && tot[1] < (1ull << 31) && tot[2] < (1ull << 31), B2V_ERR_RANGE,
+              "mc_count: %llu vertices / %llu triangles exceed int32 indices; shard along z", tot[0], tot[1]);
+  return B2V_OK;
+}
+
 extern "C" int b2v_mc_count(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
                             void* workspace, void* stream, int64_t* nverts_host, int64_t* ntris_host) {
-  return mc_count_impl(vol, dtype, nz, ny, nx, iso, 0, workspace, stream, nverts_host, ntris_host);
+  return mc_count_impl(vol, dtype, nz, ny, nx, iso, 0, 0, workspace, stream, nverts_host, ntris_host);
 }
 
 extern "C" int b2v_mc_emit(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
@@ -640,7 +822,7 @@ extern "C" int b2v_mc_emit(const void* vol, int dtype, int64_t nz, int64_t ny, i
 extern "C" int b2v_mc_count_shard(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, double iso,
                                   int skip_last_plane, void* workspace, void* stream, int64_t* nverts_host,
                                   int64_t* ntris_host) {
-  return mc_count_impl(vol, dtype, nz, ny, nx, iso, skip_last_plane ? 1 : 0, workspace, stream, nverts_host,
+  return mc_count_impl(vol, dtype, nz, ny, nx, iso, skip_last_plane ? 1 : 0, 1, workspace, stream, nverts_host,
                        ntris_host);
 }
 
@@ -657,7 +839,8 @@ extern "C" int b2v_mc_layout(int64_t nz, int64_t ny, int64_t nx, int64_t* layout
   B2V_REQUIRE(nz > 0 && ny > 0 && nx > 0 && layout_out, B2V_ERR_ARG, "mc_layout: bad arguments");
   McGeom g = make_geom(nz, ny, nx);
   McWs w = carve(nullptr, g);
-  layout_out[0] = (int64_t)((char*)w.info - (char*)nullptr);   // byte offset of the per-word records
-  layout_out[1] = (int64_t)ny * g.wx * 16;                      // bytes of records per z-plane
+  layout_out[0] = (int64_t)((char*)w.plane0 - (char*)nullptr);   // byte offset of the dense plane-0 records
+  layout_out[1] = (int64_t)ny * g.wx * 16;                        // their size in bytes
+  layout_out[2] = (int64_t)((char*)w.totals - (char*)nullptr);   // uint64 totals: [0] V, [1] T (device)
   return B2V_OK;
 }

@@ -131,22 +131,46 @@ class _PinnedPool:
     to the pool when the numpy array handed to the caller (and every view of it) is gone."""
 
     def __init__(self):
+        import os
         self.free: dict[int, list] = {}
+        self.held = 0                    # bytes parked in `free`
+        self.cap = int(os.environ.get("B2V_PINNED_POOL_MB", "2048")) << 20
+
+    @staticmethod
+    def _bucket(nbytes: int) -> int:
+        """Power of two up to 64 MiB, then multiples of 64 MiB (no 2x waste on large meshes)."""
+        if nbytes <= (64 << 20):
+            return 1 << max(20, int(nbytes - 1).bit_length())
+        return -(-nbytes // (64 << 20)) * (64 << 20)
 
     def take(self, nbytes: int) -> torch.Tensor:
-        bucket = 1 << max(20, int(nbytes - 1).bit_length())
+        bucket = self._bucket(nbytes)
         lst = self.free.get(bucket)
         if lst:
+            self.held -= bucket
             return lst.pop()
         return torch.empty(bucket, dtype=torch.uint8).pin_memory()
 
     def give(self, block: torch.Tensor) -> None:
-        lst = self.free.setdefault(block.numel(), [])
-        if len(lst) < 4:
+        n = block.numel()
+        lst = self.free.setdefault(n, [])
+        if len(lst) < 4 and self.held + n <= self.cap:
             lst.append(block)
+            self.held += n
+        # otherwise the block is dropped and its page-locked memory released
+
+    def trim(self) -> None:
+        """Release every parked block."""
+        self.free.clear()
+        self.held = 0
 
 
 _pool = _PinnedPool()
+
+
+def trim_pinned_pool() -> None:
+    """Release the page-locked result blocks parked by to_numpy() (cap: B2V_PINNED_POOL_MB, default 2048)."""
+    _pool.trim()
 
 
 def to_numpy(t: torch.Tensor) -> np.ndarray:

@@ -8,17 +8,22 @@ op of the path is sharded the same way:
   threshold            independent voxels: no communication
   MaxIP/MinIP/MeanIP   axis 1/2: rows stay with their shard (optional all_gather);
                        axis 0: partial planes, one all_reduce
-  MIDA / LMIP axis 1/2 all_reduce of the global (min, max) for MIDA, then local rays (built);
-                       axis 0 needs a pipelined ray-state hand-off between shards (not built)
+  MIDA / LMIP axis 1/2 all_reduce of the global (min, max) for MIDA, then local rays;
+                       axis 0: the per-ray state is handed from shard to shard (bit-exact)
   flood fill           local convergence on slab + one halo plane per inner side, then the
                        reached bits of the two shared planes are swapped with each neighbour
-                       (2 x dy x dx/8 bytes) and merged; repeat until no shard gains a bit
-                       (one 4-byte all_reduce per outer iteration)
+                       (2 x dy x dx/8 bytes) and merged; repeat until no shard gains a bit.
+                       With a PeerLink (NVLink peer mailboxes) the whole loop — rounds, plane
+                       exchange, the "anyone gained?" vote — runs inside ONE persistent kernel
+                       per GPU (b2v_floodfill_threshold_peer); without one (gloo tests, no
+                       peer access) it is staged through torch.distributed.
   marching cubes       each shard contours its slab plus the next shard's first plane; the
                        vertices of that shared plane are owned by the next shard, whose
                        per-word records (one plane) and vertex base are sent down; counts
-                       are all_gathered for the global bases. Concatenating the shards'
-                       outputs in rank order is bit-identical to the single-GPU mesh.
+                       are exchanged for the global bases (PeerLink: one small kernel writes
+                       them into every mailbox; otherwise all_gather + send/recv).
+                       Concatenating the shards' outputs in rank order is bit-identical to the
+                       single-GPU mesh.
 
 All tensors handed to these functions are "extended slabs": the shard's own planes plus
 one halo plane below (if it has a lower neighbour) and above (if it has an upper one);
@@ -88,6 +93,89 @@ class ZShard:
             if self.ze0 <= z < self.ze1:
                 out.append((x, y, z - self.ze0))
         return out
+
+
+class PeerLink:
+    """NVLink peer mailboxes of one job (csrc/peer.cuh): every rank allocates one mailbox in its
+    HBM, exports it with cudaIpc, and maps everyone else's. The handles travel once through
+    torch.distributed (all_gather_object); afterwards the sharded flood fill and the
+    marching-cubes stitch exchange their boundary data with plain stores over NVLink from
+    inside their own kernels — no NCCL call, no host round trip per exchange.
+    `epoch` is the job-wide exchange counter every rank advances identically."""
+
+    def __init__(self, shard: ZShard, dy: int, dx: int):
+        from . import _lib, device
+        device.require_cuda()
+        self._lib = _lib
+        lib = _lib.load()
+        self.shard, self.dy, self.dx = shard, int(dy), int(dx)
+        self.plane_bytes = self.dy * ((self.dx + 31) // 32) * 4
+        self.bytes = int(lib.b2v_peer_mailbox_bytes(self.dy, self.dx))
+        own = C.c_void_p(0)
+        handle = (C.c_uint8 * 64)()
+        _lib.call("b2v_peer_alloc", self.bytes, C.byref(own), handle)
+        self.own = own.value
+        handles = [None] * shard.world
+        dist.all_gather_object(handles, bytes(handle), group=shard.group)
+        self.ptrs = (C.c_void_p * shard.world)()
+        self._mapped = []
+        for r, h in enumerate(handles):
+            if r == shard.rank:
+                self.ptrs[r] = self.own
+                continue
+            p = C.c_void_p(0)
+            buf = (C.c_uint8 * 64).from_buffer_copy(h)
+            _lib.call("b2v_peer_open", buf, C.byref(p))
+            self.ptrs[r] = p.value
+            self._mapped.append(p.value)
+        self.epoch = 1
+        self.barrier()          # proves that every mailbox is mapped and writable from every rank
+
+    def barrier(self):
+        from .device import _stream
+        self._lib.call("b2v_peer_barrier", self.shard.rank, self.shard.world, self.ptrs, self.plane_bytes, self.epoch,
+                       _stream())
+        self.epoch += 1
+
+    def fits(self, dy: int, dx: int) -> bool:
+        return int(dy) * ((int(dx) + 31) // 32) * 4 <= self.plane_bytes
+
+    def mc_inbox(self, epoch: int) -> int:
+        """Device address of the upper neighbour's plane-0 records for `epoch`."""
+        return self.own + int(self._lib.load().b2v_peer_mc_inbox_offset(self.plane_bytes, epoch))
+
+    def describe(self) -> str:
+        return (f"peer mailboxes over NVLink (cudaIpc, {self.bytes >> 10} KiB per rank): flood planes + vote inside "
+                f"the persistent kernel, MC counts/records by one exchange kernel; no NCCL on the data path")
+
+    def close(self):
+        for p in self._mapped:
+            try:
+                self._lib.call("b2v_peer_close", C.c_void_p(p))
+            except Exception:   # noqa: BLE001
+                pass
+        self._mapped = []
+        if self.own:
+            try:
+                self._lib.call("b2v_peer_free", C.c_void_p(self.own))
+            except Exception:   # noqa: BLE001
+                pass
+            self.own = 0
+
+
+def peer_link(shard: ZShard, dy: int, dx: int):
+    """A PeerLink for shards with dy x dx planes, or None when the job cannot use one (gloo
+    backend, CPU tensors, several ranks on one GPU, no peer access between the devices)."""
+    if shard.world < 2 or not torch.cuda.is_available():
+        return None
+    if dist.get_backend(shard.group) != "nccl" or shard.world > 16:
+        return None
+    try:
+        return PeerLink(shard, dy, dx)
+    except Exception as e:   # noqa: BLE001
+        import warnings
+        warnings.warn(f"peer mailboxes unavailable, falling back to torch.distributed exchanges: {e}")
+        return None
 
 
 def _stage(shard: ZShard, t: torch.Tensor):
@@ -218,7 +306,8 @@ class DeviceBackend:
         return self.dev.mip(img, axis, kind)
 
     def sum_axis0(self, img):
-        return img.to(torch.int64).sum(dim=0)  # partial sums for MeanIP axis 0 (tiny plane op)
+        # partial sums for MeanIP axis 0 (tiny plane op); float64 volumes are summed in float64
+        return img.sum(dim=0, dtype=torch.float64 if img.dtype.is_floating_point else torch.int64)
 
     def minmax(self, img):
         return self.dev.minmax(img)
@@ -360,9 +449,11 @@ def mip(img_slab, axis, kind, shard: ZShard, gather=True, backend=None):
             # tensor / tensor is a true IEEE division (tensor / python-scalar multiplies by the
             # reciprocal on CUDA and would differ from NumPy's mean in the last bit)
             return part.to(torch.float64) / torch.full((), float(shard.DZ), dtype=torch.float64, device=part.device)
-        part = be.mip(img_slab, 0, kind).to(torch.int32)   # NCCL has no int16
-        _all_reduce(shard, part, dist.ReduceOp.MAX if kind == "max" else dist.ReduceOp.MIN)
-        return part.to(img_slab.dtype)
+        part = be.mip(img_slab, 0, kind)
+        # NCCL has no int16: integer planes travel as int32; float64 planes as they are
+        wide = part if part.dtype.is_floating_point else part.to(torch.int32)
+        _all_reduce(shard, wide, dist.ReduceOp.MAX if kind == "max" else dist.ReduceOp.MIN)
+        return wide.to(img_slab.dtype)
     rows = be.mip(img_slab, axis, kind)
     if not gather:
         return rows
@@ -432,11 +523,39 @@ def fast_countour_mip(img_ext, n, axis, wl, ww, tmip, shard: ZShard, gather=True
     return _all_gather_rows(shard, rows, sizes)
 
 
+def _floodfill_peer(data_ext, seeds_local, t0, t1, fill, strct, out_ext, shard: ZShard, link: PeerLink):
+    """The fused path: ONE persistent kernel per GPU runs the rounds, pushes / merges the boundary
+    planes through the peer mailboxes and takes the job-wide vote (b2v_floodfill_threshold_peer)."""
+    from . import _lib, device as dev
+    s, st = dev._seed_array(seeds_local), dev._strct_array(strct)
+    dz, dy, dx = data_ext.shape
+    if dz < 2 or not link.fits(dy, dx):
+        raise ValueError("the shard's planes do not fit this PeerLink")
+    dev._dense(data_ext, "data"); dev._dense(out_ext, "out")
+    if out_ext.dtype != torch.uint8 or out_ext.shape != data_ext.shape:
+        raise TypeError("floodfill_threshold: out must be uint8 with data's 3-D shape")
+    ws = dev._workspace(_lib.load().b2v_floodfill_workspace_bytes(dz, dy, dx, max(len(s), 1)), data_ext.device)
+    rounds, used = C.c_int(0), C.c_int(0)
+    try:
+        with torch.cuda.device(data_ext.device):
+            _lib.call("b2v_floodfill_threshold_peer", dev._p(data_ext), dev.dtype_code(data_ext), dz, dy, dx,
+                      C.c_void_p(s.ctypes.data if len(s) else 0), len(s), float(t0), float(t1), int(fill),
+                      C.c_void_p(st.ctypes.data), *st.shape, dev._p(out_ext), dev._p(ws), dev._stream(), shard.rank,
+                      shard.world, link.ptrs, link.plane_bytes, link.epoch, C.byref(rounds), C.byref(used))
+    finally:
+        link.epoch += used.value
+    return used.value
+
+
 def floodfill_threshold(data_ext, seeds, t0, t1, fill, strct, out_ext, shard: ZShard, backend=None,
-                        max_outer=10000):
+                        max_outer=10000, link: PeerLink | None = None):
     """Region grow over the Z-sharded volume. data_ext / out_ext are extended slabs with
     valid halo planes (exchange_halo). seeds are GLOBAL (x, y, z). Returns the number of
-    outer (exchange) iterations."""
+    outer (exchange) iterations. With `link` (and the device backend) the exchange is fused
+    into the persistent flood kernel over NVLink peer memory; otherwise it is staged through
+    torch.distributed."""
+    if link is not None and backend is None:
+        return _floodfill_peer(data_ext, shard.local_seeds(seeds), t0, t1, fill, strct, out_ext, shard, link)
     be = _backend(backend)
     st = be.ff_begin(data_ext, out_ext, shard.local_seeds(seeds), t0, t1, fill, strct)
     n = data_ext.shape[0]
@@ -469,12 +588,50 @@ def floodfill_threshold(data_ext, seeds, t0, t1, fill, strct, out_ext, shard: ZS
     return outer
 
 
-def marching_cubes(vol_ext_hi, iso, spacing, origin_index, flip_y, shard: ZShard, backend=None):
+def _marching_cubes_peer(vol, iso, spacing, origin_index, flip_y, shard: ZShard, link: PeerLink):
+    """Counts and plane-0 records travel through the peer mailboxes (one exchange kernel queued
+    behind classify); the host reads every rank's (V, T) in the same copy as its own."""
+    from . import _lib, device as dev
+    dev._dense(vol, "vol")
+    nz, ny, nx = vol.shape
+    if not link.fits(ny, nx):
+        raise ValueError("the shard's planes do not fit this PeerLink")
+    code = dev.dtype_code(vol)
+    lib = _lib.load()
+    ws = dev._workspace(lib.b2v_mc_workspace_bytes(nz, ny, nx), vol.device)
+    counts = (C.c_int64 * (2 * shard.world))()
+    epoch = link.epoch
+    link.epoch += 1
+    with torch.cuda.device(vol.device):
+        _lib.call("b2v_mc_count_shard_peer", dev._p(vol), code, nz, ny, nx, float(iso), int(shard.has_hi), dev._p(ws),
+                  dev._stream(), shard.rank, shard.world, link.ptrs, link.plane_bytes, epoch, counts)
+        allc = np.frombuffer(counts, dtype=np.int64).reshape(shard.world, 2)
+        vbases = np.cumsum(allc[:, 0]) - allc[:, 0]
+        total_v, total_t = int(allc[:, 0].sum()), int(allc[:, 1].sum())
+        if total_v >= 2 ** 31:
+            raise ValueError("more than 2^31 vertices: int32 indices overflow")
+        V, T = int(allc[shard.rank, 0]), int(allc[shard.rank, 1])
+        verts = torch.empty((V, 3), dtype=torch.float32, device=vol.device)
+        tris = torch.empty((T, 3), dtype=torch.int32, device=vol.device)
+        fbase = int(vbases[shard.rank + 1]) if shard.has_hi else 0
+        ox, oy, oz = origin_index
+        if V or T:
+            _lib.call("b2v_mc_emit_shard", dev._p(vol), code, nz, ny, nx, float(iso), dev._p(ws), float(spacing[0]),
+                      float(spacing[1]), float(spacing[2]), int(ox), int(oy), int(oz + shard.z0), int(bool(flip_y)),
+                      int(shard.has_hi), int(vbases[shard.rank]), C.c_void_p(link.mc_inbox(epoch)), fbase,
+                      dev._p(verts), dev._p(tris), dev._stream())
+    return verts, tris, int(vbases[shard.rank]), total_v, total_t
+
+
+def marching_cubes(vol_ext_hi, iso, spacing, origin_index, flip_y, shard: ZShard, backend=None,
+                   link: PeerLink | None = None):
     """Iso-surface of the Z-sharded volume. vol_ext_hi = this shard's own planes followed by
     the next shard's first plane (no lower halo). origin_index = (ox, oy, oz) of the GLOBAL
     volume; the shard's z offset is added here. Returns (vertices, triangles, vertex_base,
     total_vertices, total_triangles): triangle indices are global; concatenating all shards
     in rank order gives the single-GPU mesh."""
+    if link is not None and backend is None:
+        return _marching_cubes_peer(vol_ext_hi, iso, spacing, origin_index, flip_y, shard, link)
     be = _backend(backend)
     st = be.mc_count(vol_ext_hi, iso, skip_last=shard.has_hi)
     counts = torch.tensor([[st["V"], st["T"]]], dtype=torch.int64, device=vol_ext_hi.device)

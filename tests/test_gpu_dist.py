@@ -20,6 +20,9 @@ def rank_all(rank, world, device):
     g = global_volume((37, 40, 96), seed=3)
     shard = d.ZShard(g.shape[0], rank, world)
     res = {}
+    # NVLink peer mailboxes (one rank per GPU, NCCL job): the fused exchange paths are run as well
+    link = d.peer_link(shard, g.shape[1], g.shape[2]) if device == "nccl" else None
+    res["link"] = link is not None
     own = torch.from_numpy(np.ascontiguousarray(g[shard.z0:shard.z1])).to(_dev())
     for axis in (0, 1, 2):
         for kind in ("max", "min", "mean"):
@@ -44,13 +47,22 @@ def rank_all(rank, world, device):
         if shard.has_lo: data[0] = 0; out[0] = 0
         if shard.has_hi: data[-1] = 0; out[-1] = 0
         d.exchange_halo(data, shard); d.exchange_halo(out, shard)
+        out2 = out.clone()
         outer = d.floodfill_threshold(data, seeds, 100, 3071, 254, strct, out, shard)
         res[("ff", ci)] = (shard.interior(out).cpu().numpy(), outer)
+        if link is not None:
+            outer = d.floodfill_threshold(data, seeds, 100, 3071, 254, strct, out2, shard, link=link)
+            res[("ffp", ci)] = (shard.interior(out2).cpu().numpy(), outer)
     # marching cubes on the thresholded mask
     mask = ((g >= THR[0]) & (g <= THR[1])).astype(np.uint8) * 255
     vol = torch.from_numpy(ext_slab(mask, shard, lo=False, hi=True)).to(_dev())
     v, t, vbase, tv, tt = d.marching_cubes(vol, 127, (0.5, 0.75, 1.5), (-1, -1, 3), True, shard)
     res["mc"] = (v.cpu().numpy(), t.cpu().numpy(), vbase, tv, tt)
+    if link is not None:
+        for rep in range(3):    # epochs alternate the mailbox halves
+            v, t, vbase, tv, tt = d.marching_cubes(vol, 127, (0.5, 0.75, 1.5), (-1, -1, 3), True, shard, link=link)
+        res["mcp"] = (v.cpu().numpy(), t.cpu().numpy(), vbase, tv, tt)
+        link.close()
     return res
 
 
@@ -79,12 +91,20 @@ def _check(out, orc):
         orc.floodfill_threshold(g, seeds, 100, 3071, 254, strct, want)
         got = np.concatenate([out[r][("ff", ci)][0] for r in (0, 1)])
         assert np.array_equal(got, want), ci
+        if out[0]["link"]:
+            got = np.concatenate([out[r][("ffp", ci)][0] for r in (0, 1)])
+            assert np.array_equal(got, want), ("peer", ci)
     mask = ((g >= THR[0]) & (g <= THR[1])).astype(np.uint8) * 255
     V, T = orc.marching_cubes(mask, 127, (0.5, 0.75, 1.5), (-1, -1, 3), True)
     gv = np.concatenate([out[0]["mc"][0], out[1]["mc"][0]])
     gt = np.concatenate([out[0]["mc"][1], out[1]["mc"][1]])
     assert out[0]["mc"][3] == len(V) and out[0]["mc"][4] == len(T)
     assert np.array_equal(gv, V) and np.array_equal(gt.astype(np.int64), T)
+    if out[0]["link"]:
+        gv = np.concatenate([out[0]["mcp"][0], out[1]["mcp"][0]])
+        gt = np.concatenate([out[0]["mcp"][1], out[1]["mcp"][1]])
+        assert out[1]["mcp"][3] == len(V) and out[1]["mcp"][4] == len(T)
+        assert np.array_equal(gv, V) and np.array_equal(gt.astype(np.int64), T)
 
 
 def test_sharded_ops_two_ranks_one_gpu_gloo(orc):
@@ -93,4 +113,6 @@ def test_sharded_ops_two_ranks_one_gpu_gloo(orc):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_sharded_ops_two_ranks_nccl(orc):
-    _check(run_ranks("rank_all", "test_gpu_dist", device="nccl"), orc)
+    out = run_ranks("rank_all", "test_gpu_dist", device="nccl")
+    assert out[0]["link"] and out[1]["link"], "peer mailboxes (cudaIpc over NVLink) could not be set up"
+    _check(out, orc)
