@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kClsThreads) k_mc_classify(const uint32_t* __r
       }
       // lanes up to (and including) the nearest inclusive prefix contribute
       const unsigned m2 = __ballot_sync(0xffffffffu, idx < 0 || f == 2);
-      const int stop = __ffs(m2) - 1;     // m2 != 0: tile 0 or the lanes past it always qualify
+      const int stop = m2 ? __ffs(m2) - 1 : 31;   // no inclusive prefix in this window: all 32 aggregates count
 #pragma unroll
       for (int q = 0; q < Q_N; ++q) {
         uint32_t c = (lane <= stop && idx >= 0) ? v[q] : 0u;

@@ -121,3 +121,116 @@ int orc_watershed_skimage(const uint16_t* image, const int16_t* markers, int64_t
   free(nb);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Order-independence model of the two sequential floods (TEST INFRASTRUCTURE).
+ *
+ * Both references label a voxel p from the neighbour that reaches it first in queue order.
+ * Whatever that order is, the parent of p is one of its ADMISSIBLE predecessors:
+ *   mode 0 (scipy.ndimage.watershed_ift): v -> p with max(C(v), |I(v) - I(p)|) == C(p), where C
+ *          is the exact minimax path cost (SciPy relabels only on a strictly smaller cost and
+ *          pops in non-decreasing cost order, so the final parent offered exactly C(p));
+ *          neighbourhood = flat index + structure offset inside [0, N) as SciPy walks it;
+ *   mode 1 (skimage.segmentation.watershed): p is labelled when its FIRST neighbour is popped;
+ *          pops are ordered by flood level, so that neighbour has the smallest C among p's
+ *          neighbours (C(marker) = I(marker), C(p) = max(I(p), min over neighbours C)).
+ * set_out[p] = the label if every chain of admissible predecessors back to the markers
+ * carries the same label (the reference's answer CANNOT depend on its queue order there),
+ * INT32_MIN if two different labels can reach p (order dependent), 0 if unreachable.
+ * cost_out = C. Costs by a bucket-queue Dijkstra (uint16 weights), sets by a worklist to the
+ * least fixed point of  S(p) = join over admissible v of S(v).
+ * ------------------------------------------------------------------------------------------ */
+#define WS_MULTI INT32_MIN
+
+int orc_ws_model(const uint16_t* image, const int16_t* markers, int64_t nz, int64_t ny, int64_t nx,
+                 const uint8_t* strct, int64_t sz, int64_t sy, int64_t sx, int mode, uint32_t* cost_out,
+                 int32_t* set_out) {
+  const int64_t n = nz * ny * nx;
+  int64_t noff = 0, off[27][3];
+  for (int64_t k = 0; k < sz; ++k)
+    for (int64_t j = 0; j < sy; ++j)
+      for (int64_t i = 0; i < sx; ++i)
+        if (strct[(k * sy + j) * sx + i]) {
+          int64_t dz = k - sz / 2, dy = j - sy / 2, dx = i - sx / 2;
+          if (dz == 0 && dy == 0 && dx == 0) continue;
+          off[noff][0] = dz; off[noff][1] = dy; off[noff][2] = dx;
+          ++noff;
+        }
+  const uint32_t INF = 0xffffffffu;
+  /* neighbour of p by offset o (the voxel p + o), or -1 */
+#define WS_NB(p, o, sign, q)                                                                          \
+  do {                                                                                                \
+    if (mode == 0) {                                                                                  \
+      int64_t qq = (p) + (sign) * ((off[o][0] * ny + off[o][1]) * nx + off[o][2]);                    \
+      (q) = (qq >= 0 && qq < n) ? qq : -1;                                                            \
+    } else {                                                                                          \
+      int64_t z = (p) / (ny * nx), r = (p) % (ny * nx), y = r / nx, x = r % nx;                       \
+      int64_t zz = z + (sign)*off[o][0], yy = y + (sign)*off[o][1], xx = x + (sign)*off[o][2];        \
+      (q) = (zz >= 0 && zz < nz && yy >= 0 && yy < ny && xx >= 0 && xx < nx) ? (zz * ny + yy) * nx + xx : -1; \
+    }                                                                                                 \
+  } while (0)
+  /* ---- costs: label-correcting with a FIFO worklist (small test volumes) */
+  int64_t* queue = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+  uint8_t* inq = (uint8_t*)calloc((size_t)n, 1);
+  int64_t qh = 0, qt = 0, qn = 0;
+  for (int64_t p = 0; p < n; ++p) {
+    if (markers[p]) {
+      cost_out[p] = mode == 0 ? 0u : (uint32_t)image[p];
+      queue[qt] = p; qt = (qt + 1) % n; ++qn; inq[p] = 1;
+    } else cost_out[p] = INF;
+    set_out[p] = markers[p];
+  }
+  while (qn) {
+    int64_t v = queue[qh]; qh = (qh + 1) % n; --qn; inq[v] = 0;
+    for (int64_t o = 0; o < noff; ++o) {
+      int64_t p;
+      WS_NB(v, o, 1, p);
+      if (p < 0 || markers[p]) continue;
+      uint32_t w = mode == 0 ? (uint32_t)abs((int)image[v] - (int)image[p]) : (uint32_t)image[p];
+      uint32_t cand = cost_out[v] > w ? cost_out[v] : w;
+      if (cand < cost_out[p]) {
+        cost_out[p] = cand;
+        if (!inq[p]) { queue[qt] = p; qt = (qt + 1) % n; ++qn; inq[p] = 1; }
+      }
+    }
+  }
+  /* ---- label sets */
+  qh = qt = qn = 0;
+  for (int64_t p = 0; p < n; ++p)
+    if (markers[p]) { queue[qt] = p; qt = (qt + 1) % n; ++qn; inq[p] = 1; }
+  while (qn) {
+    int64_t v = queue[qh]; qh = (qh + 1) % n; --qn; inq[v] = 0;
+    const int32_t sv = set_out[v];
+    if (sv == 0) continue;
+    for (int64_t o = 0; o < noff; ++o) {
+      int64_t p;
+      WS_NB(v, o, 1, p);
+      if (p < 0 || markers[p] || cost_out[p] == INF) continue;
+      int admissible;
+      if (mode == 0) {
+        uint32_t w = (uint32_t)abs((int)image[v] - (int)image[p]);
+        uint32_t via = cost_out[v] > w ? cost_out[v] : w;
+        admissible = via == cost_out[p];
+      } else {
+        uint32_t cmin = INF;
+        for (int64_t o2 = 0; o2 < noff; ++o2) {
+          int64_t u;
+          WS_NB(p, o2, -1, u);      /* the voxels that reach p */
+          if (u >= 0 && cost_out[u] < cmin) cmin = cost_out[u];
+        }
+        admissible = cost_out[v] == cmin;
+      }
+      if (!admissible) continue;
+      int32_t sp = set_out[p], ns = sp == 0 ? sv : (sp == sv ? sp : WS_MULTI);
+      if (sv == WS_MULTI) ns = WS_MULTI;
+      if (ns != sp) {
+        set_out[p] = ns;
+        if (!inq[p]) { queue[qt] = p; qt = (qt + 1) % n; ++qn; inq[p] = 1; }
+      }
+    }
+  }
+  free(queue);
+  free(inq);
+#undef WS_NB
+  return 0;
+}

@@ -55,3 +55,22 @@ def do_watershed_array(image, markers, bstruct, algorithm, mg_size, use_ww_wl, w
         return watershed_skimage(grad, markers.astype("int16"), bstruct)
     mk = markers.astype("int16") if use_ww_wl else markers.astype("int8")
     return ndimage.watershed_ift(pre, mk, bstruct)
+
+
+MULTI = np.iinfo(np.int32).min
+
+
+def order_independence_model(image_u16, markers_i16, bstruct, mode):
+    """(cost uint32, label set int32) of oracle/watershed.c::orc_ws_model: set == label where
+    the reference's answer cannot depend on its queue order, MULTI where it can, 0 unreachable.
+    mode 0 = scipy.ndimage.watershed_ift, mode 1 = skimage.segmentation.watershed."""
+    img = np.ascontiguousarray(image_u16, dtype=np.uint16)
+    mk = np.ascontiguousarray(markers_i16, dtype=np.int16)
+    st = np.ascontiguousarray(bstruct, dtype=np.uint8)
+    if img.ndim == 2:
+        img, mk, st = img[None], mk[None], st[None]
+    cost = np.zeros(img.shape, np.uint32)
+    sets = np.zeros(img.shape, np.int32)
+    lib().orc_ws_model(_ptr(img), _ptr(mk), *map(C.c_int64, img.shape), _ptr(st), *map(C.c_int64, st.shape),
+                       C.c_int(mode), _ptr(cost), _ptr(sets))
+    return cost.reshape(np.shape(image_u16)), sets.reshape(np.shape(image_u16))
