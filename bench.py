@@ -357,8 +357,9 @@ def run_gpu(args):
         if world == 1:
             info["rounds"] = dev.floodfill_threshold(data_ext, seeds, THR[0], THR[1], FILL, strct, out_ext)
         else:
-            info["rounds"] = zd.floodfill_threshold(data_ext, seeds, THR[0], THR[1], FILL, strct, out_ext, shard,
-                                                    link=link)
+            info["exchanges"] = zd.floodfill_threshold(data_ext, seeds, THR[0], THR[1], FILL, strct, out_ext, shard,
+                                                       link=link)
+            info["rounds"] = link.last_rounds if link is not None else info["exchanges"]
 
     def do_surface(out_ext):
         if world == 1:
@@ -459,7 +460,7 @@ def run_gpu(args):
         tsum, vsum = checksums(v, f)
         gc, gt, gv = sum_over_ranks(count, tsum, vsum)
         timed[name] = {"ms_per_step": total_ms / args.steps, "stage_ms": stage_ms / args.steps,
-                       "rounds": info["rounds"], "V": info["V"], "T": info["T"], "reached": gc, "tsum": gt, "vsum": gv,
+                       "rounds": info["rounds"], "exchanges": info.get("exchanges", 0), "V": info["V"], "T": info["T"], "reached": gc, "tsum": gt, "vsum": gv,
                        "nseeds": len(seeds)}
     head = timed["global"]
     ms_per_step = head["ms_per_step"]
@@ -570,7 +571,7 @@ def run_gpu(args):
     for name, t in timed.items():
         seeding[name] = {"ms_per_step": round(t["ms_per_step"], 4),
                          "Mvoxel/s": round(world * N / (t["ms_per_step"] * 1e-3) / 1e6, 1), "seeds": t["nseeds"],
-                         "flood_rounds": t["rounds"],
+                         "flood_rounds": t["rounds"], "flood_exchanges": t["exchanges"],
                          "stage_ms": {k: round(float(m), 4) for k, m in zip(names, t["stage_ms"])}}
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -22,7 +22,9 @@ namespace {
 struct McGeom {
   int64_t nz, ny, nx;
   int wx;           // words per row
-  int64_t nwords;
+  int64_t nwords;   // < 2^31 (checked on entry): word indices and dims fit 32 bits in the kernels
+  int inz, iny;     // 32-bit copies
+  int wx_sh, ny_sh; // log2 when a power of two (the usual case), else -1
 };
 
 McGeom make_geom(int64_t nz, int64_t ny, int64_t nx) {
@@ -30,7 +32,20 @@ McGeom make_geom(int64_t nz, int64_t ny, int64_t nx) {
   g.nz = nz; g.ny = ny; g.nx = nx;
   g.wx = (int)ceil_div64(nx, 32);
   g.nwords = nz * ny * g.wx;
+  g.inz = (int)nz; g.iny = (int)ny;
+  auto lg = [](int64_t v) { int s = 0; while ((1ll << s) < v) ++s; return (1ll << s) == v ? s : -1; };
+  g.wx_sh = lg(g.wx);
+  g.ny_sh = lg(ny);
   return g;
+}
+
+// word index -> (z, y, w) in 32-bit arithmetic, shifts when the dims are powers of two
+__device__ __forceinline__ void split_word(const McGeom& g, uint32_t wi, int& z, int& y, int& w) {
+  uint32_t row;
+  if (g.wx_sh >= 0) { row = wi >> g.wx_sh; w = (int)(wi & (uint32_t)(g.wx - 1)); }
+  else { row = wi / (uint32_t)g.wx; w = (int)(wi - row * (uint32_t)g.wx); }
+  if (g.ny_sh >= 0) { z = (int)(row >> g.ny_sh); y = (int)(row & (uint32_t)(g.iny - 1)); }
+  else { z = (int)(row / (uint32_t)g.iny); y = (int)(row - (uint32_t)z * (uint32_t)g.iny); }
 }
 
 constexpr int kClsThreads = 256;
@@ -201,7 +216,7 @@ __device__ __forceinline__ uint32_t shift_in(uint32_t lo, uint32_t hi) { return 
 
 // bits i with x = 32 w + i and x + 1 < nx
 __device__ __forceinline__ uint32_t valid_x1(const McGeom& g, int w) {
-  int64_t rem = g.nx - 1 - (int64_t)w * 32;  // number of valid bits
+  const int rem = (int)g.nx - 1 - w * 32;  // number of valid bits
   return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
 }
 
@@ -213,12 +228,11 @@ __device__ __forceinline__ int cell_case(const Rows& r, int i) {
   return (int)(a | (b << 2) | (c << 4) | (d << 6));
 }
 
-__device__ __forceinline__ Rows load_rows(const uint32_t* __restrict__ bits, const McGeom& g, int64_t z, int64_t y,
-                                          int w) {
+__device__ __forceinline__ Rows load_rows(const uint32_t* __restrict__ bits, const McGeom& g, int z, int y, int w) {
   Rows r;
-  const bool hy = y + 1 < g.ny, hz = z + 1 < g.nz, hn = w + 1 < g.wx;
-  const int64_t b00 = (z * g.ny + y) * g.wx + w;
-  const int64_t b01 = b00 + g.wx, b10 = b00 + (int64_t)g.ny * g.wx, b11 = b10 + g.wx;
+  const bool hy = y + 1 < g.iny, hz = z + 1 < g.inz, hn = w + 1 < g.wx;
+  const uint32_t b00 = ((uint32_t)z * (uint32_t)g.iny + (uint32_t)y) * (uint32_t)g.wx + (uint32_t)w;
+  const uint32_t b01 = b00 + (uint32_t)g.wx, b10 = b00 + (uint32_t)g.iny * (uint32_t)g.wx, b11 = b10 + (uint32_t)g.wx;
   r.i00 = __ldg(bits + b00);
   r.i01 = hy ? __ldg(bits + b01) : 0u;
   r.i10 = hz ? __ldg(bits + b10) : 0u;
@@ -279,19 +293,20 @@ __global__ void __launch_bounds__(kClsThreads) k_mc_classify(const uint32_t* __r
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
   const int tile = (int)s_tile;
-  const int64_t wi0 = ((int64_t)tile * kClsThreads + tid) * WPT;
+  const uint32_t wi0 = ((uint32_t)tile * kClsThreads + tid) * WPT;
+  const uint32_t nwords = (uint32_t)g.nwords;
   WordClass wc[WPT];
   // packed thread sums: X = nv (20) | listed-v (12) | cells (20) | listed-c (12), Y = triangles
   unsigned long long X = 0;
   uint32_t Y = 0;
-  if (wi0 < g.nwords) {
-    const int64_t row = wi0 / g.wx;
-    const int w0 = (int)(wi0 - row * g.wx);
-    const int64_t z = row / g.ny, y = row - z * g.ny;
-    const bool hy = y + 1 < g.ny, hz = z + 1 < g.nz;
-    const bool own = !(skip_last && z == g.nz - 1);
+  if (wi0 < nwords) {
+    int z, y, w0;
+    split_word(g, wi0, z, y, w0);
+    const bool hy = y + 1 < g.iny, hz = z + 1 < g.inz;
+    const bool own = !(skip_last && z == g.inz - 1);
     uint32_t a00[WPT + 1], a01[WPT + 1], a10[WPT + 1], a11[WPT + 1];
-    const int64_t b00 = wi0, b01 = b00 + g.wx, b10 = b00 + (int64_t)g.ny * g.wx, b11 = b10 + g.wx;
+    const uint32_t b00 = wi0, b01 = b00 + (uint32_t)g.wx, b10 = b00 + (uint32_t)g.iny * (uint32_t)g.wx,
+                   b11 = b10 + (uint32_t)g.wx;
     if (WPT == 4) {   // wx % 4 == 0: the four words of a thread are one aligned 128-bit load per row
       const uint4 q00 = __ldg((const uint4*)(bits + b00));
       const uint4 q01 = hy ? __ldg((const uint4*)(bits + b01)) : make_uint4(0, 0, 0, 0);
@@ -315,6 +330,12 @@ __global__ void __launch_bounds__(kClsThreads) k_mc_classify(const uint32_t* __r
 #pragma unroll
     for (int j = 0; j < WPT; ++j) {
       Rows r = {a00[j], a01[j], a10[j], a11[j], a00[j + 1], a01[j + 1], a10[j + 1], a11[j + 1]};
+      // a word whose whole 2 x 2-row neighbourhood is uniform (most of the volume) holds nothing:
+      // all outside (missing rows / words read as 0), or all inside with every neighbour present
+      const uint32_t o_ = r.i00 | r.i01 | r.i10 | r.i11 | ((r.n00 | r.n01 | r.n10 | r.n11) & 1u);
+      const bool ones = hy && hz && w0 + j + 1 < g.wx && (r.i00 & r.i01 & r.i10 & r.i11) == 0xffffffffu &&
+                        ((r.n00 & r.n01 & r.n10 & r.n11) & 1u);
+      if (o_ == 0u || ones) { wc[j] = WordClass{0u, 0u, 0u, 0u, 0u, 0u}; continue; }
       wc[j] = classify_word(r, valid_x1(g, w0 + j), hy, hz, own, s_ntri);
       X += (unsigned long long)wc[j].nv | ((unsigned long long)(wc[j].nv != 0) << 20) |
            ((unsigned long long)__popc(wc[j].act) << 32) | ((unsigned long long)(wc[j].act != 0) << 52);
@@ -344,70 +365,73 @@ __global__ void __launch_bounds__(kClsThreads) k_mc_classify(const uint32_t* __r
   }
   const unsigned long long ex = ox + ix - X;     // exclusive within the block
   const uint32_t ey = oy + iy - Y;
-  // tile totals -> look-back (warp 0)
-  if (warp == 0) {
-    uint32_t tot[Q_N];
-    tot[Q_V] = (uint32_t)(tx & 0xfffffu); tot[Q_VW] = (uint32_t)((tx >> 20) & 0xfffu);
-    tot[Q_C] = (uint32_t)((tx >> 32) & 0xfffffu); tot[Q_CW] = (uint32_t)((tx >> 52) & 0xfffu);
-    tot[Q_T] = ty;
-    TileState* me = tiles + tile;
-    if (lane == 0) {
+  // tile totals -> look-back. The WHOLE block looks back, 256 predecessors per step: with a
+  // thousand tiles resident at once the nearest inclusive prefix is hundreds of tiles away, and
+  // the wave of inclusive prefixes advances one window per L2 round trip (a 32-wide window
+  // measured 105 us for 4096 tiles at 512^3: latency-bound).
+  uint32_t tot[Q_N];
+  tot[Q_V] = (uint32_t)(tx & 0xfffffu); tot[Q_VW] = (uint32_t)((tx >> 20) & 0xfffu);
+  tot[Q_C] = (uint32_t)((tx >> 32) & 0xfffffu); tot[Q_CW] = (uint32_t)((tx >> 52) & 0xfffu);
+  tot[Q_T] = ty;
+  TileState* me = tiles + tile;
+  if (tid == 0) {
 #pragma unroll
-      for (int q = 0; q < Q_N; ++q) { me->agg[q] = tot[q]; if (tile == 0) me->incl[q] = tot[q]; }
+    for (int q = 0; q < Q_N; ++q) { me->agg[q] = tot[q]; if (tile == 0) me->incl[q] = tot[q]; s_base[q] = 0; }
+    __threadfence();
+    *(volatile int*)&me->flag = tile == 0 ? 2 : 1;
+  }
+  __syncthreads();
+  for (int look = tile - 1; look >= 0; look -= kClsThreads) {
+    const int idx = look - tid;
+    int f = 2;
+    uint32_t v[Q_N];
+#pragma unroll
+    for (int q = 0; q < Q_N; ++q) v[q] = 0;
+    if (idx >= 0) {
+      const TileState* t = tiles + idx;
+      do { f = ld_flag(&t->flag); } while (f == 0);
       __threadfence();
-      *(volatile int*)&me->flag = tile == 0 ? 2 : 1;
+#pragma unroll
+      for (int q = 0; q < Q_N; ++q) v[q] = __ldcg(f == 2 ? &t->incl[q] : &t->agg[q]);
     }
-    uint32_t pre[Q_N];
+    // the nearest predecessor that already holds an inclusive prefix ends the walk
+    const unsigned m2 = __ballot_sync(0xffffffffu, idx < 0 || f == 2);
+    if (lane == 0) s_wy[warp] = m2 ? (uint32_t)(warp * 32 + __ffs(m2) - 1) : 0xffffffffu;
+    __syncthreads();
+    uint32_t stop = 0xffffffffu;
 #pragma unroll
-    for (int q = 0; q < Q_N; ++q) pre[q] = 0;
-    for (int look = tile - 1; look >= 0; look -= 32) {
-      const int idx = look - lane;
-      int f = 2;
-      uint32_t v[Q_N];
+    for (int k = 0; k < kClsThreads / 32; ++k) stop = s_wy[k] < stop ? s_wy[k] : stop;
+    const bool mine = idx >= 0 && (uint32_t)tid <= stop;
 #pragma unroll
-      for (int q = 0; q < Q_N; ++q) v[q] = 0;
-      if (idx >= 0) {
-        const TileState* t = tiles + idx;
-        do { f = ld_flag(&t->flag); } while (f == 0);
-        __threadfence();
+    for (int q = 0; q < Q_N; ++q) {
+      uint32_t c = mine ? v[q] : 0u;
 #pragma unroll
-        for (int q = 0; q < Q_N; ++q) v[q] = __ldcg(f == 2 ? &t->incl[q] : &t->agg[q]);
-      }
-      // lanes up to (and including) the nearest inclusive prefix contribute
-      const unsigned m2 = __ballot_sync(0xffffffffu, idx < 0 || f == 2);
-      const int stop = m2 ? __ffs(m2) - 1 : 31;   // no inclusive prefix in this window: all 32 aggregates count
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0 && c) atomicAdd(&s_base[q], c);
+    }
+    __syncthreads();    // s_base complete, s_wy free for the next window
+    if (stop != 0xffffffffu) break;
+  }
+  if (tid == 0) {
+    if (tile > 0) {
 #pragma unroll
       for (int q = 0; q < Q_N; ++q) {
-        uint32_t c = (lane <= stop && idx >= 0) ? v[q] : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        pre[q] += c;
+        me->incl[q] = s_base[q] + tot[q];
+        if (s_base[q] + tot[q] < s_base[q]) totals[5] = 1;   // a 32-bit running total wrapped: reported by the host
       }
-      if (m2) break;
+      __threadfence();
+      *(volatile int*)&me->flag = 2;
     }
-    if (lane == 0) {
-      if (tile > 0) {
-#pragma unroll
-        for (int q = 0; q < Q_N; ++q) {
-          me->incl[q] = pre[q] + tot[q];
-          if (pre[q] + tot[q] < pre[q]) totals[5] = 1;   // a 32-bit running total wrapped: reported by the host
-        }
-        __threadfence();
-        *(volatile int*)&me->flag = 2;
-      }
-#pragma unroll
-      for (int q = 0; q < Q_N; ++q) s_base[q] = pre[q];
-      if (tile == ntiles - 1) {
-        totals[0] = pre[Q_V] + tot[Q_V];
-        totals[1] = pre[Q_T] + tot[Q_T];
-        totals[2] = pre[Q_C] + tot[Q_C];
-        totals[3] = pre[Q_VW] + tot[Q_VW];
-        totals[4] = pre[Q_CW] + tot[Q_CW];
-      }
+    if (tile == ntiles - 1) {
+      totals[0] = s_base[Q_V] + tot[Q_V];
+      totals[1] = s_base[Q_T] + tot[Q_T];
+      totals[2] = s_base[Q_C] + tot[Q_C];
+      totals[3] = s_base[Q_VW] + tot[Q_VW];
+      totals[4] = s_base[Q_CW] + tot[Q_CW];
     }
   }
   __syncthreads();
-  if (wi0 >= g.nwords) return;
+  if (wi0 >= nwords) return;
   uint32_t rv = s_base[Q_V] + (uint32_t)(ex & 0xfffffu), rvw = s_base[Q_VW] + (uint32_t)((ex >> 20) & 0xfffu);
   uint32_t rc = s_base[Q_C] + (uint32_t)((ex >> 32) & 0xfffffu), rcw = s_base[Q_CW] + (uint32_t)((ex >> 52) & 0xfffu);
   uint32_t rt = s_base[Q_T] + ey;
@@ -434,14 +458,14 @@ __global__ void __launch_bounds__(kClsThreads) k_mc_classify(const uint32_t* __r
 __global__ void __launch_bounds__(256) k_mc_plane0(const uint32_t* __restrict__ bits, McGeom g,
                                                    const uint32_t* __restrict__ vslot,
                                                    const uint4* __restrict__ vinfo, uint4* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.ny * g.wx) return;
-  const int64_t y = i / g.wx;
-  const int w = (int)(i - y * g.wx);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.iny * g.wx) return;
+  const int y = i / g.wx;
+  const int w = i - y * g.wx;
   const Rows r = load_rows(bits, g, 0, y, w);
   const uint32_t cx = (r.i00 ^ shift_in(r.i00, r.n00)) & valid_x1(g, w);
-  const uint32_t cy = y + 1 < g.ny ? (r.i00 ^ r.i01) : 0u;
-  const uint32_t cz = g.nz > 1 ? (r.i00 ^ r.i10) : 0u;
+  const uint32_t cy = y + 1 < g.iny ? (r.i00 ^ r.i01) : 0u;
+  const uint32_t cz = g.inz > 1 ? (r.i00 ^ r.i10) : 0u;
   const uint32_t voff = (cx | cy | cz) ? __ldg(&vinfo[__ldg(&vslot[i])].w) : 0u;
   out[i] = make_uint4(cx, cy, cz, voff);
 }
@@ -507,7 +531,7 @@ __global__ void __launch_bounds__(256) k_mc_emit_verts(const T* __restrict__ vol
     inf.y = __shfl_sync(0xffffffffu, ent.y, j);
     inf.z = __shfl_sync(0xffffffffu, ent.z, j);
     inf.w = __shfl_sync(0xffffffffu, ent.w, j);
-    const int64_t wi = __shfl_sync(0xffffffffu, wd, j);
+    const uint32_t wi = __shfl_sync(0xffffffffu, wd, j);
     if (k >= V) continue;
     const uint32_t r = k - inf.w;
     // voxel: largest i with (#vertices of voxels below i) <= r
@@ -525,15 +549,14 @@ __global__ void __launch_bounds__(256) k_mc_emit_verts(const T* __restrict__ vol
     int axis;
     if (bx && rr == 0) axis = 0;
     else { rr -= bx; if (by && rr == 0) axis = 1; else axis = 2; }
-    const int64_t row = wi / g.wx;
-    const int w = (int)(wi - row * g.wx);
-    const int64_t z = row / g.ny, y = row - z * g.ny;
-    const int64_t x = (int64_t)w * 32 + i;
-    const int64_t p = row * g.nx + x;
+    int z, y, w;
+    split_word(g, wi, z, y, w);
+    const int x = w * 32 + i;
+    const int64_t p = ((int64_t)z * g.iny + y) * g.nx + x;
     const int64_t step = axis == 0 ? 1 : (axis == 1 ? g.nx : g.nx * g.ny);
     const float s0 = (float)vol[p], s1 = (float)vol[p + step];
     const float t = __fdiv_rn(__fsub_rn(xf.iso, s0), __fsub_rn(s1, s0));
-    float fx = (float)((int)x + xf.ox), fy = (float)((int)y + xf.oy), fz = (float)((int)z + xf.oz);
+    float fx = (float)(x + xf.ox), fy = (float)(y + xf.oy), fz = (float)(z + xf.oz);
     if (axis == 0) fx = __fadd_rn(fx, t); else if (axis == 1) fy = __fadd_rn(fy, t); else fz = __fadd_rn(fz, t);
     const float py = __fmul_rn(fy, xf.sy);
     float* o = verts + 3ll * k;
@@ -584,15 +607,14 @@ __global__ void __launch_bounds__(256) k_mc_emit_tris(McGeom g, const uint32_t* 
     uint4 ent = make_uint4(0u, 0u, 0u, 0xffffffffu);
     if (e0 + lane < nlist) ent = __ldg(cinfo + e0 + lane);
     const int j = warp_locate(ent.w, k, lane);
-    const int64_t wi = __shfl_sync(0xffffffffu, ent.x, j);
+    const uint32_t wi = __shfl_sync(0xffffffffu, ent.x, j);
     const uint32_t act = __shfl_sync(0xffffffffu, ent.y, j);
-    int64_t tbase = __shfl_sync(0xffffffffu, ent.z, j);
+    uint32_t tbase = __shfl_sync(0xffffffffu, ent.z, j);
     const uint32_t coff = __shfl_sync(0xffffffffu, ent.w, j);
     if (k >= C) continue;
     const int i = (int)__fns(act, 0, (int)(k - coff) + 1);   // this thread's cell bit
-    const int64_t row = wi / g.wx;
-    const int w = (int)(wi - row * g.wx);
-    const int64_t z = row / g.ny, y = row - z * g.ny;
+    int z, y, w;
+    split_word(g, wi, z, y, w);
     const Rows r = load_rows(bits, g, z, y, w);
     // triangles of the active cells before mine in this word
     for (uint32_t e = act & below(i); e; e &= e - 1) tbase += s_tri[cell_case(r, __ffs(e) - 1)][15];
@@ -605,17 +627,18 @@ __global__ void __launch_bounds__(256) k_mc_emit_tris(McGeom g, const uint32_t* 
       if (!need) continue;
       const int ox = s & 1, oy = (s >> 1) & 1, oz = s >> 2;
       const int qx = i + ox;                                   // 0..32 within the word pair
-      const int64_t qy = y + oy, qz = z + oz;
+      const int qy = y + oy, qz = z + oz;
       const int ob = qx & 31;
       const uint32_t ol = (1u << ob) - 1u;
       uint4 oi;
       int v;
-      if (skip_last && qz == g.nz - 1) {
+      if (skip_last && qz == g.inz - 1) {
         // owned by the next shard: its records of that plane, its numbering
-        oi = __ldg(foreign + qy * g.wx + (w + (qx >> 5)));
+        oi = __ldg(foreign + (qy * g.wx + (w + (qx >> 5))));
         v = foreign_base;
       } else {
-        oi = __ldg(vinfo + __ldg(vslot + (qz * g.ny + qy) * g.wx + (w + (qx >> 5))));
+        oi = __ldg(vinfo + __ldg(vslot + (((uint32_t)qz * (uint32_t)g.iny + (uint32_t)qy) * (uint32_t)g.wx +
+                                          (uint32_t)(w + (qx >> 5)))));
         v = vbase;
       }
       v += (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
@@ -630,7 +653,7 @@ __global__ void __launch_bounds__(256) k_mc_emit_tris(McGeom g, const uint32_t* 
     for (int t = 0; t < ntri; ++t) {
       const int i0 = s_id[s_tri[c][3 * t] * 256 + tid], i1 = s_id[s_tri[c][3 * t + 1] * 256 + tid],
                 i2 = s_id[s_tri[c][3 * t + 2] * 256 + tid];
-      int* o = tris + 3 * (tbase + t);
+      int* o = tris + 3ll * (tbase + t);
       o[0] = i0;
       o[1] = flip_y ? i2 : i1;
       o[2] = flip_y ? i1 : i2;

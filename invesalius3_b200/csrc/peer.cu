@@ -61,10 +61,16 @@ int peer_make_set(int rank, int world, const void* const* mailboxes_host, int64_
   out->world = world;
   out->epoch = epoch;
   out->pc = plane_bytes;
-  int dev = 0, khz = 0;
-  B2V_CUDA(cudaGetDevice(&dev));
-  B2V_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
-  out->timeout = (long long)(khz > 0 ? khz : 1500000) * 1000ll * 4ll;   // ~4 s of SM clocks
+  // ~4 s of SM clocks. The clock-rate attribute is one of the slow driver queries (~0.5 ms):
+  // asked once per process, not per call.
+  static long long cached_timeout = 0;
+  if (cached_timeout == 0) {
+    int dev = 0, khz = 0;
+    B2V_CUDA(cudaGetDevice(&dev));
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1500000;
+    cached_timeout = (long long)khz * 1000ll * 4ll;
+  }
+  out->timeout = cached_timeout;
   for (int r = 0; r < world; ++r) {
     B2V_REQUIRE(mailboxes_host[r], B2V_ERR_ARG, "peer: mailbox of rank %d is not mapped", r);
     out->box[r] = (char*)const_cast<void*>(mailboxes_host[r]);

@@ -129,6 +129,7 @@ class PeerLink:
             self.ptrs[r] = p.value
             self._mapped.append(p.value)
         self.epoch = 1
+        self.last_rounds = 0
         self.barrier()          # proves that every mailbox is mapped and writable from every rank
 
     def barrier(self):
@@ -544,6 +545,7 @@ def _floodfill_peer(data_ext, seeds_local, t0, t1, fill, strct, out_ext, shard: 
                       shard.world, link.ptrs, link.plane_bytes, link.epoch, C.byref(rounds), C.byref(used))
     finally:
         link.epoch += used.value
+    link.last_rounds = rounds.value     # flood rounds inside the kernel (all exchanges together)
     return used.value
 
 
