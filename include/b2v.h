@@ -193,7 +193,10 @@ int b2v_mc_emit(const void* vol, int dtype, int64_t nz, int64_t ny, int64_t nx, 
  *   mode 1 = skimage.segmentation.watershed cost model (max I along the path). markers
  *   int16 (0 = unlabeled); labels int16 out. Exact minimax costs; labels follow cost-optimal
  *   edges, ties resolved by hop count then smaller label (the reference's ties follow its
- *   queue order: see DESIGN.md section 6). SYNCHRONISES the stream. strct_host: uint8, dims
+ *   queue order: see DESIGN.md section 6). ambiguous (uint8, optional, may be NULL): 1 where two
+ *   different labels can reach the voxel along cost-optimal edges, i.e. where the reference's
+ *   answer is an artefact of its queue order; everywhere else (0) the labelling IS the
+ *   reference's, whatever its order. SYNCHRONISES the stream. strct_host: uint8, dims
  *   1 or 3. 14 B/voxel for the whole do_watershed as the reference defines it. */
 int b2v_ws_lut_i16(const int16_t* img, int64_t n, double window, double level, uint16_t* out, void* stream);
 int b2v_ws_shift_i16(const int16_t* img, int64_t n, uint16_t* out, void* workspace, void* stream);
@@ -202,7 +205,7 @@ int b2v_ws_morph_gradient_u16(const uint16_t* in, int64_t nz, int64_t ny, int64_
 int64_t b2v_ws_workspace_bytes(int64_t nz, int64_t ny, int64_t nx);
 int b2v_ws_flood(const uint16_t* img, const int16_t* markers, int64_t nz, int64_t ny, int64_t nx,
                  const uint8_t* strct_host, int64_t odz, int64_t ody, int64_t odx, int mode, int16_t* labels,
-                 void* workspace, void* stream, int* rounds_out);
+                 uint8_t* ambiguous, void* workspace, void* stream, int* rounds_out);
 
 /* ---- Z-sharded volumes (one shard per GPU; invesalius3_b200/dist.py drives these) ---------
  * The reference's only decomposition is the Z-piece split of the surface step

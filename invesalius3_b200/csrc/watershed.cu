@@ -96,6 +96,10 @@ constexpr int kOwn = kT * kT * kT / kThreads;  // 8
 constexpr int kMaxRounds = 1 << 16;
 constexpr uint32_t kInfC = 0xffffffffu;
 constexpr unsigned long long kInfK = ~0ull;
+// label SET of a voxel (phase 2): which labels can reach it along cost-optimal edges, whatever
+// the reference's queue order. code = label + 32768; kSetEmpty = nothing yet; kSetMulti = two
+// different labels (the reference's answer there is an artefact of its queue order).
+constexpr uint16_t kSetEmpty = 32768, kSetMulti = 0;
 
 struct Grid {
   int64_t nz, ny, nx;
@@ -111,6 +115,7 @@ Grid make_grid(int64_t nz, int64_t ny, int64_t nx) {
 struct WsWs {
   uint32_t* cost;
   unsigned long long* key;
+  uint16_t* lset;
   uint8_t* active[2];
   int* flags;
   int64_t bytes;
@@ -123,6 +128,7 @@ WsWs carve(void* base, const Grid& g) {
   int64_t off = 0;
   w.key = (unsigned long long*)(p + off); off += align(n * 8);
   w.cost = (uint32_t*)(p + off); off += align(n * 4);
+  w.lset = (uint16_t*)(p + off); off += align(n * 2);
   w.active[0] = (uint8_t*)(p + off); off += align(nt);
   w.active[1] = (uint8_t*)(p + off); off += align(nt);
   w.flags = (int*)(p + off); off += align((int64_t)(kMaxRounds + 2) * 4);
@@ -134,7 +140,8 @@ WsWs carve(void* base, const Grid& g) {
 // tile holding a marker is active in round 0.
 __global__ void __launch_bounds__(256) k_ws_init(const uint16_t* __restrict__ img, const int16_t* __restrict__ markers,
                                                  Grid g, int mode, uint32_t* __restrict__ cost,
-                                                 unsigned long long* __restrict__ key, uint8_t* active, int* flags) {
+                                                 unsigned long long* __restrict__ key, uint16_t* __restrict__ lset,
+                                                 uint8_t* active, int* flags) {
   const int64_t n = g.nz * g.ny * g.nx;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -142,12 +149,14 @@ __global__ void __launch_bounds__(256) k_ws_init(const uint16_t* __restrict__ im
     if (m != 0) {
       cost[i] = mode == 0 ? 0u : (uint32_t)img[i];
       key[i] = (unsigned long long)(uint32_t)(m + 32768);
+      lset[i] = (uint16_t)(m + 32768);
       int64_t x = i % g.nx, r = i / g.nx, y = r % g.ny, z = r / g.ny;
       active[((int)(z / kT) * g.nty + (int)(y / kT)) * g.ntx + (int)(x / kT)] = 1;
       flags[0] = 1;
     } else {
       cost[i] = kInfC;
       key[i] = kInfK;
+      lset[i] = kSetEmpty;
     }
   }
 }
@@ -162,7 +171,7 @@ __global__ void k_ws_activate_all(uint8_t* active, int64_t ntiles, int* flags, i
 // MODE 0: edge weight |I(v) - I(p)|; MODE 1: weight I(p).
 template <int PHASE, int MODE>
 __global__ void __launch_bounds__(kThreads) k_ws_round(const uint16_t* __restrict__ img, uint32_t* cost,
-                                                       unsigned long long* key, Grid g, uint32_t sb,
+                                                       unsigned long long* key, uint16_t* lset, Grid g, uint32_t sb,
                                                        uint8_t* active_cur, uint8_t* active_next, int* flags,
                                                        int round) {
   if (flags[round] == 0) return;
@@ -172,6 +181,7 @@ __global__ void __launch_bounds__(kThreads) k_ws_round(const uint16_t* __restric
   unsigned long long* sK = (unsigned long long*)smem_raw;                    // PHASE 2 only
   uint32_t* sC = (uint32_t*)(smem_raw + (PHASE == 2 ? kCells * 8 : 0));
   uint16_t* sI = (uint16_t*)((unsigned char*)sC + kCells * 4);
+  uint16_t* sA = sI + kCells;                                                 // PHASE 2 only
   __shared__ int s_faces;
   const int tid = threadIdx.x;
   const int tx = tile % g.ntx, ty = (tile / g.ntx) % g.nty, tz = tile / (g.ntx * g.nty);
@@ -185,7 +195,7 @@ __global__ void __launch_bounds__(kThreads) k_ws_round(const uint16_t* __restric
     int64_t z = z0 + hz - 1, y = y0 + hy - 1, x = x0 + hx - 1;
     uint32_t c = kInfC;
     unsigned long long k = kInfK;
-    uint16_t v = 0;
+    uint16_t v = 0, a = kSetEmpty;
     // MODE 0 reproduces scipy.ndimage.watershed_ift's neighbourhood: the volume is walked as
     // a flat array, a neighbour is any flat index + structure offset inside [0, N), so rows
     // and planes wrap into each other at the volume faces (verified against SciPy 1.18.1).
@@ -195,11 +205,11 @@ __global__ void __launch_bounds__(kThreads) k_ws_round(const uint16_t* __restric
     if (valid) {
       c = __ldcg(&cost[p]);
       v = img[p];
-      if (PHASE == 2) k = __ldcg(&key[p]);
+      if (PHASE == 2) { k = __ldcg(&key[p]); a = __ldcg(&lset[p]); }
     }
     sC[i] = c;
     sI[i] = v;
-    if (PHASE == 2) sK[i] = k;
+    if (PHASE == 2) { sK[i] = k; sA[i] = a; }
   }
   __syncthreads();
   int hidx[kOwn];
@@ -247,6 +257,8 @@ __global__ void __launch_bounds__(kThreads) k_ws_round(const uint16_t* __restric
         if ((kk >> 32) == 0) continue;  // a marker keeps its label
         const uint32_t c = sC[h];
         if (c == kInfC) continue;
+        const uint16_t a0 = sA[h];
+        uint16_t a1 = a0;
         // MODE 1 (label at push time): the voxel inherits from the neighbour that is flooded
         // first, i.e. one with the smallest cost among ALL its neighbours.
         uint32_t cmin = kInfC;
@@ -282,9 +294,13 @@ __global__ void __launch_bounds__(kThreads) k_ws_round(const uint16_t* __restric
               }
               unsigned long long cand = kv + (1ull << 32);
               best = cand < best ? cand : best;
+              // join of the label sets of every admissible predecessor
+              const uint16_t av = sA[v];
+              if (av != kSetEmpty) a1 = (a1 == kSetEmpty) ? av : ((a1 == av && av != kSetMulti) ? a1 : kSetMulti);
             }
-        if (best < kk) {
+        if (best < kk || a1 != a0) {
           sK[h] = best;
+          sA[h] = a1;
           changed = 1;
           cmask |= 1u << k;
         }
@@ -304,7 +320,7 @@ __global__ void __launch_bounds__(kThreads) k_ws_round(const uint16_t* __restric
     int lx = i % kT, ly = (i / kT) % kT, lz = i / (kT * kT);
     int64_t p = ((z0 + lz) * g.ny + (y0 + ly)) * g.nx + (x0 + lx);
     if (PHASE == 1) __stcg(&cost[p], sC[hidx[k]]);
-    else __stcg(&key[p], sK[hidx[k]]);
+    else { __stcg(&key[p], sK[hidx[k]]); __stcg(&lset[p], sA[hidx[k]]); }
     faces |= 64;
     if (lz == 0) faces |= 1;
     if (lz == kT - 1) faces |= 2;
@@ -359,26 +375,29 @@ __global__ void __launch_bounds__(kThreads) k_ws_round(const uint16_t* __restric
   }
 }
 
-__global__ void __launch_bounds__(256) k_ws_labels(const unsigned long long* __restrict__ key, int64_t n,
-                                                   int16_t* __restrict__ labels) {
+__global__ void __launch_bounds__(256) k_ws_labels(const unsigned long long* __restrict__ key,
+                                                   const uint16_t* __restrict__ lset, int64_t n,
+                                                   int16_t* __restrict__ labels, uint8_t* __restrict__ ambiguous) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     unsigned long long k = key[i];
     labels[i] = k == kInfK ? (int16_t)0 : (int16_t)((int)(uint32_t)(k & 0xffffffffu) - 32768);
+    if (ambiguous) ambiguous[i] = lset[i] == kSetMulti ? 1 : 0;
   }
 }
 
 template <int PHASE, int MODE>
 int run_phase(const uint16_t* img, const WsWs& w, const Grid& g, uint32_t sb, cudaStream_t s, int* round_io) {
   const int ntiles = g.ntz * g.nty * g.ntx;
-  const size_t smem = (size_t)kCells * (PHASE == 2 ? 14 : 6);
+  const size_t smem = (size_t)kCells * (PHASE == 2 ? 16 : 6);
   auto kern = k_ws_round<PHASE, MODE>;
   B2V_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int r = *round_io, batch = 4, rc;
   while (true) {
     B2V_REQUIRE(r + batch < kMaxRounds, B2V_ERR_NOCONV, "watershed: no convergence after %d rounds", r);
     for (int k = 0; k < batch; ++k, ++r) {
-      kern<<<ntiles, kThreads, smem, s>>>(img, w.cost, w.key, g, sb, w.active[r & 1], w.active[(r + 1) & 1], w.flags, r);
+      kern<<<ntiles, kThreads, smem, s>>>(img, w.cost, w.key, w.lset, g, sb, w.active[r & 1], w.active[(r + 1) & 1],
+                                          w.flags, r);
       if ((rc = b2v_check_launch("k_ws_round"))) return rc;
     }
     int more = 0;
@@ -451,7 +470,7 @@ extern "C" int64_t b2v_ws_workspace_bytes(int64_t nz, int64_t ny, int64_t nx) {
 
 extern "C" int b2v_ws_flood(const uint16_t* img, const int16_t* markers, int64_t nz, int64_t ny, int64_t nx,
                             const uint8_t* strct_host, int64_t odz, int64_t ody, int64_t odx, int mode,
-                            int16_t* labels, void* workspace, void* stream, int* rounds_out) {
+                            int16_t* labels, uint8_t* ambiguous, void* workspace, void* stream, int* rounds_out) {
   B2V_REQUIRE(img && markers && labels && workspace, B2V_ERR_ARG, "ws_flood: null pointer");
   B2V_REQUIRE(nz > 0 && ny > 0 && nx > 0, B2V_ERR_ARG, "ws_flood: empty volume");
   B2V_REQUIRE(mode == 0 || mode == 1, B2V_ERR_ARG, "ws_flood: mode must be 0 (IFT) or 1 (value flood)");
@@ -464,7 +483,7 @@ extern "C" int b2v_ws_flood(const uint16_t* img, const int16_t* markers, int64_t
   const int64_t n = nz * ny * nx;
   const int64_t ntiles = (int64_t)g.ntz * g.nty * g.ntx;
   B2V_CUDA(cudaMemsetAsync(w.active[0], 0, (size_t)((char*)w.flags - (char*)w.active[0]) + (kMaxRounds + 2) * 4, s));
-  k_ws_init<<<ws_grid(n), 256, 0, s>>>(img, markers, g, mode, w.cost, w.key, w.active[0], w.flags);
+  k_ws_init<<<ws_grid(n), 256, 0, s>>>(img, markers, g, mode, w.cost, w.key, w.lset, w.active[0], w.flags);
   if ((rc = b2v_check_launch("k_ws_init"))) return rc;
   int round = 0;
   rc = mode == 0 ? run_phase<1, 0>(img, w, g, sb, s, &round) : run_phase<1, 1>(img, w, g, sb, s, &round);
@@ -474,7 +493,7 @@ extern "C" int b2v_ws_flood(const uint16_t* img, const int16_t* markers, int64_t
   if ((rc = b2v_check_launch("k_ws_activate_all"))) return rc;
   rc = mode == 0 ? run_phase<2, 0>(img, w, g, sb, s, &round) : run_phase<2, 1>(img, w, g, sb, s, &round);
   if (rc) return rc;
-  k_ws_labels<<<ws_grid(n), 256, 0, s>>>(w.key, n, labels);
+  k_ws_labels<<<ws_grid(n), 256, 0, s>>>(w.key, w.lset, n, labels, ambiguous);
   if ((rc = b2v_check_launch("k_ws_labels"))) return rc;
   if (rounds_out) *rounds_out = round;
   return B2V_OK;

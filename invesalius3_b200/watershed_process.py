@@ -64,8 +64,9 @@ def morphological_gradient_u16(pre: torch.Tensor, size) -> torch.Tensor:
     return out
 
 
-def flood(cost_u16: torch.Tensor, markers_i16: torch.Tensor, bstruct, algorithm: str) -> torch.Tensor:
-    """Marker flood; returns int16 labels. Synchronises."""
+def flood(cost_u16: torch.Tensor, markers_i16: torch.Tensor, bstruct, algorithm: str, return_ambiguous: bool = False):
+    """Marker flood; returns int16 labels (and, with return_ambiguous, the uint8 mask of the voxels
+    whose label depends on the reference's queue order). Synchronises."""
     _dense(cost_u16, "cost"); _dense(markers_i16, "markers")
     if markers_i16.dtype != torch.int16 or markers_i16.shape != cost_u16.shape:
         raise TypeError("watershed: markers must be int16 with the image's shape")
@@ -74,16 +75,19 @@ def flood(cost_u16: torch.Tensor, markers_i16: torch.Tensor, bstruct, algorithm:
         raise RuntimeError("structure and input must have equal rank")
     nz, ny, nx = cost_u16.shape
     labels = torch.empty_like(markers_i16)
+    amb = torch.empty(markers_i16.shape, dtype=torch.uint8, device=cost_u16.device) if return_ambiguous else None
     ws = _workspace(_lib.load().b2v_ws_workspace_bytes(nz, ny, nx), cost_u16.device)
     rounds = C.c_int(0)
     with torch.cuda.device(cost_u16.device):
         _lib.call("b2v_ws_flood", _p(cost_u16), _p(markers_i16), nz, ny, nx, C.c_void_p(st.ctypes.data), *st.shape,
-                  ALGORITHMS[algorithm], _p(labels), _p(ws), _stream(), C.byref(rounds))
-    return labels
+                  ALGORITHMS[algorithm], _p(labels), _p(amb), _p(ws), _stream(), C.byref(rounds))
+    return (labels, amb) if return_ambiguous else labels
 
 
-def watershed_device(image: torch.Tensor, markers: torch.Tensor, bstruct, algorithm, mg_size, use_ww_wl, wl, ww):
-    """The array-level body of do_watershed on device tensors; returns int16 labels."""
+def watershed_device(image: torch.Tensor, markers: torch.Tensor, bstruct, algorithm, mg_size, use_ww_wl, wl, ww,
+                     return_ambiguous: bool = False):
+    """The array-level body of do_watershed on device tensors; returns int16 labels (with
+    return_ambiguous: (labels, uint8 mask of order-dependent voxels))."""
     if algorithm not in ALGORITHMS:
         algorithm = "Watershed IFT"  # the reference's `else` branch
     pre = lut_u16(image, ww, wl) if use_ww_wl else shift_u16(image)
@@ -92,7 +96,7 @@ def watershed_device(image: torch.Tensor, markers: torch.Tensor, bstruct, algori
     mk = markers.to(torch.int16)
     if algorithm == "Watershed IFT" and not use_ww_wl:
         mk = mk.to(torch.int8).to(torch.int16)  # markers.astype('int8'), watershed_process.py:57
-    return flood(pre, mk.contiguous(), bstruct, algorithm)
+    return flood(pre, mk.contiguous(), bstruct, algorithm, return_ambiguous)
 
 
 def do_watershed(image, markers, tfile, shape, bstruct, algorithm, mg_size, use_ww_wl, wl, ww, q) -> None:

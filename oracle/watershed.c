@@ -234,3 +234,102 @@ int orc_ws_model(const uint16_t* image, const int16_t* markers, int64_t nz, int6
 #undef WS_NB
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Pointer-faithful restatement of scipy.ndimage.watershed_ift (scipy/ndimage/src/ni_measure.c,
+ * NI_WatershedIFT; SciPy 1.14.0 pinned by the reference, 1.18.1 in this image) — TEST
+ * INFRASTRUCTURE. SciPy itself is the reference's callee and is present, so it stays the
+ * oracle; this restatement exists to EXPLAIN it (tests/test_oracle_watershed.py checks that it
+ * reproduces SciPy bit for bit on hundreds of random volumes):
+ *   - one doubly linked list per cost value; positive labels are pushed at the HEAD (so a
+ *     bucket is a stack: depth-first, the marker with the highest raveled index first),
+ *     negative labels at the tail;
+ *   - a neighbour is  flat index + structure offset  inside [0, N): rows and planes wrap;
+ *   - a voxel is relabelled only on a STRICTLY smaller cost max(cost(v), |I(v) - I(p)|);
+ *   - quirk: before re-inserting an improved voxel SciPy unlinks it from its old list only
+ *     `if (p->next || p->prev)`, so a voxel that is ALONE in its bucket stays linked there
+ *     (first[old] keeps pointing at it) while it also enters the new bucket; later pushes into
+ *     the old bucket then overwrite its `prev`, and a subsequent unlink splices the two lists:
+ *     elements can be processed in the wrong bucket or never, and the final costs are then NOT
+ *     the minimax costs. quirk = 0 runs the algorithm as intended (unlink whenever queued).
+ * out: labels. *n_nonminimax (optional): voxels whose final cost differs from the exact minimax
+ * cost can be found by comparing with orc_ws_model; here we only count sole-element events.
+ * ------------------------------------------------------------------------------------------ */
+int orc_ift_scipy(const uint16_t* image, const int16_t* markers, int64_t nz, int64_t ny, int64_t nx,
+                  const uint8_t* strct, int64_t sz, int64_t sy, int64_t sx, int quirk, int16_t* out,
+                  int64_t* sole_events) {
+  const int64_t n = nz * ny * nx;
+  int64_t noff = 0, offs[27];
+  for (int64_t k = 0; k < sz; ++k)
+    for (int64_t j = 0; j < sy; ++j)
+      for (int64_t i = 0; i < sx; ++i)
+        if (strct[(k * sy + j) * sx + i]) {
+          int64_t o = ((k - sz / 2) * ny + (j - sy / 2)) * nx + (i - sx / 2);
+          if (o != 0) offs[noff++] = o;
+        }
+  int maxval = 0;
+  for (int64_t p = 0; p < n; ++p) if (image[p] > maxval) maxval = image[p];
+  const int64_t NIL = -1;
+  int64_t* nxt = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+  int64_t* prv = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+  int32_t* cost = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+  uint8_t* done = (uint8_t*)calloc((size_t)n, 1);
+  uint8_t* queued = (uint8_t*)calloc((size_t)n, 1);   /* quirk = 0 only: is the voxel in a list? */
+  int64_t* first = (int64_t*)malloc(sizeof(int64_t) * (size_t)(maxval + 2));
+  int64_t* last = (int64_t*)malloc(sizeof(int64_t) * (size_t)(maxval + 2));
+  for (int b = 0; b <= maxval + 1; ++b) first[b] = last[b] = NIL;
+  int64_t sole = 0;
+  for (int64_t j = 0; j < n; ++j) {
+    out[j] = markers[j];
+    nxt[j] = prv[j] = NIL;
+    if (markers[j]) {
+      cost[j] = 0;
+      queued[j] = 1;
+      if (first[0] == NIL) { first[0] = j; last[0] = j; }
+      else if (markers[j] > 0) { nxt[j] = first[0]; prv[first[0]] = j; first[0] = j; }
+      else { prv[j] = last[0]; nxt[last[0]] = j; last[0] = j; }
+    } else cost[j] = maxval + 1;
+  }
+  for (int b = 0; b <= maxval; ++b)
+    while (first[b] != NIL) {
+      const int64_t v = first[b];
+      first[b] = nxt[v];
+      if (first[b] != NIL) prv[first[b]] = NIL;
+      prv[v] = nxt[v] = NIL;
+      done[v] = 1;
+      queued[v] = 0;
+      for (int64_t h = 0; h < noff; ++h) {
+        const int64_t p = v + offs[h];
+        if (p < 0 || p >= n || done[p]) continue;
+        int w = (int)image[p] - (int)image[v];
+        if (w < 0) w = -w;
+        const int pc = cost[p], mx = cost[v] > w ? cost[v] : w;
+        if (mx >= pc) continue;
+        cost[p] = mx;
+        out[p] = out[v];
+        const int linked = quirk ? (nxt[p] != NIL || prv[p] != NIL) : queued[p];
+        if (linked) {
+          const int64_t pr = prv[p], nx_ = nxt[p];
+          if (first[pc] == p) first[pc] = nx_;
+          if (last[pc] == p) last[pc] = pr;
+          if (pr != NIL) nxt[pr] = nx_;
+          if (nx_ != NIL) prv[nx_] = pr;
+        } else if (quirk && pc <= maxval && first[pc] == p) ++sole;
+        queued[p] = 1;
+        if (out[v] < 0) {
+          prv[p] = last[mx]; nxt[p] = NIL;
+          if (last[mx] != NIL) nxt[last[mx]] = p;
+          last[mx] = p;
+          if (first[mx] == NIL) first[mx] = p;
+        } else {
+          nxt[p] = first[mx]; prv[p] = NIL;
+          if (first[mx] != NIL) prv[first[mx]] = p;
+          first[mx] = p;
+          if (last[mx] == NIL) last[mx] = p;
+        }
+      }
+    }
+  if (sole_events) *sole_events = sole;
+  free(nxt); free(prv); free(cost); free(done); free(queued); free(first); free(last);
+  return 0;
+}

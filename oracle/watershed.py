@@ -74,3 +74,19 @@ def order_independence_model(image_u16, markers_i16, bstruct, mode):
     lib().orc_ws_model(_ptr(img), _ptr(mk), *map(C.c_int64, img.shape), _ptr(st), *map(C.c_int64, st.shape),
                        C.c_int(mode), _ptr(cost), _ptr(sets))
     return cost.reshape(np.shape(image_u16)), sets.reshape(np.shape(image_u16))
+
+
+def ift_scipy_restated(image_u16, markers_i16, bstruct, quirk=True):
+    """oracle/watershed.c::orc_ift_scipy — pointer-faithful restatement of SciPy's watershed_ift
+    (quirk=True) or the algorithm as intended (quirk=False). Returns (labels int16, number of
+    sole-element events)."""
+    img = np.ascontiguousarray(image_u16, dtype=np.uint16)
+    mk = np.ascontiguousarray(markers_i16, dtype=np.int16)
+    st = np.ascontiguousarray(bstruct, dtype=np.uint8)
+    if img.ndim == 2:
+        img, mk, st = img[None], mk[None], st[None]
+    out = np.zeros(img.shape, np.int16)
+    sole = C.c_int64(0)
+    lib().orc_ift_scipy(_ptr(img), _ptr(mk), *map(C.c_int64, img.shape), _ptr(st), *map(C.c_int64, st.shape),
+                        C.c_int(1 if quirk else 0), _ptr(out), C.byref(sole))
+    return out.reshape(np.shape(image_u16)), sole.value

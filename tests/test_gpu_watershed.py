@@ -2,10 +2,15 @@
   LUT / shift / morphological gradient: bit-exact against NumPy / SciPy (SciPy is the
   reference's own callee).
   Flood: SciPy's watershed_ift (true callee) and the restated skimage heap flood are
-  sequential, queue-ordered algorithms; the GPU computes the exact minimax cost field and a
-  deterministic labelling. Exact agreement is asserted where the reference's answer does not
-  depend on queue order (tie-free inputs) and on the reference's own smoke test; on CT-like
-  data with plateaus the agreement fraction is measured and bounded from below.
+  sequential, queue-ordered algorithms. The GPU computes the exact minimax cost field, the SET
+  of labels that can reach every voxel along cost-optimal edges, and a deterministic labelling.
+  Asserted, with no tolerance:
+    * the GPU's order-dependence mask equals the CPU model's (oracle/watershed.c::orc_ws_model);
+    * on every order-INDEPENDENT voxel the GPU label equals the model's — and equals the
+      reference's own output (SciPy / restated skimage) whenever SciPy's list-unlink quirk did
+      not corrupt its queues (tests/test_oracle_watershed.py explains and pins that quirk).
+  On order-dependent voxels (genuine queue-order ties) the agreement is measured, printed and
+  bounded from below at the measured value minus one point.
 """
 import multiprocessing
 import os
@@ -95,7 +100,72 @@ def test_ift_matches_scipy_when_tie_free(wp, conn):
     want = ndimage.watershed_ift(img, mk, st)
     got = wp.flood(_t(img.view(np.int16)), _t(mk), st, "Watershed IFT").cpu().numpy()
     print(f"narrow-range (tie-heavy) IFT agreement, conn {conn}: {(got == want).mean():.4f}")
-    assert (got == want).mean() >= 0.6, (got == want).mean()
+    assert (got == want).mean() >= FLOOR_NARROW[conn], (got == want).mean()
+
+
+# measured agreement on inputs with genuine queue-order ties, minus one point (a regression
+# below these values fails; the exact part of the parity is asserted separately, below)
+FLOOR_NARROW = {1: 0.60, 3: 0.60}
+FLOOR_CT = {"Watershed": 0.98, "Watershed IFT": 0.98}
+
+
+def _cases(rng, n, signed=False):
+    from test_oracle_watershed import random_case
+    return [random_case(rng, maxdim=14, signed=signed) for _ in range(n)]
+
+
+@pytest.mark.parametrize("algorithm,mode", [("Watershed IFT", 0), ("Watershed", 1)])
+def test_exact_on_order_independent_voxels_random(wp, algorithm, mode):
+    """Random volumes (3 .. 65536 grey levels, 1-4 markers, 6/18/26 neighbourhoods): the GPU's
+    order-dependence mask equals the model's, its labels equal the model's on every
+    order-independent voxel, and those equal the reference's output unless SciPy's unlink quirk
+    corrupted its queues for that input."""
+    from oracle import watershed as W
+    rng = np.random.default_rng(100 + mode)
+    checked = amb_total = n_total = quirk_cases = 0
+    for img, mk, st in _cases(rng, 60):
+        got, amb = wp.flood(_t(img.view(np.int16)), _t(mk), st, algorithm, return_ambiguous=True)
+        got, amb = got.cpu().numpy(), amb.cpu().numpy().astype(bool)
+        _, sets = W.order_independence_model(img, mk, st, mode)
+        assert np.array_equal(amb, sets == W.MULTI), "order-dependence masks differ"
+        ok = ~amb
+        assert np.array_equal(got[ok], sets[ok].astype(np.int16)), "label differs on an order-independent voxel"
+        assert (got != 0).all() and np.array_equal(got[mk != 0], mk[mk != 0])
+        if mode == 0:
+            want = ndimage.watershed_ift(img, mk, st)
+            clean, _ = W.ift_scipy_restated(img, mk, st, quirk=False)
+            if np.array_equal(clean, want):
+                assert np.array_equal(got[ok], want[ok])
+            else:
+                quirk_cases += 1
+        else:
+            assert np.array_equal(got[ok], W.watershed_skimage(img, mk, st)[ok])
+        checked += int(ok.sum()); amb_total += int(amb.sum()); n_total += img.size
+    print(f"{algorithm}: {checked} order-independent voxels exact, {amb_total}/{n_total} order-dependent, "
+          f"{quirk_cases} inputs where SciPy's unlink quirk fired")
+
+
+@pytest.mark.parametrize("shape", [(48, 96, 96), (128, 128, 128)])
+def test_exact_on_order_independent_voxels_ct(wp, shape):
+    """BASELINE configs[3] in small (CT phantom, Cranium window ww 406 / wl -18, 6-connected):
+    exact on every order-independent voxel against the reference's callee itself."""
+    from oracle import watershed as W
+    from test_oracle_watershed import ct_case
+    vol, markers = ct_case(shape)
+    st = generate_binary_structure(3, 1)
+    for algorithm, mode in (("Watershed", 1), ("Watershed IFT", 0)):
+        want = W.do_watershed_array(vol, markers, st, algorithm, 3, True, -18, 406)
+        got, amb = wp.watershed_device(_t(vol), _t(markers), st, algorithm, 3, True, -18, 406, return_ambiguous=True)
+        got, amb = got.cpu().numpy(), amb.cpu().numpy().astype(bool)
+        pre = W.preprocess(vol, True, -18, 406)
+        if algorithm == "Watershed":
+            pre = ndimage.morphological_gradient(pre, 3)
+        _, sets = W.order_independence_model(pre, markers.astype(np.int16), st, mode)
+        assert np.array_equal(amb, sets == W.MULTI)
+        assert np.array_equal(got[~amb], want[~amb]), f"{algorithm}: differs from the reference on an order-independent voxel"
+        frac = float((got == want).mean())
+        print(f"{algorithm} {shape}: order-independent {1 - amb.mean():.5f} (exact), overall agreement {frac:.5f}")
+        assert frac >= FLOOR_CT[algorithm]
 
 
 def test_ift_simple_known_answers(wp):
@@ -152,7 +222,7 @@ def test_do_watershed_reference_smoke(wp):
         # the cube interior / exterior are decided by cost, not by queue order
         assert result[1:4, 1:4, 1:4].min() == 1 or algorithm == "Watershed"
         agree = (result == want.astype(np.uint8)).mean()
-        assert agree >= 0.75, (algorithm, agree)
+        assert agree >= 0.75, (algorithm, agree)   # 125 voxels, most of them plateau ties
 
 
 def test_ct_phantom_agreement_fraction(wp):
@@ -176,4 +246,4 @@ def test_ct_phantom_agreement_fraction(wp):
         frac = float((got == want).mean())
         print(f"agreement[{algorithm}] = {frac:.4f}")
         assert set(np.unique(got)) <= {1, 2}
-        assert frac >= 0.5, (algorithm, frac)
+        assert frac >= FLOOR_CT[algorithm], (algorithm, frac)
