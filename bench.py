@@ -129,20 +129,87 @@ def crossing_edges(mask_u8, iso=127):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled DURING the warm-up and the timed region.
+
+    In-process NVML (the library behind nvidia-smi) on a background thread: an `nvidia-smi -lms`
+    child stalls this process's host-synchronous CUDA calls for milliseconds at every poll (measured:
+    +0.3 .. +0.6 ms per step on a 1.3 ms step), which a 13 ms timed region cannot absorb. The
+    subprocess remains as the fallback when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, pci_bus_id=None, period=0.01, force_smi=False):
+        self.samples = []        # (sm MHz, reasons bitmask)
+        self.max_mhz = None
+        self.skip = 0
+        self.p = self.f = self.thread = None
+        try:
+            if force_smi:
+                raise RuntimeError("nvidia-smi requested")
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode() if isinstance(pci_bus_id, str) else pci_bus_id) \
+                if pci_bus_id else nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                         "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                         "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                         "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            self.stop_flag = False
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                             int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(period)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.thread = None
+        self.source = "nvidia-smi"
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def rows(self):
+        if self.thread is not None:
+            return len(self.samples)
+        try:
+            return sum(1 for r in open(self.f.name).read().splitlines() if r.count(",") >= 8)
+        except Exception:
+            return 0
+
+    def wait_ready(self, timeout=15.0):
+        """Wait for the first sample BEFORE the load starts (nvidia-smi needs up to a second to attach
+        on a fresh box); samples taken up to here are idle ones and are dropped."""
+        t0 = time.perf_counter()
+        alive = lambda: self.thread is not None or (self.p is not None and self.p.poll() is None)
+        while alive() and self.rows() == 0 and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+        self.skip = self.rows()
+
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            rows = self.samples[self.skip:] or self.samples
+            if not rows:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "source": "nvml"}
+            sm = sorted(r[0] for r in rows)
+            reasons = sorted(k for k, bit in self.bits.items() if any(r[1] & bit for r in rows))
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(rows),
+                    "source": "nvml"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -153,6 +220,8 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        if len(rows) > self.skip:
+            rows = rows[self.skip:]      # under load only (warm-up + timed region)
         os.unlink(self.f.name)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
@@ -163,7 +232,7 @@ class ClockSampler:
                 if "Active" in v and "Not" not in v:
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
-                "samples": len(rows)}
+                "samples": len(rows), "source": "nvidia-smi"}
 
 
 def bind_to_gpu_numa(local_rank):
@@ -363,7 +432,7 @@ def run_gpu(args):
 
     def do_surface(out_ext):
         if world == 1:
-            v, f = marching_cubes(out_ext, 127, SPACING, (0, 0, 0), True)
+            v, f = marching_cubes(out_ext, 127, SPACING, (0, 0, 0), True, _events=info.get("mc_events"))
             info["V"], info["T"] = int(v.shape[0]), int(f.shape[0])
         else:
             v, f, _, info["V"], info["T"] = zd.marching_cubes(out_ext[int(shard.has_lo):], 127, SPACING, (0, 0, 0),
@@ -434,21 +503,40 @@ def run_gpu(args):
     launches = 0
     for name in ("per_shard", "global") if world > 1 else ("global",):
         seeds = seedings[name]
-        for _ in range(max(args.warmup, 3)):
-            step_device(seeds)
-        barrier()
         head = name == "global"
-        sampler = ClockSampler(local) if (rank == 0 and head) else None
+        sampler = None
+        if rank == 0 and head:
+            try:
+                bus = torch.cuda.get_device_properties(local)
+                bus_id = f"{getattr(bus, 'pci_domain_id', 0):08x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+            except Exception:
+                bus_id = None
+            sampler = ClockSampler(local, bus_id, force_smi=bool(os.environ.get("B2V_BENCH_SMI")))
+        if sampler:
+            sampler.wait_ready()
+        v = f = None
+        for _ in range(max(args.warmup, 3)):
+            v, f = step_device(seeds)     # results stay bound as in the timed loop: the caching allocator
+        barrier()                         # reaches its steady state (two sets of output blocks) here
         lib.b2v_launch_count_reset()
         stage_ms = np.zeros(3)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
+        dbg = []
+        if os.environ.get("B2V_BENCH_DEBUG"):
+            info["mc_events"] = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         for _ in range(args.steps):
             v, f = step_device(seeds, ev)
             torch.cuda.synchronize()
             stage_ms += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+            if info.get("mc_events"):
+                me = info["mc_events"]
+                dbg.append([round(x, 3) for x in (ev[2].elapsed_time(me[0]), me[0].elapsed_time(me[1]),
+                                                  me[1].elapsed_time(me[2]), me[2].elapsed_time(ev[3]))])
+        if dbg:
+            sys.stderr.write("mc [ws alloc, count, out alloc, emit] per step: " + json.dumps(dbg) + "\n")
         e1.record()
         barrier()
         if head:

@@ -48,27 +48,21 @@ __device__ __forceinline__ void split_word(const McGeom& g, uint32_t wi, int& z,
   else { z = (int)(row / (uint32_t)g.iny); y = (int)(row - (uint32_t)z * (uint32_t)g.iny); }
 }
 
-constexpr int kClsThreads = 256;
-enum { Q_VW = 0, Q_V = 1, Q_CW = 2, Q_C = 3, Q_T = 4, Q_N = 5 };   // listed words (verts), vertices, listed
-                                                                    // words (cells), active cells, triangles
-struct TileState {     // chained-scan state of one classify tile
-  uint32_t agg[Q_N];
-  uint32_t incl[Q_N];
-  uint32_t pad;
-  int flag;            // 0 nothing yet, 1 aggregate valid, 2 inclusive prefix valid
-};
+constexpr int kTileThreads = 256;
+constexpr int kWPT = 4;                              // words per thread
+constexpr int kTileWords = kTileThreads * kWPT;      // one tile = 1024 consecutive words
+constexpr int kTileShift = 10;
 
 struct McWs {
   uint32_t* bits;    // [nwords] inside bits
-  uint32_t* vslot;   // [nwords] dense map word -> slot in the vertex list (written for listed words only)
-  uint4* vinfo;      // [<= nwords] listed words that own vertices: (cx, cy, cz, exclusive vertex offset)
-  uint32_t* vword;   // [<= nwords] their word indices
-  uint4* cinfo;      // [<= nwords] listed words with active cells: (word, cell mask, triangle offset, cell offset)
-  uint4* plane0;     // [ny * wx] dense records of plane 0 (Z-sharded volumes)
-  TileState* tiles;  // [ntiles4 or ntiles1]
-  unsigned long long* totals;  // [0] V, [1] T, [2] active cells, [3] listed v-words, [4] listed c-words, [5] overflow
-  unsigned int* ticket;
-  int64_t ctl_bytes; // tiles + totals + ticket: zeroed before every classify
+  uint4* vrec;       // [ntiles * 1024] per word (cx, cy, cz, exclusive vertex offset INSIDE its tile); written for
+                     // the tiles that hold vertices only
+  uint4* tcnt;       // [ntiles] per tile (vertices, active cells, triangles, 0)
+  uint4* toff;       // [ntiles] their exclusive prefixes over the tiles
+  uint4* plane0;     // [ny * wx] dense records of plane 0 with GLOBAL vertex offsets (Z-sharded volumes)
+  unsigned long long* totals;  // [0] V, [1] T, [2] active cells
+  unsigned int* ticket;        // tiles done (the last one scans the tile counts)
+  int64_t ctl_bytes; // totals + ticket: zeroed before every classify
   int64_t bytes;
 };
 
@@ -77,15 +71,13 @@ McWs carve(void* base, const McGeom& g) {
   auto align = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
   char* p = (char*)base;
   int64_t off = 0;
-  const int64_t ntiles = ceil_div64(g.nwords, kClsThreads);   // capacity for one word per thread
+  const int64_t ntiles = ceil_div64(g.nwords, kTileWords);
   w.bits = (uint32_t*)(p + off); off += align(g.nwords * 4 + 64);
-  w.vslot = (uint32_t*)(p + off); off += align(g.nwords * 4);
-  w.vinfo = (uint4*)(p + off); off += align(g.nwords * 16);
-  w.vword = (uint32_t*)(p + off); off += align(g.nwords * 4);
-  w.cinfo = (uint4*)(p + off); off += align(g.nwords * 16);
+  w.vrec = (uint4*)(p + off); off += align(ntiles * kTileWords * 16);
+  w.tcnt = (uint4*)(p + off); off += align(ntiles * 16);
+  w.toff = (uint4*)(p + off); off += align(ntiles * 16);
   w.plane0 = (uint4*)(p + off); off += align(g.ny * g.wx * 16);
   const int64_t ctl0 = off;
-  w.tiles = (TileState*)(p + off); off += align(ntiles * (int64_t)sizeof(TileState));
   w.totals = (unsigned long long*)(p + off); off += 256;
   w.ticket = (unsigned int*)(p + off); off += 256;
   w.ctl_bytes = off - ctl0;
@@ -192,20 +184,15 @@ __global__ void __launch_bounds__(256) k_mc_bits_i16_vec(const int16_t* __restri
   }
 }
 
-// ---- 2. classify + compact (one pass, decoupled look-back) -----------------------------------
-// The surface touches a few per cent of the words. One pass over the bit volume classifies every
-// word (crossing masks towards +x/+y/+z, active cells, triangle count) and appends the non-empty
-// ones, IN WORD ORDER, to two compact lists:
-//   vertex list   words that own vertices:   vinfo[slot] = (cx, cy, cz, exclusive vertex offset),
-//                 vword[slot] = word index, and the dense map vslot[word] = slot (written only
-//                 for listed words: a crossing edge's owner is always listed);
-//   cell list     words with active cells:   cinfo[slot] = (word index, active-cell mask,
-//                 exclusive triangle offset, exclusive active-cell offset).
-// The five running totals (listed words x2, vertices, cells, triangles) are carried from tile to
-// tile by a chained scan: a tile publishes its aggregate, looks back over its predecessors until
-// it meets an inclusive prefix, then publishes its own. Tiles are numbered by an atomic ticket,
-// so every predecessor of a running tile is itself running (no deadlock). Nothing is written for
-// empty words and no second pass re-reads per-word records.
+// ---- 2. classify (one pass over the bits, per-TILE counts, scan of the tile counts) ----------
+// The surface touches a few per cent of the words. A tile is 1024 consecutive words (4 per
+// thread). One pass classifies every word (crossing masks towards +x/+y/+z, active cells,
+// triangle count); a tile that holds nothing writes one zero count and leaves. The others scan
+// their words' vertex counts inside the block and write the dense per-word records
+// vrec[word] = (cx, cy, cz, exclusive vertex offset inside the tile): what a triangle corner
+// needs to turn "crossing edge owned by word W, bit b" into a vertex id. Only per-TILE counts
+// are scanned across the volume (4096 entries at 512^3): the last tile to finish does it in the
+// same launch. The emit kernels re-derive everything else from the bits.
 struct Rows {       // the four bit rows a cell row touches, word w and bit 0 of word w+1
   uint32_t i00, i01, i10, i11;  // [cz][cy]
   uint32_t n00, n01, n10, n11;  // next word in x (0 past the row end)
@@ -244,220 +231,200 @@ __device__ __forceinline__ Rows load_rows(const uint32_t* __restrict__ bits, con
   return r;
 }
 
-struct WordClass {
-  uint32_t cx, cy, cz, act;
-  uint32_t nv, nt;
+// The four words of one thread: rows, position, validity. VEC (wx % 4 == 0): the four words lie
+// in one row and every bit row is one aligned 128-bit load.
+struct Word4 {
+  Rows r[kWPT];
+  int z[kWPT], y[kWPT], w[kWPT];
+  bool ok[kWPT];
 };
 
-__device__ __forceinline__ WordClass classify_word(const Rows& r, uint32_t vx, bool hy, bool hz, bool own_verts,
-                                                   const unsigned char* s_ntri) {
-  WordClass c;
-  const uint32_t s00 = shift_in(r.i00, r.n00);
-  c.cx = (r.i00 ^ s00) & vx;
-  c.cy = hy ? (r.i00 ^ r.i01) : 0u;
-  c.cz = hz ? (r.i00 ^ r.i10) : 0u;
-  // a Z shard does not own the vertices of its last (shared) plane: the next shard does
-  c.nv = own_verts ? __popc(c.cx) + __popc(c.cy) + __popc(c.cz) : 0;
-  c.act = 0;
-  c.nt = 0;
-  if (hy && hz) {
-    const uint32_t s01 = shift_in(r.i01, r.n01), s10 = shift_in(r.i10, r.n10), s11 = shift_in(r.i11, r.n11);
-    const uint32_t any = r.i00 | r.i01 | r.i10 | r.i11 | s00 | s01 | s10 | s11;
-    const uint32_t all = r.i00 & r.i01 & r.i10 & r.i11 & s00 & s01 & s10 & s11;
-    c.act = any & ~all & vx;
-    for (uint32_t m = c.act; m; m &= m - 1) c.nt += s_ntri[cell_case(r, __ffs(m) - 1)];
-  }
-  return c;
-}
-
-__device__ __forceinline__ int ld_flag(const int* p) {
-  int v;
-  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-
-template <int WPT>
-__global__ void __launch_bounds__(kClsThreads) k_mc_classify(const uint32_t* __restrict__ bits, McGeom g,
-                                                             int skip_last, uint32_t* __restrict__ vslot,
-                                                             uint4* __restrict__ vinfo, uint32_t* __restrict__ vword,
-                                                             uint4* __restrict__ cinfo, TileState* tiles,
-                                                             unsigned int* ticket, unsigned long long* totals,
-                                                             int ntiles) {
-  __shared__ unsigned char s_ntri[256];
-  __shared__ unsigned int s_tile;
-  __shared__ unsigned long long s_wx[kClsThreads / 32];
-  __shared__ uint32_t s_wy[kClsThreads / 32];
-  __shared__ uint32_t s_base[Q_N];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  s_ntri[tid] = B2V_MC_NTRI[tid];
-  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  __syncthreads();
-  const int tile = (int)s_tile;
-  const uint32_t wi0 = ((uint32_t)tile * kClsThreads + tid) * WPT;
+template <bool VEC>
+__device__ __forceinline__ void load_word4(const uint32_t* __restrict__ bits, const McGeom& g, uint32_t wi0,
+                                           Word4& q) {
   const uint32_t nwords = (uint32_t)g.nwords;
-  WordClass wc[WPT];
-  // packed thread sums: X = nv (20) | listed-v (12) | cells (20) | listed-c (12), Y = triangles
-  unsigned long long X = 0;
-  uint32_t Y = 0;
-  if (wi0 < nwords) {
-    int z, y, w0;
-    split_word(g, wi0, z, y, w0);
-    const bool hy = y + 1 < g.iny, hz = z + 1 < g.inz;
-    const bool own = !(skip_last && z == g.inz - 1);
-    uint32_t a00[WPT + 1], a01[WPT + 1], a10[WPT + 1], a11[WPT + 1];
-    const uint32_t b00 = wi0, b01 = b00 + (uint32_t)g.wx, b10 = b00 + (uint32_t)g.iny * (uint32_t)g.wx,
-                   b11 = b10 + (uint32_t)g.wx;
-    if (WPT == 4) {   // wx % 4 == 0: the four words of a thread are one aligned 128-bit load per row
+  if (VEC) {
+    const bool ok = wi0 < nwords;
+    int z = 0, y = 0, w0 = 0;
+    uint32_t a00[kWPT + 1] = {0, 0, 0, 0, 0}, a01[kWPT + 1] = {0, 0, 0, 0, 0}, a10[kWPT + 1] = {0, 0, 0, 0, 0},
+             a11[kWPT + 1] = {0, 0, 0, 0, 0};
+    if (ok) {
+      split_word(g, wi0, z, y, w0);
+      const bool hy = y + 1 < g.iny, hz = z + 1 < g.inz, hn = w0 + kWPT < g.wx;
+      const uint32_t b00 = wi0, b01 = b00 + (uint32_t)g.wx, b10 = b00 + (uint32_t)g.iny * (uint32_t)g.wx,
+                     b11 = b10 + (uint32_t)g.wx;
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
       const uint4 q00 = __ldg((const uint4*)(bits + b00));
-      const uint4 q01 = hy ? __ldg((const uint4*)(bits + b01)) : make_uint4(0, 0, 0, 0);
-      const uint4 q10 = hz ? __ldg((const uint4*)(bits + b10)) : make_uint4(0, 0, 0, 0);
-      const uint4 q11 = (hy && hz) ? __ldg((const uint4*)(bits + b11)) : make_uint4(0, 0, 0, 0);
+      const uint4 q01 = hy ? __ldg((const uint4*)(bits + b01)) : z4;
+      const uint4 q10 = hz ? __ldg((const uint4*)(bits + b10)) : z4;
+      const uint4 q11 = (hy && hz) ? __ldg((const uint4*)(bits + b11)) : z4;
       a00[0] = q00.x; a00[1] = q00.y; a00[2] = q00.z; a00[3] = q00.w;
       a01[0] = q01.x; a01[1] = q01.y; a01[2] = q01.z; a01[3] = q01.w;
       a10[0] = q10.x; a10[1] = q10.y; a10[2] = q10.z; a10[3] = q10.w;
       a11[0] = q11.x; a11[1] = q11.y; a11[2] = q11.z; a11[3] = q11.w;
-    } else {
-      a00[0] = __ldg(bits + b00);
-      a01[0] = hy ? __ldg(bits + b01) : 0u;
-      a10[0] = hz ? __ldg(bits + b10) : 0u;
-      a11[0] = (hy && hz) ? __ldg(bits + b11) : 0u;
+      a00[kWPT] = hn ? __ldg(bits + b00 + kWPT) : 0u;
+      a01[kWPT] = (hn && hy) ? __ldg(bits + b01 + kWPT) : 0u;
+      a10[kWPT] = (hn && hz) ? __ldg(bits + b10 + kWPT) : 0u;
+      a11[kWPT] = (hn && hy && hz) ? __ldg(bits + b11 + kWPT) : 0u;
     }
-    const bool hn = w0 + WPT < g.wx;
-    a00[WPT] = hn ? __ldg(bits + b00 + WPT) : 0u;
-    a01[WPT] = (hn && hy) ? __ldg(bits + b01 + WPT) : 0u;
-    a10[WPT] = (hn && hz) ? __ldg(bits + b10 + WPT) : 0u;
-    a11[WPT] = (hn && hy && hz) ? __ldg(bits + b11 + WPT) : 0u;
 #pragma unroll
-    for (int j = 0; j < WPT; ++j) {
-      Rows r = {a00[j], a01[j], a10[j], a11[j], a00[j + 1], a01[j + 1], a10[j + 1], a11[j + 1]};
-      // a word whose whole 2 x 2-row neighbourhood is uniform (most of the volume) holds nothing:
-      // all outside (missing rows / words read as 0), or all inside with every neighbour present
-      const uint32_t o_ = r.i00 | r.i01 | r.i10 | r.i11 | ((r.n00 | r.n01 | r.n10 | r.n11) & 1u);
-      const bool ones = hy && hz && w0 + j + 1 < g.wx && (r.i00 & r.i01 & r.i10 & r.i11) == 0xffffffffu &&
-                        ((r.n00 & r.n01 & r.n10 & r.n11) & 1u);
-      if (o_ == 0u || ones) { wc[j] = WordClass{0u, 0u, 0u, 0u, 0u, 0u}; continue; }
-      wc[j] = classify_word(r, valid_x1(g, w0 + j), hy, hz, own, s_ntri);
-      X += (unsigned long long)wc[j].nv | ((unsigned long long)(wc[j].nv != 0) << 20) |
-           ((unsigned long long)__popc(wc[j].act) << 32) | ((unsigned long long)(wc[j].act != 0) << 52);
-      Y += wc[j].nt;
+    for (int j = 0; j < kWPT; ++j) {
+      q.r[j] = Rows{a00[j], a01[j], a10[j], a11[j], a00[j + 1], a01[j + 1], a10[j + 1], a11[j + 1]};
+      q.z[j] = z; q.y[j] = y; q.w[j] = w0 + j; q.ok[j] = ok;
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < WPT; ++j) wc[j] = WordClass{0u, 0u, 0u, 0u, 0u, 0u};
-  }
-  // block exclusive scan of (X, Y)
-  unsigned long long ix = X;
-  uint32_t iy = Y;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long px = __shfl_up_sync(0xffffffffu, ix, o);
-    const uint32_t py = __shfl_up_sync(0xffffffffu, iy, o);
-    if (lane >= o) { ix += px; iy += py; }
-  }
-  if (lane == 31) { s_wx[warp] = ix; s_wy[warp] = iy; }
-  __syncthreads();
-  unsigned long long ox = 0, tx = 0;
-  uint32_t oy = 0, ty = 0;
-#pragma unroll
-  for (int k = 0; k < kClsThreads / 32; ++k) {
-    if (k < warp) { ox += s_wx[k]; oy += s_wy[k]; }
-    tx += s_wx[k]; ty += s_wy[k];
-  }
-  const unsigned long long ex = ox + ix - X;     // exclusive within the block
-  const uint32_t ey = oy + iy - Y;
-  // tile totals -> look-back. The WHOLE block looks back, 256 predecessors per step: with a
-  // thousand tiles resident at once the nearest inclusive prefix is hundreds of tiles away, and
-  // the wave of inclusive prefixes advances one window per L2 round trip (a 32-wide window
-  // measured 105 us for 4096 tiles at 512^3: latency-bound).
-  uint32_t tot[Q_N];
-  tot[Q_V] = (uint32_t)(tx & 0xfffffu); tot[Q_VW] = (uint32_t)((tx >> 20) & 0xfffu);
-  tot[Q_C] = (uint32_t)((tx >> 32) & 0xfffffu); tot[Q_CW] = (uint32_t)((tx >> 52) & 0xfffu);
-  tot[Q_T] = ty;
-  TileState* me = tiles + tile;
-  if (tid == 0) {
-#pragma unroll
-    for (int q = 0; q < Q_N; ++q) { me->agg[q] = tot[q]; if (tile == 0) me->incl[q] = tot[q]; s_base[q] = 0; }
-    __threadfence();
-    *(volatile int*)&me->flag = tile == 0 ? 2 : 1;
-  }
-  __syncthreads();
-  for (int look = tile - 1; look >= 0; look -= kClsThreads) {
-    const int idx = look - tid;
-    int f = 2;
-    uint32_t v[Q_N];
-#pragma unroll
-    for (int q = 0; q < Q_N; ++q) v[q] = 0;
-    if (idx >= 0) {
-      const TileState* t = tiles + idx;
-      do { f = ld_flag(&t->flag); } while (f == 0);
-      __threadfence();
-#pragma unroll
-      for (int q = 0; q < Q_N; ++q) v[q] = __ldcg(f == 2 ? &t->incl[q] : &t->agg[q]);
-    }
-    // the nearest predecessor that already holds an inclusive prefix ends the walk
-    const unsigned m2 = __ballot_sync(0xffffffffu, idx < 0 || f == 2);
-    if (lane == 0) s_wy[warp] = m2 ? (uint32_t)(warp * 32 + __ffs(m2) - 1) : 0xffffffffu;
-    __syncthreads();
-    uint32_t stop = 0xffffffffu;
-#pragma unroll
-    for (int k = 0; k < kClsThreads / 32; ++k) stop = s_wy[k] < stop ? s_wy[k] : stop;
-    const bool mine = idx >= 0 && (uint32_t)tid <= stop;
-#pragma unroll
-    for (int q = 0; q < Q_N; ++q) {
-      uint32_t c = mine ? v[q] : 0u;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-      if (lane == 0 && c) atomicAdd(&s_base[q], c);
-    }
-    __syncthreads();    // s_base complete, s_wy free for the next window
-    if (stop != 0xffffffffu) break;
-  }
-  if (tid == 0) {
-    if (tile > 0) {
-#pragma unroll
-      for (int q = 0; q < Q_N; ++q) {
-        me->incl[q] = s_base[q] + tot[q];
-        if (s_base[q] + tot[q] < s_base[q]) totals[5] = 1;   // a 32-bit running total wrapped: reported by the host
+    for (int j = 0; j < kWPT; ++j) {
+      q.ok[j] = wi0 + j < nwords;
+      q.z[j] = q.y[j] = q.w[j] = 0;
+      q.r[j] = Rows{0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      if (q.ok[j]) {
+        split_word(g, wi0 + j, q.z[j], q.y[j], q.w[j]);
+        q.r[j] = load_rows(bits, g, q.z[j], q.y[j], q.w[j]);
       }
-      __threadfence();
-      *(volatile int*)&me->flag = 2;
-    }
-    if (tile == ntiles - 1) {
-      totals[0] = s_base[Q_V] + tot[Q_V];
-      totals[1] = s_base[Q_T] + tot[Q_T];
-      totals[2] = s_base[Q_C] + tot[Q_C];
-      totals[3] = s_base[Q_VW] + tot[Q_VW];
-      totals[4] = s_base[Q_CW] + tot[Q_CW];
-    }
-  }
-  __syncthreads();
-  if (wi0 >= nwords) return;
-  uint32_t rv = s_base[Q_V] + (uint32_t)(ex & 0xfffffu), rvw = s_base[Q_VW] + (uint32_t)((ex >> 20) & 0xfffu);
-  uint32_t rc = s_base[Q_C] + (uint32_t)((ex >> 32) & 0xfffffu), rcw = s_base[Q_CW] + (uint32_t)((ex >> 52) & 0xfffu);
-  uint32_t rt = s_base[Q_T] + ey;
-#pragma unroll
-  for (int j = 0; j < WPT; ++j) {
-    if (wc[j].nv) {
-      vinfo[rvw] = make_uint4(wc[j].cx, wc[j].cy, wc[j].cz, rv);
-      vword[rvw] = (uint32_t)(wi0 + j);
-      vslot[wi0 + j] = rvw;
-      ++rvw;
-      rv += wc[j].nv;
-    }
-    if (wc[j].act) {
-      cinfo[rcw] = make_uint4((uint32_t)(wi0 + j), wc[j].act, rt, rc);
-      ++rcw;
-      rc += __popc(wc[j].act);
-      rt += wc[j].nt;
     }
   }
 }
 
-// dense per-word records (cx, cy, cz, exclusive vertex offset) of plane 0: what the shard BELOW
-// needs to number the vertices of the plane it shares with this one (b2v_mc_emit_shard)
+// a word whose whole 2 x 2-row neighbourhood is uniform (most of the volume) holds nothing: all
+// outside (missing rows / words read as 0), or all inside with every neighbour present
+__device__ __forceinline__ bool word_uniform(const Rows& r, const McGeom& g, int z, int y, int w) {
+  const uint32_t o_ = r.i00 | r.i01 | r.i10 | r.i11 | ((r.n00 | r.n01 | r.n10 | r.n11) & 1u);
+  if (o_ == 0u) return true;
+  return y + 1 < g.iny && z + 1 < g.inz && w + 1 < g.wx && (r.i00 & r.i01 & r.i10 & r.i11) == 0xffffffffu &&
+         ((r.n00 & r.n01 & r.n10 & r.n11) & 1u);
+}
+
+// active cells of a word: corners neither all outside nor all inside
+__device__ __forceinline__ uint32_t active_cells(const Rows& r, uint32_t vx) {
+  const uint32_t s00 = shift_in(r.i00, r.n00), s01 = shift_in(r.i01, r.n01), s10 = shift_in(r.i10, r.n10),
+                 s11 = shift_in(r.i11, r.n11);
+  const uint32_t any = r.i00 | r.i01 | r.i10 | r.i11 | s00 | s01 | s10 | s11;
+  const uint32_t all = r.i00 & r.i01 & r.i10 & r.i11 & s00 & s01 & s10 & s11;
+  return any & ~all & vx;
+}
+
+// block-wide exclusive scan of a 64-bit value (256 threads); returns the exclusive prefix, *total = block sum.
+// s_w: 8 words of shared scratch; two barriers.
+__device__ __forceinline__ unsigned long long block_scan_u64(unsigned long long x, unsigned long long* s_w,
+                                                             unsigned long long* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long ix = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long p = __shfl_up_sync(0xffffffffu, ix, o);
+    if (lane >= o) ix += p;
+  }
+  __syncthreads();            // s_w free (previous use read)
+  if (lane == 31) s_w[warp] = ix;
+  __syncthreads();
+  unsigned long long before = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < kTileThreads / 32; ++k) {
+    const unsigned long long v = s_w[k];
+    if (k < warp) before += v;
+    tot += v;
+  }
+  *total = tot;
+  return before + ix - x;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kTileThreads) k_mc_classify(const uint32_t* __restrict__ bits, McGeom g,
+                                                              int skip_last, uint4* __restrict__ vrec,
+                                                              uint4* tcnt, uint4* toff, unsigned int* ticket,
+                                                              unsigned long long* totals, int ntiles) {
+  __shared__ unsigned char s_ntri[256];
+  __shared__ unsigned long long s_w[kTileThreads / 32];
+  __shared__ unsigned long long s_carry[3];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  s_ntri[tid] = B2V_MC_NTRI[tid];
+  __syncthreads();
+  const int tile = blockIdx.x;
+  const uint32_t wi0 = ((uint32_t)tile * kTileThreads + tid) * kWPT;
+  Word4 q;
+  load_word4<VEC>(bits, g, wi0, q);
+  uint32_t cx[kWPT], cy[kWPT], cz[kWPT], nv[kWPT];
+  // packed thread sums: vertices (bits 0..19) | active cells (20..39) | triangles (40..63)
+  unsigned long long X = 0;
+#pragma unroll
+  for (int j = 0; j < kWPT; ++j) {
+    cx[j] = cy[j] = cz[j] = nv[j] = 0u;
+    if (!q.ok[j] || word_uniform(q.r[j], g, q.z[j], q.y[j], q.w[j])) continue;
+    const Rows& r = q.r[j];
+    const bool hy = q.y[j] + 1 < g.iny, hz = q.z[j] + 1 < g.inz;
+    const uint32_t vx = valid_x1(g, q.w[j]);
+    cx[j] = (r.i00 ^ shift_in(r.i00, r.n00)) & vx;
+    cy[j] = hy ? (r.i00 ^ r.i01) : 0u;
+    cz[j] = hz ? (r.i00 ^ r.i10) : 0u;
+    // a Z shard does not own the vertices of its last (shared) plane: the next shard does
+    const bool own = !(skip_last && q.z[j] == g.inz - 1);
+    nv[j] = own ? __popc(cx[j]) + __popc(cy[j]) + __popc(cz[j]) : 0;
+    uint32_t nt = 0, act = 0;
+    if (hy && hz) {
+      act = active_cells(r, vx);
+      for (uint32_t m = act; m; m &= m - 1) nt += s_ntri[cell_case(r, __ffs(m) - 1)];
+    }
+    X += (unsigned long long)nv[j] | ((unsigned long long)__popc(act) << 20) | ((unsigned long long)nt << 40);
+  }
+  if (__syncthreads_or(X != 0ull)) {
+    unsigned long long tot;
+    const unsigned long long ex = block_scan_u64(X, s_w, &tot);
+    const uint32_t tv = (uint32_t)(tot & 0xfffffu);
+    if (tv) {   // the records are read by the vertex emitter (this tile) and by triangle corners (any tile)
+      uint32_t run = (uint32_t)(ex & 0xfffffu);
+#pragma unroll
+      for (int j = 0; j < kWPT; ++j) {
+        vrec[wi0 + j] = make_uint4(cx[j], cy[j], cz[j], run);
+        run += nv[j];
+      }
+    }
+    if (tid == 0) tcnt[tile] = make_uint4(tv, (uint32_t)((tot >> 20) & 0xfffffu), (uint32_t)(tot >> 40), 0u);
+  } else if (tid == 0) {
+    tcnt[tile] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  // the last tile to finish turns the tile counts into exclusive prefixes
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(ticket, 1u) == (unsigned)(ntiles - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < 3) s_carry[tid] = 0ull;
+  constexpr int kPer = 8;
+  for (int base = 0; base < ntiles; base += kTileThreads * kPer) {
+    uint4 c[kPer];
+    unsigned long long sv = 0, sc = 0, st = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = base + tid * kPer + k;
+      c[k] = i < ntiles ? __ldcg(tcnt + i) : make_uint4(0u, 0u, 0u, 0u);
+      sv += c[k].x; sc += c[k].y; st += c[k].z;
+    }
+    unsigned long long tv, tc, tt;
+    unsigned long long ev = block_scan_u64(sv, s_w, &tv);
+    unsigned long long ec = block_scan_u64(sc, s_w, &tc);
+    unsigned long long et = block_scan_u64(st, s_w, &tt);
+    ev += s_carry[0]; ec += s_carry[1]; et += s_carry[2];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = base + tid * kPer + k;
+      if (i < ntiles) toff[i] = make_uint4((uint32_t)ev, (uint32_t)ec, (uint32_t)et, 0u);
+      ev += c[k].x; ec += c[k].y; et += c[k].z;
+    }
+    __syncthreads();
+    if (tid == 0) { s_carry[0] += tv; s_carry[1] += tc; s_carry[2] += tt; }
+    __syncthreads();
+  }
+  if (tid == 0) { totals[0] = s_carry[0]; totals[1] = s_carry[2]; totals[2] = s_carry[1]; }
+}
+
+// dense per-word records (cx, cy, cz, GLOBAL exclusive vertex offset) of plane 0: what the shard
+// BELOW needs to number the vertices of the plane it shares with this one (b2v_mc_emit_shard)
 __global__ void __launch_bounds__(256) k_mc_plane0(const uint32_t* __restrict__ bits, McGeom g,
-                                                   const uint32_t* __restrict__ vslot,
-                                                   const uint4* __restrict__ vinfo, uint4* __restrict__ out) {
+                                                   const uint4* __restrict__ vrec, const uint4* __restrict__ tcnt,
+                                                   const uint4* __restrict__ toff, uint4* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.iny * g.wx) return;
   const int y = i / g.wx;
@@ -466,16 +433,16 @@ __global__ void __launch_bounds__(256) k_mc_plane0(const uint32_t* __restrict__ 
   const uint32_t cx = (r.i00 ^ shift_in(r.i00, r.n00)) & valid_x1(g, w);
   const uint32_t cy = y + 1 < g.iny ? (r.i00 ^ r.i01) : 0u;
   const uint32_t cz = g.inz > 1 ? (r.i00 ^ r.i10) : 0u;
-  const uint32_t voff = (cx | cy | cz) ? __ldg(&vinfo[__ldg(&vslot[i])].w) : 0u;
+  const int t = i >> kTileShift;
+  const uint32_t voff = ((cx | cy | cz) && __ldg(&tcnt[t].x)) ? __ldg(&toff[t].x) + __ldg(&vrec[i].w) : 0u;
   out[i] = make_uint4(cx, cy, cz, voff);
 }
 
 // ---- 3. emit ---------------------------------------------------------------------------------
-// One thread per VERTEX and one thread per ACTIVE CELL (the surface touches a few cells per word:
-// a warp-per-word emitter leaves most lanes idle). A warp's 32 consecutive outputs live in at
-// most 32 consecutive list entries (every entry holds at least one): lane 0 bisects the compact
-// list once, the lanes load 32 entries together, and each lane finds its own with five shuffles.
-// Outputs of consecutive threads are consecutive in memory.
+// One block per tile that holds something; one thread per VERTEX and one thread per ACTIVE CELL
+// (the surface touches a few cells per word: a warp-per-word emitter leaves most lanes idle). A
+// thread finds its word by bisecting the tile's 1024 exclusive offsets in shared memory, then its
+// voxel / cell by popcounts. Outputs of consecutive threads are consecutive in memory.
 struct McXform {
   float sx, sy, sz;
   int ox, oy, oz;
@@ -483,86 +450,68 @@ struct McXform {
   float iso;
 };
 
-// largest i in [0, n) with key(i) <= k; key is non-decreasing and key(0) <= k
-template <typename F>
-__device__ __forceinline__ int64_t last_le(int64_t n, uint32_t k, F key) {
-  int64_t lo = 0, hi = n;
-  while (hi - lo > 1) {
-    int64_t mid = (lo + hi) >> 1;
-    if (key(mid) <= k) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
 __device__ __forceinline__ uint32_t below(int i) { return i >= 32 ? 0xffffffffu : ((1u << i) - 1u); }
 
-// the lane's entry among the warp's 32 loaded ones: the last j <= lane with key_j <= k
-__device__ __forceinline__ int warp_locate(uint32_t my_key, uint32_t k, int lane) {
-  int lo = 0, hi = lane + 1;
+// largest l in [0, 1024) with key[l] <= k (key non-decreasing, key[0] <= k)
+template <typename F>
+__device__ __forceinline__ int tile_locate(uint32_t k, F key) {
+  int lo = 0;
 #pragma unroll
-  for (int it = 0; it < 5; ++it) {
-    const int mid = (lo + hi) >> 1;
-    const uint32_t v = __shfl_sync(0xffffffffu, my_key, mid);
-    if (hi - lo > 1) { if (v <= k) lo = mid; else hi = mid; }
-  }
+  for (int step = kTileWords / 2; step > 0; step >>= 1)
+    if (key(lo + step) <= k) lo += step;
   return lo;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_mc_emit_verts(const T* __restrict__ vol, McGeom g,
-                                                       const uint4* __restrict__ vinfo,
-                                                       const uint32_t* __restrict__ vword,
-                                                       const unsigned long long* __restrict__ totals, McXform xf,
-                                                       float* __restrict__ verts) {
-  const uint32_t V = (uint32_t)totals[0];
-  const int64_t nlist = (int64_t)totals[3];
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const int lane = threadIdx.x & 31;
-  for (uint32_t kb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); kb < V; kb += stride) {
-    const uint32_t k = kb + lane;
-    int64_t e0 = lane == 0 ? last_le(nlist, kb, [&](int64_t i) { return __ldg(&vinfo[i].w); }) : 0;
-    e0 = __shfl_sync(0xffffffffu, e0, 0);
-    uint4 ent = make_uint4(0u, 0u, 0u, 0xffffffffu);
-    uint32_t wd = 0;
-    if (e0 + lane < nlist) { ent = __ldg(vinfo + e0 + lane); wd = __ldg(vword + e0 + lane); }
-    const int j = warp_locate(ent.w, k, lane);
-    uint4 inf;
-    inf.x = __shfl_sync(0xffffffffu, ent.x, j);
-    inf.y = __shfl_sync(0xffffffffu, ent.y, j);
-    inf.z = __shfl_sync(0xffffffffu, ent.z, j);
-    inf.w = __shfl_sync(0xffffffffu, ent.w, j);
-    const uint32_t wi = __shfl_sync(0xffffffffu, wd, j);
-    if (k >= V) continue;
-    const uint32_t r = k - inf.w;
-    // voxel: largest i with (#vertices of voxels below i) <= r
-    int lo = 0, hi = 32;
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      uint32_t m = below(mid);
-      if ((uint32_t)(__popc(inf.x & m) + __popc(inf.y & m) + __popc(inf.z & m)) <= r) lo = mid; else hi = mid;
+__global__ void __launch_bounds__(kTileThreads) k_mc_emit_verts(const T* __restrict__ vol, McGeom g,
+                                                                const uint4* __restrict__ vrec,
+                                                                const uint4* __restrict__ tcnt,
+                                                                const uint4* __restrict__ toff, int ntiles,
+                                                                McXform xf, float* __restrict__ verts) {
+  __shared__ uint4 s_rec[kTileWords];
+  const int tid = threadIdx.x;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t V = __ldg(&tcnt[tile].x);
+    if (V == 0u) continue;
+    const uint32_t vbase = __ldg(&toff[tile].x);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kWPT; ++k) s_rec[tid + k * kTileThreads] = __ldg(vrec + ((size_t)tile << kTileShift) + tid + k * kTileThreads);
+    __syncthreads();
+    for (uint32_t k = tid; k < V; k += kTileThreads) {
+      const int l = tile_locate(k, [&](int i) { return s_rec[i].w; });
+      const uint4 inf = s_rec[l];
+      const uint32_t wi = ((uint32_t)tile << kTileShift) + (uint32_t)l;
+      const uint32_t r = k - inf.w;
+      // voxel: largest i with (#vertices of voxels below i) <= r
+      int i = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t m = below(i + step);
+        if ((uint32_t)(__popc(inf.x & m) + __popc(inf.y & m) + __popc(inf.z & m)) <= r) i += step;
+      }
+      const uint32_t m = below(i);
+      int rr = (int)(r - (uint32_t)(__popc(inf.x & m) + __popc(inf.y & m) + __popc(inf.z & m)));
+      const int bx = (inf.x >> i) & 1, by = (inf.y >> i) & 1;
+      // rr-th crossing edge of the voxel in x, y, z order
+      int axis;
+      if (bx && rr == 0) axis = 0;
+      else { rr -= bx; if (by && rr == 0) axis = 1; else axis = 2; }
+      int z, y, w;
+      split_word(g, wi, z, y, w);
+      const int x = w * 32 + i;
+      const int64_t p = ((int64_t)z * g.iny + y) * g.nx + x;
+      const int64_t step = axis == 0 ? 1 : (axis == 1 ? g.nx : g.nx * g.ny);
+      const float s0 = (float)vol[p], s1 = (float)vol[p + step];
+      const float t = __fdiv_rn(__fsub_rn(xf.iso, s0), __fsub_rn(s1, s0));
+      float fx = (float)(x + xf.ox), fy = (float)(y + xf.oy), fz = (float)(z + xf.oz);
+      if (axis == 0) fx = __fadd_rn(fx, t); else if (axis == 1) fy = __fadd_rn(fy, t); else fz = __fadd_rn(fz, t);
+      const float py = __fmul_rn(fy, xf.sy);
+      float* o = verts + 3ll * (vbase + k);
+      o[0] = __fmul_rn(fx, xf.sx);
+      o[1] = xf.flip_y ? -py : py;
+      o[2] = __fmul_rn(fz, xf.sz);
     }
-    const int i = lo;
-    const uint32_t m = below(i);
-    int rr = (int)(r - (uint32_t)(__popc(inf.x & m) + __popc(inf.y & m) + __popc(inf.z & m)));
-    const int bx = (inf.x >> i) & 1, by = (inf.y >> i) & 1;
-    // rr-th crossing edge of the voxel in x, y, z order
-    int axis;
-    if (bx && rr == 0) axis = 0;
-    else { rr -= bx; if (by && rr == 0) axis = 1; else axis = 2; }
-    int z, y, w;
-    split_word(g, wi, z, y, w);
-    const int x = w * 32 + i;
-    const int64_t p = ((int64_t)z * g.iny + y) * g.nx + x;
-    const int64_t step = axis == 0 ? 1 : (axis == 1 ? g.nx : g.nx * g.ny);
-    const float s0 = (float)vol[p], s1 = (float)vol[p + step];
-    const float t = __fdiv_rn(__fsub_rn(xf.iso, s0), __fsub_rn(s1, s0));
-    float fx = (float)(x + xf.ox), fy = (float)(y + xf.oy), fz = (float)(z + xf.oz);
-    if (axis == 0) fx = __fadd_rn(fx, t); else if (axis == 1) fy = __fadd_rn(fy, t); else fz = __fadd_rn(fz, t);
-    const float py = __fmul_rn(fy, xf.sy);
-    float* o = verts + 3ll * k;
-    o[0] = __fmul_rn(fx, xf.sx);
-    o[1] = xf.flip_y ? -py : py;
-    o[2] = __fmul_rn(fz, xf.sz);
   }
 }
 
@@ -580,84 +529,111 @@ __constant__ unsigned short kSlotEdges[8] = {
     (1u << 3),                           // oy = oz = 1
     0};
 
-__global__ void __launch_bounds__(256) k_mc_emit_tris(McGeom g, const uint32_t* __restrict__ bits,
-                                                      const uint32_t* __restrict__ vslot,
-                                                      const uint4* __restrict__ vinfo,
-                                                      const uint4* __restrict__ cinfo,
-                                                      const unsigned long long* __restrict__ totals, int flip_y,
-                                                      int skip_last, int vbase, const uint4* __restrict__ foreign,
-                                                      int foreign_base, int* __restrict__ tris) {
+template <bool VEC>
+__global__ void __launch_bounds__(kTileThreads) k_mc_emit_tris(McGeom g, const uint32_t* __restrict__ bits,
+                                                               const uint4* __restrict__ vrec,
+                                                               const uint4* __restrict__ tcnt,
+                                                               const uint4* __restrict__ toff, int ntiles,
+                                                               int flip_y, int skip_last, int vbase,
+                                                               const uint4* __restrict__ foreign, int foreign_base,
+                                                               int* __restrict__ tris) {
   __shared__ signed char s_tri[256][16];  // 15 edge ids + triangle count
   __shared__ unsigned short s_emask[256];
-  __shared__ int s_id[12 * 256];          // [edge][thread]
-  for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+  __shared__ int s_id[12 * kTileThreads];  // [edge][thread]
+  __shared__ uint32_t s_act[kTileWords];
+  __shared__ uint32_t s_coff[kTileWords];
+  __shared__ unsigned long long s_w[kTileThreads / 32];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 256 * 16; i += kTileThreads) {
     int c = i >> 4, k = i & 15;
     s_tri[c][k] = k < 15 ? B2V_MC_TRI[c][k] : (signed char)B2V_MC_NTRI[c];
   }
-  s_emask[threadIdx.x] = B2V_MC_EDGEMASK[threadIdx.x];
-  __syncthreads();
-  const uint32_t C = (uint32_t)totals[2];
-  const int64_t nlist = (int64_t)totals[4];
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const int lane = threadIdx.x & 31, tid = threadIdx.x;
-  for (uint32_t kb = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); kb < C; kb += stride) {
-    const uint32_t k = kb + lane;
-    int64_t e0 = lane == 0 ? last_le(nlist, kb, [&](int64_t i) { return __ldg(&cinfo[i].w); }) : 0;
-    e0 = __shfl_sync(0xffffffffu, e0, 0);
-    uint4 ent = make_uint4(0u, 0u, 0u, 0xffffffffu);
-    if (e0 + lane < nlist) ent = __ldg(cinfo + e0 + lane);
-    const int j = warp_locate(ent.w, k, lane);
-    const uint32_t wi = __shfl_sync(0xffffffffu, ent.x, j);
-    const uint32_t act = __shfl_sync(0xffffffffu, ent.y, j);
-    uint32_t tbase = __shfl_sync(0xffffffffu, ent.z, j);
-    const uint32_t coff = __shfl_sync(0xffffffffu, ent.w, j);
-    if (k >= C) continue;
-    const int i = (int)__fns(act, 0, (int)(k - coff) + 1);   // this thread's cell bit
-    int z, y, w;
-    split_word(g, wi, z, y, w);
-    const Rows r = load_rows(bits, g, z, y, w);
-    // triangles of the active cells before mine in this word
-    for (uint32_t e = act & below(i); e; e &= e - 1) tbase += s_tri[cell_case(r, __ffs(e) - 1)][15];
-    const int c = cell_case(r, i);
-    const int ntri = s_tri[c][15];
-    const uint32_t em = s_emask[c];
+  s_emask[tid] = B2V_MC_EDGEMASK[tid];
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t C = __ldg(&tcnt[tile].y);
+    if (C == 0u) continue;
+    uint32_t tbase = __ldg(&toff[tile].z);
+    // active-cell masks of the tile's words and their exclusive offsets
+    const uint32_t wi0 = ((uint32_t)tile * kTileThreads + tid) * kWPT;
+    {
+      Word4 q;
+      load_word4<VEC>(bits, g, wi0, q);
+      uint32_t act[kWPT], nc = 0;
 #pragma unroll
-    for (int s = 0; s < 7; ++s) {
-      const uint32_t need = em & kSlotEdges[s];
-      if (!need) continue;
-      const int ox = s & 1, oy = (s >> 1) & 1, oz = s >> 2;
-      const int qx = i + ox;                                   // 0..32 within the word pair
-      const int qy = y + oy, qz = z + oz;
-      const int ob = qx & 31;
-      const uint32_t ol = (1u << ob) - 1u;
-      uint4 oi;
-      int v;
-      if (skip_last && qz == g.inz - 1) {
-        // owned by the next shard: its records of that plane, its numbering
-        oi = __ldg(foreign + (qy * g.wx + (w + (qx >> 5))));
-        v = foreign_base;
-      } else {
-        oi = __ldg(vinfo + __ldg(vslot + (((uint32_t)qz * (uint32_t)g.iny + (uint32_t)qy) * (uint32_t)g.wx +
-                                          (uint32_t)(w + (qx >> 5)))));
-        v = vbase;
+      for (int j = 0; j < kWPT; ++j) {
+        act[j] = 0u;
+        if (q.ok[j] && q.y[j] + 1 < g.iny && q.z[j] + 1 < g.inz && !word_uniform(q.r[j], g, q.z[j], q.y[j], q.w[j]))
+          act[j] = active_cells(q.r[j], valid_x1(g, q.w[j]));
+        nc += __popc(act[j]);
       }
-      v += (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
-      const int bx = (oi.x >> ob) & 1, by = (oi.y >> ob) & 1;
-      // the slot's edges: at most one per axis; ids in x, y, z order among the owner's crossing edges
+      unsigned long long tot;
+      uint32_t run = (uint32_t)block_scan_u64(nc, s_w, &tot);   // barriers inside: s_act / s_coff free
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const uint32_t ea = need & (0xfu << (4 * a));
-        if (ea) s_id[(__ffs(ea) - 1) * 256 + tid] = v + (a > 0 ? bx : 0) + (a > 1 ? by : 0);
+      for (int j = 0; j < kWPT; ++j) {
+        s_act[tid * kWPT + j] = act[j];
+        s_coff[tid * kWPT + j] = run;
+        run += __popc(act[j]);
       }
     }
-    for (int t = 0; t < ntri; ++t) {
-      const int i0 = s_id[s_tri[c][3 * t] * 256 + tid], i1 = s_id[s_tri[c][3 * t + 1] * 256 + tid],
-                i2 = s_id[s_tri[c][3 * t + 2] * 256 + tid];
-      int* o = tris + 3ll * (tbase + t);
-      o[0] = i0;
-      o[1] = flip_y ? i2 : i1;
-      o[2] = flip_y ? i1 : i2;
+    __syncthreads();
+    for (uint32_t k0 = 0; k0 < C; k0 += kTileThreads) {
+      const uint32_t k = k0 + tid;
+      const bool valid = k < C;
+      int i = 0, c = 0, ntri = 0, z = 0, y = 0, w = 0;
+      if (valid) {
+        const int l = tile_locate(k, [&](int j) { return s_coff[j]; });
+        i = (int)__fns(s_act[l], 0, (int)(k - s_coff[l]) + 1);   // this thread's cell bit
+        split_word(g, ((uint32_t)tile << kTileShift) + (uint32_t)l, z, y, w);
+        const Rows r = load_rows(bits, g, z, y, w);
+        c = cell_case(r, i);
+        ntri = s_tri[c][15];
+      }
+      // triangles of the cells before mine: scan over the chunk, running base across chunks
+      unsigned long long tot;
+      const uint32_t tex = (uint32_t)block_scan_u64((unsigned long long)ntri, s_w, &tot);
+      if (valid) {
+        const uint32_t em = s_emask[c];
+#pragma unroll
+        for (int s = 0; s < 7; ++s) {
+          const uint32_t need = em & kSlotEdges[s];
+          if (!need) continue;
+          const int ox = s & 1, oy = (s >> 1) & 1, oz = s >> 2;
+          const int qx = i + ox;                                   // 0..32 within the word pair
+          const int qy = y + oy, qz = z + oz;
+          const int ob = qx & 31;
+          const uint32_t ol = (1u << ob) - 1u;
+          uint4 oi;
+          int v;
+          if (skip_last && qz == g.inz - 1) {
+            // owned by the next shard: its records of that plane, its numbering
+            oi = __ldg(foreign + (qy * g.wx + (w + (qx >> 5))));
+            v = foreign_base;
+          } else {
+            const uint32_t ow = ((uint32_t)qz * (uint32_t)g.iny + (uint32_t)qy) * (uint32_t)g.wx + (uint32_t)(w + (qx >> 5));
+            oi = __ldg(vrec + ow);
+            v = vbase + (int)__ldg(&toff[ow >> kTileShift].x);
+          }
+          v += (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
+          const int bx = (oi.x >> ob) & 1, by = (oi.y >> ob) & 1;
+          // the slot's edges: at most one per axis; ids in x, y, z order among the owner's crossing edges
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const uint32_t ea = need & (0xfu << (4 * a));
+            if (ea) s_id[(__ffs(ea) - 1) * kTileThreads + tid] = v + (a > 0 ? bx : 0) + (a > 1 ? by : 0);
+          }
+        }
+        for (int t = 0; t < ntri; ++t) {
+          const int i0 = s_id[s_tri[c][3 * t] * kTileThreads + tid], i1 = s_id[s_tri[c][3 * t + 1] * kTileThreads + tid],
+                    i2 = s_id[s_tri[c][3 * t + 2] * kTileThreads + tid];
+          int* o = tris + 3ll * (tbase + tex + t);
+          o[0] = i0;
+          o[1] = flip_y ? i2 : i1;
+          o[2] = flip_y ? i1 : i2;
+        }
+      }
+      tbase += (uint32_t)tot;
     }
+    __syncthreads();   // s_act / s_coff are rewritten by the next tile
   }
 }
 
@@ -696,7 +672,7 @@ static int mc_count_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int
   McWs w = carve(workspace, g);
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
-  B2V_CUDA(cudaMemsetAsync(w.tiles, 0, (size_t)w.ctl_bytes, s));
+  B2V_CUDA(cudaMemsetAsync(w.totals, 0, (size_t)w.ctl_bytes, s));
   if (dtype == B2V_U8) {
     int thr = int_threshold(iso, 0, 255);
     if (nx % 16 == 0 && b2v_aligned16(vol))
@@ -714,25 +690,23 @@ static int mc_count_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int
       k_mc_bits<int16_t><<<grid_for(g.nwords, 8), 256, 0, s>>>((const int16_t*)vol, g, thr, w.bits);
   }
   if ((rc = b2v_check_launch("k_mc_bits"))) return rc;
-  if (g.wx % 4 == 0) {
-    const int ntiles = (int)ceil_div64(g.nwords, kClsThreads * 4);
-    k_mc_classify<4><<<ntiles, kClsThreads, 0, s>>>(w.bits, g, skip_last, w.vslot, w.vinfo, w.vword, w.cinfo, w.tiles,
-                                                    w.ticket, w.totals, ntiles);
-  } else {
-    const int ntiles = (int)ceil_div64(g.nwords, kClsThreads);
-    k_mc_classify<1><<<ntiles, kClsThreads, 0, s>>>(w.bits, g, skip_last, w.vslot, w.vinfo, w.vword, w.cinfo, w.tiles,
-                                                    w.ticket, w.totals, ntiles);
-  }
+  const int ntiles = (int)ceil_div64(g.nwords, kTileWords);
+  if (g.wx % 4 == 0)
+    k_mc_classify<true><<<ntiles, kTileThreads, 0, s>>>(w.bits, g, skip_last, w.vrec, w.tcnt, w.toff, w.ticket,
+                                                         w.totals, ntiles);
+  else
+    k_mc_classify<false><<<ntiles, kTileThreads, 0, s>>>(w.bits, g, skip_last, w.vrec, w.tcnt, w.toff, w.ticket,
+                                                          w.totals, ntiles);
   if ((rc = b2v_check_launch("k_mc_classify"))) return rc;
   if (shard) {
-    k_mc_plane0<<<(unsigned)ceil_div64(g.ny * g.wx, 256), 256, 0, s>>>(w.bits, g, w.vslot, w.vinfo, w.plane0);
+    k_mc_plane0<<<(unsigned)ceil_div64(g.ny * g.wx, 256), 256, 0, s>>>(w.bits, g, w.vrec, w.tcnt, w.toff, w.plane0);
     if ((rc = b2v_check_launch("k_mc_plane0"))) return rc;
   }
   if (no_sync) return B2V_OK;   // the caller queues the peer exchange behind and reads everything at once
   unsigned long long tot[6] = {0, 0, 0, 0, 0, 0};
   B2V_CUDA(cudaMemcpyAsync(tot, w.totals, sizeof(tot), cudaMemcpyDeviceToHost, s));
   B2V_CUDA(cudaStreamSynchronize(s));
-  B2V_REQUIRE(tot[5] == 0 && tot[0] < (1ull << 31) && tot[1] < (1ull << 31) && tot[2] < (1ull << 31), B2V_ERR_RANGE,
+  B2V_REQUIRE(tot[0] < (1ull << 31) && tot[1] < (1ull << 31) && tot[2] < (1ull << 31), B2V_ERR_RANGE,
               "mc_count: %llu vertices / %llu triangles exceed int32 indices; shard along z", tot[0], tot[1]);
   *nverts_host = (int64_t)tot[0];
   *ntris_host = (int64_t)tot[1];
@@ -750,18 +724,24 @@ static int mc_emit_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int6
   McWs w = carve(const_cast<void*>(workspace), g);
   cudaStream_t s = (cudaStream_t)stream;
   McXform xf = {sx, sy, sz, ox, oy, oz, flip_y ? 1 : 0, (float)iso};
-  const int grid = b2v_sm_count() * 8;   // grid-stride over the counts that live on the device
+  const int ntiles = (int)ceil_div64(g.nwords, kTileWords);   // one block per tile; empty tiles leave at once
   int rc;
   if (verts) {
     if (dtype == B2V_U8)
-      k_mc_emit_verts<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)vol, g, w.vinfo, w.vword, w.totals, xf, verts);
+      k_mc_emit_verts<uint8_t><<<ntiles, kTileThreads, 0, s>>>((const uint8_t*)vol, g, w.vrec, w.tcnt, w.toff, ntiles,
+                                                               xf, verts);
     else
-      k_mc_emit_verts<int16_t><<<grid, 256, 0, s>>>((const int16_t*)vol, g, w.vinfo, w.vword, w.totals, xf, verts);
+      k_mc_emit_verts<int16_t><<<ntiles, kTileThreads, 0, s>>>((const int16_t*)vol, g, w.vrec, w.tcnt, w.toff, ntiles,
+                                                               xf, verts);
     if ((rc = b2v_check_launch("k_mc_emit_verts"))) return rc;
   }
   if (tris) {
-    k_mc_emit_tris<<<grid, 256, 0, s>>>(g, w.bits, w.vslot, w.vinfo, w.cinfo, w.totals, flip_y ? 1 : 0, skip_last,
-                                        vbase, (const uint4*)foreign, foreign_base, tris);
+    if (g.wx % 4 == 0)
+      k_mc_emit_tris<true><<<ntiles, kTileThreads, 0, s>>>(g, w.bits, w.vrec, w.tcnt, w.toff, ntiles, flip_y ? 1 : 0,
+                                                           skip_last, vbase, (const uint4*)foreign, foreign_base, tris);
+    else
+      k_mc_emit_tris<false><<<ntiles, kTileThreads, 0, s>>>(g, w.bits, w.vrec, w.tcnt, w.toff, ntiles, flip_y ? 1 : 0,
+                                                            skip_last, vbase, (const uint4*)foreign, foreign_base, tris);
     if ((rc = b2v_check_launch("k_mc_emit_tris"))) return rc;
   }
   return B2V_OK;
@@ -823,7 +803,7 @@ extern "C" int b2v_mc_count_shard_peer(const void* vol, int dtype, int64_t nz, i
   B2V_CUDA(cudaMemcpyAsync(tot, w.totals, sizeof(tot), cudaMemcpyDeviceToHost, s));
   B2V_CUDA(cudaStreamSynchronize(s));
   B2V_REQUIRE(ok == 1, B2V_ERR_NOCONV, "mc_count_shard_peer: a rank did not publish its counts in time (epoch %u)", epoch);
-  B2V_REQUIRE(tot[5] == 0 && tot[0] < (1ull << 31) && tot[1] < (1ull << 31) && tot[2] < (1ull << 31), B2V_ERR_RANGE,
+  B2V_REQUIRE(tot[0] < (1ull << 31) && tot[1] < (1ull << 31) && tot[2] < (1ull << 31), B2V_ERR_RANGE,
               "mc_count: %llu vertices / %llu triangles exceed int32 indices; shard along z", tot[0], tot[1]);
   return B2V_OK;
 }

@@ -10,7 +10,7 @@ from .device import _dense, _p, _stream, _workspace, dtype_code
 
 
 def marching_cubes(vol: torch.Tensor, iso: float, spacing=(1.0, 1.0, 1.0), origin_index=(0, 0, 0),
-                   flip_y: bool = True):
+                   flip_y: bool = True, _events: list | None = None):
     """Iso-surface of a dense uint8/int16 [nz][ny][nx] device volume.
 
     spacing = (sx, sy, sz); origin_index = (ox, oy, oz) is added to the (x, y, z) voxel
@@ -29,9 +29,12 @@ def marching_cubes(vol: torch.Tensor, iso: float, spacing=(1.0, 1.0, 1.0), origi
     ws = _workspace(lib.b2v_mc_workspace_bytes(nz, ny, nx), vol.device)
     nv, nt = C.c_int64(0), C.c_int64(0)
     with torch.cuda.device(vol.device):
+        if _events is not None: _events[0].record()
         _lib.call("b2v_mc_count", _p(vol), code, nz, ny, nx, float(iso), _p(ws), _stream(), C.byref(nv), C.byref(nt))
+        if _events is not None: _events[1].record()
         verts = torch.empty((nv.value, 3), dtype=torch.float32, device=vol.device)
         tris = torch.empty((nt.value, 3), dtype=torch.int32, device=vol.device)
+        if _events is not None: _events[2].record()
         if nv.value or nt.value:
             _lib.call("b2v_mc_emit", _p(vol), code, nz, ny, nx, float(iso), _p(ws), float(spacing[0]),
                       float(spacing[1]), float(spacing[2]), int(origin_index[0]), int(origin_index[1]),
