@@ -250,7 +250,7 @@ __device__ __forceinline__ void load_word4(const uint32_t* __restrict__ bits, co
              a11[kWPT + 1] = {0, 0, 0, 0, 0};
     if (ok) {
       split_word(g, wi0, z, y, w0);
-      const bool hy = y + 1 < g.iny, hz = z + 1 < g.inz, hn = w0 + kWPT < g.wx;
+      const bool hy = y + 1 < g.iny, hz = z + 1 < g.inz;
       const uint32_t b00 = wi0, b01 = b00 + (uint32_t)g.wx, b10 = b00 + (uint32_t)g.iny * (uint32_t)g.wx,
                      b11 = b10 + (uint32_t)g.wx;
       const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
@@ -262,10 +262,24 @@ __device__ __forceinline__ void load_word4(const uint32_t* __restrict__ bits, co
       a01[0] = q01.x; a01[1] = q01.y; a01[2] = q01.z; a01[3] = q01.w;
       a10[0] = q10.x; a10[1] = q10.y; a10[2] = q10.z; a10[3] = q10.w;
       a11[0] = q11.x; a11[1] = q11.y; a11[2] = q11.z; a11[3] = q11.w;
-      a00[kWPT] = hn ? __ldg(bits + b00 + kWPT) : 0u;
-      a01[kWPT] = (hn && hy) ? __ldg(bits + b01 + kWPT) : 0u;
-      a10[kWPT] = (hn && hz) ? __ldg(bits + b10 + kWPT) : 0u;
-      a11[kWPT] = (hn && hy && hz) ? __ldg(bits + b11 + kWPT) : 0u;
+    }
+    // the word after my four is the first word of the next lane (same row unless mine end it)
+    {
+      const int lane = threadIdx.x & 31;
+      const uint32_t s00 = __shfl_down_sync(0xffffffffu, a00[0], 1), s01 = __shfl_down_sync(0xffffffffu, a01[0], 1),
+                     s10 = __shfl_down_sync(0xffffffffu, a10[0], 1), s11 = __shfl_down_sync(0xffffffffu, a11[0], 1);
+      if (ok && w0 + kWPT < g.wx) {
+        if (lane < 31) { a00[kWPT] = s00; a01[kWPT] = s01; a10[kWPT] = s10; a11[kWPT] = s11; }
+        else {
+          const bool hy = y + 1 < g.iny, hz = z + 1 < g.inz;
+          const uint32_t b00 = wi0 + kWPT, b01 = b00 + (uint32_t)g.wx, b10 = b00 + (uint32_t)g.iny * (uint32_t)g.wx,
+                         b11 = b10 + (uint32_t)g.wx;
+          a00[kWPT] = __ldg(bits + b00);
+          a01[kWPT] = hy ? __ldg(bits + b01) : 0u;
+          a10[kWPT] = hz ? __ldg(bits + b10) : 0u;
+          a11[kWPT] = (hy && hz) ? __ldg(bits + b11) : 0u;
+        }
+      }
     }
 #pragma unroll
     for (int j = 0; j < kWPT; ++j) {
@@ -329,8 +343,42 @@ __device__ __forceinline__ unsigned long long block_scan_u64(unsigned long long 
   return before + ix - x;
 }
 
+// same for a 32-bit value (s_w: 8 words)
+__device__ __forceinline__ uint32_t block_scan_u32(uint32_t x, uint32_t* s_w, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t ix = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t p = __shfl_up_sync(0xffffffffu, ix, o);
+    if (lane >= o) ix += p;
+  }
+  __syncthreads();
+  if (lane == 31) s_w[warp] = ix;
+  __syncthreads();
+  uint32_t before = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < kTileThreads / 32; ++k) {
+    const uint32_t v = s_w[k];
+    if (k < warp) before += v;
+    tot += v;
+  }
+  *total = tot;
+  return before + ix - x;
+}
+
+// position of the n-th (0-based) set bit of m (n < popc(m))
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
+  int pos = 0;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const int c = __popc((m >> pos) & ((1u << s) - 1u));
+    if (n >= c) { n -= c; pos += s; }
+  }
+  return pos;
+}
+
 template <bool VEC>
-__global__ void __launch_bounds__(kTileThreads) k_mc_classify(const uint32_t* __restrict__ bits, McGeom g,
+__global__ void __launch_bounds__(kTileThreads, 4) k_mc_classify(const uint32_t* __restrict__ bits, McGeom g,
                                                               int skip_last, uint4* __restrict__ vrec,
                                                               uint4* tcnt, uint4* toff, unsigned int* ticket,
                                                               unsigned long long* totals, int ntiles) {
@@ -384,10 +432,12 @@ __global__ void __launch_bounds__(kTileThreads) k_mc_classify(const uint32_t* __
   } else if (tid == 0) {
     tcnt[tile] = make_uint4(0u, 0u, 0u, 0u);
   }
-  // the last tile to finish turns the tile counts into exclusive prefixes
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = atomicAdd(ticket, 1u) == (unsigned)(ntiles - 1);
+  // the last tile to finish turns the tile counts into exclusive prefixes (thread 0 wrote this
+  // tile's count: its fence orders that store before the ticket)
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == (unsigned)(ntiles - 1);
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -515,19 +565,18 @@ __global__ void __launch_bounds__(kTileThreads) k_mc_emit_verts(const T* __restr
   }
 }
 
-// Crossing edges of a cell are owned by seven of its corner voxels: slot s = oz*4 + oy*2 + ox
-// owns the cell edges kSlotEdges[s] (edge id = axis*4 + cu + 2*cv as in mc_tables.h). A cell
-// resolves each NEEDED slot once (one record: exclusive vertex offset + popcounts below the
-// owner bit) and every triangle corner is then a shared-memory lookup by edge id.
-__constant__ unsigned short kSlotEdges[8] = {
-    (1u << 0) | (1u << 4) | (1u << 8),   // (0,0,0): x, y, z edges at the origin
-    (1u << 5) | (1u << 9),               // ox = 1
-    (1u << 1) | (1u << 10),              // oy = 1
-    (1u << 11),                          // ox = oy = 1
-    (1u << 2) | (1u << 6),               // oz = 1
-    (1u << 7),                           // ox = oz = 1
-    (1u << 3),                           // oy = oz = 1
-    0};
+// Crossing edges of a cell are owned by seven of its corner voxels, which live in FOUR bit rows:
+// row (y + oy, z + oz) holds the owners at bit i (ox = 0) and bit i + 1 (ox = 1; bit 0 of the next
+// word when i = 31). One record per row resolves all of the row's edges:
+//   id(bit b, axis a) = vertex base of the word + #crossings below bit b + #crossings of bit b on axes < a.
+// Edge ids (axis*4 + cu + 2*cv as in mc_tables.h) per row:
+//   (y, z):     0 (x@i)  4 (y@i)  8 (z@i)  5 (y@i+1)  9 (z@i+1)
+//   (y+1, z):   1 (x@i)  10 (z@i)  11 (z@i+1)
+//   (y, z+1):   2 (x@i)  6 (y@i)   7 (y@i+1)
+//   (y+1, z+1): 3 (x@i)
+// All twelve ids go to shared memory ([edge][thread]; the ones of non-crossing edges are never
+// read) and every triangle corner is a lookup by edge id.
+struct RowIds { int x0, y0, z0, y1, z1; };   // ids at bit i (x, y, z) and at bit i + 1 (y, z)
 
 template <bool VEC>
 __global__ void __launch_bounds__(kTileThreads) k_mc_emit_tris(McGeom g, const uint32_t* __restrict__ bits,
@@ -538,20 +587,22 @@ __global__ void __launch_bounds__(kTileThreads) k_mc_emit_tris(McGeom g, const u
                                                                const uint4* __restrict__ foreign, int foreign_base,
                                                                int* __restrict__ tris) {
   __shared__ signed char s_tri[256][16];  // 15 edge ids + triangle count
-  __shared__ unsigned short s_emask[256];
   __shared__ int s_id[12 * kTileThreads];  // [edge][thread]
   __shared__ uint32_t s_act[kTileWords];
   __shared__ uint32_t s_coff[kTileWords];
-  __shared__ unsigned long long s_w[kTileThreads / 32];
+  __shared__ uint32_t s_w[kTileThreads / 32];
   const int tid = threadIdx.x;
-  for (int i = tid; i < 256 * 16; i += kTileThreads) {
-    int c = i >> 4, k = i & 15;
-    s_tri[c][k] = k < 15 ? B2V_MC_TRI[c][k] : (signed char)B2V_MC_NTRI[c];
-  }
-  s_emask[tid] = B2V_MC_EDGEMASK[tid];
+  bool tables = false;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint32_t C = __ldg(&tcnt[tile].y);
-    if (C == 0u) continue;
+    if (C == 0u) continue;     // most tiles: nothing but this load
+    if (!tables) {             // (made visible by the barriers of the scan below)
+      for (int i = tid; i < 256 * 16; i += kTileThreads) {
+        int c = i >> 4, k = i & 15;
+        s_tri[c][k] = k < 15 ? B2V_MC_TRI[c][k] : (signed char)B2V_MC_NTRI[c];
+      }
+      tables = true;
+    }
     uint32_t tbase = __ldg(&toff[tile].z);
     // active-cell masks of the tile's words and their exclusive offsets
     const uint32_t wi0 = ((uint32_t)tile * kTileThreads + tid) * kWPT;
@@ -566,8 +617,8 @@ __global__ void __launch_bounds__(kTileThreads) k_mc_emit_tris(McGeom g, const u
           act[j] = active_cells(q.r[j], valid_x1(g, q.w[j]));
         nc += __popc(act[j]);
       }
-      unsigned long long tot;
-      uint32_t run = (uint32_t)block_scan_u64(nc, s_w, &tot);   // barriers inside: s_act / s_coff free
+      uint32_t tot;
+      uint32_t run = block_scan_u32(nc, s_w, &tot);   // barriers inside: s_act / s_coff free
 #pragma unroll
       for (int j = 0; j < kWPT; ++j) {
         s_act[tid * kWPT + j] = act[j];
@@ -582,56 +633,76 @@ __global__ void __launch_bounds__(kTileThreads) k_mc_emit_tris(McGeom g, const u
       int i = 0, c = 0, ntri = 0, z = 0, y = 0, w = 0;
       if (valid) {
         const int l = tile_locate(k, [&](int j) { return s_coff[j]; });
-        i = (int)__fns(s_act[l], 0, (int)(k - s_coff[l]) + 1);   // this thread's cell bit
+        i = nth_set_bit(s_act[l], (int)(k - s_coff[l]));   // this thread's cell bit
         split_word(g, ((uint32_t)tile << kTileShift) + (uint32_t)l, z, y, w);
         const Rows r = load_rows(bits, g, z, y, w);
         c = cell_case(r, i);
         ntri = s_tri[c][15];
       }
       // triangles of the cells before mine: scan over the chunk, running base across chunks
-      unsigned long long tot;
-      const uint32_t tex = (uint32_t)block_scan_u64((unsigned long long)ntri, s_w, &tot);
+      uint32_t tot;
+      const uint32_t tex = block_scan_u32((uint32_t)ntri, s_w, &tot);
       if (valid) {
-        const uint32_t em = s_emask[c];
-#pragma unroll
-        for (int s = 0; s < 7; ++s) {
-          const uint32_t need = em & kSlotEdges[s];
-          if (!need) continue;
-          const int ox = s & 1, oy = (s >> 1) & 1, oz = s >> 2;
-          const int qx = i + ox;                                   // 0..32 within the word pair
-          const int qy = y + oy, qz = z + oz;
-          const int ob = qx & 31;
-          const uint32_t ol = (1u << ob) - 1u;
+        const uint32_t ol = (1u << i) - 1u;
+        const uint32_t row0 = ((uint32_t)z * (uint32_t)g.iny + (uint32_t)y) * (uint32_t)g.wx + (uint32_t)w;
+        // one row: record of word (row, w), ids at bit i and bit i + 1
+        auto row_ids = [&](uint32_t ow, bool is_foreign) -> RowIds {
           uint4 oi;
           int v;
-          if (skip_last && qz == g.inz - 1) {
-            // owned by the next shard: its records of that plane, its numbering
-            oi = __ldg(foreign + (qy * g.wx + (w + (qx >> 5))));
+          if (is_foreign) {   // owned by the next shard: its records of that plane, its numbering
+            oi = __ldg(foreign + (ow - (uint32_t)(g.inz - 1) * (uint32_t)g.iny * (uint32_t)g.wx));
             v = foreign_base;
           } else {
-            const uint32_t ow = ((uint32_t)qz * (uint32_t)g.iny + (uint32_t)qy) * (uint32_t)g.wx + (uint32_t)(w + (qx >> 5));
             oi = __ldg(vrec + ow);
             v = vbase + (int)__ldg(&toff[ow >> kTileShift].x);
           }
-          v += (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
-          const int bx = (oi.x >> ob) & 1, by = (oi.y >> ob) & 1;
-          // the slot's edges: at most one per axis; ids in x, y, z order among the owner's crossing edges
-#pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            const uint32_t ea = need & (0xfu << (4 * a));
-            if (ea) s_id[(__ffs(ea) - 1) * kTileThreads + tid] = v + (a > 0 ? bx : 0) + (a > 1 ? by : 0);
+          RowIds o;
+          const int bx = (oi.x >> i) & 1, by = (oi.y >> i) & 1, bz = (oi.z >> i) & 1;
+          o.x0 = v + (int)(oi.w + __popc(oi.x & ol) + __popc(oi.y & ol) + __popc(oi.z & ol));
+          o.y0 = o.x0 + bx;
+          o.z0 = o.y0 + by;
+          int n1, bx1;
+          if (i < 31) {
+            n1 = o.z0 + bz;
+            bx1 = (oi.x >> (i + 1)) & 1;
+            o.y1 = n1 + bx1;
+            o.z1 = o.y1 + (int)((oi.y >> (i + 1)) & 1);
+          } else {            // bit 0 of the next word of the row
+            uint4 on;
+            int vn;
+            if (is_foreign) {
+              on = __ldg(foreign + (ow + 1u - (uint32_t)(g.inz - 1) * (uint32_t)g.iny * (uint32_t)g.wx));
+              vn = foreign_base;
+            } else {
+              on = __ldg(vrec + ow + 1u);
+              vn = vbase + (int)__ldg(&toff[(ow + 1u) >> kTileShift].x);
+            }
+            n1 = vn + (int)on.w;
+            o.y1 = n1 + (int)(on.x & 1u);
+            o.z1 = o.y1 + (int)(on.y & 1u);
           }
-        }
-        for (int t = 0; t < ntri; ++t) {
-          const int i0 = s_id[s_tri[c][3 * t] * kTileThreads + tid], i1 = s_id[s_tri[c][3 * t + 1] * kTileThreads + tid],
-                    i2 = s_id[s_tri[c][3 * t + 2] * kTileThreads + tid];
-          int* o = tris + 3ll * (tbase + tex + t);
+          return o;
+        };
+        const bool f0 = skip_last && z == g.inz - 1, f1 = skip_last && z + 1 == g.inz - 1;
+        const uint32_t dy = (uint32_t)g.wx, dz = (uint32_t)g.iny * (uint32_t)g.wx;
+        const RowIds r00 = row_ids(row0, f0), r01 = row_ids(row0 + dy, f0), r10 = row_ids(row0 + dz, f1),
+                     r11 = row_ids(row0 + dz + dy, f1);
+        int* sid = s_id + tid;
+        sid[0 * kTileThreads] = r00.x0; sid[4 * kTileThreads] = r00.y0; sid[8 * kTileThreads] = r00.z0;
+        sid[5 * kTileThreads] = r00.y1; sid[9 * kTileThreads] = r00.z1;
+        sid[1 * kTileThreads] = r01.x0; sid[10 * kTileThreads] = r01.z0; sid[11 * kTileThreads] = r01.z1;
+        sid[2 * kTileThreads] = r10.x0; sid[6 * kTileThreads] = r10.y0; sid[7 * kTileThreads] = r10.y1;
+        sid[3 * kTileThreads] = r11.x0;
+        int* o = tris + 3ll * (tbase + tex);
+        for (int t = 0; t < ntri; ++t, o += 3) {
+          const int i0 = sid[s_tri[c][3 * t] * kTileThreads], i1 = sid[s_tri[c][3 * t + 1] * kTileThreads],
+                    i2 = sid[s_tri[c][3 * t + 2] * kTileThreads];
           o[0] = i0;
           o[1] = flip_y ? i2 : i1;
           o[2] = flip_y ? i1 : i2;
         }
       }
-      tbase += (uint32_t)tot;
+      tbase += tot;
     }
     __syncthreads();   // s_act / s_coff are rewritten by the next tile
   }
