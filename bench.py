@@ -694,7 +694,7 @@ def run_gpu(args):
         del d_ext, d_mask, d_out
         torch.cuda.empty_cache()
         line["extra"] = extra_results(peak)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -721,17 +721,38 @@ def run_reference(args):
     v = vol.size / s / 1e6
     sample = (f"the full {vol.shape[0]}x{vol.shape[1]}x{vol.shape[2]} volume per step: NumPy threshold (1 thread) + serial "
               f"flood fill (1 thread) + marching cubes over 21-slice pieces on {cores} threads")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(s * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
         "config": {"workload": workload_desc(n, 1), "reached_voxels": count, "triangles": ntri},
         "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Exactly ONE line may reach stdout (the JSON result). Libraries print there too (NCCL's version
+    banner, for one): point fd 1 at stderr for the life of the process and keep the real stdout for
+    the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
