@@ -19,7 +19,10 @@
 // Wherever the reference's result does not depend on its queue order (no cost ties between
 // different labels) this is exactly the reference's labelling; on plateaus it is a
 // deterministic geodesic split instead of the reference's order artefact.
+#include <stdlib.h>
+
 #include "b2v_common.cuh"
+#include "watershed.cuh"
 
 namespace {
 
@@ -465,7 +468,9 @@ extern "C" int64_t b2v_ws_workspace_bytes(int64_t nz, int64_t ny, int64_t nx) {
   if (nz <= 0 || ny <= 0 || nx <= 0) return 0;
   int64_t a = carve(nullptr, make_grid(nz, ny, nx)).bytes;
   int64_t b = 256 + b2v_minmax_workspace_bytes(nz * ny * nx);
-  return a > b ? a : b;
+  int64_t c = b2v_wsf_workspace_bytes(nz, ny, nx);
+  a = a > b ? a : b;
+  return a > c ? a : c;
 }
 
 extern "C" int b2v_ws_flood(const uint16_t* img, const int16_t* markers, int64_t nz, int64_t ny, int64_t nx,
@@ -478,6 +483,20 @@ extern "C" int b2v_ws_flood(const uint16_t* img, const int16_t* markers, int64_t
   int rc;
   if ((rc = ws_strct_bits(strct_host, odz, ody, odx, &sb))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    // 6-connected (the InVesalius default, generate_binary_structure(3, 1)): the persistent engine.
+    // Offsets along an axis of extent 1 never apply, so they do not count.
+    const uint32_t zb = (1u << 4) | (1u << 22), yb = (1u << 10) | (1u << 16), xb = (1u << 12) | (1u << 14);
+    const uint32_t six = zb | yb | xb;
+    uint32_t eff = sb | (nz == 1 ? zb : 0u) | (ny == 1 ? yb : 0u) | (nx == 1 ? xb : 0u);
+    if (eff == six && !getenv("B2V_WS_GENERIC")) {
+      int rounds = 0;
+      rc = b2v_wsf_run(31, img, markers, nz, ny, nx, mode, 0, 0, labels, ambiguous, ambiguous ? 1 : 0, workspace, stream,
+                       &rounds);
+      if (rounds_out) *rounds_out = rounds;
+      return rc;
+    }
+  }
   Grid g = make_grid(nz, ny, nx);
   WsWs w = carve(workspace, g);
   const int64_t n = nz * ny * nx;

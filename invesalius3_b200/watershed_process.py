@@ -81,7 +81,12 @@ def flood(cost_u16: torch.Tensor, markers_i16: torch.Tensor, bstruct, algorithm:
     with torch.cuda.device(cost_u16.device):
         _lib.call("b2v_ws_flood", _p(cost_u16), _p(markers_i16), nz, ny, nx, C.c_void_p(st.ctypes.data), *st.shape,
                   ALGORITHMS[algorithm], _p(labels), _p(amb), _p(ws), _stream(), C.byref(rounds))
+    global LAST_ROUNDS
+    LAST_ROUNDS = rounds.value
     return (labels, amb) if return_ambiguous else labels
+
+
+LAST_ROUNDS = 0   # rounds of the last flood (diagnostics)
 
 
 def watershed_device(image: torch.Tensor, markers: torch.Tensor, bstruct, algorithm, mg_size, use_ww_wl, wl, ww,
