@@ -207,6 +207,29 @@ int b2v_ws_flood(const uint16_t* img, const int16_t* markers, int64_t nz, int64_
                  const uint8_t* strct_host, int64_t odz, int64_t ody, int64_t odx, int mode, int16_t* labels,
                  uint8_t* ambiguous, void* workspace, void* stream, int* rounds_out);
 
+/* The flood in stages, for Z-sharded volumes (6-connected only; dist.watershed drives it). The slab
+ * passed in is an extended slab: with frozen_lo / frozen_hi its first / last plane is a halo plane
+ * that is never relaxed locally; b2v_ws_plane reads a plane (merge = 0) or merges a neighbour's
+ * values into one (merge = 1: minimum of the costs / of the keys, join of the label sets; tiles
+ * next to a voxel that changed are queued for the next *_CONVERGE; *changed_host = 1 if any did).
+ * what = 0: uint32 costs (phase 1); what = 1: uint64 keys followed by uint16 label sets (phase 2);
+ * plane buffers are device memory of b2v_ws_plane_bytes(ny, nx, what) bytes.
+ * stages (bit mask, executed in this order): 1 INIT, 2 COST_CONVERGE, 4 LABEL_BEGIN (admissible
+ * predecessors from the final costs), 8 LABEL_CONVERGE, 16 FINISH (labels + ambiguous mask out).
+ * *rounds_io accumulates the rounds. Every *_CONVERGE synchronises the stream.
+ * b2v_ws_shift_i16_with: (image - min).astype('uint16') with the minimum supplied on the device
+ * (minmax_dev[0], float32: the global minimum of a sharded volume after its all_reduce). */
+int b2v_ws_flood_staged(int stages, const uint16_t* img, const int16_t* markers, int64_t nz, int64_t ny, int64_t nx,
+                        int mode, int frozen_lo, int frozen_hi, int16_t* labels, uint8_t* ambiguous, void* workspace,
+                        void* stream, int* rounds_io);
+int64_t b2v_ws_plane_bytes(int64_t ny, int64_t nx, int what);
+int b2v_ws_plane(int merge, int what, int64_t nz, int64_t ny, int64_t nx, int mode, int frozen_lo, int frozen_hi,
+                 int64_t z, void* plane, void* workspace, void* stream, int* changed_host);
+int b2v_ws_shift_i16_with(const int16_t* img, int64_t n, const float* minmax_dev, uint16_t* out, void* stream);
+/* diagnostics of the persistent engine: [0..2] phase-1 tile visits / sweep sets / visits that
+ * changed something, [4..6] the same for phase 2; reset != 0 clears them */
+int b2v_ws_stats(int* out8, int reset);
+
 /* ---- Z-sharded volumes (one shard per GPU; invesalius3_b200/dist.py drives these) ---------
  * The reference's only decomposition is the Z-piece split of the surface step
  * (invesalius/data/surface.py:1360-1381: pieces of 20 slices + 1 overlap, stitched by

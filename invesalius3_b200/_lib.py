@@ -53,6 +53,11 @@ PROTOTYPES = {
     "b2v_ws_shift_i16": (cint, [vp, i64, vp, vp, vp]),
     "b2v_ws_morph_gradient_u16": (cint, [vp, i64, i64, i64, cint, cint, cint, vp, vp]),
     "b2v_ws_workspace_bytes": (i64, [i64, i64, i64]),
+    "b2v_ws_flood_staged": (cint, [cint, vp, vp, i64, i64, i64, cint, cint, cint, vp, vp, vp, vp, C.POINTER(cint)]),
+    "b2v_ws_plane_bytes": (i64, [i64, i64, cint]),
+    "b2v_ws_plane": (cint, [cint, cint, i64, i64, i64, cint, cint, cint, i64, vp, vp, vp, C.POINTER(cint)]),
+    "b2v_ws_shift_i16_with": (cint, [vp, i64, vp, vp, vp]),
+    "b2v_ws_stats": (cint, [C.POINTER(cint), cint]),
     "b2v_ws_flood": (cint, [vp, vp, i64, i64, i64, vp, i64, i64, i64, cint, vp, vp, vp, vp, C.POINTER(cint)]),
     "b2v_floodfill_threshold_staged": (cint, [cint, vp, cint, i64, i64, i64, vp, i64, dbl, dbl, u8, vp, i64, i64, i64,
                                               vp, vp, vp, C.POINTER(cint)]),

@@ -90,6 +90,53 @@ __global__ void __launch_bounds__(256) k_ws_morph_gradient(const uint16_t* __res
   }
 }
 
+// Same result, far fewer loads: a thread owns one (y, x) column and marches along z. Per plane it
+// reduces the 2-D window (sy x sx values, neighbours' loads hit L1) to the plane's erosion minimum
+// and dilation maximum, keeps the last W plane results in registers and combines them: sy * sx
+// loads per voxel instead of sz * sy * sx, no 64-bit division per voxel. W = window length along z
+// (sz, + 1 for even sizes).
+template <int W>
+__global__ void __launch_bounds__(256) k_ws_morph_gradient_cols(const uint16_t* __restrict__ in, int nz, int ny, int nx,
+                                                                int sz, int sy, int sx, int zchunk,
+                                                                uint16_t* __restrict__ out) {
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int z_begin = blockIdx.z * zchunk, z_end = min(nz, z_begin + zchunk);
+  if (x >= nx || y >= ny) return;
+  const int ez = (sz & 1) ? 0 : 1, ey = (sy & 1) ? 0 : 1, ex = (sx & 1) ? 0 : 1;
+  const int lo = sz / 2;                      // window along z: offsets [-lo, W - 1 - lo]
+  // column / row indices of the 2-D window, reflected once (they do not depend on z)
+  int pmin[W], pmax[W];
+  auto plane = [&](int zz, int& mn, int& mx) {
+    const uint16_t* pl = in + (size_t)reflect(zz, nz) * ny * nx;
+    mn = 65535; mx = 0;
+    for (int ky = 0; ky < sy + ey; ++ky) {
+      const uint16_t* row = pl + (size_t)reflect(y - sy / 2 + ky, ny) * nx;
+      const bool ero_y = ky < sy, dil_y = ky >= ey;
+      for (int kx = 0; kx < sx + ex; ++kx) {
+        const int v = row[reflect(x - sx / 2 + kx, nx)];
+        if (ero_y && kx < sx) mn = min(mn, v);
+        if (dil_y && kx >= ex) mx = max(mx, v);
+      }
+    }
+  };
+  // ring: entry k holds plane z - lo + k
+#pragma unroll
+  for (int k = 1; k < W; ++k) plane(z_begin - lo + k - 1, pmin[k], pmax[k]);
+  for (int z = z_begin; z < z_end; ++z) {
+#pragma unroll
+    for (int k = 0; k < W - 1; ++k) { pmin[k] = pmin[k + 1]; pmax[k] = pmax[k + 1]; }
+    plane(z - lo + W - 1, pmin[W - 1], pmax[W - 1]);
+    int mn = 65535, mx = 0;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      if (k < sz) mn = min(mn, pmin[k]);        // erosion: offsets [-lo, sz - 1 - lo]
+      if (k >= ez) mx = max(mx, pmax[k]);       // dilation: shifted by one for even sizes
+    }
+    out[((size_t)z * ny + y) * nx + x] = (uint16_t)(mx - mn);
+  }
+}
+
 // ---- tiled relaxation --------------------------------------------------------------------
 constexpr int kT = 16;            // tile edge (voxels)
 constexpr int kH = kT + 2;        // with halo
@@ -455,11 +502,34 @@ extern "C" int b2v_ws_shift_i16(const int16_t* img, int64_t n, uint16_t* out, vo
   return b2v_check_launch("k_ws_shift");
 }
 
+extern "C" int b2v_ws_shift_i16_with(const int16_t* img, int64_t n, const float* minmax_dev, uint16_t* out, void* stream) {
+  B2V_REQUIRE(img && out && minmax_dev && n > 0, B2V_ERR_ARG, "ws_shift: bad arguments");
+  k_ws_shift<<<ws_grid(n), 256, 0, (cudaStream_t)stream>>>(img, n, minmax_dev, out);
+  return b2v_check_launch("k_ws_shift");
+}
+
 extern "C" int b2v_ws_morph_gradient_u16(const uint16_t* in, int64_t nz, int64_t ny, int64_t nx, int sz, int sy,
                                          int sx, uint16_t* out, void* stream) {
   B2V_REQUIRE(in && out && nz > 0 && ny > 0 && nx > 0, B2V_ERR_ARG, "ws_morph_gradient: bad arguments");
   B2V_REQUIRE(sz >= 1 && sy >= 1 && sx >= 1 && sz <= 31 && sy <= 31 && sx <= 31, B2V_ERR_ARG,
               "ws_morph_gradient: size must be in 1..31");
+  const int W = sz + ((sz & 1) ? 0 : 1);
+  if (W <= 6 && nz < (1ll << 30) && ny < (1ll << 30) && nx < (1ll << 30)) {
+    int zchunk = 64;
+    dim3 grid((unsigned)ceil_div64(nx, 64), (unsigned)ceil_div64(ny, 4), (unsigned)ceil_div64(nz, zchunk));
+    cudaStream_t s = (cudaStream_t)stream;
+#define B2V_MG(WW) k_ws_morph_gradient_cols<WW><<<grid, 256, 0, s>>>(in, (int)nz, (int)ny, (int)nx, sz, sy, sx, zchunk, out)
+    switch (W) {
+      case 1: B2V_MG(1); break;
+      case 2: B2V_MG(2); break;
+      case 3: B2V_MG(3); break;
+      case 4: B2V_MG(4); break;
+      case 5: B2V_MG(5); break;
+      default: B2V_MG(6); break;
+    }
+#undef B2V_MG
+    return b2v_check_launch("k_ws_morph_gradient_cols");
+  }
   k_ws_morph_gradient<<<ws_grid(nz * ny * nx), 256, 0, (cudaStream_t)stream>>>(in, nz, ny, nx, sz, sy, sx, out);
   return b2v_check_launch("k_ws_morph_gradient");
 }

@@ -46,6 +46,7 @@ struct FGrid {
   long long n;
   int fz0, fz1;      // planes [fz0, fz1) are relaxed; the others are frozen halo planes
   int mode;          // 0: flat-array neighbourhood of scipy.ndimage.watershed_ift; 1: proper bounds
+  int vec;           // rows of full tiles are 16-byte aligned in every array (nx % 16 == 0, aligned bases)
 };
 
 struct Lists {
@@ -77,6 +78,7 @@ FGrid make_fgrid(int64_t nz, int64_t ny, int64_t nx, int mode, int frozen_lo, in
   g.fz0 = frozen_lo ? 1 : 0;
   g.fz1 = frozen_hi ? (int)nz - 1 : (int)nz;
   g.mode = mode;
+  g.vec = (nx % 16 == 0) ? 1 : 0;
   return g;
 }
 
@@ -209,6 +211,8 @@ __global__ void __launch_bounds__(256) k_wsf_adm(const uint16_t* __restrict__ im
 }
 
 // ---- tile visits ---------------------------------------------------------------------------------
+__device__ int g_stats[8];   // diagnostics: phase 1 visits / sweep sets / visits that changed, [4..6] phase 2
+
 struct TileGeom {
   int tz, ty, tx, z0, y0, x0;
   int vz, vy, vx;      // valid own cells per axis
@@ -295,6 +299,113 @@ __device__ __forceinline__ int line_faces(int axis, int a, int b, bool any, bool
   return f;
 }
 
+// ---- full tiles (16^3 relaxed cells, aligned rows): vector loads, register chains -------------------
+__device__ __forceinline__ bool tile_full(const FGrid& g, const TileGeom& t) {
+  return g.vec && t.vx == kT && t.vy == kT && t.vz == kT && t.uz0 == 1 && t.uz1 == kT + 1;
+}
+
+// one line of 16 cells + its two ends in registers; forward and backward pass; changed cells stored
+template <int MODE, int S>
+__device__ __forceinline__ void line_full_cost(uint32_t* sC, const uint16_t* sI, int base, bool& ch, bool& first,
+                                               bool& last) {
+  uint32_t c[kT + 2], n[kT + 2];
+  int iv[kT + 2];
+#pragma unroll
+  for (int j = 0; j < kT + 2; ++j) { c[j] = sC[base + (j - 1) * S]; iv[j] = sI[base + (j - 1) * S]; n[j] = c[j]; }
+#pragma unroll
+  for (int j = 1; j <= kT; ++j) {
+    const uint32_t w = MODE == 0 ? (uint32_t)abs(iv[j] - iv[j - 1]) : (uint32_t)iv[j];
+    const uint32_t cand = n[j - 1] > w ? n[j - 1] : w;
+    n[j] = cand < n[j] ? cand : n[j];
+  }
+#pragma unroll
+  for (int j = kT; j >= 1; --j) {
+    const uint32_t w = MODE == 0 ? (uint32_t)abs(iv[j] - iv[j + 1]) : (uint32_t)iv[j];
+    const uint32_t cand = n[j + 1] > w ? n[j + 1] : w;
+    n[j] = cand < n[j] ? cand : n[j];
+  }
+#pragma unroll
+  for (int j = 1; j <= kT; ++j)
+    if (n[j] != c[j]) { sC[base + (j - 1) * S] = n[j]; ch = true; }
+  first = n[1] != c[1];
+  last = n[kT] != c[kT];
+}
+
+__device__ __forceinline__ uint16_t set_join(uint16_t a, uint16_t b) {   // b != empty
+  return a == kSetEmpty ? b : ((a == b && b != kSetMulti) ? a : kSetMulti);
+}
+
+template <bool WITH_SET, int S>
+__device__ __forceinline__ void line_full_label(unsigned long long* sK, uint16_t* sA, const uint8_t* sD, int base,
+                                                uint32_t from_lo, uint32_t from_hi, bool& ch, bool& first, bool& last) {
+  unsigned long long k[kT + 2];
+  uint32_t av[kT + 2], d[kT + 2];
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < kT + 2; ++j) {
+    k[j] = sK[base + (j - 1) * S];
+    av[j] = WITH_SET ? sA[base + (j - 1) * S] : kSetEmpty;
+    d[j] = (j >= 1 && j <= kT) ? sD[base + (j - 1) * S] : 0u;
+  }
+  // branch-free steps (selects): the lanes of a warp walk different lines
+#pragma unroll
+  for (int j = 1; j <= kT; ++j) {
+    const bool ok = (d[j] & from_lo) != 0u && k[j - 1] != kInfK;
+    const unsigned long long cand = k[j - 1] + kHop;
+    const bool better = ok && cand < k[j];
+    k[j] = better ? cand : k[j];
+    uint32_t ch1 = better ? 1u : 0u;
+    if (WITH_SET) {
+      const uint32_t j1 = set_join((uint16_t)av[j], (uint16_t)av[j - 1]);
+      const bool grow = ok && av[j - 1] != kSetEmpty && j1 != av[j];
+      av[j] = grow ? j1 : av[j];
+      ch1 |= grow ? 1u : 0u;
+    }
+    m |= ch1 << j;
+  }
+#pragma unroll
+  for (int j = kT; j >= 1; --j) {
+    const bool ok = (d[j] & from_hi) != 0u && k[j + 1] != kInfK;
+    const unsigned long long cand = k[j + 1] + kHop;
+    const bool better = ok && cand < k[j];
+    k[j] = better ? cand : k[j];
+    uint32_t ch1 = better ? 1u : 0u;
+    if (WITH_SET) {
+      const uint32_t j1 = set_join((uint16_t)av[j], (uint16_t)av[j + 1]);
+      const bool grow = ok && av[j + 1] != kSetEmpty && j1 != av[j];
+      av[j] = grow ? j1 : av[j];
+      ch1 |= grow ? 1u : 0u;
+    }
+    m |= ch1 << j;
+  }
+#pragma unroll
+  for (int j = 1; j <= kT; ++j)
+    if ((m >> j) & 1u) {
+      sK[base + (j - 1) * S] = k[j];
+      if (WITH_SET) sA[base + (j - 1) * S] = (uint16_t)av[j];
+    }
+  ch = m != 0;
+  first = (m >> 1) & 1u;
+  last = (m >> kT) & 1u;
+}
+
+// the six halo cells of a thread in a full tile: index 0/1 x ends of row (y = a, z = b), 2/3 y ends
+// of column (x = a, z = b), 4/5 z ends of column (x = a, y = b). Returns flat index (or -1) and the
+// shared-memory cell.
+__device__ __forceinline__ long long halo_cell(const FGrid& g, const TileGeom& t, int which, int a, int b, int* ci) {
+  int hz, hy, hx;
+  switch (which) {
+    case 0: hz = b + 1; hy = a + 1; hx = 0; break;
+    case 1: hz = b + 1; hy = a + 1; hx = kT + 1; break;
+    case 2: hz = b + 1; hy = 0; hx = a + 1; break;
+    case 3: hz = b + 1; hy = kT + 1; hx = a + 1; break;
+    case 4: hz = 0; hy = b + 1; hx = a + 1; break;
+    default: hz = kT + 1; hy = b + 1; hx = a + 1; break;
+  }
+  *ci = cell_index(hz, hy, hx);
+  return flat_or_invalid(g, t.z0 + hz - 1, t.y0 + hy - 1, t.x0 + hx - 1);
+}
+
 // PHASE 1: one tile visit. Returns (block-uniform) 0 nothing changed, 1 changed, 2 changed and not
 // converged within kMaxSets sweep sets. *faces_out: faces whose cells changed.
 template <int MODE>
@@ -302,19 +413,51 @@ __device__ int visit_cost(const uint16_t* __restrict__ img, uint32_t* cost, cons
                           uint32_t* sC, uint16_t* sI, int* s_faces) {
   const int tid = threadIdx.x;
   if (tid == 0) *s_faces = 0;
-  // load the tile with its six halo faces (edges / corners of the halo are not needed)
-  for (int i = tid; i < kH * kH * kH; i += kThreads) {
-    const int hx = i % kH, hy = (i / kH) % kH, hz = i / (kH * kH);
-    if (hz > t.vz + 1 || hy > t.vy + 1 || hx > t.vx + 1) continue;
-    const int nh = (hz == 0 || hz == t.vz + 1) + (hy == 0 || hy == t.vy + 1) + (hx == 0 || hx == t.vx + 1);
-    if (nh > 1) continue;
-    const long long p = flat_or_invalid(g, t.z0 + hz - 1, t.y0 + hy - 1, t.x0 + hx - 1);
-    uint32_t c = kInfC;
-    uint16_t v = 0;
-    if (p >= 0) { c = __ldcg(&cost[p]); v = img[p]; }
-    const int ci = cell_index(hz, hy, hx);
-    sC[ci] = c;
-    sI[ci] = v;
+  const bool full = tile_full(g, t);
+  if (full) {
+    const int a = tid & 15, b = tid >> 4;
+    const long long p0 = ((long long)(t.z0 + b) * g.ny + (t.y0 + a)) * g.nx + t.x0;
+    uint4 c4[4], i4[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c4[k] = __ldcg((const uint4*)(cost + p0) + k);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) i4[k] = __ldg((const uint4*)(img + p0) + k);
+    long long hp[6];
+    int hc[6];
+    uint32_t hcost[6];
+    uint16_t himg[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      hp[k] = halo_cell(g, t, k, a, b, &hc[k]);
+      hcost[k] = kInfC; himg[k] = 0;
+      if (hp[k] >= 0) { hcost[k] = __ldcg(&cost[hp[k]]); himg[k] = img[hp[k]]; }
+    }
+    const int r0 = cell_index(b + 1, a + 1, 1);
+    const uint32_t cc[16] = {c4[0].x, c4[0].y, c4[0].z, c4[0].w, c4[1].x, c4[1].y, c4[1].z, c4[1].w,
+                             c4[2].x, c4[2].y, c4[2].z, c4[2].w, c4[3].x, c4[3].y, c4[3].z, c4[3].w};
+    const uint32_t ii[8] = {i4[0].x, i4[0].y, i4[0].z, i4[0].w, i4[1].x, i4[1].y, i4[1].z, i4[1].w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      sC[r0 + k] = cc[k];
+      sI[r0 + k] = (uint16_t)((k & 1) ? (ii[k >> 1] >> 16) : (ii[k >> 1] & 0xffffu));
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { sC[hc[k]] = hcost[k]; sI[hc[k]] = himg[k]; }
+  } else {
+// load the tile with its six halo faces (edges / corners of the halo are not needed)
+    for (int i = tid; i < kH * kH * kH; i += kThreads) {
+      const int hx = i % kH, hy = (i / kH) % kH, hz = i / (kH * kH);
+      if (hz > t.vz + 1 || hy > t.vy + 1 || hx > t.vx + 1) continue;
+      const int nh = (hz == 0 || hz == t.vz + 1) + (hy == 0 || hy == t.vy + 1) + (hx == 0 || hx == t.vx + 1);
+      if (nh > 1) continue;
+      const long long p = flat_or_invalid(g, t.z0 + hz - 1, t.y0 + hy - 1, t.x0 + hx - 1);
+      uint32_t c = kInfC;
+      uint16_t v = 0;
+      if (p >= 0) { c = __ldcg(&cost[p]); v = img[p]; }
+      const int ci = cell_index(hz, hy, hx);
+      sC[ci] = c;
+      sI[ci] = v;
+    }
   }
   __syncthreads();
   const int a = tid & 15, b = tid >> 4;
@@ -349,6 +492,25 @@ __device__ int visit_cost(const uint16_t* __restrict__ img, uint32_t* cost, cons
       }
     }
   };
+  if (full) {
+    // passes x, y, z, x, ... until three in a row (one per axis) change nothing
+    int clean = 0, pass = 0;
+    changed = 0;
+    while (clean < 3 && pass < 3 * kMaxSets) {
+      bool ch = false, first = false, last = false;
+      const int axis = pass % 3;
+      if (axis == 0) line_full_cost<MODE, 1>(sC, sI, cell_index(b + 1, a + 1, 1), ch, first, last);
+      else if (axis == 1) line_full_cost<MODE, kP>(sC, sI, cell_index(b + 1, 1, a + 1), ch, first, last);
+      else line_full_cost<MODE, kH * kP>(sC, sI, cell_index(1, b + 1, a + 1), ch, first, last);
+      if (ch) faces |= line_faces(axis, a, b, true, first, last, t);
+      changed = __syncthreads_or(ch ? 1 : 0);
+      any |= changed;
+      clean = changed ? 0 : clean + 1;
+      ++pass;
+    }
+    sets = (pass + 2) / 3;
+    changed = clean < 3;   // pass cap hit before three clean passes: the tile re-queues itself
+  } else {
   do {
     changed = 0;
     // x lines: (hy = a + 1, hz = b + 1)
@@ -375,9 +537,17 @@ __device__ int visit_cost(const uint16_t* __restrict__ img, uint32_t* cost, cons
     any |= changed;
     ++sets;
   } while (changed && sets < kMaxSets);
+  }
+  if (tid == 0) { atomicAdd(&g_stats[0], 1); atomicAdd(&g_stats[1], sets); if (any) atomicAdd(&g_stats[2], 1); }
   if (!any) return 0;
   // write the relaxed planes back (whole rows: the cells that did not change keep their value)
-  if (a < t.vy && b + 1 >= t.uz0 && b + 1 < t.uz1) {
+  if (full) {
+    const long long p0 = ((long long)(t.z0 + b) * g.ny + (t.y0 + a)) * g.nx + t.x0;
+    const int c0 = cell_index(b + 1, a + 1, 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      __stcg((uint4*)(cost + p0) + k, make_uint4(sC[c0 + 4 * k], sC[c0 + 4 * k + 1], sC[c0 + 4 * k + 2], sC[c0 + 4 * k + 3]));
+  } else if (a < t.vy && b + 1 >= t.uz0 && b + 1 < t.uz1) {
     const long long p0 = ((long long)(t.z0 + b) * g.ny + (t.y0 + a)) * g.nx + t.x0;
     const int c0 = cell_index(b + 1, a + 1, 1);
     for (int x = 0; x < t.vx; ++x) __stcg(&cost[p0 + x], sC[c0 + x]);
@@ -387,34 +557,66 @@ __device__ int visit_cost(const uint16_t* __restrict__ img, uint32_t* cost, cons
   return changed ? 2 : 1;
 }
 
-__device__ __forceinline__ uint16_t set_join(uint16_t a, uint16_t b) {   // b != empty
-  return a == kSetEmpty ? b : ((a == b && b != kSetMulti) ? a : kSetMulti);
-}
-
 // PHASE 2: keys (hops << 32 | label) and label sets along admissible edges
 template <bool WITH_SET>
 __device__ int visit_label(const uint8_t* __restrict__ adm, unsigned long long* key, uint16_t* lset, const FGrid& g,
                            const TileGeom& t, unsigned long long* sK, uint16_t* sA, uint8_t* sD, int* s_faces) {
   const int tid = threadIdx.x;
   if (tid == 0) *s_faces = 0;
-  for (int i = tid; i < kH * kH * kH; i += kThreads) {
-    const int hx = i % kH, hy = (i / kH) % kH, hz = i / (kH * kH);
-    if (hz > t.vz + 1 || hy > t.vy + 1 || hx > t.vx + 1) continue;
-    const int nh = (hz == 0 || hz == t.vz + 1) + (hy == 0 || hy == t.vy + 1) + (hx == 0 || hx == t.vx + 1);
-    if (nh > 1) continue;
-    const long long p = flat_or_invalid(g, t.z0 + hz - 1, t.y0 + hy - 1, t.x0 + hx - 1);
-    unsigned long long k = kInfK;
-    uint16_t s = kSetEmpty;
-    uint8_t d = 0;
-    if (p >= 0) {
-      k = __ldcg(&key[p]);
-      if (WITH_SET) s = __ldcg(&lset[p]);
-      if (nh == 0) d = adm[p];
+  const bool full = tile_full(g, t);
+  if (full) {
+    const int a = tid & 15, b = tid >> 4;
+    const long long p0 = ((long long)(t.z0 + b) * g.ny + (t.y0 + a)) * g.nx + t.x0;
+    uint4 k4[8], a4[2], d4;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) k4[k] = __ldcg((const uint4*)(key + p0) + k);
+    if (WITH_SET) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) a4[k] = __ldcg((const uint4*)(lset + p0) + k);
     }
-    const int ci = cell_index(hz, hy, hx);
-    sK[ci] = k;
-    if (WITH_SET) sA[ci] = s;
-    sD[ci] = d;
+    d4 = __ldg((const uint4*)(adm + p0));
+    long long hp[6];
+    int hc[6];
+    unsigned long long hk[6];
+    uint16_t hs[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      hp[k] = halo_cell(g, t, k, a, b, &hc[k]);
+      hk[k] = kInfK; hs[k] = kSetEmpty;
+      if (hp[k] >= 0) { hk[k] = __ldcg(&key[hp[k]]); if (WITH_SET) hs[k] = __ldcg(&lset[hp[k]]); }
+    }
+    const int r0 = cell_index(b + 1, a + 1, 1);
+    const uint32_t aa[8] = {a4[0].x, a4[0].y, a4[0].z, a4[0].w, a4[1].x, a4[1].y, a4[1].z, a4[1].w};
+    const uint32_t dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint4 q = k4[k >> 1];
+      sK[r0 + k] = (k & 1) ? (((unsigned long long)q.w << 32) | q.z) : (((unsigned long long)q.y << 32) | q.x);
+      if (WITH_SET) sA[r0 + k] = (uint16_t)((k & 1) ? (aa[k >> 1] >> 16) : (aa[k >> 1] & 0xffffu));
+      sD[r0 + k] = (uint8_t)((dd[k >> 2] >> (8 * (k & 3))) & 0xffu);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { sK[hc[k]] = hk[k]; if (WITH_SET) sA[hc[k]] = hs[k]; sD[hc[k]] = 0; }
+  } else {
+for (int i = tid; i < kH * kH * kH; i += kThreads) {
+      const int hx = i % kH, hy = (i / kH) % kH, hz = i / (kH * kH);
+      if (hz > t.vz + 1 || hy > t.vy + 1 || hx > t.vx + 1) continue;
+      const int nh = (hz == 0 || hz == t.vz + 1) + (hy == 0 || hy == t.vy + 1) + (hx == 0 || hx == t.vx + 1);
+      if (nh > 1) continue;
+      const long long p = flat_or_invalid(g, t.z0 + hz - 1, t.y0 + hy - 1, t.x0 + hx - 1);
+      unsigned long long k = kInfK;
+      uint16_t s = kSetEmpty;
+      uint8_t d = 0;
+      if (p >= 0) {
+        k = __ldcg(&key[p]);
+        if (WITH_SET) s = __ldcg(&lset[p]);
+        if (nh == 0) d = adm[p];
+      }
+      const int ci = cell_index(hz, hy, hx);
+      sK[ci] = k;
+      if (WITH_SET) sA[ci] = s;
+      sD[ci] = d;
+    }
   }
   __syncthreads();
   const int a = tid & 15, b = tid >> 4;
@@ -461,6 +663,24 @@ __device__ int visit_label(const uint8_t* __restrict__ adm, unsigned long long* 
       }
     }
   };
+  if (full) {
+    int clean = 0, pass = 0;
+    changed = 0;
+    while (clean < 3 && pass < 3 * kMaxSets) {
+      bool ch = false, first = false, last = false;
+      const int axis = pass % 3;
+      if (axis == 0) line_full_label<WITH_SET, 1>(sK, sA, sD, cell_index(b + 1, a + 1, 1), A_XM, A_XP, ch, first, last);
+      else if (axis == 1) line_full_label<WITH_SET, kP>(sK, sA, sD, cell_index(b + 1, 1, a + 1), A_YM, A_YP, ch, first, last);
+      else line_full_label<WITH_SET, kH * kP>(sK, sA, sD, cell_index(1, b + 1, a + 1), A_ZM, A_ZP, ch, first, last);
+      if (ch) faces |= line_faces(axis, a, b, true, first, last, t);
+      changed = __syncthreads_or(ch ? 1 : 0);
+      any |= changed;
+      clean = changed ? 0 : clean + 1;
+      ++pass;
+    }
+    sets = (pass + 2) / 3;
+    changed = clean < 3;   // pass cap hit before three clean passes: the tile re-queues itself
+  } else
   do {
     changed = 0;
     if (a < t.vy && b + 1 >= t.uz0 && b + 1 < t.uz1) {
@@ -484,8 +704,26 @@ __device__ int visit_label(const uint8_t* __restrict__ adm, unsigned long long* 
     any |= changed;
     ++sets;
   } while (changed && sets < kMaxSets);
+  if (tid == 0) { atomicAdd(&g_stats[4], 1); atomicAdd(&g_stats[5], sets); if (any) atomicAdd(&g_stats[6], 1); }
   if (!any) return 0;
-  if (a < t.vy && b + 1 >= t.uz0 && b + 1 < t.uz1) {
+  if (full) {
+    const long long p0 = ((long long)(t.z0 + b) * g.ny + (t.y0 + a)) * g.nx + t.x0;
+    const int c0 = cell_index(b + 1, a + 1, 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned long long k0 = sK[c0 + 2 * k], k1 = sK[c0 + 2 * k + 1];
+      __stcg((uint4*)(key + p0) + k, make_uint4((uint32_t)k0, (uint32_t)(k0 >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32)));
+    }
+    if (WITH_SET) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        uint32_t v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = (uint32_t)sA[c0 + 8 * k + 2 * q] | ((uint32_t)sA[c0 + 8 * k + 2 * q + 1] << 16);
+        __stcg((uint4*)(lset + p0) + k, make_uint4(v[0], v[1], v[2], v[3]));
+      }
+    }
+  } else if (a < t.vy && b + 1 >= t.uz0 && b + 1 < t.uz1) {
     const long long p0 = ((long long)(t.z0 + b) * g.ny + (t.y0 + a)) * g.nx + t.x0;
     const int c0 = cell_index(b + 1, a + 1, 1);
     for (int x = 0; x < t.vx; ++x) {
@@ -502,7 +740,7 @@ __device__ int visit_label(const uint8_t* __restrict__ adm, unsigned long long* 
 // PHASE 1 (cost) / PHASE 2 (labels). Rounds until the list of a round is empty. L.cnt[4] error,
 // L.cnt[5] rounds.
 template <int PHASE, int MODE, bool WITH_SET>
-__global__ void __launch_bounds__(kThreads) k_wsf_persistent(const uint16_t* __restrict__ img, uint32_t* cost,
+__global__ void __launch_bounds__(kThreads, (PHASE == 1 || !WITH_SET) ? 3 : 2) k_wsf_persistent(const uint16_t* __restrict__ img, uint32_t* cost,
                                                              unsigned long long* key, uint16_t* lset,
                                                              const uint8_t* __restrict__ adm, FGrid g, Lists L,
                                                              int max_rounds) {
@@ -659,6 +897,7 @@ int b2v_wsf_run(int stages, const uint16_t* img, const int16_t* markers, int64_t
   B2V_REQUIRE(nz - (frozen_lo ? 1 : 0) - (frozen_hi ? 1 : 0) >= 1, B2V_ERR_ARG, "ws_flood: slab has no plane of its own");
   cudaStream_t s = (cudaStream_t)stream;
   FGrid g = make_fgrid(nz, ny, nx, mode, frozen_lo, frozen_hi);
+  if (((uintptr_t)img & 15u) || ((uintptr_t)workspace & 15u)) g.vec = 0;
   FastWs w = fcarve(workspace, nz, ny, nx);
   int rc;
   if (stages & 1) {
@@ -704,6 +943,12 @@ extern "C" int b2v_ws_flood_staged(int stages, const uint16_t* img, const int16_
                                    uint8_t* ambiguous, void* workspace, void* stream, int* rounds_io) {
   return b2v_wsf_run(stages, img, markers, nz, ny, nx, mode, frozen_lo, frozen_hi, labels, ambiguous, 1, workspace,
                      stream, rounds_io);
+}
+
+extern "C" int b2v_ws_stats(int* out8, int reset) {
+  if (out8) B2V_CUDA(cudaMemcpyFromSymbol(out8, g_stats, sizeof(int) * 8));
+  if (reset) { int z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; B2V_CUDA(cudaMemcpyToSymbol(g_stats, z, sizeof(z))); }
+  return B2V_OK;
 }
 
 extern "C" int64_t b2v_ws_plane_bytes(int64_t ny, int64_t nx, int what) {

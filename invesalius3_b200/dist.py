@@ -389,6 +389,74 @@ class DeviceBackend:
     def ff_finish(self, st):
         self._staged(st, 4)
 
+    # -- watershed (extended slab; halo planes frozen)
+    def ws_preprocess(self, image_i16, use_ww_wl, wl, ww, global_min=None):
+        """The uint16 cost image (LUT, or shift by the GLOBAL minimum: int16 arithmetic wraps like NumPy's)."""
+        from . import watershed_process as wp
+        if use_ww_wl:
+            return wp.lut_u16(image_i16, ww, wl)
+        out = torch.empty_like(image_i16)
+        mm = torch.tensor([float(global_min), 0.0], dtype=torch.float32, device=image_i16.device)
+        with torch.cuda.device(image_i16.device):
+            self._lib.call("b2v_ws_shift_i16_with", self.dev._p(image_i16), image_i16.numel(), self.dev._p(mm),
+                           self.dev._p(out), self.dev._stream())
+        return out
+
+    def ws_local_min(self, image_i16):
+        return int(self.dev.minmax(image_i16)[0].item())
+
+    def ws_gradient(self, pre, size):
+        from . import watershed_process as wp
+        return wp.morphological_gradient_u16(pre, size)
+
+    def ws_begin(self, cost_u16, markers_i16, mode, frozen_lo, frozen_hi):
+        dev, lib = self.dev, self._lib.load()
+        nz, ny, nx = cost_u16.shape
+        ws = dev._workspace(lib.b2v_ws_workspace_bytes(nz, ny, nx), cost_u16.device)
+        st = dict(img=cost_u16, mk=markers_i16.contiguous(), mode=int(mode), lo=int(frozen_lo), hi=int(frozen_hi), ws=ws,
+                  rounds=C.c_int(0), labels=None, amb=None)
+        self._ws_run(st, 1)
+        return st
+
+    def _ws_run(self, st, stages):
+        dev = self.dev
+        nz, ny, nx = st["img"].shape
+        with torch.cuda.device(st["img"].device):
+            self._lib.call("b2v_ws_flood_staged", stages, dev._p(st["img"]), dev._p(st["mk"]), nz, ny, nx, st["mode"],
+                           st["lo"], st["hi"], dev._p(st["labels"]), dev._p(st["amb"]), dev._p(st["ws"]), dev._stream(),
+                           C.byref(st["rounds"]))
+
+    def ws_converge(self, st, what):
+        self._ws_run(st, 2 if what == 0 else 8)
+
+    def ws_label_begin(self, st):
+        self._ws_run(st, 4)
+
+    def ws_get_plane(self, st, what, z):
+        dev, lib = self.dev, self._lib.load()
+        nz, ny, nx = st["img"].shape
+        buf = torch.empty(int(lib.b2v_ws_plane_bytes(ny, nx, what)), dtype=torch.uint8, device=st["img"].device)
+        with torch.cuda.device(buf.device):
+            self._lib.call("b2v_ws_plane", 0, what, nz, ny, nx, st["mode"], st["lo"], st["hi"], int(z), dev._p(buf),
+                           dev._p(st["ws"]), dev._stream(), None)
+        return buf
+
+    def ws_merge_plane(self, st, what, z, plane):
+        dev = self.dev
+        nz, ny, nx = st["img"].shape
+        ch = C.c_int(0)
+        plane = plane.contiguous()
+        with torch.cuda.device(plane.device):
+            self._lib.call("b2v_ws_plane", 1, what, nz, ny, nx, st["mode"], st["lo"], st["hi"], int(z), dev._p(plane),
+                           dev._p(st["ws"]), dev._stream(), C.byref(ch))
+        return int(ch.value)
+
+    def ws_finish(self, st, want_ambiguous):
+        st["labels"] = torch.empty(st["img"].shape, dtype=torch.int16, device=st["img"].device)
+        st["amb"] = torch.empty(st["img"].shape, dtype=torch.uint8, device=st["img"].device) if want_ambiguous else None
+        self._ws_run(st, 16)
+        return st["labels"], st["amb"]
+
     # -- marching cubes
     def mc_count(self, vol, iso, skip_last):
         dev, lib = self.dev, self._lib.load()
@@ -650,3 +718,69 @@ def marching_cubes(vol_ext_hi, iso, spacing, origin_index, flip_y, shard: ZShard
     ox, oy, oz = origin_index
     verts, tris = be.mc_emit(st, spacing, (ox, oy, oz + shard.z0), flip_y, int(vbases[shard.rank]), foreign, fbase)
     return verts, tris, int(vbases[shard.rank]), total_v, total_t
+
+
+def watershed(image_ext, markers_ext, bstruct, algorithm, mg_size, use_ww_wl, wl, ww, shard: ZShard, backend=None,
+              return_ambiguous=False, max_outer=100000):
+    """do_watershed (invesalius/data/watershed_process.py:19-60) over the Z-sharded volume.
+    image_ext (int16) and markers_ext are extended slabs with valid halo planes. Returns the int16
+    labels of the shard's OWN planes (with return_ambiguous also the uint8 mask of the voxels whose
+    label depends on the reference's queue order) and the number of plane exchanges.
+
+    Pre-processing is local (the shift needs the global minimum: one all_reduce; the gradient of
+    the own planes needs one halo plane each side, so mg_size <= 3 along z; its halo planes are
+    exchanged afterwards). Each phase of the flood then alternates local convergence (halo planes
+    frozen) with a swap of the boundary planes — costs in phase 1, keys + label sets in phase 2 —
+    until no shard's halo plane improves (all_reduce of the changed flag). The fixed point is the
+    single-GPU one: costs only ever decrease towards the unique minimax field, keys towards the
+    unique (hops, label) minimum, label sets grow towards the unique closure."""
+    be = _backend(backend)
+    st3 = np.asarray(bstruct)
+    six = np.zeros((3, 3, 3), bool)
+    six[1, 1, :] = six[1, :, 1] = six[:, 1, 1] = True
+    if st3.shape != (3, 3, 3) or not np.array_equal(st3.astype(bool) | (np.arange(27).reshape(3, 3, 3) == 13), six):
+        raise NotImplementedError("dist.watershed: 6-connected structuring element only")
+    mode = 1 if algorithm == "Watershed" else 0
+    if use_ww_wl:
+        pre = be.ws_preprocess(image_ext, True, wl, ww)
+    else:
+        mn = torch.tensor([be.ws_local_min(shard.interior(image_ext))], dtype=torch.int32, device=image_ext.device)
+        _all_reduce(shard, mn, dist.ReduceOp.MIN)
+        pre = be.ws_preprocess(image_ext, False, wl, ww, global_min=int(mn.item()))
+    if mode == 1:
+        sz = mg_size if np.isscalar(mg_size) else mg_size[0]
+        if int(sz) > 3:
+            raise NotImplementedError("dist.watershed: mg_size > 3 along z needs more than one halo plane")
+        pre = be.ws_gradient(pre, mg_size)
+        exchange_halo(pre, shard)          # the halo planes' own gradient needs planes this shard does not hold
+    mk = markers_ext.to(torch.int16)
+    if mode == 0 and not use_ww_wl:
+        mk = mk.to(torch.int8).to(torch.int16)      # markers.astype('int8'), watershed_process.py:57
+    st = be.ws_begin(pre, mk, mode, shard.has_lo, shard.has_hi)
+    n = pre.shape[0]
+    exchanges = 0
+    for what in (0, 1):
+        if what == 1:
+            be.ws_label_begin(st)
+        while True:
+            be.ws_converge(st, what)
+            send_lo = be.ws_get_plane(st, what, 1) if shard.has_lo else None          # my first own plane
+            send_hi = be.ws_get_plane(st, what, n - 2) if shard.has_hi else None      # my last own plane
+            recv_lo, recv_hi = _swap(shard, send_lo, send_hi)
+            exchanges += 1
+            changed = 0
+            if recv_lo is not None:
+                changed |= be.ws_merge_plane(st, what, 0, recv_lo)
+            if recv_hi is not None:
+                changed |= be.ws_merge_plane(st, what, n - 1, recv_hi)
+            flag = torch.tensor([changed], dtype=torch.int32, device=pre.device)
+            _all_reduce(shard, flag, dist.ReduceOp.MAX)
+            if int(flag.item()) == 0:
+                break
+            if exchanges >= max_outer:
+                raise RuntimeError("sharded watershed did not converge")
+    labels, amb = be.ws_finish(st, return_ambiguous)
+    labels = shard.interior(labels)
+    if return_ambiguous:
+        return labels, shard.interior(amb), exchanges
+    return labels, exchanges

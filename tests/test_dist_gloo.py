@@ -142,6 +142,52 @@ class CpuBackend:
     def ff_finish(self, st):
         st["out"][st["reached"]] = st["fill"]
 
+    # ---- watershed: the NumPy model of the flood (tests/ws_model.py), staged like the C ABI
+    def ws_preprocess(self, image_i16, use_ww_wl, wl, ww, global_min=None):
+        from oracle import watershed as W
+        a = image_i16.numpy()
+        if use_ww_wl:
+            return torch.from_numpy(W.get_LUT_value(a, ww, wl).astype("uint16").view(np.int16))
+        return torch.from_numpy((a - np.int16(global_min)).astype("uint16").view(np.int16))
+
+    def ws_local_min(self, image_i16):
+        return int(image_i16.numpy().min())
+
+    def ws_gradient(self, pre, size):
+        from scipy import ndimage
+        return torch.from_numpy(ndimage.morphological_gradient(pre.numpy().view(np.uint16), size).view(np.int16))
+
+    def ws_begin(self, cost_u16, markers_i16, mode, frozen_lo, frozen_hi):
+        import ws_model
+        return dict(m=ws_model.Model(cost_u16.numpy().view(np.uint16), markers_i16.numpy(), mode, frozen_lo, frozen_hi))
+
+    def ws_converge(self, st, what):
+        st["m"].converge_cost() if what == 0 else st["m"].converge_labels()
+
+    def ws_label_begin(self, st):
+        st["m"].label_begin()
+
+    def ws_get_plane(self, st, what, z):
+        if what == 0:
+            return torch.from_numpy(st["m"].get_plane(0, z).astype(np.uint32).view(np.uint8).reshape(-1).copy())
+        k, s = st["m"].get_plane(1, z)
+        return torch.from_numpy(np.concatenate([k.astype(np.uint64).view(np.uint8).reshape(-1),
+                                                s.astype(np.uint16).view(np.uint8).reshape(-1)]))
+
+    def ws_merge_plane(self, st, what, z, plane):
+        m = st["m"]
+        ny, nx = m.shape[1:]
+        b = plane.numpy()
+        if what == 0:
+            return int(m.merge_plane(0, z, b.view(np.uint32).reshape(ny, nx)))
+        k = b[: ny * nx * 8].view(np.uint64).reshape(ny, nx)
+        s = b[ny * nx * 8:].view(np.uint16).reshape(ny, nx).astype(np.int64)
+        return int(m.merge_plane(1, z, (k, s)))
+
+    def ws_finish(self, st, want_ambiguous):
+        lab, amb = st["m"].labels()
+        return torch.from_numpy(lab), (torch.from_numpy(amb) if want_ambiguous else None)
+
     # ---- marching cubes
     def mc_count(self, vol, iso, skip_last):
         a = vol.numpy()
@@ -357,3 +403,59 @@ def test_marching_cubes_two_ranks(orc):
     assert out[0][3] == len(V) and out[0][4] == len(T) and out[1][2] == len(out[0][0])
     assert np.array_equal(gv, V)
     assert np.array_equal(gt.astype(np.int64), T)
+
+
+# ---- watershed over Z shards: the plane-exchange protocol reaches the single-volume fixed point
+def ws_case():
+    g = global_volume((23, 20, 45), seed=5)
+    mk = np.zeros(g.shape, np.uint8)
+    mk[3, 4:7, 5:9] = 1; mk[19, 12:15, 30:34] = 2; mk[11, 2:4, 40:43] = 2; mk[12, 15:18, 3:6] = 1
+    return g, mk
+
+
+def rank_watershed(rank, world, device):
+    from scipy.ndimage import generate_binary_structure
+    d, _, _ = _setup(rank, world)
+    g, mk = ws_case()
+    shard = d.ZShard(g.shape[0], rank, world)
+    be = CpuBackend()
+    st6 = generate_binary_structure(3, 1)
+    res = {}
+    for alg in ("Watershed", "Watershed IFT"):
+        for ww_wl in (True, False):
+            lab, amb, ex = d.watershed(torch.from_numpy(ext_slab(g, shard)), torch.from_numpy(ext_slab(mk, shard)), st6, alg,
+                                       3, ww_wl, 300, 900, shard, backend=be, return_ambiguous=True)
+            res[(alg, ww_wl)] = (lab.numpy().copy(), amb.numpy().copy(), ex)
+    with pytest.raises(NotImplementedError):
+        d.watershed(torch.from_numpy(ext_slab(g, shard)), torch.from_numpy(ext_slab(mk, shard)),
+                    generate_binary_structure(3, 3), "Watershed", 3, True, 300, 900, shard, backend=be)
+    return res
+
+
+def ws_whole(g, mk, alg, ww_wl):
+    """The same model on the whole volume (no shards), pre-processing as the reference's."""
+    import ws_model
+    from oracle import watershed as W
+    from scipy import ndimage
+    pre = W.preprocess(g, ww_wl, 300, 900)
+    m = mk.astype("int16")
+    if alg == "Watershed":
+        pre = ndimage.morphological_gradient(pre, 3)
+    elif not ww_wl:
+        m = mk.astype("int8").astype("int16")
+    return ws_model.flood(pre, m, 1 if alg == "Watershed" else 0)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_watershed_ranks(orc, world):
+    out = run_ranks("rank_watershed", "test_dist_gloo", world=world)
+    g, mk = ws_case()
+    for alg in ("Watershed", "Watershed IFT"):
+        for ww_wl in (True, False):
+            lab = np.concatenate([out[r][(alg, ww_wl)][0] for r in range(world)])
+            amb = np.concatenate([out[r][(alg, ww_wl)][1] for r in range(world)])
+            want_lab, want_amb = ws_whole(g, mk, alg, ww_wl)
+            assert np.array_equal(lab, want_lab), (alg, ww_wl)
+            assert np.array_equal(amb, want_amb), (alg, ww_wl)
+            assert len({out[r][(alg, ww_wl)][2] for r in range(world)}) == 1      # every rank saw the same exchanges
+            assert out[0][(alg, ww_wl)][2] >= 3                                    # labels did cross the boundary

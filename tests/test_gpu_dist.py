@@ -116,3 +116,53 @@ def test_sharded_ops_two_ranks_nccl(orc):
     out = run_ranks("rank_all", "test_gpu_dist", device="nccl")
     assert out[0]["link"] and out[1]["link"], "peer mailboxes (cudaIpc over NVLink) could not be set up"
     _check(out, orc)
+
+
+# ---- watershed over Z shards (BASELINE configs[3]: boundary planes exchanged until nothing improves)
+def rank_watershed(rank, world, device):
+    from scipy.ndimage import generate_binary_structure
+    from invesalius3_b200 import dist as d, phantom
+    g = phantom.ct((40, 48, 64), seed=4)
+    mk = np.zeros(g.shape, np.uint8)
+    mk[20, 24, 30:34] = 1; mk[2, 2, 2:6] = 2; mk[30, 40, 50:54] = 1; mk[38, 5, 60:63] = 2
+    shard = d.ZShard(g.shape[0], rank, world)
+    st6 = generate_binary_structure(3, 1)
+    res = {}
+    for alg in ("Watershed", "Watershed IFT"):
+        for ww_wl in (True, False):
+            img = torch.from_numpy(ext_slab(g, shard)).to(_dev())
+            m = torch.from_numpy(ext_slab(mk, shard)).to(_dev())
+            lab, amb, ex = d.watershed(img, m, st6, alg, 3, ww_wl, -18, 406, shard, return_ambiguous=True)
+            res[(alg, ww_wl)] = (lab.cpu().numpy(), amb.cpu().numpy(), ex)
+    return res
+
+
+def _check_watershed(out, world):
+    from scipy.ndimage import generate_binary_structure
+    from invesalius3_b200 import phantom, watershed_process as wp
+    g = phantom.ct((40, 48, 64), seed=4)
+    mk = np.zeros(g.shape, np.uint8)
+    mk[20, 24, 30:34] = 1; mk[2, 2, 2:6] = 2; mk[30, 40, 50:54] = 1; mk[38, 5, 60:63] = 2
+    st6 = generate_binary_structure(3, 1)
+    for alg in ("Watershed", "Watershed IFT"):
+        for ww_wl in (True, False):
+            want = wp.watershed_device(torch.from_numpy(g).cuda(), torch.from_numpy(mk).cuda(), st6, alg, 3, ww_wl, -18, 406,
+                                       return_ambiguous=True)
+            lab = np.concatenate([out[r][(alg, ww_wl)][0] for r in range(world)])
+            amb = np.concatenate([out[r][(alg, ww_wl)][1] for r in range(world)])
+            assert np.array_equal(lab, want[0].cpu().numpy()), (alg, ww_wl)
+            assert np.array_equal(amb, want[1].cpu().numpy()), (alg, ww_wl)
+            assert out[0][(alg, ww_wl)][2] >= 3
+
+
+def test_sharded_watershed_two_ranks_one_gpu_gloo():
+    _check_watershed(run_ranks("rank_watershed", "test_gpu_dist", device="cuda"), 2)
+
+
+def test_sharded_watershed_three_ranks_one_gpu_gloo():
+    _check_watershed(run_ranks("rank_watershed", "test_gpu_dist", world=3, device="cuda"), 3)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_watershed_two_ranks_nccl():
+    _check_watershed(run_ranks("rank_watershed", "test_gpu_dist", device="nccl"), 2)

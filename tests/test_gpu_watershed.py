@@ -247,3 +247,49 @@ def test_ct_phantom_agreement_fraction(wp):
         print(f"agreement[{algorithm}] = {frac:.4f}")
         assert set(np.unique(got)) <= {1, 2}
         assert frac >= FLOOR_CT[algorithm], (algorithm, frac)
+
+
+# ---- the persistent 6-connected engine against the NumPy model of the same definition --------------
+@pytest.mark.parametrize("shape", [(7, 9, 11), (20, 33, 48), (18, 32, 64), (1, 40, 50)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_flood_equals_numpy_model(wp, shape, mode):
+    """Labels AND the order-dependence mask equal the whole-array NumPy restatement (tests/ws_model.py)
+    bit for bit: partial tiles (generic path), full aligned tiles (register chains), a 2-D slice."""
+    import torch
+    import ws_model
+    rng = np.random.default_rng(sum(shape) + mode)
+    img = ndimage.gaussian_filter(rng.normal(size=shape), 1.2)
+    img = ((img - img.min()) / (np.ptp(img) + 1e-9) * 300).astype(np.uint16)     # plateaus and ties on purpose
+    mk = np.zeros(shape, np.int16)
+    for lab in (1, 2, -3, 2):
+        z, y, x = (int(rng.integers(0, s)) for s in shape)
+        mk[z, max(0, y - 1): y + 2, max(0, x - 1): x + 2] = lab
+    st = generate_binary_structure(3, 1)
+    lab, amb = wp.flood(_t(img.view(np.int16)), _t(mk), st, "Watershed" if mode == 1 else "Watershed IFT", True)
+    want_lab, want_amb = ws_model.flood(img, mk, mode)
+    assert np.array_equal(lab.cpu().numpy(), want_lab)
+    assert np.array_equal(amb.cpu().numpy(), want_amb)
+    # labels without the set propagation (what do_watershed runs) are the same labels
+    lab2 = wp.flood(_t(img.view(np.int16)), _t(mk), st, "Watershed" if mode == 1 else "Watershed IFT")
+    assert np.array_equal(lab2.cpu().numpy(), want_lab)
+
+
+def test_engine_matches_generic_kernels(wp, monkeypatch):
+    """The same structuring element through the generic round kernels (B2V_WS_GENERIC) gives the
+    same labels and mask."""
+    import torch
+    from invesalius3_b200 import phantom
+    vol = phantom.ct((40, 48, 64), seed=4)
+    mk = np.zeros(vol.shape, np.uint8)
+    mk[20, 24, 30:34] = 1; mk[2, 2, 2:6] = 2; mk[30, 40, 50:54] = 1; mk[38, 5, 60:63] = 2
+    st = generate_binary_structure(3, 1)
+    res = {}
+    for tag in ("fast", "generic"):
+        if tag == "generic":
+            monkeypatch.setenv("B2V_WS_GENERIC", "1")
+        for alg in ("Watershed", "Watershed IFT"):
+            r = wp.watershed_device(_t(vol), _t(mk), st, alg, 3, True, -18, 406, return_ambiguous=True)
+            res[(tag, alg)] = (r[0].cpu().numpy(), r[1].cpu().numpy())
+    for alg in ("Watershed", "Watershed IFT"):
+        assert np.array_equal(res[("fast", alg)][0], res[("generic", alg)][0])
+        assert np.array_equal(res[("fast", alg)][1], res[("generic", alg)][1])
