@@ -130,6 +130,11 @@ int b2v_floodfill_equal(const void* data, int dtype, int64_t dz, int64_t dy, int
  *   floodfill_py.rs:233-249 -> floodfill.rs:51-94. mask uint8 [n] rw, labels uint32 [n].
  * modified_out (host) receives the bool. SYNCHRONISES the stream. 6 B/voxel. */
 int64_t b2v_fill_holes_workspace_bytes(uint32_t nlabels);
+/* In two stages for Z-sharded masks (labels of the WHOLE mask, mask.py:526-530): 1 = histogram
+ * of this shard's labels into the workspace (uint32 [nlabels + 1] at byte offset 256; the shards
+ * sum them with one all_reduce), 2 = qualify + apply + report. stages = 3 is b2v_fill_holes. */
+int b2v_fill_holes_staged(int stages, uint8_t* mask, const uint32_t* labels, int64_t n, uint32_t nlabels,
+                          uint32_t max_size, void* workspace, void* stream, int* modified_out);
 int b2v_fill_holes(uint8_t* mask, const uint32_t* labels, int64_t n, uint32_t nlabels, uint32_t max_size,
                    void* workspace, void* stream, int* modified_out);
 
@@ -155,8 +160,17 @@ int b2v_mida_minmax(const void* img, int dtype, int64_t dz, int64_t dy, int64_t 
 int b2v_lmip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, double tmin, double tmax,
              void* out, void* workspace, void* stream);
 /* invesalius_rs.fast_countour_mip(image, n, axis, wl, ww, tmip, out): __init__.py:98-101 ->
- * mips_py.rs:204-253 -> mips.rs:215-279. int16 or uint8, out of the same dtype. tmip 0: max,
- * 1: lmip(700, 3033), 2: mida. The reference's temp volume is never materialised. */
+ * mips_py.rs:204-253 -> mips.rs:215-279. int16, uint8 or float64, out of the same dtype. tmip 0:
+ * max, 1: lmip(700, 3033) (uint8: B2V_ERR_RANGE, the reference panics), 2: mida (float64:
+ * B2V_ERR_ARG, not built). As in the reference the contour volume tmp[z, y, x] =
+ * T(calc_fcm_intensity) (mips.rs:197-242) is materialised — b2v_fcm_volume, one stencil pass,
+ * sizeof(T) read + sizeof(T) written per voxel — and then projected by the same kernels as the
+ * plain projections. workspace: b2v_fcm_workspace_bytes (holds the contour volume).
+ * b2v_fcm_volume alone (workspace: b2v_proj_workspace_bytes) serves the Z-sharded projections:
+ * computed on an extended slab, its own planes are exact. */
+int64_t b2v_fcm_workspace_bytes(int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, int tmip);
+int b2v_fcm_volume(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, float n, int axis, void* tmp,
+                   void* workspace, void* stream);
 int b2v_fast_countour_mip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, float n, int axis,
                           double wl, double ww, int tmip, void* out, void* workspace, void* stream);
 

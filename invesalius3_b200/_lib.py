@@ -40,11 +40,14 @@ PROTOTYPES = {
                                                vp, C.POINTER(cint)]),
     "b2v_floodfill_equal": (cint, [vp, cint, i64, i64, i64, i64, i64, i64, dbl, u8, vp, vp, vp, C.POINTER(cint)]),
     "b2v_fill_holes_workspace_bytes": (i64, [u32]),
+    "b2v_fill_holes_staged": (cint, [cint, vp, vp, i64, u32, u32, vp, vp, C.POINTER(cint)]),
     "b2v_fill_holes": (cint, [vp, vp, i64, u32, u32, vp, vp, C.POINTER(cint)]),
     "b2v_proj_workspace_bytes": (i64, [i64]),
     "b2v_mida": (cint, [vp, cint, i64, i64, i64, cint, dbl, dbl, vp, cint, vp, vp]),
     "b2v_mida_minmax": (cint, [vp, cint, i64, i64, i64, cint, dbl, dbl, vp, vp, cint, vp, vp]),
     "b2v_lmip": (cint, [vp, cint, i64, i64, i64, cint, dbl, dbl, vp, vp, vp]),
+    "b2v_fcm_workspace_bytes": (i64, [cint, i64, i64, i64, cint, cint]),
+    "b2v_fcm_volume": (cint, [vp, cint, i64, i64, i64, f32, cint, vp, vp, vp]),
     "b2v_fast_countour_mip": (cint, [vp, cint, i64, i64, i64, f32, cint, dbl, dbl, cint, vp, vp, vp]),
     "b2v_mc_workspace_bytes": (i64, [i64, i64, i64]),
     "b2v_mc_count": (cint, [vp, cint, i64, i64, i64, dbl, vp, vp, C.POINTER(i64), C.POINTER(i64)]),

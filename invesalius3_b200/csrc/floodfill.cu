@@ -1499,28 +1499,42 @@ __global__ void __launch_bounds__(256) k_fh_apply(const uint32_t* __restrict__ l
 
 extern "C" int64_t b2v_fill_holes_workspace_bytes(uint32_t nlabels) { return ((int64_t)nlabels + 1) * 4 + 256; }
 
-extern "C" int b2v_fill_holes(uint8_t* mask, const uint32_t* labels, int64_t n, uint32_t nlabels, uint32_t max_size,
-                              void* workspace, void* stream, int* modified_out) {
+// stages (bit mask): 1 HISTOGRAM (label sizes of this buffer into the workspace: uint32 [nlabels + 1]
+// at byte offset 256 — a Z shard all-reduces them with its peers before stage 2), 2 APPLY (qualify,
+// write 254, report). The one-shot entry runs both.
+extern "C" int b2v_fill_holes_staged(int stages, uint8_t* mask, const uint32_t* labels, int64_t n, uint32_t nlabels,
+                                     uint32_t max_size, void* workspace, void* stream, int* modified_out) {
   B2V_REQUIRE(mask && labels && workspace && modified_out, B2V_ERR_ARG, "fill_holes: null pointer");
   B2V_REQUIRE(n >= 0, B2V_ERR_ARG, "fill_holes: negative size");
   cudaStream_t s = (cudaStream_t)stream;
-  *modified_out = 0;
-  if (n == 0) return B2V_OK;
   int* ctrl = (int*)workspace;            // [0] modified, [1] status
   uint32_t* sizes = (uint32_t*)((char*)workspace + 256);
   int64_t nbins = (int64_t)nlabels + 1;
-  B2V_CUDA(cudaMemsetAsync(workspace, 0, (size_t)(256 + nbins * 4), s));
   int rc;
-  k_fh_hist<<<grid_for(n, 256 * 8), 256, 0, s>>>(labels, n, nlabels, sizes, ctrl + 1);
-  if ((rc = b2v_check_launch("k_fh_hist"))) return rc;
-  k_fh_any<<<(unsigned)ceil_div64(nbins, 256), 256, 0, s>>>(sizes, nbins, max_size, ctrl);
-  if ((rc = b2v_check_launch("k_fh_any"))) return rc;
-  k_fh_apply<<<grid_for(n, 256), 256, 0, s>>>(labels, n, sizes, nlabels, max_size, ctrl, mask);
-  if ((rc = b2v_check_launch("k_fh_apply"))) return rc;
-  int host[2] = {0, 0};
-  B2V_CUDA(cudaMemcpyAsync(host, ctrl, sizeof(host), cudaMemcpyDeviceToHost, s));
-  B2V_CUDA(cudaStreamSynchronize(s));
-  B2V_REQUIRE(host[1] == 0, B2V_ERR_RANGE, "fill_holes: a label exceeds nlabels (the reference panics here)");
-  *modified_out = host[0];
+  if (stages & 1) {
+    B2V_CUDA(cudaMemsetAsync(workspace, 0, (size_t)(256 + nbins * 4), s));
+    if (n > 0) {
+      k_fh_hist<<<grid_for(n, 256 * 8), 256, 0, s>>>(labels, n, nlabels, sizes, ctrl + 1);
+      if ((rc = b2v_check_launch("k_fh_hist"))) return rc;
+    }
+  }
+  if (stages & 2) {
+    k_fh_any<<<(unsigned)ceil_div64(nbins, 256), 256, 0, s>>>(sizes, nbins, max_size, ctrl);
+    if ((rc = b2v_check_launch("k_fh_any"))) return rc;
+    if (n > 0) {
+      k_fh_apply<<<grid_for(n, 256), 256, 0, s>>>(labels, n, sizes, nlabels, max_size, ctrl, mask);
+      if ((rc = b2v_check_launch("k_fh_apply"))) return rc;
+    }
+    int host[2] = {0, 0};
+    B2V_CUDA(cudaMemcpyAsync(host, ctrl, sizeof(host), cudaMemcpyDeviceToHost, s));
+    B2V_CUDA(cudaStreamSynchronize(s));
+    B2V_REQUIRE(host[1] == 0, B2V_ERR_RANGE, "fill_holes: a label exceeds nlabels (the reference panics here)");
+    *modified_out = host[0];
+  }
   return B2V_OK;
+}
+
+extern "C" int b2v_fill_holes(uint8_t* mask, const uint32_t* labels, int64_t n, uint32_t nlabels, uint32_t max_size,
+                              void* workspace, void* stream, int* modified_out) {
+  return b2v_fill_holes_staged(3, mask, labels, n, nlabels, max_size, workspace, stream, modified_out);
 }

@@ -47,7 +47,15 @@ template <> __device__ __forceinline__ float wrapdiff<uint8_t>(uint8_t a, uint8_
   return (float)(uint8_t)((int)a - (int)b);
 }
 
+template <> __device__ __forceinline__ float wrapdiff<double>(double a, double b) {
+  return (float)(a - b);   // f64 difference, then to_f32 (mips.rs:190-192 on ArrayView3<f64>)
+}
+
 template <typename T> __device__ __forceinline__ bool cast_f32(float f, T* o);
+template <> __device__ __forceinline__ bool cast_f32<double>(float f, double* o) {
+  *o = (double)f;
+  return true;
+}
 template <> __device__ __forceinline__ bool cast_f32<int16_t>(float f, int16_t* o) {
   if (!(f > -32769.0f && f < 32768.0f)) return false;
   *o = (int16_t)f;
@@ -58,41 +66,6 @@ template <> __device__ __forceinline__ bool cast_f32<uint8_t>(float f, uint8_t* 
   *o = (uint8_t)f;
   return true;
 }
-
-// calc_fcm_intensity (mips.rs:197-213) cast to T (mips.rs:241)
-template <typename T>
-struct FcmSampler {
-  static constexpr int kBatch = 1;   // a contour sample is expensive: never compute past the ray's end
-  static constexpr bool kLinear = false;
-  const T* __restrict__ vol;
-  Dims d;
-  float n;
-  float dirx, diry, dirz;  // dir[0], dir[1], dir[2] of mips.rs:229-235 (x, y, z components)
-  __device__ __forceinline__ T at(int64_t z, int64_t y, int64_t x, int* status) const {
-    const int64_t px = x == 0 ? 0 : x - 1, fx = x == d.nx - 1 ? d.nx - 1 : x + 1;
-    const int64_t py = y == 0 ? 0 : y - 1, fy = y == d.ny - 1 ? d.ny - 1 : y + 1;
-    const int64_t pz = z == 0 ? 0 : z - 1, fz = z == d.nz - 1 ? d.nz - 1 : z + 1;
-    const int64_t row = (z * d.ny + y) * d.nx;
-    const float two_h = 2.0f;  // 2.0 * h with h = 1
-    float gx = __fdiv_rn(wrapdiff<T>(vol[row + fx], vol[row + px]), two_h);
-    float gy = __fdiv_rn(wrapdiff<T>(vol[(z * d.ny + fy) * d.nx + x], vol[(z * d.ny + py) * d.nx + x]), two_h);
-    float gz = __fdiv_rn(wrapdiff<T>(vol[(fz * d.ny + y) * d.nx + x], vol[(pz * d.ny + y) * d.nx + x]), two_h);
-    float gm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz)));
-    float val = 0.0f;
-    if (gm != 0.0f) {
-      float dd = __fadd_rn(__fadd_rn(__fmul_rn(gx, dirx), __fmul_rn(gy, diry)), __fmul_rn(gz, dirz));
-      float base = __fsub_rn(1.0f, fabsf(__fdiv_rn(dd, gm)));
-      // powf of the reference is libm's (<1 ulp); a double pow rounded once is within the
-      // same ulp. See DESIGN.md (contour-MIP tolerance).
-      // n == 1 (InVesalius' default border size) and n == 2 are exact in any libm
-      float sf = n == 1.0f ? base : (n == 2.0f ? __fmul_rn(base, base) : (float)pow((double)base, (double)n));
-      val = __fmul_rn(gm, sf);
-    }
-    T o = 0;
-    if (!cast_f32<T>(val, &o)) *status = B2V_ERR_RANGE;
-    return o;
-  }
-};
 
 // ---- per-ray operators --------------------------------------------------------------------
 // get_opacity (mips.rs:88-100). The window bounds are ray-invariant: computed once per thread
@@ -376,40 +349,6 @@ __global__ void __launch_bounds__(kRays) k_rays_alongx(S smp, Op op0, U* __restr
   if (st) *status = st;
 }
 
-// min / max of the sampled (T-typed) volume, for contour-MIDA
-template <typename T, typename S>
-__global__ void __launch_bounds__(256) k_sampled_minmax(S smp, int* __restrict__ mm, int* status) {
-  const Dims d = smp.d;
-  const int64_t n = d.nz * d.ny * d.nx;
-  int mn = 2147483647, mx = -2147483647 - 1, st = 0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    int64_t x = i % d.nx, yz = i / d.nx, y = yz % d.ny, z = yz / d.ny;
-    int v = (int)smp.at(z, y, x, &st);
-    mn = min(mn, v);
-    mx = max(mx, v);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMin(&mm[0], mn);
-    atomicMax(&mm[1], mx);
-  }
-  if (st) *status = st;
-}
-
-__global__ void k_mm_init(int* mm, int* status) {
-  mm[0] = 2147483647;
-  mm[1] = -2147483647 - 1;
-  *status = 0;
-}
-__global__ void k_mm_to_float(const int* mm, float* out) {
-  out[0] = (float)mm[0];
-  out[1] = (float)mm[1];
-}
 __global__ void k_status_init(int* status) { *status = 0; }
 
 template <typename T, typename U, typename S, typename Op>
@@ -656,55 +595,147 @@ extern "C" int b2v_lmip(const void* img, int dtype, int64_t dz, int64_t dy, int6
   return rc;
 }
 
-namespace {
+// ---- the contour volume itself (mips.rs:238-242: tmp[z, y, x] = T(calc_fcm_intensity)) -------------
+// One pass over the volume, HBM-bound on paper (sizeof(T) read + sizeof(T) written per voxel) and
+// in practice bounded by the IEEE sqrt and division of every sample. A block owns a 64 x 8 (x, y)
+// column and marches along z: the plane being differentiated sits in shared memory with its x / y
+// halo (every voxel is read from global memory once, plus 1.3 halo reads per 64 x 8 plane), the
+// z neighbours of a voxel are the thread's own previous / next values (registers). Central
+// differences clamp at the volume faces exactly as finite_difference does (mips.rs:182-187).
+constexpr int kFcmX = 64, kFcmY = 8, kFcmThreads = kFcmX * kFcmY;
+
 template <typename T>
-int run_fcm(const T* img, Dims d, float n, int axis, double wl, double ww, int tmip, T* out, ProjWs w,
-            cudaStream_t s) {
-  FcmSampler<T> smp = {img, d, n, axis == 2 ? 1.0f : 0.0f, axis == 1 ? 1.0f : 0.0f, axis == 0 ? 1.0f : 0.0f};
-  int rc;
-  if (tmip == 0) {
-    MaxOp<T> op = {};
-    rc = launch_rays<T, T>(smp, axis, op, out, w.status, s);
-  } else if (tmip == 1) {
-    // lmip(tmp, axis, 700, 3033): NumCast::from(700) does not fit uint8 -> the reference panics
-    B2V_REQUIRE(sizeof(T) == 2, B2V_ERR_RANGE, "fast_countour_mip: LMIP bounds 700/3033 do not fit uint8");
-    LmipOp<T> op;
-    op.tmin = (T)700; op.tmax = (T)3033;
-    rc = launch_rays<T, T>(smp, axis, op, out, w.status, s);
-  } else {
-    k_mm_init<<<1, 1, 0, s>>>(w.mm_i, w.status);
-    if ((rc = b2v_check_launch("k_mm_init"))) return rc;
-    int64_t nvox = d.nz * d.ny * d.nx;
-    int64_t blocks = ceil_div64(nvox, 256 * 8);
-    int64_t cap = (int64_t)b2v_sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    k_sampled_minmax<T, FcmSampler<T>><<<(unsigned)blocks, 256, 0, s>>>(smp, w.mm_i, w.status);
-    if ((rc = b2v_check_launch("k_sampled_minmax"))) return rc;
-    k_mm_to_float<<<1, 1, 0, s>>>(w.mm_i, w.mm_f);
-    if ((rc = b2v_check_launch("k_mm_to_float"))) return rc;
-    rc = launch_mida<T, T>(smp, axis, w.mm_f, (float)(T)wl, (float)(T)ww, out, w.status, s);
+__global__ void __launch_bounds__(kFcmThreads) k_fcm_volume(const T* __restrict__ vol, Dims d, float n, float dirx,
+                                                           float diry, float dirz, int zchunk, T* __restrict__ out,
+                                                           int* status) {
+  __shared__ T s[2][kFcmY + 2][kFcmX + 2];
+  const int tid = threadIdx.x, tx = tid % kFcmX, ty = tid / kFcmX;
+  const int64_t x = (int64_t)blockIdx.x * kFcmX + tx, y = (int64_t)blockIdx.y * kFcmY + ty;
+  const bool active = x < d.nx && y < d.ny;
+  const int64_t cx = x < d.nx ? x : d.nx - 1, cy = y < d.ny ? y : d.ny - 1;
+  const int64_t z0 = (int64_t)blockIdx.z * zchunk;
+  const int64_t z1 = z0 + zchunk < d.nz ? z0 + zchunk : d.nz;
+  if (z0 >= z1) return;
+  // halo cell of this thread (the first 2 * 64 + 2 * 8 threads): row above / below, column left / right
+  int hy = -1, hx = -1;   // shared-memory coordinates
+  if (tid < kFcmX) { hy = 0; hx = tid + 1; }
+  else if (tid < 2 * kFcmX) { hy = kFcmY + 1; hx = tid - kFcmX + 1; }
+  else if (tid < 2 * kFcmX + kFcmY) { hy = tid - 2 * kFcmX + 1; hx = 0; }
+  else if (tid < 2 * kFcmX + 2 * kFcmY) { hy = tid - 2 * kFcmX - kFcmY + 1; hx = kFcmX + 1; }
+  int64_t gy = (int64_t)blockIdx.y * kFcmY + hy - 1, gx = (int64_t)blockIdx.x * kFcmX + hx - 1;
+  gy = gy < 0 ? 0 : (gy > d.ny - 1 ? d.ny - 1 : gy);
+  gx = gx < 0 ? 0 : (gx > d.nx - 1 ? d.nx - 1 : gx);
+  const int64_t plane = d.ny * d.nx;
+  const int64_t own = cy * d.nx + cx, hal = gy * d.nx + gx;
+  T prev = vol[(z0 > 0 ? z0 - 1 : 0) * plane + own];
+  T cur = vol[z0 * plane + own];
+  int b = 0;
+  s[0][ty + 1][tx + 1] = cur;
+  if (hy >= 0) s[0][hy][hx] = vol[z0 * plane + hal];
+  __syncthreads();
+  for (int64_t z = z0; z < z1; ++z) {
+    const int64_t zn = z + 1 < d.nz ? z + 1 : d.nz - 1;
+    const T nxt = vol[zn * plane + own];
+    T hv = 0;
+    if (hy >= 0) hv = vol[zn * plane + hal];
+    if (active) {
+      const float gxf = __fmul_rn(wrapdiff<T>(s[b][ty + 1][tx + 2], s[b][ty + 1][tx]), 0.5f);   // / (2.0 * h), h = 1
+      const float gyf = __fmul_rn(wrapdiff<T>(s[b][ty + 2][tx + 1], s[b][ty][tx + 1]), 0.5f);
+      const float gzf = __fmul_rn(wrapdiff<T>(nxt, prev), 0.5f);
+      const float gm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(gxf, gxf), __fmul_rn(gyf, gyf)), __fmul_rn(gzf, gzf)));
+      float val = 0.0f;
+      if (gm != 0.0f) {
+        const float dd = __fadd_rn(__fadd_rn(__fmul_rn(gxf, dirx), __fmul_rn(gyf, diry)), __fmul_rn(gzf, dirz));
+        const float base = __fsub_rn(1.0f, fabsf(__fdiv_rn(dd, gm)));
+        // powf of the reference is libm's (<1 ulp); a double pow rounded once is within the same ulp;
+        // n == 1 (InVesalius' default border size) and n == 2 are exact in any libm
+        const float sf = n == 1.0f ? base : (n == 2.0f ? __fmul_rn(base, base) : (float)pow((double)base, (double)n));
+        val = __fmul_rn(gm, sf);
+      }
+      T o = 0;
+      if (!cast_f32<T>(val, &o)) *status = B2V_ERR_RANGE;
+      out[z * plane + y * d.nx + x] = o;
+    }
+    s[b ^ 1][ty + 1][tx + 1] = nxt;
+    if (hy >= 0) s[b ^ 1][hy][hx] = hv;
+    __syncthreads();
+    b ^= 1;
+    prev = z + 1 < d.nz ? cur : prev;   // unused past the last plane
+    cur = nxt;
   }
-  return rc;
 }
-}  // namespace
+
+template <typename T>
+int launch_fcm_volume(const T* img, Dims d, float n, int axis, T* tmp, int* status, cudaStream_t s) {
+  const int64_t gx = ceil_div64(d.nx, kFcmX), gy = ceil_div64(d.ny, kFcmY);
+  B2V_REQUIRE(gy <= 65535, B2V_ERR_ARG, "fcm_volume: more than 524280 rows");
+  int64_t nchunk = ceil_div64((int64_t)b2v_sm_count() * 4, gx * gy);
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > d.nz) nchunk = d.nz;
+  const int zchunk = (int)ceil_div64(d.nz, nchunk);
+  nchunk = ceil_div64(d.nz, zchunk);
+  B2V_REQUIRE(nchunk <= 65535, B2V_ERR_ARG, "fcm_volume: too many z chunks");
+  k_fcm_volume<T><<<dim3((unsigned)gx, (unsigned)gy, (unsigned)nchunk), kFcmThreads, 0, s>>>(
+      img, d, n, axis == 2 ? 1.0f : 0.0f, axis == 1 ? 1.0f : 0.0f, axis == 0 ? 1.0f : 0.0f, zchunk, tmp, status);
+  return b2v_check_launch("k_fcm_volume");
+}
+
+static int fcm_volume_impl(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, float n, int axis, void* tmp,
+                           int* status, cudaStream_t s) {
+  Dims d = {dz, dy, dx};
+  if (dtype == B2V_I16) return launch_fcm_volume<int16_t>((const int16_t*)img, d, n, axis, (int16_t*)tmp, status, s);
+  if (dtype == B2V_U8) return launch_fcm_volume<uint8_t>((const uint8_t*)img, d, n, axis, (uint8_t*)tmp, status, s);
+  if (dtype == B2V_F64) return launch_fcm_volume<double>((const double*)img, d, n, axis, (double*)tmp, status, s);
+  B2V_REQUIRE(false, B2V_ERR_ARG, "Invalid image or output type");
+}
+
+extern "C" int b2v_fcm_volume(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, float n, int axis,
+                              void* tmp, void* workspace, void* stream) {
+  B2V_REQUIRE(img && tmp && workspace, B2V_ERR_ARG, "fcm_volume: null pointer");
+  B2V_REQUIRE(check_axis_dims(dz, dy, dx, axis), B2V_ERR_ARG, "fcm_volume: bad shape or axis");
+  cudaStream_t s = (cudaStream_t)stream;
+  ProjWs w = carve(workspace);
+  int rc;
+  k_status_init<<<1, 1, 0, s>>>(w.status);
+  if ((rc = b2v_check_launch("k_status_init"))) return rc;
+  if ((rc = fcm_volume_impl(img, dtype, dz, dy, dx, n, axis, tmp, w.status, s))) return rc;
+  return finish_status(w.status, s, "fast_countour_mip");
+}
+
+static int64_t dtype_bytes(int dtype) { return dtype == B2V_I16 ? 2 : (dtype == B2V_U8 ? 1 : 8); }
+static int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+
+// workspace of b2v_fast_countour_mip: [projection workspace | contour volume | MaxIP workspace]
+extern "C" int64_t b2v_fcm_workspace_bytes(int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, int tmip) {
+  if (dz <= 0 || dy <= 0 || dx <= 0) return 0;
+  const int64_t n = dz * dy * dx;
+  return align256(b2v_proj_workspace_bytes(n)) + align256(n * dtype_bytes(dtype)) +
+         (tmip == 0 ? align256(b2v_mip_workspace_bytes(dtype, dz, dy, dx, axis, 0)) : 0) + 256;
+}
 
 extern "C" int b2v_fast_countour_mip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, float n,
                                      int axis, double wl, double ww, int tmip, void* out, void* workspace,
                                      void* stream) {
+  // As the reference does (mips.rs:236-278): the contour volume first, then the projection of it.
+  // workspace: b2v_fcm_workspace_bytes.
   B2V_REQUIRE(img && out && workspace, B2V_ERR_ARG, "fast_countour_mip: null pointer");
   B2V_REQUIRE(check_axis_dims(dz, dy, dx, axis), B2V_ERR_ARG, "fast_countour_mip: bad shape or axis");
   B2V_REQUIRE(tmip >= 0 && tmip <= 2, B2V_ERR_ARG, "fast_countour_mip: tmip must be 0, 1 or 2");
-  cudaStream_t s = (cudaStream_t)stream;
-  ProjWs w = carve(workspace);
-  Dims d = {dz, dy, dx};
+  B2V_REQUIRE(dtype == B2V_I16 || dtype == B2V_U8 || dtype == B2V_F64, B2V_ERR_ARG, "Invalid image or output type");
+  // lmip(tmp, axis, 700, 3033): NumCast::from(700) does not fit uint8 -> the reference panics
+  B2V_REQUIRE(!(tmip == 1 && dtype == B2V_U8), B2V_ERR_RANGE, "fast_countour_mip: LMIP bounds 700/3033 do not fit uint8");
+  B2V_REQUIRE(!(tmip == 2 && dtype == B2V_F64), B2V_ERR_ARG,
+              "fast_countour_mip: float64 contour-MIDA (float64 output) is not supported on the device");
+  const int64_t nvox = dz * dy * dx;
+  char* p = (char*)workspace;
+  void* proj_ws = p;
+  void* tmp = p + align256(b2v_proj_workspace_bytes(nvox));
+  void* mip_ws = (char*)tmp + align256(nvox * dtype_bytes(dtype));
   int rc;
-  k_status_init<<<1, 1, 0, s>>>(w.status);
-  if ((rc = b2v_check_launch("k_status_init"))) return rc;
-  if (dtype == B2V_I16) rc = run_fcm<int16_t>((const int16_t*)img, d, n, axis, wl, ww, tmip, (int16_t*)out, w, s);
-  else if (dtype == B2V_U8) rc = run_fcm<uint8_t>((const uint8_t*)img, d, n, axis, wl, ww, tmip, (uint8_t*)out, w, s);
-  else B2V_REQUIRE(false, B2V_ERR_ARG, "fast_countour_mip: only int16 and uint8 volumes are supported on the device");
-  if (rc) return rc;
-  return finish_status(w.status, s, "fast_countour_mip");
+  if ((rc = b2v_fcm_volume(img, dtype, dz, dy, dx, n, axis, tmp, proj_ws, stream))) return rc;
+  if (tmip == 0) return b2v_mip(tmp, dtype, dz, dy, dx, axis, 0 /* max */, out, mip_ws, stream);
+  if (tmip == 1) return b2v_lmip(tmp, dtype, dz, dy, dx, axis, 700.0, 3033.0, out, proj_ws, stream);
+  return b2v_mida(tmp, dtype, dz, dy, dx, axis, wl, ww, out, dtype, proj_ws, stream);
 }
 
 extern "C" int b2v_mida_z_partial(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, double wl, double ww,

@@ -10,6 +10,11 @@ op of the path is sharded the same way:
                        axis 0: partial planes, one all_reduce
   MIDA / LMIP axis 1/2 all_reduce of the global (min, max) for MIDA, then local rays;
                        axis 0: the per-ray state is handed from shard to shard (bit-exact)
+  contour-MIP          the contour volume on the extended slab (halo planes feed the central
+                       differences), then the sharded MaxIP / LMIP / MIDA of its own planes
+  watershed            local convergence with frozen halo planes, boundary planes swapped (costs,
+                       then keys + label sets) until no halo plane improves
+  fill holes           per-shard label histogram, one all_reduce, local apply
   flood fill           local convergence on slab + one halo plane per inner side, then the
                        reached bits of the two shared planes are swapped with each neighbour
                        (2 x dy x dx/8 bytes) and merged; repeat until no shard gains a bit.
@@ -321,9 +326,9 @@ class DeviceBackend:
         from . import projection
         return projection.lmip(img, axis, tmin, tmax)
 
-    def fcm(self, img, n, axis, wl, ww, tmip):
+    def fcm_volume(self, img, n, axis):
         from . import projection
-        return projection.fast_countour_mip(img, n, axis, wl, ww, tmip)
+        return projection.fcm_volume(img, n, axis)
 
     def ray_state(self, img):
         from . import projection
@@ -388,6 +393,28 @@ class DeviceBackend:
 
     def ff_finish(self, st):
         self._staged(st, 4)
+
+    # -- fill holes (labels of the whole mask; sizes summed over the shards)
+    def fh_hist(self, mask, labels, nlabels):
+        dev, lib = self.dev, self._lib.load()
+        ws = dev._workspace(lib.b2v_fill_holes_workspace_bytes(int(nlabels)), mask.device)
+        st = dict(mask=mask, labels=labels, nlabels=int(nlabels), ws=ws, mod=C.c_int(0))
+        self._fh(st, 1, 0)
+        return st
+
+    def _fh(self, st, stages, max_size):
+        dev = self.dev
+        with torch.cuda.device(st["mask"].device):
+            self._lib.call("b2v_fill_holes_staged", stages, dev._p(st["mask"]), dev._p(st["labels"]), st["mask"].numel(),
+                           st["nlabels"], int(max_size), dev._p(st["ws"]), dev._stream(), C.byref(st["mod"]))
+
+    def fh_sizes(self, st):
+        """int32 view (uint32 bits) of the label sizes inside the workspace: all-reduced in place."""
+        return st["ws"][256: 256 + 4 * (st["nlabels"] + 1)].view(torch.int32)
+
+    def fh_apply(self, st, max_size):
+        self._fh(st, 2, max_size)
+        return bool(st["mod"].value)
 
     # -- watershed (extended slab; halo planes frozen)
     def ws_preprocess(self, image_i16, use_ww_wl, wl, ww, global_min=None):
@@ -571,25 +598,26 @@ def lmip(img_slab, axis, tmin, tmax, shard: ZShard, gather=True, backend=None):
 
 
 def fast_countour_mip(img_ext, n, axis, wl, ww, tmip, shard: ZShard, gather=True, backend=None):
-    """Contour-enhanced projection (mips.rs:215-279) of the Z-sharded volume, rays along y or
-    x (axis 1 / 2), tmip 0 (maximum) or 1 (LMIP). img_ext is the extended slab with valid halo
-    planes (exchange_halo): the central differences of a shard's first and last own plane
-    read the neighbour's plane there, and clamp only at the true ends of the volume
-    (mips.rs:170-195). Every output row depends on its own plane and the two next to it, so
-    the rows of the halo planes are simply dropped. Not built yet: rays along z (the contour
-    sampler would have to skip the halo planes) and tmip 2, whose MIDA needs the extrema of
-    the contour volume over own planes only."""
-    if axis == 0:
-        raise NotImplementedError("contour-MIP along z over Z shards: the sampler cannot skip halo planes yet (next)")
-    if tmip not in (0, 1):
-        raise NotImplementedError("contour-MIDA over Z shards needs a min/max restricted to the own planes (next)")
-    rows = _backend(backend).fcm(img_ext, n, axis, wl, ww, tmip)
-    lo, hi = int(shard.has_lo), int(shard.has_hi)
-    rows = rows[lo:rows.shape[0] - hi].contiguous()
-    if not gather:
-        return rows
-    sizes = [shard.bounds(r)[1] - shard.bounds(r)[0] for r in range(shard.world)]
-    return _all_gather_rows(shard, rows, sizes)
+    """Contour-enhanced projection (mips.rs:215-279) of the Z-sharded volume: any axis, tmip 0
+    (maximum), 1 (LMIP 700 / 3033) or 2 (MIDA). img_ext is the extended slab with valid halo planes
+    (exchange_halo). As in the reference the contour volume comes first (b2v_fcm_volume): on the
+    extended slab the central differences of a shard's first and last own plane read the
+    neighbour's plane, and clamp only at the true ends of the volume (mips.rs:170-195), so the own
+    planes are exact and the halo planes' values are dropped. The projection of the own planes is
+    then the sharded projection of any volume: rows stay local for rays along y / x, partial planes
+    are all-reduced (MaxIP) or the ray state travels up the chain of shards (LMIP, MIDA) for rays
+    along z, and MIDA's extrema are all-reduced over the own planes of the contour volume."""
+    if tmip not in (0, 1, 2):
+        raise ValueError("fast_countour_mip: tmip must be 0, 1 or 2")
+    if tmip == 1 and img_ext.dtype == torch.uint8:
+        raise ValueError("fast_countour_mip: LMIP bounds 700/3033 do not fit uint8")   # the reference panics
+    be = _backend(backend)
+    tmp = shard.interior(be.fcm_volume(img_ext, n, axis)).contiguous()
+    if tmip == 0:
+        return mip(tmp, axis, "max", shard, gather=gather, backend=backend)
+    if tmip == 1:
+        return lmip(tmp, axis, 700, 3033, shard, gather=gather, backend=backend)
+    return mida(tmp, axis, wl, ww, shard, gather=gather, backend=backend)
 
 
 def _floodfill_peer(data_ext, seeds_local, t0, t1, fill, strct, out_ext, shard: ZShard, link: PeerLink):
@@ -784,3 +812,16 @@ def watershed(image_ext, markers_ext, bstruct, algorithm, mg_size, use_ww_wl, wl
     if return_ambiguous:
         return labels, shard.interior(amb), exchanges
     return labels, exchanges
+
+
+def fill_holes_automatically(mask_slab, labels_slab, nlabels, max_size, shard: ZShard, backend=None) -> bool:
+    """fill_holes_automatically (invesalius/data/mask.py:519-562 -> floodfill.rs:51-94) on a
+    Z-sharded mask. labels_slab holds this shard's planes of the label image of the WHOLE mask
+    (uint32 bits in an int32 tensor). The only global quantity is the size of every label: each
+    shard histograms its planes, one all_reduce (uint32 sums wrap like the reference's) makes the
+    sizes global, then every shard rewrites its own voxels. Returns the reference's bool (any label
+    qualified), identical on every rank."""
+    be = _backend(backend)
+    st = be.fh_hist(mask_slab, labels_slab, nlabels)
+    _all_reduce(shard, be.fh_sizes(st), dist.ReduceOp.SUM)
+    return be.fh_apply(st, max_size)

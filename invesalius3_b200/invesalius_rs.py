@@ -208,10 +208,10 @@ def fast_countour_mip(image, n, axis, wl, ww, tmip, out):
     _need3(image, "image")
     suf = _SUFFIX[image.dtype]
     wl, ww = _extract(int(wl), suf), _extract(int(ww), suf)
-    if suf == "f64":
-        raise NotImplementedError("fast_countour_mip: float64 volumes are not supported by the device core")
     if axis > 2 or tmip > 2:
         raise ValueError("fast_countour_mip: axis and tmip must be 0, 1 or 2")
     _need_2d_out(out, image.shape, axis)
+    if suf == "f64" and tmip == 2:
+        raise NotImplementedError("fast_countour_mip: float64 contour-MIDA (float64 output) is not built on the device")
     res = projection.fast_countour_mip(dev.to_device(image), float(n), axis, wl, ww, tmip)
     dev.to_host(res[None], out[None])

@@ -62,15 +62,33 @@ def lmip(image: torch.Tensor, axis: int, tmin, tmax, out: torch.Tensor | None = 
     return out
 
 
+def fcm_volume(image: torch.Tensor, n: float, axis: int) -> torch.Tensor:
+    """The contour volume tmp[z, y, x] = T(calc_fcm_intensity(image, x, y, z, n, dir(axis)))
+    (mips.rs:197-242), same dtype as the image (int16, uint8 or float64)."""
+    _dense(image, "image")
+    if image.dim() != 3:
+        raise TypeError("image must be 3-dimensional")
+    if axis not in (0, 1, 2):
+        raise ValueError("axis must be 0, 1 or 2")
+    tmp = torch.empty_like(image)
+    ws = _workspace(_lib.load().b2v_proj_workspace_bytes(image.numel()), image.device)
+    dz, dy, dx = image.shape
+    with torch.cuda.device(image.device):
+        _lib.call("b2v_fcm_volume", _p(image), dtype_code(image), dz, dy, dx, float(n), axis, _p(tmp), _p(ws), _stream())
+    return tmp
+
+
 def fast_countour_mip(image: torch.Tensor, n: float, axis: int, wl, ww, tmip: int,
                       out: torch.Tensor | None = None) -> torch.Tensor:
-    """mips.rs:215-279 (tmip 0 max, 1 LMIP(700, 3033), 2 MIDA)."""
-    out, ws = _prep(image, axis, out, image.dtype)
+    """mips.rs:215-279 (tmip 0 max, 1 LMIP(700, 3033), 2 MIDA): contour volume, then its projection."""
+    out, _ = _prep(image, axis, out, image.dtype)
     if out.dtype != image.dtype:
         raise TypeError("Invalid image or output type")
     dz, dy, dx = image.shape
+    code = dtype_code(image)
+    ws = _workspace(_lib.load().b2v_fcm_workspace_bytes(code, dz, dy, dx, axis, int(tmip)), image.device)
     with torch.cuda.device(image.device):
-        _lib.call("b2v_fast_countour_mip", _p(image), dtype_code(image), dz, dy, dx, float(n), axis, float(wl),
+        _lib.call("b2v_fast_countour_mip", _p(image), code, dz, dy, dx, float(n), axis, float(wl),
                   float(ww), int(tmip), _p(out), _p(ws), _stream())
     return out
 

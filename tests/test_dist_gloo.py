@@ -142,6 +142,38 @@ class CpuBackend:
     def ff_finish(self, st):
         st["out"][st["reached"]] = st["fill"]
 
+    # ---- contour volume / projections of own planes (rays along y or x ride on the z-ray walkers)
+    def fcm_volume(self, img, n, axis):
+        return torch.from_numpy(self.o.fcm_volume(img.numpy(), n, axis))
+
+    def _as_z(self, img, axis):
+        return img.permute(1, 0, 2).contiguous() if axis == 1 else img.permute(2, 0, 1).contiguous()
+
+    def mida(self, img, axis, wl, ww, minmax):
+        t = self._as_z(img, axis)
+        return self.mida_z(t, wl, ww, minmax, self.ray_state(t), True, True)
+
+    def lmip(self, img, axis, tmin, tmax):
+        t = self._as_z(img, axis)
+        return self.lmip_z(t, tmin, tmax, self.ray_state(t), True, True)
+
+    # ---- fill holes
+    def fh_hist(self, mask, labels, nlabels):
+        sizes = np.bincount(labels.numpy().view(np.uint32).ravel(), minlength=nlabels + 1).astype(np.uint32)
+        return dict(mask=mask, labels=labels, sizes=torch.from_numpy(sizes.view(np.int32).copy()))
+
+    def fh_sizes(self, st):
+        return st["sizes"]
+
+    def fh_apply(self, st, max_size):
+        sizes = st["sizes"].numpy().view(np.uint32)
+        ok = (sizes > 0) & (sizes <= max_size)
+        if not ok.any():
+            return False
+        m = st["mask"].numpy()
+        m[ok[st["labels"].numpy().view(np.uint32)]] = 254
+        return True
+
     # ---- watershed: the NumPy model of the flood (tests/ws_model.py), staged like the C ABI
     def ws_preprocess(self, image_i16, use_ww_wl, wl, ww, global_min=None):
         from oracle import watershed as W
@@ -278,8 +310,8 @@ def rank_contour_mip(rank, world, device):
     be = CpuBackend()
     ext = torch.from_numpy(ext_slab(g, shard).copy())
     res = {}
-    for axis in (1, 2):
-        for tmip in (0, 1):
+    for axis in (0, 1, 2):
+        for tmip in (0, 1, 2):
             res[(axis, tmip)] = d.fast_countour_mip(ext, 2.0, axis, 300, 600, tmip, shard, backend=be).numpy()
     return res
 
@@ -289,7 +321,7 @@ def test_contour_mip_two_ranks(orc):
     out = run_ranks("rank_contour_mip", "test_dist_gloo")
     g = global_volume()
     for (axis, tmip), got in out[0].items():
-        want = np.zeros([None, (g.shape[0], g.shape[2]), (g.shape[0], g.shape[1])][axis], np.int16)
+        want = np.zeros([(g.shape[1], g.shape[2]), (g.shape[0], g.shape[2]), (g.shape[0], g.shape[1])][axis], np.int16)
         orc.fast_countour_mip(g, 2.0, axis, 300, 600, tmip, want)
         assert np.array_equal(got, want), (axis, tmip)
         assert np.array_equal(out[1][(axis, tmip)], want), (axis, tmip)
@@ -332,19 +364,17 @@ def test_mida_lmip_along_z_three_ranks(orc):
             assert np.array_equal(out[r][key], want), (key, r)
 
 
-def test_contour_mip_three_ranks_and_unsupported_modes(orc):
+def test_contour_mip_three_ranks(orc):
     out = run_ranks("rank_contour_mip", "test_dist_gloo", world=3)
     g = global_volume()
     for (axis, tmip), got in out[1].items():   # the middle shard has a halo plane on both sides
-        want = np.zeros([None, (g.shape[0], g.shape[2]), (g.shape[0], g.shape[1])][axis], np.int16)
+        want = np.zeros([(g.shape[1], g.shape[2]), (g.shape[0], g.shape[2]), (g.shape[0], g.shape[1])][axis], np.int16)
         orc.fast_countour_mip(g, 2.0, axis, 300, 600, tmip, want)
         assert np.array_equal(got, want), (axis, tmip)
     from invesalius3_b200 import dist as d
-    shard = d.ZShard(g.shape[0], 0, 1)
-    with pytest.raises(NotImplementedError):
-        d.fast_countour_mip(torch.zeros((4, 4, 4), dtype=torch.int16), 2.0, 0, 300, 600, 0, shard, backend=CpuBackend())
-    with pytest.raises(NotImplementedError):
-        d.fast_countour_mip(torch.zeros((4, 4, 4), dtype=torch.int16), 2.0, 1, 300, 600, 2, shard, backend=CpuBackend())
+    shard = d.ZShard(4, 0, 1)
+    with pytest.raises(ValueError):    # LMIP bounds 700 / 3033 do not fit uint8: the reference panics
+        d.fast_countour_mip(torch.zeros((4, 4, 4), dtype=torch.uint8), 2.0, 1, 30, 60, 1, shard, backend=CpuBackend())
 
 
 def ff_cases(g):
@@ -459,3 +489,37 @@ def test_watershed_ranks(orc, world):
             assert np.array_equal(amb, want_amb), (alg, ww_wl)
             assert len({out[r][(alg, ww_wl)][2] for r in range(world)}) == 1      # every rank saw the same exchanges
             assert out[0][(alg, ww_wl)][2] >= 3                                    # labels did cross the boundary
+
+
+# ---- fill holes over Z shards: one all_reduce of the label sizes
+def fh_case():
+    from scipy import ndimage
+    rng = np.random.default_rng(11)
+    mask = (ndimage.gaussian_filter(rng.normal(size=(23, 20, 45)), 1.0) > 0.02).astype(np.uint8) * 255
+    labels, nlabels = ndimage.label(mask == 0, ndimage.generate_binary_structure(3, 1), output=np.uint32)
+    return mask, labels, int(nlabels)
+
+
+def rank_fill_holes(rank, world, device):
+    d, _, _ = _setup(rank, world)
+    mask, labels, nlabels = fh_case()
+    shard = d.ZShard(mask.shape[0], rank, world)
+    res = {}
+    for max_size in (0, 5, 40, 10 ** 6):
+        m = torch.from_numpy(mask[shard.z0:shard.z1].copy())
+        lab = torch.from_numpy(labels[shard.z0:shard.z1].view(np.int32).copy())
+        ret = d.fill_holes_automatically(m, lab, nlabels, max_size, shard, backend=CpuBackend())
+        res[max_size] = (ret, m.numpy().copy())
+    return res
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fill_holes_ranks(orc, world):
+    out = run_ranks("rank_fill_holes", "test_dist_gloo", world=world)
+    mask, labels, nlabels = fh_case()
+    for max_size in (0, 5, 40, 10 ** 6):
+        want = mask.copy()
+        ret = orc.fill_holes_automatically(want, labels, nlabels, max_size)
+        got = np.concatenate([out[r][max_size][1] for r in range(world)])
+        assert np.array_equal(got, want), max_size
+        assert all(out[r][max_size][0] == ret for r in range(world)), max_size

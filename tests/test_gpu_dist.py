@@ -33,9 +33,18 @@ def rank_all(rank, world, device):
         res[("lmip", axis)] = d.lmip(own, axis, 700, 3033, shard).cpu().numpy()
     # contour-MIP on the extended slab (n = 1: the power is exact, so the result is bit-exact)
     ext = torch.from_numpy(ext_slab(g, shard).copy()).to(_dev())
-    for axis in (1, 2):
-        for tmip in (0, 1):
+    for axis in (0, 1, 2):   # axis 0: rays cross the shards; tmip 2: extrema of the contour volume all-reduced
+        for tmip in (0, 1, 2):
             res[("fcm", axis, tmip)] = d.fast_countour_mip(ext, 1.0, axis, 300, 600, tmip, shard).cpu().numpy()
+    # fill holes: labels of the whole mask, sizes summed over the shards
+    from scipy import ndimage
+    hm = (g > 600).astype(np.uint8) * 255
+    lab, nlab = ndimage.label(hm == 0, ndimage.generate_binary_structure(3, 1), output=np.uint32)
+    for max_size in (3, 50):
+        m = torch.from_numpy(hm[shard.z0:shard.z1].copy()).to(_dev())
+        lt = torch.from_numpy(lab[shard.z0:shard.z1].view(np.int32).copy()).to(_dev())
+        ret = d.fill_holes_automatically(m, lt, int(nlab), max_size, shard)
+        res[("fh", max_size)] = (ret, m.cpu().numpy())
     # flood fill
     for ci, (strct, seeds) in enumerate(ff_cases(g)):
         data = torch.from_numpy(ext_slab(g, shard)).to(_dev())
@@ -79,13 +88,21 @@ def _check(out, orc):
             assert np.array_equal(out[rank][("mida", axis)], want), ("mida", rank, axis)
             orc.lmip(g, axis, 700, 3033, want)
             assert np.array_equal(out[rank][("lmip", axis)], want), ("lmip", rank, axis)
-            for tmip in ((0, 1) if axis else ()):
+            for tmip in (0, 1, 2):
                 orc.fast_countour_mip(g, 1.0, axis, 300, 600, tmip, want)
                 assert np.array_equal(out[rank][("fcm", axis, tmip)], want), ("fcm", rank, axis, tmip)
         z0, z1, m = out[rank]["thr"]
         want = np.zeros(g.shape, np.uint8)
         orc.threshold(g, *THR, want, False)
         assert np.array_equal(m, want[z0:z1])
+    from scipy import ndimage
+    hm = (g > 600).astype(np.uint8) * 255
+    lab, nlab = ndimage.label(hm == 0, ndimage.generate_binary_structure(3, 1), output=np.uint32)
+    for max_size in (3, 50):
+        want = hm.copy()
+        ret = orc.fill_holes_automatically(want, lab, int(nlab), max_size)
+        assert np.array_equal(np.concatenate([out[r][("fh", max_size)][1] for r in (0, 1)]), want), max_size
+        assert out[0][("fh", max_size)][0] == out[1][("fh", max_size)][0] == ret
     for ci, (strct, seeds) in enumerate(ff_cases(g)):
         want = np.zeros(g.shape, np.uint8); want[:, 10, :] = 254
         orc.floodfill_threshold(g, seeds, 100, 3071, 254, strct, want)

@@ -127,6 +127,29 @@ def test_fast_countour_mip_n1_exact(rs, orc):
         rs.fast_countour_mip(u8, 1.0, 0, 100, 50, 1, got)  # 700 does not fit u8: reference panics
 
 
+def test_fcm_volume_and_float64(rs, orc):
+    """The contour volume itself (mips.rs:236-242) against the oracle's, every dtype the reference
+    dispatches (int16, uint8, float64), shapes with partial 64 x 8 columns and a single plane; the
+    float64 projections (mips_py.rs:240-251) for tmip 0 / 1."""
+    import torch
+    from invesalius3_b200 import projection
+    for shape in ((20, 33, 47), (1, 9, 70), (5, 8, 64), (3, 70, 5)):
+        img = _ct_like(shape, 9)
+        for a in (img, (img // 16 + 64).clip(0, 255).astype(np.uint8), img.astype(np.float64) * 0.37):
+            for axis in (0, 1, 2):
+                got = projection.fcm_volume(torch.from_numpy(a).cuda(), 1.0, axis).cpu().numpy()
+                assert np.array_equal(got, orc.fcm_volume(a, 1.0, axis)), (shape, a.dtype, axis)
+    f = _ct_like((20, 33, 47), 6).astype(np.float64) * 0.75
+    for axis in (0, 1, 2):
+        for tmip in (0, 1):
+            want = np.zeros(_oshape(f.shape, axis), np.float64); got = want.copy()
+            orc.fast_countour_mip(f, 1.0, axis, 300, 300, tmip, want)
+            rs.fast_countour_mip(f, 1.0, axis, 300, 300, tmip, got)
+            assert np.array_equal(got, want), (axis, tmip)
+    with pytest.raises(NotImplementedError):
+        rs.fast_countour_mip(f, 1.0, 0, 300, 300, 2, np.zeros(_oshape(f.shape, 0), np.float64))
+
+
 def test_mida_1024_slab_properties():
     """Large input: MIDA of a volume whose rays all saturate in the first slice equals that slice."""
     import torch
