@@ -311,6 +311,14 @@ def extra_results(peak):
             ms = timeit(lambda: projection.mida(vol, axis, 32000, 2, out=o), iters=3)
             res[f"mida_fullrays_1024_axis{axis}"] = {"ms": round(ms, 4), "GBs": round(4 * N / ms / 1e6, 1),
                                                       "frac": round(4 * N / ms / 1e6 / peak, 4)}
+        # contour-MIP (n = 2): contour volume (2 B read + 2 B written per voxel) + projection of it (2 B/voxel)
+        for tmip, name in ((0, "max"), (2, "mida")):
+            for axis in (0, 2):
+                o = projection.fast_countour_mip(vol, 2.0, axis, 300, 300, tmip)
+                ms = timeit(lambda: projection.fast_countour_mip(vol, 2.0, axis, 300, 300, tmip, out=o), iters=3)
+                res[f"contour_{name}_1024_axis{axis}"] = {"ms": round(ms, 4), "GBs_2B_per_voxel": round(2 * N / ms / 1e6, 1),
+                                                          "frac_2B_per_voxel": round(2 * N / ms / 1e6 / peak, 4),
+                                                          "frac_moved_bytes": round((6 if tmip == 0 else 8) * N / ms / 1e6 / peak, 4)}
         del vol
         torch.cuda.empty_cache()
     except Exception as e:   # noqa: BLE001

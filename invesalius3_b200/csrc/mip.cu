@@ -353,10 +353,59 @@ int run_mip(const T* img, int64_t dz, int64_t dy, int64_t dx, int axis, int kind
   }
 }
 
+// ---- float64 volumes (the third dtype invesalius_rs dispatches, types.rs:5-70): MaxIP / MinIP
+// with NumPy's NaN propagation. 8 B/voxel; one thread per output pixel (rays along z / y: coalesced
+// over x) or one warp per row (rays along x).
+__device__ __forceinline__ double pick_f64(double a, double b, bool want_max) {
+  if (a != a) return a;
+  if (b != b) return b;
+  return want_max ? (a > b ? a : b) : (a < b ? a : b);
+}
+
+__global__ void __launch_bounds__(256) k_mip_f64_keepx(const double* __restrict__ img, KeepX g, int want_max,
+                                                       double* __restrict__ out) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t o = blockIdx.y;
+  if (x >= g.nx) return;
+  const double* p = img + o * g.so + x;
+  double acc = p[0];
+  for (int64_t r = 1; r < g.nr; ++r) acc = pick_f64(acc, p[r * g.sr], want_max != 0);
+  out[o * g.nx + x] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_mip_f64_alongx(const double* __restrict__ img, int64_t nrows, int64_t nx,
+                                                        int want_max, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrows; row += nwarps) {
+    const double* p = img + row * nx;
+    double acc = p[lane < nx ? lane : 0];
+    for (int64_t x = lane + 32; x < nx; x += 32) acc = pick_f64(acc, p[x], want_max != 0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = pick_f64(acc, __shfl_xor_sync(0xffffffffu, acc, o), want_max != 0);
+    if (lane == 0) out[row] = acc;
+  }
+}
+
+int run_mip_f64(const double* img, int64_t dz, int64_t dy, int64_t dx, int axis, int kind, double* out, cudaStream_t st) {
+  B2V_REQUIRE(kind == KMAX || kind == KMIN, B2V_ERR_ARG, "mip: MeanIP of a float64 volume is not built (NumPy sums pairwise)");
+  if (axis == 2) {
+    int64_t blocks = ceil_div64(dz * dy, 8);
+    int64_t cap = (int64_t)b2v_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_mip_f64_alongx<<<(unsigned)blocks, 256, 0, st>>>(img, dz * dy, dx, kind == KMAX, out);
+    return b2v_check_launch("k_mip_f64_alongx");
+  }
+  KeepX g = keepx_geom(dz, dy, dx, axis);
+  B2V_REQUIRE(g.no <= 65535, B2V_ERR_ARG, "mip: more than 65535 slices along the kept axis");
+  k_mip_f64_keepx<<<dim3((unsigned)ceil_div64(g.nx, 256), (unsigned)g.no), 256, 0, st>>>(img, g, kind == KMAX, out);
+  return b2v_check_launch("k_mip_f64_keepx");
+}
+
 }  // namespace
 
 extern "C" int64_t b2v_mip_workspace_bytes(int dtype, int64_t dz, int64_t dy, int64_t dx, int axis, int kind) {
-  if (axis == 2 || axis < 0 || dz <= 0 || dy <= 0 || dx <= 0) return 0;
+  if (axis == 2 || axis < 0 || dz <= 0 || dy <= 0 || dx <= 0 || dtype == B2V_F64) return 0;
   KeepX g = keepx_geom(dz, dy, dx, axis);
   int S = keepx_splits(g);
   if (S == 1) return 0;
@@ -373,5 +422,6 @@ extern "C" int b2v_mip(const void* img, int dtype, int64_t dz, int64_t dy, int64
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2V_I16) return run_mip<int16_t>((const int16_t*)img, dz, dy, dx, axis, kind, out, workspace, st);
   if (dtype == B2V_U8) return run_mip<uint8_t>((const uint8_t*)img, dz, dy, dx, axis, kind, out, workspace, st);
-  B2V_REQUIRE(false, B2V_ERR_ARG, "mip: dtype code %d not supported (int16, uint8)", dtype);
+  if (dtype == B2V_F64) return run_mip_f64((const double*)img, dz, dy, dx, axis, kind, (double*)out, st);
+  B2V_REQUIRE(false, B2V_ERR_ARG, "mip: dtype code %d not supported (int16, uint8, float64)", dtype);
 }

@@ -603,9 +603,10 @@ extern "C" int b2v_lmip(const void* img, int dtype, int64_t dz, int64_t dy, int6
 // z neighbours of a voxel are the thread's own previous / next values (registers). Central
 // differences clamp at the volume faces exactly as finite_difference does (mips.rs:182-187).
 constexpr int kFcmX = 64, kFcmY = 8, kFcmThreads = kFcmX * kFcmY;
+constexpr int kFcmAhead = 2;   // planes in flight per block
 
 template <typename T>
-__global__ void __launch_bounds__(kFcmThreads) k_fcm_volume(const T* __restrict__ vol, Dims d, float n, float dirx,
+__global__ void __launch_bounds__(kFcmThreads, 3) k_fcm_volume(const T* __restrict__ vol, Dims d, float n, float dirx,
                                                            float diry, float dirz, int zchunk, T* __restrict__ out,
                                                            int* status) {
   __shared__ T s[2][kFcmY + 2][kFcmX + 2];
@@ -627,17 +628,35 @@ __global__ void __launch_bounds__(kFcmThreads) k_fcm_volume(const T* __restrict_
   gx = gx < 0 ? 0 : (gx > d.nx - 1 ? d.nx - 1 : gx);
   const int64_t plane = d.ny * d.nx;
   const int64_t own = cy * d.nx + cx, hal = gy * d.nx + gx;
+  // software pipeline: planes z + 1 .. z + kFcmAhead travel in registers (own voxel + halo cell of
+  // each); the loads of plane z + kFcmAhead + 1 are issued before plane z is differentiated. The
+  // kernel is bound by instruction issue (IEEE sqrt and division per sample: ~75 instructions per
+  // voxel), not by bandwidth: pointers advance by one plane per step, no 64-bit products in the loop.
   T prev = vol[(z0 > 0 ? z0 - 1 : 0) * plane + own];
   T cur = vol[z0 * plane + own];
+  T pf[kFcmAhead], hpf[kFcmAhead];
+  int64_t zl = z0;                               // plane the read pointers stand on
+  const T* p_own = vol + z0 * plane + own;
+  const T* p_hal = vol + z0 * plane + hal;
+  auto advance = [&]() { if (zl + 1 < d.nz) { ++zl; p_own += plane; p_hal += plane; } };   // clamps at the last plane
+#pragma unroll
+  for (int k = 0; k < kFcmAhead; ++k) {
+    advance();
+    pf[k] = *p_own;
+    hpf[k] = 0;
+    if (hy >= 0) hpf[k] = *p_hal;
+  }
   int b = 0;
   s[0][ty + 1][tx + 1] = cur;
   if (hy >= 0) s[0][hy][hx] = vol[z0 * plane + hal];
   __syncthreads();
-  for (int64_t z = z0; z < z1; ++z) {
-    const int64_t zn = z + 1 < d.nz ? z + 1 : d.nz - 1;
-    const T nxt = vol[zn * plane + own];
-    T hv = 0;
-    if (hy >= 0) hv = vol[zn * plane + hal];
+  T* p_out = out + z0 * plane + y * d.nx + x;
+  for (int64_t z = z0; z < z1; ++z, p_out += plane) {
+    advance();
+    const T nn = *p_own;
+    T hnn = 0;
+    if (hy >= 0) hnn = *p_hal;
+    const T nxt = pf[0];
     if (active) {
       const float gxf = __fmul_rn(wrapdiff<T>(s[b][ty + 1][tx + 2], s[b][ty + 1][tx]), 0.5f);   // / (2.0 * h), h = 1
       const float gyf = __fmul_rn(wrapdiff<T>(s[b][ty + 2][tx + 1], s[b][ty][tx + 1]), 0.5f);
@@ -654,14 +673,18 @@ __global__ void __launch_bounds__(kFcmThreads) k_fcm_volume(const T* __restrict_
       }
       T o = 0;
       if (!cast_f32<T>(val, &o)) *status = B2V_ERR_RANGE;
-      out[z * plane + y * d.nx + x] = o;
+      *p_out = o;
     }
     s[b ^ 1][ty + 1][tx + 1] = nxt;
-    if (hy >= 0) s[b ^ 1][hy][hx] = hv;
+    if (hy >= 0) s[b ^ 1][hy][hx] = hpf[0];
     __syncthreads();
     b ^= 1;
-    prev = z + 1 < d.nz ? cur : prev;   // unused past the last plane
+    prev = cur;
     cur = nxt;
+#pragma unroll
+    for (int k = 0; k + 1 < kFcmAhead; ++k) { pf[k] = pf[k + 1]; hpf[k] = hpf[k + 1]; }
+    pf[kFcmAhead - 1] = nn;
+    hpf[kFcmAhead - 1] = hnn;
   }
 }
 
@@ -669,7 +692,7 @@ template <typename T>
 int launch_fcm_volume(const T* img, Dims d, float n, int axis, T* tmp, int* status, cudaStream_t s) {
   const int64_t gx = ceil_div64(d.nx, kFcmX), gy = ceil_div64(d.ny, kFcmY);
   B2V_REQUIRE(gy <= 65535, B2V_ERR_ARG, "fcm_volume: more than 524280 rows");
-  int64_t nchunk = ceil_div64((int64_t)b2v_sm_count() * 4, gx * gy);
+  int64_t nchunk = ceil_div64((int64_t)b2v_sm_count() * 4 * 16, gx * gy);   // >= 16 waves of blocks: short tail
   if (nchunk < 1) nchunk = 1;
   if (nchunk > d.nz) nchunk = d.nz;
   const int zchunk = (int)ceil_div64(d.nz, nchunk);
