@@ -215,3 +215,48 @@ def fast_countour_mip(image, n, axis, wl, ww, tmip, out):
         raise NotImplementedError("fast_countour_mip: float64 contour-MIDA (float64 output) is not built on the device")
     res = projection.fast_countour_mip(dev.to_device(image), float(n), axis, wl, ww, tmip)
     dev.to_host(res[None], out[None])
+
+
+# ---- the rest of the crate's surface (invesalius_rs/__init__.py:273-300) ---------------------------
+# The functions above replace the hot path. Everything else the reference imports from
+# `invesalius_rs` under its other aliases (`import invesalius_rs as transforms / cy_mesh / ...`:
+# interpolation, apply_view_matrix_transform, convolve_non_zero, mask_cut, polygon2mask_rs,
+# brush_mask_rs, Mesh, ca_smoothing, count_regions, jump_flooding, floodfill_voronoi,
+# floodfill_auto_threshold) is forwarded, on first use, to the compiled crate installed beside this
+# package — so binding this module under every alias keeps the rest of InVesalius working. Without
+# the crate the attribute error says which name is missing and why.
+FORWARDED = (
+    "trilin_interpolate_py", "nearest_neighbour_interp", "tricub_interpolate_py", "tricub_interpolate2_py",
+    "lanczos_interpolate_py", "floodfill_auto_threshold", "floodfill_voronoi", "jump_flooding",
+    "apply_view_matrix_transform", "convolve_non_zero", "mask_cut", "polygon2mask_rs", "brush_mask_rs", "Mesh",
+    "ca_smoothing", "count_regions", "_native",
+)
+
+__all__ = ["floodfill", "floodfill_threshold", "floodfill_threshold_inplace", "fill_holes_automatically", "mida", "lmip",
+           "fast_countour_mip", *[n for n in FORWARDED if not n.startswith("_")]]
+
+_crate = None
+
+
+def _load_crate():
+    global _crate
+    if _crate is None:
+        import importlib
+        try:
+            mod = importlib.import_module("invesalius_rs")     # the reference's own package (top level)
+        except ImportError as e:
+            raise ImportError("the compiled invesalius_rs crate is not installed: only the hot path "
+                              f"({', '.join(__all__[:7])}) is provided by invesalius3_b200") from e
+        if mod is globals().get("__spec__") or getattr(mod, "__file__", None) == __file__:
+            raise ImportError("invesalius_rs resolves to this shim; install the reference crate under its own name")
+        _crate = mod
+    return _crate
+
+
+def __getattr__(name):
+    if name in FORWARDED:
+        try:
+            return getattr(_load_crate(), name)
+        except ImportError as e:
+            raise AttributeError(f"invesalius3_b200.invesalius_rs.{name}: {e}") from e
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

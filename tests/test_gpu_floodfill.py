@@ -260,6 +260,29 @@ def test_floodfill_512_properties(rs):
     assert torch.equal(out, out2)
 
 
+def test_floodfill_and_surface_full_size_exact(rs, orc):
+    """Full-size volume (a 256 x 512 x 512 half of BASELINE config 2) against the serial CPU checker,
+    exactly: the grown mask for 6- and 26-connectivity, and the mesh contoured from it (triangle
+    indices bit for bit, vertices equal)."""
+    import torch
+    from invesalius3_b200 import device as dev, phantom
+    from invesalius3_b200.mesh import marching_cubes
+    vol = phantom.ct((256, 512, 512), seed=2)
+    seed = phantom.first_seed_in_range(vol, 128, 226, 3071)
+    t = torch.from_numpy(vol).cuda()
+    for conn in (1, 3):
+        st = generate_binary_structure(3, conn)
+        out = torch.zeros(vol.shape, dtype=torch.uint8, device="cuda")
+        dev.floodfill_threshold(t, [seed], 226, 3071, 254, st, out)
+        want = np.zeros(vol.shape, np.uint8)
+        orc.floodfill_threshold(vol, [seed], 226, 3071, 254, st, want)
+        assert np.array_equal(out.cpu().numpy(), want), conn
+        if conn == 1:
+            v, f = marching_cubes(out, 127, (1.0, 1.0, 1.0), (0, 0, 0), True)
+            vo, fo = orc.marching_cubes(want, 127, (1.0, 1.0, 1.0), (0, 0, 0), True)
+            assert np.array_equal(f.cpu().numpy(), fo) and np.array_equal(v.cpu().numpy(), vo)
+
+
 def test_floodfill_wide_rows_many_x_tiles(rs, orc):
     """2048-wide rows (BASELINE config 5 geometry): 64 words per row = 4 tiles along x."""
     rng = np.random.default_rng(12)

@@ -111,6 +111,51 @@ def test_contour_piece_matches_reference_pipeline(sp, orc):
             assert np.array_equal(F, np.concatenate([F1, F2 + len(V1)]))
 
 
+def _piece_worker(args):
+    """Runs in a SPAWNED process, like the reference's surface workers (surface.py:1368-1369)."""
+    from invesalius3_b200 import surface_process
+    return surface_process.create_surface_piece(*args)
+
+
+def test_create_surface_piece_in_spawned_workers(sp, orc, tmp_path):
+    """The reference's own entry (20 arguments in, .vtp file name out; surface_process.py:71-201) over
+    the piece loop of SurfaceManager.AddNewActor (surface.py:1360-1381), each piece in a spawned
+    process: the files hold exactly the meshes of contour_piece / the oracle."""
+    import multiprocessing as mp
+    rng = np.random.default_rng(12)
+    dz, dy, dx = 45, 24, 40
+    body = (ndimage.gaussian_filter(rng.normal(size=(dz, dy, dx)), 1.3) > 0).astype(np.uint8) * 255
+    img = (ndimage.gaussian_filter(rng.normal(size=(dz, dy, dx)), 1.3) * 3000).astype(np.int16)
+    img_fn, mask_fn = str(tmp_path / "matrix.dat"), str(tmp_path / "mask.dat")
+    np.memmap(img_fn, mode="w+", dtype=np.int16, shape=img.shape)[:] = img
+    mm = np.memmap(mask_fn, mode="w+", dtype=np.uint8, shape=(dz + 1, dy + 1, dx + 1))
+    mm[:] = 0
+    mm[1:, 1:, 1:] = body
+    mm.flush()
+    spacing = (0.9570312, 0.9570312, 1.5)
+    piece_size, o_piece = 20, 1
+    n_pieces = int(round(dz / piece_size + 0.5))
+    rois = [slice(i * piece_size, (i + 1) * piece_size + o_piece) for i in range(n_pieces)]
+    jobs = []
+    for from_binary in (True, False):
+        for roi in rois:
+            jobs.append((img_fn, img.shape, "int16", mask_fn, (dz + 1, dy + 1, dx + 1), "uint8", roi, spacing, "CONTOUR", 226,
+                         3071, 0.0, 0.0, 0, "en", False, from_binary, "Default", 0, True))
+    with mp.get_context("spawn").Pool(2) as pool:
+        names = pool.map(_piece_worker, jobs)
+    for job, fn in zip(jobs, names):
+        roi, from_binary = job[6], job[16]
+        assert fn.endswith("_%d_%d.vtp" % (roi.start, roi.stop))
+        V, F = sp.read_vtp(fn)
+        Vw, Fw = sp.contour_piece(img, mm, roi, spacing, 226, 3071, from_binary=from_binary, fill_border_holes=True,
+                                  index_dtype=np.int64)
+        assert np.array_equal(V, Vw) and np.array_equal(F, Fw), (roi, from_binary)
+        import os
+        os.unlink(fn)
+    with pytest.raises(NotImplementedError):
+        sp.create_surface_piece(*(jobs[-1][:17] + ("InVesalius 3.b2",) + jobs[-1][18:]))
+
+
 def test_mc_512_properties(sp):
     """BASELINE config-2 size, properties only: closed oriented manifold (the padded phantom
     mask does not touch the border), counts consistent, every index used."""
@@ -170,3 +215,18 @@ def test_mc_config5_shard_properties(sp):
     assert torch.unique(key).numel() == key.numel()
     assert torch.equal(torch.sort(key).values, torch.sort(rkey).values)
     assert bool(torch.isfinite(V).all())
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_cranium_surface_matches_checker_and_envelope(sp, orc, cranium, i):
+    """The reference's own Cranium masks (bit-packed golden): the device mesh equals the CPU checker's
+    bit for bit and encloses the volume the reference recorded for its surface to within 2 %."""
+    from test_oracle_mc import cranium_mask, mesh_volume_area
+    sx, sy, sz = (float(v) for v in cranium["spacing"])
+    pad = cranium_mask(cranium, i)
+    V, F = sp.contour(pad, 127, (sx, sy, sz), 0, True, padding=(1, 1, 1))
+    Vo, Fo = orc.marching_cubes(pad, 127, (sx, sy, sz), (-1, -1, -1), True)
+    assert np.array_equal(F, Fo) and np.array_equal(V, Vo)
+    vol, _ = mesh_volume_area(V, F.astype(np.int64))
+    want = float(cranium[f"surface_{i}_volume_mm3"])
+    assert abs(vol - want) / want < 0.02, (vol, want)

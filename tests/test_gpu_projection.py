@@ -249,3 +249,19 @@ def test_rays_along_z_in_stretches(rs, orc, dtype):
         if not np.array_equal(got.cpu().numpy(), want):
             bad.append(("lmip", tmin, tmax, int((got.cpu().numpy() != want).sum())))
     assert not bad, bad
+
+
+def test_projections_1024_slab_exact(orc):
+    """One 64-plane slab of BASELINE config 3 (64 x 1024 x 1024) against the CPU checker / NumPy,
+    exactly: MaxIP on the three axes, MIDA and LMIP with rays along every axis."""
+    import torch
+    from invesalius3_b200 import device as dev, phantom, projection
+    vol = phantom.ct((64, 1024, 1024), seed=3)
+    t = torch.from_numpy(vol).cuda()
+    for axis in (0, 1, 2):
+        assert np.array_equal(dev.mip(t, axis, "max").cpu().numpy(), vol.max(axis)), axis
+        want = np.zeros(_oshape(vol.shape, axis), np.int16)
+        orc.mida(vol, axis, 300, 300, want)
+        assert np.array_equal(projection.mida(t, axis, 300, 300).cpu().numpy(), want), ("mida", axis)
+        orc.lmip(vol, axis, 700, 3033, want)
+        assert np.array_equal(projection.lmip(t, axis, 700, 3033).cpu().numpy(), want), ("lmip", axis)

@@ -86,3 +86,55 @@ def test_phantom_is_shard_consistent():
     assert a.dtype == np.int16 and a.min() >= -1024 and a.max() <= 3071
     assert np.array_equal(phantom.ct((20, 24, 28), seed=5, zrange=(7, 13)), a[7:13])
     assert not np.array_equal(phantom.ct((20, 24, 28), seed=6), a)
+
+
+def test_vtp_round_trip_and_layout(tmp_path):
+    """write_vtp emits what vtkXMLPolyDataWriter would for a triangle mesh (Points + Polys with
+    connectivity / offsets, inline base64 with UInt32 byte counts); read_vtp inverts it."""
+    import base64
+    import xml.etree.ElementTree as ET
+    from invesalius3_b200 import surface_process as sp
+    rng = np.random.default_rng(0)
+    v = rng.normal(size=(11, 3)).astype(np.float32)
+    for dt in (np.int32, np.int64):
+        f = rng.integers(0, 11, (7, 3)).astype(dt)
+        fn = str(tmp_path / f"m_{np.dtype(dt).name}.vtp")
+        sp.write_vtp(fn, v, f)
+        v2, f2 = sp.read_vtp(fn)
+        assert np.array_equal(v, v2) and np.array_equal(f, f2) and f2.dtype == dt
+        root = ET.parse(fn).getroot()
+        assert root.tag == "VTKFile" and root.get("type") == "PolyData" and root.get("byte_order") == "LittleEndian"
+        piece = root.find("PolyData").find("Piece")
+        assert piece.get("NumberOfPoints") == "11" and piece.get("NumberOfPolys") == "7"
+        offs = [d for d in piece.find("Polys").findall("DataArray") if d.get("Name") == "offsets"][0]
+        raw = base64.b64decode(offs.text.strip())
+        assert int(np.frombuffer(raw[:4], np.uint32)[0]) == 7 * np.dtype(dt).itemsize
+        assert np.array_equal(np.frombuffer(raw[4:], dt), np.arange(1, 8) * 3)
+    sp.write_vtp(str(tmp_path / "empty.vtp"), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int64))
+    v0, f0 = sp.read_vtp(str(tmp_path / "empty.vtp"))
+    assert v0.shape == (0, 3) and f0.shape == (0, 3)
+
+
+def test_non_hot_exports_are_forwarded_to_the_crate(monkeypatch):
+    """invesalius_rs/__init__.py:273-300: names outside the hot path resolve to the reference crate
+    when it is installed, and fail with a message naming the reason when it is not."""
+    import sys
+    import types
+    from invesalius3_b200 import invesalius_rs as rs
+    monkeypatch.setattr(rs, "_crate", None)
+    monkeypatch.delitem(sys.modules, "invesalius_rs", raising=False)
+    with pytest.raises(AttributeError, match="crate is not installed"):
+        rs.Mesh
+    with pytest.raises(AttributeError):
+        rs.no_such_symbol
+    fake = types.ModuleType("invesalius_rs")
+    fake.__file__ = "/somewhere/invesalius_rs/__init__.py"
+    fake.count_regions = lambda image, n: ("crate", n)
+    fake.Mesh = type("Mesh", (), {})
+    monkeypatch.setitem(sys.modules, "invesalius_rs", fake)
+    assert rs.count_regions(None, 4) == ("crate", 4) and rs.Mesh is fake.Mesh
+    for name in ("floodfill", "floodfill_threshold", "floodfill_threshold_inplace", "fill_holes_automatically", "mida",
+                 "lmip", "fast_countour_mip"):
+        assert callable(getattr(rs, name)) and getattr(rs, name).__module__ == rs.__name__   # hot path: ours
+    assert set(rs.FORWARDED) >= {"apply_view_matrix_transform", "convolve_non_zero", "mask_cut", "polygon2mask_rs",
+                                 "brush_mask_rs", "Mesh", "ca_smoothing", "count_regions"}

@@ -46,6 +46,14 @@ def main():
         # per-slice counts pin the whole volume without shipping it
         out[f"mask_{i}_slice_counts"] = (body == 255).sum(axis=(1, 2)).astype(np.int64)
     out["matrix_slice_sums"] = matrix.astype(np.int64).sum(axis=(1, 2))
+    # the two WHOLE reference masks, bit-packed (the marching-cubes envelope check contours them), and
+    # what the reference recorded for the surfaces it built from them (surface_N.plist: volume in mm^3
+    # of the smoothed / decimated mesh shipped in the project — an envelope, not a golden mesh)
+    with tarfile.open(SRC, "r:*") as tf:
+        files = {Path(m.name).name: tf.extractfile(m).read() for m in tf.getmembers() if m.isfile()}
+    for i, (thr, m) in enumerate(masks):
+        out[f"mask_{i}_bits_full"] = np.packbits(m[1:, 1:, 1:] == 255)
+        out[f"surface_{i}_volume_mm3"] = np.array(float(plistlib.loads(files[f"surface_{i}.plist"])["volume"]))
     np.savez_compressed(DST, **out)
     print(DST, DST.stat().st_size, {k: v.shape for k, v in out.items()})
 
