@@ -461,6 +461,15 @@ def run_gpu(args):
     e2e_min = {}
     e2e_calls = {"set_mask_threshold": 0.0, "zero_out_mask": 0.0, "floodfill_threshold": 0.0, "contour": 0.0}
 
+    def step_e2e_session():
+        """The same action through the device-resident session (image uploaded once, results into
+        the same pinned host arrays)."""
+        from invesalius3_b200.session import VolumeSession
+        with VolumeSession(np_vol) as s:
+            s.set_mask_threshold(np_mask, THR)
+            s.floodfill_threshold([gseed], THR[0], THR[1], FILL, strct, np_out)
+            return s.contour([127], SPACING, 0, True)
+
     def step_e2e():
         if world == 1:
             t0 = time.perf_counter()
@@ -637,6 +646,21 @@ def run_gpu(args):
         v, f = step_e2e()
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    sess = None
+    if world == 1:
+        vs, fs = step_e2e_session()
+        vs, fs = step_e2e_session()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            vs, fs = step_e2e_session()
+        torch.cuda.synchronize()
+        sess_s = (time.perf_counter() - t0) / e2e_steps
+        same = bool(vs.shape == v.shape and fs.shape == f.shape and np.array_equal(fs, f) and np.array_equal(vs, v))
+        sess = {"value": round(N / sess_s / 1e6, 1), "unit": UNIT, "ms_per_step": round(sess_s * 1e3, 3),
+                "h2d_bytes_per_step": int(2 * N), "d2h_bytes_per_step": int(2 * N + vs.nbytes + fs.nbytes),
+                "same_results_as_numpy_api": same,
+                "api": "session.VolumeSession: image uploaded once per step, mask / grown mask / mesh read back"}
     if world == 1:
         h2d = 2 * N * 2 + 2 * N            # image twice (threshold, flood fill), out in, out again for MC
     else:
@@ -688,7 +712,8 @@ def run_gpu(args):
                 "ms_per_call_min": {k: round(v * 1e3, 3) for k, v in e2e_min.items()} if world == 1 else None,
                 "api": ("slice_ops.set_mask_threshold + invesalius_rs.floodfill_threshold + surface_process.contour "
                         "on pinned numpy buffers (image uploaded by each call, as the numpy API implies)") if world == 1 else
-                       "dist.* sharded pipeline fed from / drained to pinned host buffers (image uploaded once per step)"},
+                       "dist.* sharded pipeline fed from / drained to pinned host buffers (image uploaded once per step)",
+                "session": sess},
         "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak,
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                      "traffic_source": traffic_src,

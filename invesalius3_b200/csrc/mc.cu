@@ -576,6 +576,10 @@ __global__ void __launch_bounds__(kTileThreads) k_mc_emit_verts(const T* __restr
 //   (y+1, z+1): 3 (x@i)
 // All twelve ids go to shared memory ([edge][thread]; the ones of non-crossing edges are never
 // read) and every triangle corner is a lookup by edge id.
+// the triangle table as the emitter wants it: 16 bytes per case (15 edge ids + the triangle count),
+// filled once per process from mc_tables.h (mc_tables_ready)
+__device__ uint4 g_tri_packed[256];
+
 struct RowIds { int x0, y0, z0, y1, z1; };   // ids at bit i (x, y, z) and at bit i + 1 (y, z)
 
 template <bool VEC>
@@ -586,7 +590,7 @@ __global__ void __launch_bounds__(kTileThreads) k_mc_emit_tris(McGeom g, const u
                                                                int flip_y, int skip_last, int vbase,
                                                                const uint4* __restrict__ foreign, int foreign_base,
                                                                int* __restrict__ tris) {
-  __shared__ signed char s_tri[256][16];  // 15 edge ids + triangle count
+  __shared__ __align__(16) signed char s_tri[256][16];  // 15 edge ids + triangle count
   __shared__ int s_id[12 * kTileThreads];  // [edge][thread]
   __shared__ uint32_t s_act[kTileWords];
   __shared__ uint32_t s_coff[kTileWords];
@@ -597,10 +601,7 @@ __global__ void __launch_bounds__(kTileThreads) k_mc_emit_tris(McGeom g, const u
     const uint32_t C = __ldg(&tcnt[tile].y);
     if (C == 0u) continue;     // most tiles: nothing but this load
     if (!tables) {             // (made visible by the barriers of the scan below)
-      for (int i = tid; i < 256 * 16; i += kTileThreads) {
-        int c = i >> 4, k = i & 15;
-        s_tri[c][k] = k < 15 ? B2V_MC_TRI[c][k] : (signed char)B2V_MC_NTRI[c];
-      }
+      reinterpret_cast<uint4*>(&s_tri[0][0])[tid] = g_tri_packed[tid];   // 16 bytes per case, one load per thread
       tables = true;
     }
     uint32_t tbase = __ldg(&toff[tile].z);
@@ -716,6 +717,27 @@ int grid_for(int64_t items, int per_block) {
   return (int)blocks;
 }
 
+__global__ void k_mc_pack_tables() {
+  signed char e[16];
+  for (int k = 0; k < 15; ++k) e[k] = B2V_MC_TRI[threadIdx.x][k];
+  e[15] = (signed char)B2V_MC_NTRI[threadIdx.x];
+  uint4 v;
+  memcpy(&v, e, 16);
+  g_tri_packed[threadIdx.x] = v;
+}
+
+int mc_tables_ready(cudaStream_t s) {
+  static int done_for_device[64] = {0};
+  int devi = 0;
+  B2V_CUDA(cudaGetDevice(&devi));
+  if (devi >= 0 && devi < 64 && done_for_device[devi]) return B2V_OK;
+  k_mc_pack_tables<<<1, 256, 0, s>>>();
+  int rc = b2v_check_launch("k_mc_pack_tables");
+  if (rc) return rc;
+  if (devi >= 0 && devi < 64) done_for_device[devi] = 1;
+  return B2V_OK;
+}
+
 // inside(p) <=> (double)S >= iso  <=>  S >= ceil(iso) for integer S
 int int_threshold(double iso, int lo, int hi) {
   double c = ceil(iso);
@@ -797,6 +819,7 @@ static int mc_emit_impl(const void* vol, int dtype, int64_t nz, int64_t ny, int6
   McXform xf = {sx, sy, sz, ox, oy, oz, flip_y ? 1 : 0, (float)iso};
   const int ntiles = (int)ceil_div64(g.nwords, kTileWords);   // one block per tile; empty tiles leave at once
   int rc;
+  if ((rc = mc_tables_ready(s))) return rc;
   if (verts) {
     if (dtype == B2V_U8)
       k_mc_emit_verts<uint8_t><<<ntiles, kTileThreads, 0, s>>>((const uint8_t*)vol, g, w.vrec, w.tcnt, w.toff, ntiles,
