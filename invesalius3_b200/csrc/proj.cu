@@ -18,6 +18,7 @@
 // The contour variants never materialise the reference's temp volume: a sampler computes
 // the T-typed contour intensity of a voxel on the fly from its six neighbours.
 #include <math.h>
+#include <stdlib.h>
 
 #include "b2v_common.cuh"
 
@@ -349,6 +350,115 @@ __global__ void __launch_bounds__(kRays) k_rays_alongx(S smp, Op op0, U* __restr
   if (st) *status = st;
 }
 
+// ---- rays along x, int16: rows staged by the TMA engine ---------------------------------------------
+// cp.async.bulk (1-D bulk tensor copy, global -> shared, completion counted on an mbarrier): every
+// thread asks the copy engine for the next 64-sample segment (128 B) of ITS ray and goes back to
+// the float32 recurrence; no thread spends issue slots on loads, and the segment after next is in
+// flight while the current one is consumed (two stages). Rows sit 144 B apart in shared memory, so
+// the 16-byte reads of eight consecutive threads fall into eight different bank groups.
+// Needs 16-byte aligned rows (nx % 8 == 0, aligned base); otherwise the lane-load kernels above run.
+constexpr int kTmaChunk = 64;                                  // samples per stage and ray
+constexpr int kTmaPitch = kTmaChunk * 2 + 16;                  // bytes between rows in shared memory
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// the block's 128 rays through `op` (one per thread); returns false if a result does not fit
+template <typename U, typename Op>
+__device__ __forceinline__ void rays_alongx_tma(const int16_t* __restrict__ vol, Dims d, Op& op, bool call_first,
+                                                U* __restrict__ out, int* status) {
+  __shared__ __align__(16) unsigned char stage[2][kRays * kTmaPitch];
+  __shared__ __align__(8) uint64_t bar[2];
+  const int64_t nrows = d.nz * d.ny;
+  const int tid = threadIdx.x;
+  const int64_t myrow = (int64_t)blockIdx.x * kRays + tid;
+  const bool live = myrow < nrows;
+  const int nchunks = (int)ceil_div64(d.nx, kTmaChunk);
+  if (tid == 0) {
+    mbar_init(&bar[0], kRays);
+    mbar_init(&bar[1], kRays);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int16_t* row = vol + (live ? myrow : 0) * d.nx;
+  auto issue = [&](int k) {
+    const int b = k & 1;
+    const int64_t x0 = (int64_t)k * kTmaChunk;
+    const uint32_t bytes = live ? (uint32_t)(((d.nx - x0) < kTmaChunk ? (d.nx - x0) : kTmaChunk) * 2) : 0u;
+    mbar_arrive_expect_tx(&bar[b], bytes);
+    if (bytes) tma_load_1d(&stage[b][tid * kTmaPitch], row + x0, bytes, &bar[b]);
+  };
+  issue(0);
+  if (nchunks > 1) issue(1);
+  int issued = nchunks > 1 ? 2 : 1, waited = 0;
+  int st = 0;
+  bool done = !live;
+  for (int k = 0; k < nchunks; ++k) {
+    const int b = k & 1;
+    mbar_wait(&bar[b], (uint32_t)((k >> 1) & 1));
+    ++waited;
+    if (!done) {
+      const uint4* w = reinterpret_cast<const uint4*>(&stage[b][tid * kTmaPitch]);
+      const int lim = (int)((d.nx - (int64_t)k * kTmaChunk) < kTmaChunk ? (d.nx - (int64_t)k * kTmaChunk) : kTmaChunk);
+      if (k == 0 && call_first) op.first((int16_t)(w[0].x & 0xffffu));
+      for (int j = 0; j < kTmaChunk / 8 && !done; ++j) {
+        const uint4 q = w[j];
+        const uint32_t ww4[4] = {q.x, q.y, q.z, q.w};
+        const int base = j * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (!done && base + e < lim) done = op.step((int16_t)((e & 1) ? (ww4[e >> 1] >> 16) : (ww4[e >> 1] & 0xffffu)));
+        }
+        if (base + 8 >= lim) break;
+      }
+    }
+    const bool all_done = __syncthreads_and(done);   // also: everyone has finished reading stage b
+    if (all_done) break;
+    if (k + 2 < nchunks) { issue(k + 2); ++issued; }
+  }
+  // a segment may still be in flight when the rays ended early: let it land before the block leaves
+  for (int k = waited; k < issued; ++k) mbar_wait(&bar[k & 1], (uint32_t)((k >> 1) & 1));
+  if (live) {
+    U o;
+    if (op.result(&o)) out[myrow] = o; else st = B2V_ERR_RANGE;
+  }
+  if (st) *status = st;
+}
+
+template <typename U, typename Op>
+__global__ void __launch_bounds__(kRays) k_rays_alongx_tma(const int16_t* __restrict__ vol, Dims d, Op op0,
+                                                           U* __restrict__ out, int* status) {
+  Op op = op0;
+  op.init();
+  rays_alongx_tma<U, Op>(vol, d, op, true, out, status);
+}
+
+// Measured at 1024^3 (tools/mida_axis2.py, profiles/README.md): MIDA full rays 1.83 ms (TMA rows) vs
+// 1.68 ms (lane loads), LMIP 0.088 vs 0.052 ms — 128-byte bulk copies per thread are too small for the
+// copy engine to beat 32-bit lane loads here, and the rays are bound by the recurrence, not by the
+// loads. The lane-load kernels stay the default; b2v_proj_set_tma(1) (or B2V_TMA=1) selects this path.
+int g_proj_tma = -1;
+inline bool tma_rows_ok(const void* vol, const Dims& d) {
+  if (g_proj_tma < 0) g_proj_tma = getenv("B2V_TMA") != nullptr ? 1 : 0;
+  return g_proj_tma == 1 && d.nx % 8 == 0 && (reinterpret_cast<uintptr_t>(vol) & 15u) == 0;
+}
+
 __global__ void k_status_init(int* status) { *status = 0; }
 
 template <typename T, typename U, typename S, typename Op>
@@ -356,6 +466,13 @@ int launch_rays(S smp, int axis, Op op, U* out, int* status, cudaStream_t s) {
   const Dims d = smp.d;
   if (axis == 2) {
     int64_t nrows = d.nz * d.ny;
+    if constexpr (S::kLinear && sizeof(T) == 2) {
+      if (tma_rows_ok(smp.vol, d)) {
+        k_rays_alongx_tma<U, Op><<<(unsigned)ceil_div64(nrows, kRays), kRays, 0, s>>>((const int16_t*)smp.vol, d, op, out,
+                                                                                     status);
+        return b2v_check_launch("k_rays_alongx_tma");
+      }
+    }
     k_rays_alongx<T, U, S, Op><<<(unsigned)ceil_div64(nrows, kRays), kRays, 0, s>>>(smp, op, out, status);
     return b2v_check_launch("k_rays_alongx");
   }
@@ -430,10 +547,26 @@ __global__ void __launch_bounds__(kRays) k_mida_alongx(S smp, const float* __res
   if (st) *status = st;
 }
 
+template <typename U>
+__global__ void __launch_bounds__(kRays) k_mida_alongx_tma(const int16_t* __restrict__ vol, Dims d,
+                                                           const float* __restrict__ mm, float wl, float ww,
+                                                           U* __restrict__ out, int* status) {
+  MidaOp<int16_t, U> op = make_mida<int16_t, U>(mm, wl, ww);
+  op.init();
+  rays_alongx_tma<U, MidaOp<int16_t, U>>(vol, d, op, false, out, status);
+}
+
 template <typename T, typename U, typename S>
 int launch_mida(S smp, int axis, const float* mm, float wl, float ww, U* out, int* status, cudaStream_t s) {
   const Dims d = smp.d;
   if (axis == 2) {
+    if constexpr (S::kLinear && sizeof(T) == 2) {
+      if (tma_rows_ok(smp.vol, d)) {
+        k_mida_alongx_tma<U><<<(unsigned)ceil_div64(d.nz * d.ny, kRays), kRays, 0, s>>>((const int16_t*)smp.vol, d, mm, wl,
+                                                                                      ww, out, status);
+        return b2v_check_launch("k_mida_alongx_tma");
+      }
+    }
     k_mida_alongx<T, U, S><<<(unsigned)ceil_div64(d.nz * d.ny, kRays), kRays, 0, s>>>(smp, mm, wl, ww, out, status);
     return b2v_check_launch("k_mida_alongx");
   }
@@ -515,6 +648,8 @@ __global__ void __launch_bounds__(128) k_lmip_z_partial(PlainSampler<T> smp, Lmi
 }
 
 }  // namespace
+
+extern "C" void b2v_proj_set_tma(int on) { g_proj_tma = on ? 1 : 0; }
 
 extern "C" int64_t b2v_proj_workspace_bytes(int64_t n) { return 256 + b2v_minmax_workspace_bytes(n); }
 

@@ -265,3 +265,30 @@ def test_projections_1024_slab_exact(orc):
         assert np.array_equal(projection.mida(t, axis, 300, 300).cpu().numpy(), want), ("mida", axis)
         orc.lmip(vol, axis, 700, 3033, want)
         assert np.array_equal(projection.lmip(t, axis, 700, 3033).cpu().numpy(), want), ("lmip", axis)
+
+
+def test_tma_staged_rows_equal_lane_loads(orc):
+    """Rays along x with the rows staged by the TMA engine (cp.async.bulk + mbarrier) give the same
+    images as the lane-load kernels and the oracle: MIDA (full rays and early exit) and LMIP, row
+    counts that do not fill the last block, a tail segment shorter than a stage."""
+    import torch
+    from invesalius3_b200 import _lib, projection
+    lib = _lib.load()
+    for shape in ((9, 37, 200), (4, 33, 64), (3, 5, 72)):
+        vol = _ct_like(shape, 21)
+        t = torch.from_numpy(vol).cuda()
+        res = {}
+        for on in (0, 1):
+            lib.b2v_proj_set_tma(on)
+            try:
+                res[on] = (projection.mida(t, 2, 300, 300).cpu().numpy(), projection.mida(t, 2, 32000, 2).cpu().numpy(),
+                           projection.lmip(t, 2, 700, 3033).cpu().numpy())
+            finally:
+                lib.b2v_proj_set_tma(0)
+        for a, b in zip(res[0], res[1]):
+            assert np.array_equal(a, b), shape
+        want = np.zeros(_oshape(shape, 2), np.int16)
+        orc.mida(vol, 2, 300, 300, want)
+        assert np.array_equal(res[1][0], want)
+        orc.lmip(vol, 2, 700, 3033, want)
+        assert np.array_equal(res[1][2], want)
