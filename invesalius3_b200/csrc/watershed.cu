@@ -562,7 +562,7 @@ extern "C" int b2v_ws_flood(const uint16_t* img, const int16_t* markers, int64_t
     if (eff == six && !getenv("B2V_WS_GENERIC")) {
       int rounds = 0;
       rc = b2v_wsf_run(31, img, markers, nz, ny, nx, mode, 0, 0, labels, ambiguous, ambiguous ? 1 : 0, workspace, stream,
-                       &rounds);
+                       &rounds, 1);
       if (rounds_out) *rounds_out = rounds;
       return rc;
     }

@@ -18,6 +18,7 @@
 // only overwritten by the neighbour shard's values through b2v_ws_plane); a frozen plane that
 // improves re-activates the tiles next to it.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "b2v_common.cuh"
 #include "watershed.cuh"
@@ -36,6 +37,18 @@ constexpr uint32_t kInfC = 0xffffffffu;
 constexpr unsigned long long kInfK = ~0ull;
 constexpr unsigned long long kHop = 1ull << 32;
 constexpr uint16_t kSetEmpty = 32768, kSetMulti = 0;
+// phase-2 key: hops above the label. 64 bits hold any label (uint16 code) and any hop count; when
+// the markers carry at most 256 distinct labels the key is hops << 8 | rank of the label (32 bits):
+// half the chain instructions, shared memory and traffic. kKeyFull32: keys at or above it mean the
+// hop count is about to overflow (the caller falls back to 64-bit keys).
+template <typename K> struct KeyT;
+template <> struct KeyT<unsigned long long> {
+  static constexpr unsigned long long inf = ~0ull, hop = 1ull << 32;
+};
+template <> struct KeyT<uint32_t> {
+  static constexpr uint32_t inf = 0xffffffffu, hop = 1u << 8;
+};
+constexpr uint32_t kKeyFull32 = 0xff000000u;
 enum { F_ZLO = 1, F_ZHI = 2, F_YLO = 4, F_YHI = 8, F_XLO = 16, F_XHI = 32 };
 // admissibility bits: predecessor at x-1, x+1, y-1, y+1, z-1, z+1
 enum { A_XM = 1, A_XP = 2, A_YM = 4, A_YP = 8, A_ZM = 16, A_ZP = 32 };
@@ -61,6 +74,10 @@ struct FastWs {
   unsigned long long* key;
   uint16_t* lset;
   uint8_t* adm;
+  uint32_t* key32;      // phase-2 keys when the markers carry <= 256 distinct labels
+  uint32_t* present;    // [2048] which label codes occur among the markers (bitmap over uint16)
+  uint32_t* prefix;     // [2048] label codes below each bitmap word
+  uint32_t* inv;        // [256] rank -> label code; inv[256] = number of distinct labels
   Lists L;
   int* init_list;   // marker tiles (both phases start from them)
   int* init_cnt;
@@ -94,6 +111,10 @@ FastWs fcarve(void* base, int64_t nz, int64_t ny, int64_t nx) {
   w.cost = (uint32_t*)(p + off); off += align(n * 4);
   w.lset = (uint16_t*)(p + off); off += align(n * 2);
   w.adm = (uint8_t*)(p + off); off += align(n);
+  w.key32 = (uint32_t*)(p + off); off += align(n * 4);
+  w.present = (uint32_t*)(p + off); off += 2048 * 4;
+  w.prefix = (uint32_t*)(p + off); off += 2048 * 4;
+  w.inv = (uint32_t*)(p + off); off += align(257 * 4);
   w.init_list = (int*)(p + off); off += align(nt * 4);
   w.init_cnt = (int*)(p + off); off += 256;
   w.lists_begin = p + off;
@@ -128,11 +149,13 @@ __device__ __forceinline__ long long flat_or_invalid(const FGrid& g, int z, int 
 __global__ void __launch_bounds__(256) k_wsf_init(const uint16_t* __restrict__ img, const int16_t* __restrict__ markers,
                                                   FGrid g, uint32_t* __restrict__ cost,
                                                   unsigned long long* __restrict__ key, uint16_t* __restrict__ lset,
-                                                  Lists L, int* init_list, int* init_cnt) {
+                                                  Lists L, int* init_list, int* init_cnt, uint32_t* present) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += stride) {
     const int m = markers[i];
     if (m != 0) {
+      const uint32_t code = (uint32_t)(m + 32768);
+      if (!((present[code >> 5] >> (code & 31)) & 1u)) atomicOr(&present[code >> 5], 1u << (code & 31));
       cost[i] = g.mode == 0 ? 0u : (uint32_t)img[i];
       key[i] = (unsigned long long)(uint32_t)(m + 32768);
       lset[i] = (uint16_t)(m + 32768);
@@ -163,6 +186,65 @@ __global__ void k_wsf_seed_lists(Lists L, const int* __restrict__ init_list, con
     L.list[i] = tile;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) L.cnt[0] = n;
+}
+
+// ---- label ranks (32-bit keys) ------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_wsf_ranks(const uint32_t* __restrict__ present, uint32_t* prefix, uint32_t* inv) {
+  __shared__ uint32_t s_w[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t w0 = present[2 * tid], w1 = present[2 * tid + 1];
+  const uint32_t c = __popc(w0) + __popc(w1);
+  uint32_t incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t v = s_w[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    s_w[lane] = v;
+  }
+  __syncthreads();
+  const uint32_t before = (warp ? s_w[warp - 1] : 0u) + incl - c;
+  prefix[2 * tid] = before;
+  prefix[2 * tid + 1] = before + __popc(w0);
+  uint32_t r = before;
+  for (uint32_t m = w0; m; m &= m - 1, ++r) if (r < 256) inv[r] = (uint32_t)(2 * tid) * 32 + (uint32_t)(__ffs(m) - 1);
+  for (uint32_t m = w1; m; m &= m - 1, ++r) if (r < 256) inv[r] = (uint32_t)(2 * tid + 1) * 32 + (uint32_t)(__ffs(m) - 1);
+  if (tid == 1023) inv[256] = s_w[31];
+}
+
+__global__ void __launch_bounds__(256) k_wsf_key32_init(const unsigned long long* __restrict__ key, long long n,
+                                                        const uint32_t* __restrict__ present,
+                                                        const uint32_t* __restrict__ prefix, uint32_t* __restrict__ key32) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long k = key[i];
+    uint32_t v = 0xffffffffu;
+    if (k != kInfK && (k >> 32) == 0) {     // a marker: rank of its label code
+      const uint32_t code = (uint32_t)k;
+      v = prefix[code >> 5] + __popc(present[code >> 5] & ((1u << (code & 31)) - 1u));
+    }
+    key32[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_wsf_labels32(const uint32_t* __restrict__ key32, const uint16_t* __restrict__ lset,
+                                                      const uint32_t* __restrict__ inv, long long n,
+                                                      int16_t* __restrict__ labels, uint8_t* __restrict__ ambiguous) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t k = key32[i];
+    labels[i] = k == 0xffffffffu ? (int16_t)0 : (int16_t)((int)inv[k & 0xffu] - 32768);
+    if (ambiguous) ambiguous[i] = lset[i] == kSetMulti ? 1 : 0;
+  }
 }
 
 // ---- admissible predecessors (phase 2 input) -------------------------------------------------------
@@ -335,10 +417,10 @@ __device__ __forceinline__ uint16_t set_join(uint16_t a, uint16_t b) {   // b !=
   return a == kSetEmpty ? b : ((a == b && b != kSetMulti) ? a : kSetMulti);
 }
 
-template <bool WITH_SET, int S>
-__device__ __forceinline__ void line_full_label(unsigned long long* sK, uint16_t* sA, const uint8_t* sD, int base,
+template <typename K, bool WITH_SET, int S>
+__device__ __forceinline__ void line_full_label(K* sK, uint16_t* sA, const uint8_t* sD, int base,
                                                 uint32_t from_lo, uint32_t from_hi, bool& ch, bool& first, bool& last) {
-  unsigned long long k[kT + 2];
+  K k[kT + 2];
   uint32_t av[kT + 2], d[kT + 2];
   uint32_t m = 0;
 #pragma unroll
@@ -350,8 +432,8 @@ __device__ __forceinline__ void line_full_label(unsigned long long* sK, uint16_t
   // branch-free steps (selects): the lanes of a warp walk different lines
 #pragma unroll
   for (int j = 1; j <= kT; ++j) {
-    const bool ok = (d[j] & from_lo) != 0u && k[j - 1] != kInfK;
-    const unsigned long long cand = k[j - 1] + kHop;
+    const bool ok = (d[j] & from_lo) != 0u && k[j - 1] != KeyT<K>::inf;
+    const K cand = k[j - 1] + KeyT<K>::hop;
     const bool better = ok && cand < k[j];
     k[j] = better ? cand : k[j];
     uint32_t ch1 = better ? 1u : 0u;
@@ -365,8 +447,8 @@ __device__ __forceinline__ void line_full_label(unsigned long long* sK, uint16_t
   }
 #pragma unroll
   for (int j = kT; j >= 1; --j) {
-    const bool ok = (d[j] & from_hi) != 0u && k[j + 1] != kInfK;
-    const unsigned long long cand = k[j + 1] + kHop;
+    const bool ok = (d[j] & from_hi) != 0u && k[j + 1] != KeyT<K>::inf;
+    const K cand = k[j + 1] + KeyT<K>::hop;
     const bool better = ok && cand < k[j];
     k[j] = better ? cand : k[j];
     uint32_t ch1 = better ? 1u : 0u;
@@ -558,18 +640,20 @@ __device__ int visit_cost(const uint16_t* __restrict__ img, uint32_t* cost, cons
 }
 
 // PHASE 2: keys (hops << 32 | label) and label sets along admissible edges
-template <bool WITH_SET>
-__device__ int visit_label(const uint8_t* __restrict__ adm, unsigned long long* key, uint16_t* lset, const FGrid& g,
-                           const TileGeom& t, unsigned long long* sK, uint16_t* sA, uint8_t* sD, int* s_faces) {
+template <typename K, bool WITH_SET>
+__device__ int visit_label(const uint8_t* __restrict__ adm, K* key, uint16_t* lset, const FGrid& g,
+                           const TileGeom& t, K* sK, uint16_t* sA, uint8_t* sD, int* s_faces, int* err) {
+  constexpr bool K64 = sizeof(K) == 8;
+  constexpr int KV = K64 ? 8 : 4;     // 128-bit vectors per row of 16 keys
   const int tid = threadIdx.x;
   if (tid == 0) *s_faces = 0;
   const bool full = tile_full(g, t);
   if (full) {
     const int a = tid & 15, b = tid >> 4;
     const long long p0 = ((long long)(t.z0 + b) * g.ny + (t.y0 + a)) * g.nx + t.x0;
-    uint4 k4[8], a4[2], d4;
+    uint4 k4[KV], a4[2], d4;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) k4[k] = __ldcg((const uint4*)(key + p0) + k);
+    for (int k = 0; k < KV; ++k) k4[k] = __ldcg((const uint4*)(key + p0) + k);
     if (WITH_SET) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) a4[k] = __ldcg((const uint4*)(lset + p0) + k);
@@ -577,12 +661,12 @@ __device__ int visit_label(const uint8_t* __restrict__ adm, unsigned long long* 
     d4 = __ldg((const uint4*)(adm + p0));
     long long hp[6];
     int hc[6];
-    unsigned long long hk[6];
+    K hk[6];
     uint16_t hs[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       hp[k] = halo_cell(g, t, k, a, b, &hc[k]);
-      hk[k] = kInfK; hs[k] = kSetEmpty;
+      hk[k] = KeyT<K>::inf; hs[k] = kSetEmpty;
       if (hp[k] >= 0) { hk[k] = __ldcg(&key[hp[k]]); if (WITH_SET) hs[k] = __ldcg(&lset[hp[k]]); }
     }
     const int r0 = cell_index(b + 1, a + 1, 1);
@@ -590,8 +674,13 @@ __device__ int visit_label(const uint8_t* __restrict__ adm, unsigned long long* 
     const uint32_t dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const uint4 q = k4[k >> 1];
-      sK[r0 + k] = (k & 1) ? (((unsigned long long)q.w << 32) | q.z) : (((unsigned long long)q.y << 32) | q.x);
+      if constexpr (K64) {
+        const uint4 q = k4[k >> 1];
+        sK[r0 + k] = (k & 1) ? (((unsigned long long)q.w << 32) | q.z) : (((unsigned long long)q.y << 32) | q.x);
+      } else {
+        const uint4 q = k4[k >> 2];
+        sK[r0 + k] = (k & 3) == 0 ? q.x : ((k & 3) == 1 ? q.y : ((k & 3) == 2 ? q.z : q.w));
+      }
       if (WITH_SET) sA[r0 + k] = (uint16_t)((k & 1) ? (aa[k >> 1] >> 16) : (aa[k >> 1] & 0xffffu));
       sD[r0 + k] = (uint8_t)((dd[k >> 2] >> (8 * (k & 3))) & 0xffu);
     }
@@ -604,7 +693,7 @@ for (int i = tid; i < kH * kH * kH; i += kThreads) {
       const int nh = (hz == 0 || hz == t.vz + 1) + (hy == 0 || hy == t.vy + 1) + (hx == 0 || hx == t.vx + 1);
       if (nh > 1) continue;
       const long long p = flat_or_invalid(g, t.z0 + hz - 1, t.y0 + hy - 1, t.x0 + hx - 1);
-      unsigned long long k = kInfK;
+      K k = KeyT<K>::inf;
       uint16_t s = kSetEmpty;
       uint8_t d = 0;
       if (p >= 0) {
@@ -623,15 +712,15 @@ for (int i = tid; i < kH * kH * kH; i += kThreads) {
   int faces = 0, any = 0, changed, sets = 0;
   auto line = [&](int base, int s, int len, uint32_t from_lo, uint32_t from_hi, bool& ch, bool& first, bool& last) {
     {
-      unsigned long long kp = sK[base - s];
+      K kp = sK[base - s];
       uint16_t ap = WITH_SET ? sA[base - s] : kSetEmpty;
       for (int j = 0; j < len; ++j) {
         const int idx = base + j * s;
-        unsigned long long k = sK[idx];
+        K k = sK[idx];
         uint16_t av = WITH_SET ? sA[idx] : kSetEmpty;
-        if ((sD[idx] & from_lo) && kp != kInfK) {
+        if ((sD[idx] & from_lo) && kp != KeyT<K>::inf) {
           bool c = false;
-          const unsigned long long cand = kp + kHop;
+          const K cand = kp + KeyT<K>::hop;
           if (cand < k) { k = cand; sK[idx] = k; c = true; }
           if (WITH_SET && ap != kSetEmpty) {
             const uint16_t j1 = set_join(av, ap);
@@ -643,15 +732,15 @@ for (int i = tid; i < kH * kH * kH; i += kThreads) {
       }
     }
     {
-      unsigned long long kp = sK[base + len * s];
+      K kp = sK[base + len * s];
       uint16_t ap = WITH_SET ? sA[base + len * s] : kSetEmpty;
       for (int j = len - 1; j >= 0; --j) {
         const int idx = base + j * s;
-        unsigned long long k = sK[idx];
+        K k = sK[idx];
         uint16_t av = WITH_SET ? sA[idx] : kSetEmpty;
-        if ((sD[idx] & from_hi) && kp != kInfK) {
+        if ((sD[idx] & from_hi) && kp != KeyT<K>::inf) {
           bool c = false;
-          const unsigned long long cand = kp + kHop;
+          const K cand = kp + KeyT<K>::hop;
           if (cand < k) { k = cand; sK[idx] = k; c = true; }
           if (WITH_SET && ap != kSetEmpty) {
             const uint16_t j1 = set_join(av, ap);
@@ -669,9 +758,9 @@ for (int i = tid; i < kH * kH * kH; i += kThreads) {
     while (clean < 3 && pass < 3 * kMaxSets) {
       bool ch = false, first = false, last = false;
       const int axis = pass % 3;
-      if (axis == 0) line_full_label<WITH_SET, 1>(sK, sA, sD, cell_index(b + 1, a + 1, 1), A_XM, A_XP, ch, first, last);
-      else if (axis == 1) line_full_label<WITH_SET, kP>(sK, sA, sD, cell_index(b + 1, 1, a + 1), A_YM, A_YP, ch, first, last);
-      else line_full_label<WITH_SET, kH * kP>(sK, sA, sD, cell_index(1, b + 1, a + 1), A_ZM, A_ZP, ch, first, last);
+      if (axis == 0) line_full_label<K, WITH_SET, 1>(sK, sA, sD, cell_index(b + 1, a + 1, 1), A_XM, A_XP, ch, first, last);
+      else if (axis == 1) line_full_label<K, WITH_SET, kP>(sK, sA, sD, cell_index(b + 1, 1, a + 1), A_YM, A_YP, ch, first, last);
+      else line_full_label<K, WITH_SET, kH * kP>(sK, sA, sD, cell_index(1, b + 1, a + 1), A_ZM, A_ZP, ch, first, last);
       if (ch) faces |= line_faces(axis, a, b, true, first, last, t);
       changed = __syncthreads_or(ch ? 1 : 0);
       any |= changed;
@@ -709,10 +798,22 @@ for (int i = tid; i < kH * kH * kH; i += kThreads) {
   if (full) {
     const long long p0 = ((long long)(t.z0 + b) * g.ny + (t.y0 + a)) * g.nx + t.x0;
     const int c0 = cell_index(b + 1, a + 1, 1);
+    if constexpr (K64) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const unsigned long long k0 = sK[c0 + 2 * k], k1 = sK[c0 + 2 * k + 1];
-      __stcg((uint4*)(key + p0) + k, make_uint4((uint32_t)k0, (uint32_t)(k0 >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32)));
+      for (int k = 0; k < 8; ++k) {
+        const unsigned long long k0 = sK[c0 + 2 * k], k1 = sK[c0 + 2 * k + 1];
+        __stcg((uint4*)(key + p0) + k, make_uint4((uint32_t)k0, (uint32_t)(k0 >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32)));
+      }
+    } else {
+      bool full32 = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint4 q = make_uint4(sK[c0 + 4 * k], sK[c0 + 4 * k + 1], sK[c0 + 4 * k + 2], sK[c0 + 4 * k + 3]);
+        full32 |= (q.x != KeyT<K>::inf && q.x >= kKeyFull32) || (q.y != KeyT<K>::inf && q.y >= kKeyFull32) ||
+                  (q.z != KeyT<K>::inf && q.z >= kKeyFull32) || (q.w != KeyT<K>::inf && q.w >= kKeyFull32);
+        __stcg((uint4*)(key + p0) + k, q);
+      }
+      if (full32) *err = 2;     // hop count about to overflow 24 bits: the host re-runs phase 2 with 64-bit keys
     }
     if (WITH_SET) {
 #pragma unroll
@@ -727,6 +828,7 @@ for (int i = tid; i < kH * kH * kH; i += kThreads) {
     const long long p0 = ((long long)(t.z0 + b) * g.ny + (t.y0 + a)) * g.nx + t.x0;
     const int c0 = cell_index(b + 1, a + 1, 1);
     for (int x = 0; x < t.vx; ++x) {
+      if (!K64 && sK[c0 + x] != KeyT<K>::inf && sK[c0 + x] >= (K)kKeyFull32) *err = 2;
       __stcg(&key[p0 + x], sK[c0 + x]);
       if (WITH_SET) __stcg(&lset[p0 + x], sA[c0 + x]);
     }
@@ -739,18 +841,17 @@ for (int i = tid; i < kH * kH * kH; i += kThreads) {
 // ---- the persistent kernels ---------------------------------------------------------------------
 // PHASE 1 (cost) / PHASE 2 (labels). Rounds until the list of a round is empty. L.cnt[4] error,
 // L.cnt[5] rounds.
-template <int PHASE, int MODE, bool WITH_SET>
-__global__ void __launch_bounds__(kThreads, (PHASE == 1 || !WITH_SET) ? 3 : 2) k_wsf_persistent(const uint16_t* __restrict__ img, uint32_t* cost,
-                                                             unsigned long long* key, uint16_t* lset,
-                                                             const uint8_t* __restrict__ adm, FGrid g, Lists L,
-                                                             int max_rounds) {
+template <int PHASE, int MODE, bool WITH_SET, typename K>
+__global__ void __launch_bounds__(kThreads, (PHASE == 1 || !WITH_SET || sizeof(K) == 4) ? 3 : 2)
+    k_wsf_persistent(const uint16_t* __restrict__ img, uint32_t* cost, K* key, uint16_t* lset,
+                     const uint8_t* __restrict__ adm, FGrid g, Lists L, int max_rounds) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ unsigned long long s_raw[];
   __shared__ int s_faces;
-  // phase 1: cost u32 + intensity u16; phase 2: key u64 + set u16 + admissibility u8
+  // phase 1: cost u32 + intensity u16; phase 2: key (u64 or u32) + set u16 + admissibility u8
   uint32_t* sC = (uint32_t*)s_raw;
   uint16_t* sI = (uint16_t*)(sC + kCells);
-  unsigned long long* sK = s_raw;
+  K* sK = (K*)s_raw;
   uint16_t* sA = (uint16_t*)(sK + kCells);
   uint8_t* sD = WITH_SET ? (uint8_t*)(sA + kCells) : (uint8_t*)(sK + kCells);
   const int tid = threadIdx.x;
@@ -769,7 +870,7 @@ __global__ void __launch_bounds__(kThreads, (PHASE == 1 || !WITH_SET) ? 3 : 2) k
       if (t.uz0 >= t.uz1) continue;
       int res;
       if (PHASE == 1) res = visit_cost<MODE>(img, cost, g, t, sC, sI, &s_faces);
-      else res = visit_label<WITH_SET>(adm, key, lset, g, t, sK, sA, sD, &s_faces);
+      else res = visit_label<K, WITH_SET>(adm, key, lset, g, t, sK, sA, sD, &s_faces, &L.cnt[4]);
       if (res) {
         __threadfence();
         post_neighbours(g, L, nxt, t, s_faces);
@@ -850,7 +951,7 @@ int wsf_grid(long long n) {
 }
 
 template <typename K>
-int launch_persistent(K kern, size_t smem, const uint16_t* img, FastWs& w, FGrid g, cudaStream_t s) {
+int launch_persistent(K kern, size_t smem, const uint16_t* img, FastWs& w, FGrid g, cudaStream_t s, void* keyptr = nullptr) {
   B2V_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   B2V_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, kThreads, smem));
@@ -858,7 +959,7 @@ int launch_persistent(K kern, size_t smem, const uint16_t* img, FastWs& w, FGrid
   int grid = per_sm * b2v_sm_count();
   if (grid > g.ntiles) grid = g.ntiles;
   uint32_t* cost = w.cost;
-  unsigned long long* key = w.key;
+  void* key = keyptr ? keyptr : (void*)w.key;
   uint16_t* lset = w.lset;
   const uint8_t* adm = w.adm;
   Lists L = w.L;
@@ -868,11 +969,12 @@ int launch_persistent(K kern, size_t smem, const uint16_t* img, FastWs& w, FGrid
   return b2v_check_launch("k_wsf_persistent");
 }
 
-int read_ctl(FastWs& w, cudaStream_t s, int* rounds, int* changed) {
+int read_ctl(FastWs& w, cudaStream_t s, int* rounds, int* changed, int* key_overflow = nullptr) {
   int ctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   B2V_CUDA(cudaMemcpyAsync(ctl, w.L.cnt, sizeof(ctl), cudaMemcpyDeviceToHost, s));
   B2V_CUDA(cudaStreamSynchronize(s));
-  B2V_REQUIRE(ctl[4] == 0, B2V_ERR_NOCONV, "watershed: no convergence within the round cap");
+  if (key_overflow) *key_overflow = ctl[4] == 2;
+  B2V_REQUIRE(ctl[4] == 0 || (ctl[4] == 2 && key_overflow), B2V_ERR_NOCONV, "watershed: no convergence within the round cap");
   if (rounds) *rounds += ctl[5];
   if (changed) *changed = ctl[6];
   return B2V_OK;
@@ -890,7 +992,7 @@ int64_t b2v_wsf_workspace_bytes(int64_t nz, int64_t ny, int64_t nx) { return fca
 //   16 FINISH          labels (and the ambiguous mask) out
 int b2v_wsf_run(int stages, const uint16_t* img, const int16_t* markers, int64_t nz, int64_t ny, int64_t nx, int mode,
                 int frozen_lo, int frozen_hi, int16_t* labels, uint8_t* ambiguous, int with_set, void* workspace,
-                void* stream, int* rounds_io) {
+                void* stream, int* rounds_io, int allow_key32) {
   B2V_REQUIRE(img && workspace, B2V_ERR_ARG, "ws_flood: null pointer");
   B2V_REQUIRE(nz > 0 && ny > 0 && nx > 0 && nz * ny * nx < (1ll << 40), B2V_ERR_ARG, "ws_flood: bad volume shape");
   B2V_REQUIRE(mode == 0 || mode == 1, B2V_ERR_ARG, "ws_flood: mode must be 0 (IFT) or 1 (value flood)");
@@ -903,13 +1005,26 @@ int b2v_wsf_run(int stages, const uint16_t* img, const int16_t* markers, int64_t
   if (stages & 1) {
     B2V_REQUIRE(markers, B2V_ERR_ARG, "ws_flood: null markers");
     B2V_CUDA(cudaMemsetAsync(w.init_cnt, 0, 256 + (size_t)w.lists_bytes, s));
-    k_wsf_init<<<wsf_grid(g.n), 256, 0, s>>>(img, markers, g, w.cost, w.key, w.lset, w.L, w.init_list, w.init_cnt);
+    B2V_CUDA(cudaMemsetAsync(w.present, 0, 2048 * 4, s));
+    k_wsf_init<<<wsf_grid(g.n), 256, 0, s>>>(img, markers, g, w.cost, w.key, w.lset, w.L, w.init_list, w.init_cnt,
+                                             w.present);
     if ((rc = b2v_check_launch("k_wsf_init"))) return rc;
+    k_wsf_ranks<<<1, 1024, 0, s>>>(w.present, w.prefix, w.inv);
+    if ((rc = b2v_check_launch("k_wsf_ranks"))) return rc;
+  }
+  // 32-bit keys: one-shot runs only (the staged / sharded protocol exchanges 64-bit keys), markers
+  // with at most 256 distinct labels
+  bool use32 = false;
+  if (allow_key32 && stages == 31 && !getenv("B2V_WS_KEY64")) {
+    uint32_t nlab = 0;
+    B2V_CUDA(cudaMemcpyAsync(&nlab, w.inv + 256, 4, cudaMemcpyDeviceToHost, s));
+    B2V_CUDA(cudaStreamSynchronize(s));
+    use32 = nlab <= 256;
   }
   if (stages & 2) {
     const size_t smem = (size_t)kCells * 6;
-    rc = mode == 0 ? launch_persistent(k_wsf_persistent<1, 0, false>, smem, img, w, g, s)
-                   : launch_persistent(k_wsf_persistent<1, 1, false>, smem, img, w, g, s);
+    rc = mode == 0 ? launch_persistent(k_wsf_persistent<1, 0, false, unsigned long long>, smem, img, w, g, s)
+                   : launch_persistent(k_wsf_persistent<1, 1, false, unsigned long long>, smem, img, w, g, s);
     if (rc) return rc;
     if ((rc = read_ctl(w, s, rounds_io, nullptr))) return rc;
     B2V_CUDA(cudaMemsetAsync(w.lists_begin, 0, (size_t)w.lists_bytes, s));
@@ -921,10 +1036,26 @@ int b2v_wsf_run(int stages, const uint16_t* img, const int16_t* markers, int64_t
     k_wsf_seed_lists<<<8, 256, 0, s>>>(w.L, w.init_list, w.init_cnt);
     if ((rc = b2v_check_launch("k_wsf_seed_lists"))) return rc;
   }
-  if (stages & 8) {
+  if ((stages & 8) && use32) {
+    k_wsf_key32_init<<<wsf_grid(g.n), 256, 0, s>>>(w.key, g.n, w.present, w.prefix, w.key32);
+    if ((rc = b2v_check_launch("k_wsf_key32_init"))) return rc;
+    const size_t smem = (size_t)kCells * (with_set ? 7 : 5) + 16;
+    rc = with_set ? launch_persistent(k_wsf_persistent<2, 0, true, uint32_t>, smem, img, w, g, s, w.key32)
+                  : launch_persistent(k_wsf_persistent<2, 0, false, uint32_t>, smem, img, w, g, s, w.key32);
+    if (rc) return rc;
+    int overflow = 0;
+    if ((rc = read_ctl(w, s, rounds_io, nullptr, &overflow))) return rc;
+    B2V_CUDA(cudaMemsetAsync(w.lists_begin, 0, (size_t)w.lists_bytes, s));
+    if (overflow) {      // more than 2^24 hops: start phase 2 again with 64-bit keys (the sets only grow)
+      use32 = false;
+      k_wsf_seed_lists<<<8, 256, 0, s>>>(w.L, w.init_list, w.init_cnt);
+      if ((rc = b2v_check_launch("k_wsf_seed_lists"))) return rc;
+    }
+  }
+  if ((stages & 8) && !use32) {
     const size_t smem = (size_t)kCells * (with_set ? 11 : 9) + 16;
-    rc = with_set ? launch_persistent(k_wsf_persistent<2, 0, true>, smem, img, w, g, s)
-                  : launch_persistent(k_wsf_persistent<2, 0, false>, smem, img, w, g, s);
+    rc = with_set ? launch_persistent(k_wsf_persistent<2, 0, true, unsigned long long>, smem, img, w, g, s)
+                  : launch_persistent(k_wsf_persistent<2, 0, false, unsigned long long>, smem, img, w, g, s);
     if (rc) return rc;
     if ((rc = read_ctl(w, s, rounds_io, nullptr))) return rc;
     B2V_CUDA(cudaMemsetAsync(w.lists_begin, 0, (size_t)w.lists_bytes, s));
@@ -932,7 +1063,8 @@ int b2v_wsf_run(int stages, const uint16_t* img, const int16_t* markers, int64_t
   if (stages & 16) {
     B2V_REQUIRE(labels, B2V_ERR_ARG, "ws_flood: null labels");
     B2V_REQUIRE(!ambiguous || with_set, B2V_ERR_ARG, "ws_flood: the ambiguous mask needs the label sets");
-    k_wsf_labels<<<wsf_grid(g.n), 256, 0, s>>>(w.key, w.lset, g.n, labels, ambiguous);
+    if (use32) k_wsf_labels32<<<wsf_grid(g.n), 256, 0, s>>>(w.key32, w.lset, w.inv, g.n, labels, ambiguous);
+    else k_wsf_labels<<<wsf_grid(g.n), 256, 0, s>>>(w.key, w.lset, g.n, labels, ambiguous);
     if ((rc = b2v_check_launch("k_wsf_labels"))) return rc;
   }
   return B2V_OK;
@@ -942,7 +1074,7 @@ extern "C" int b2v_ws_flood_staged(int stages, const uint16_t* img, const int16_
                                    int64_t nx, int mode, int frozen_lo, int frozen_hi, int16_t* labels,
                                    uint8_t* ambiguous, void* workspace, void* stream, int* rounds_io) {
   return b2v_wsf_run(stages, img, markers, nz, ny, nx, mode, frozen_lo, frozen_hi, labels, ambiguous, 1, workspace,
-                     stream, rounds_io);
+                     stream, rounds_io, 0);
 }
 
 extern "C" int b2v_ws_stats(int* out8, int reset) {

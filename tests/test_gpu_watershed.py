@@ -293,3 +293,23 @@ def test_engine_matches_generic_kernels(wp, monkeypatch):
     for alg in ("Watershed", "Watershed IFT"):
         assert np.array_equal(res[("fast", alg)][0], res[("generic", alg)][0])
         assert np.array_equal(res[("fast", alg)][1], res[("generic", alg)][1])
+
+
+def test_many_labels_take_the_64_bit_keys(wp):
+    """More than 256 distinct marker labels do not fit the ranked 32-bit key (hops << 8 | rank): the
+    one-shot call then runs phase 2 on 64-bit keys. Same model, same answer; negative labels included."""
+    import ws_model
+    rng = np.random.default_rng(5)
+    shape = (20, 33, 48)
+    img = (ndimage.gaussian_filter(rng.normal(size=shape), 1.0) * 200 + 300).clip(0, 600).astype(np.uint16)
+    for nlab in (200, 300):
+        mk = np.zeros(shape, np.int16)
+        pos = rng.choice(img.size, nlab, replace=False)
+        labs = np.concatenate([np.arange(1, nlab // 2 + 1), -np.arange(1, nlab - nlab // 2 + 1)]).astype(np.int16)
+        mk.ravel()[pos] = labs
+        st = generate_binary_structure(3, 1)
+        for mode, alg in ((0, "Watershed IFT"), (1, "Watershed")):
+            lab, amb = wp.flood(_t(img.view(np.int16)), _t(mk), st, alg, True)
+            want_lab, want_amb = ws_model.flood(img, mk, mode)
+            assert np.array_equal(lab.cpu().numpy(), want_lab), (nlab, alg)
+            assert np.array_equal(amb.cpu().numpy(), want_amb), (nlab, alg)
