@@ -324,9 +324,40 @@ def extra_results(peak):
     except Exception as e:   # noqa: BLE001
         res["error_1024"] = f"{type(e).__name__}: {e}"
     try:
+        res["view_transform_512"] = view_transform_results(timeit)
+    except Exception as e:   # noqa: BLE001
+        res["view_transform_512"] = {"error": f"{type(e).__name__}: {e}"}
+    try:
         res["watershed_512"] = watershed_results()
     except Exception as e:   # noqa: BLE001
         res["watershed_512"] = {"error": f"{type(e).__name__}: {e}"}
+    return res
+
+
+def view_transform_results(timeit):
+    """apply_view_matrix_transform of a whole 512^3 int16 volume (apply_reorientation,
+    slice_.py:1980) through a rotation about its centre, device-resident, per interpolator; algorithmic
+    bytes 2 read + 2 written per voxel (the gathers hit L1 / L2)."""
+    import ctypes as C
+    import torch
+    from invesalius3_b200 import _lib, device as dev, phantom
+    n = 512
+    vol = torch.from_numpy(phantom.ct((n, n, n), seed=2)).cuda()
+    out = torch.empty_like(vol)
+    ws = dev._workspace(256, vol.device)
+    a = 0.3
+    c = n / 2.0
+    R = np.array([[1, 0, 0, 0], [0, np.cos(a), -np.sin(a), 0], [0, np.sin(a), np.cos(a), 0], [0, 0, 0, 1.0]])
+    T0 = np.eye(4); T0[:3, 3] = -c
+    T1 = np.eye(4); T1[:3, 3] = c
+    M = np.ascontiguousarray(T1 @ R @ T0)
+    sp = np.ones(3)
+    res = {}
+    for interp, name in ((0, "nearest"), (1, "trilinear"), (2, "tricubic"), (3, "lanczos4")):
+        fn = lambda: _lib.call("b2v_apply_view_matrix_transform", dev._p(vol), _lib.I16, n, n, n, C.c_void_p(sp.ctypes.data),
+                               C.c_void_p(M.ctypes.data), 0, 0, interp, -1024.0, dev._p(out), n, n, n, dev._p(ws), dev._stream())
+        ms = timeit(fn, iters=3, warmup=1)
+        res[name] = {"ms": round(ms, 3), "Mvoxel/s": round(n ** 3 / ms / 1e3, 1), "GBs_4B_per_voxel": round(4 * n ** 3 / ms / 1e6, 1)}
     return res
 
 

@@ -178,6 +178,21 @@ int b2v_fcm_volume(const void* img, int dtype, int64_t dz, int64_t dy, int64_t d
 int b2v_fast_countour_mip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, float n, int axis,
                           double wl, double ww, int tmip, void* out, void* workspace, void* stream);
 
+/* ---- view-matrix resampling --------------------------------------------
+ * invesalius_rs.apply_view_matrix_transform(volume, spacing, M, n, orientation, minterpol, cval,
+ * out): __init__.py:84 -> transforms_py.rs:96-148 -> transforms.rs:9-55 -> interpolation.rs.
+ * out[cz, cy, cx] samples `volume` at M * (z sz, y sy, x sx, 1) with (z, y, x) = the output
+ * index shifted by n along the slab axis (orientation 0 AXIAL: z, 1 CORONAL: y, 2 SAGITAL: x,
+ * anything else: no shift); minterpol 0 nearest, 1 trilinear, 2 tricubic, else Lanczos-4; outside
+ * [0, d - 1) on any axis: cval. float64 arithmetic in the reference's order. spacing_host =
+ * (sx, sy, sz), m_host = 16 doubles row-major, both on the HOST. volume / out: dense device
+ * arrays of the same dtype (int16, uint8, float64). workspace: >= 256 bytes. SYNCHRONISES (a value
+ * that does not fit the output type is B2V_ERR_RANGE: the reference panics). */
+int b2v_apply_view_matrix_transform(const void* volume, int dtype, int64_t dz, int64_t dy, int64_t dx,
+                                    const double* spacing_host, const double* m_host, int64_t n, int orientation,
+                                    int minterpol, double cval, void* out, int64_t odz, int64_t ody, int64_t odx,
+                                    void* workspace, void* stream);
+
 /* ---- marching cubes ---------------------------------------------------------------
  * Replaces the contour step of create_surface_piece, invesalius/data/surface_process.py:
  * 156-186 (vtkImageFlip about the origin + vtkContourFilter at iso 127 on the uint8 mask,

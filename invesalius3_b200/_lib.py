@@ -50,6 +50,8 @@ PROTOTYPES = {
     "b2v_fcm_workspace_bytes": (i64, [cint, i64, i64, i64, cint, cint]),
     "b2v_fcm_volume": (cint, [vp, cint, i64, i64, i64, f32, cint, vp, vp, vp]),
     "b2v_fast_countour_mip": (cint, [vp, cint, i64, i64, i64, f32, cint, dbl, dbl, cint, vp, vp, vp]),
+    "b2v_apply_view_matrix_transform": (cint, [vp, cint, i64, i64, i64, vp, vp, i64, cint, cint, dbl, vp, i64, i64, i64, vp,
+                                               vp]),
     "b2v_mc_workspace_bytes": (i64, [i64, i64, i64]),
     "b2v_mc_count": (cint, [vp, cint, i64, i64, i64, dbl, vp, vp, C.POINTER(i64), C.POINTER(i64)]),
     "b2v_mc_emit": (cint, [vp, cint, i64, i64, i64, dbl, vp, f32, f32, f32, i32, i32, i32, cint, vp, vp, vp]),

@@ -217,6 +217,42 @@ def fast_countour_mip(image, n, axis, wl, ww, tmip, out):
     dev.to_host(res[None], out[None])
 
 
+ORIENTATIONS = {"AXIAL": 0, "CORONAL": 1, "SAGITAL": 2}
+
+
+def apply_view_matrix_transform(volume, spacing, m, n, orientation, minterpol, cval, out):
+    """invesalius_rs/__init__.py:84 -> transforms_py.rs:96-148: resample `volume` through the 4x4
+    view matrix into the slab `out` (callers: slice_.py:865, 949, 1036, 1980, 2038). The volume is
+    shipped to the device whole (the rotation gathers from anywhere in it); `out` is written in place."""
+    import ctypes as C
+    from . import _lib
+    if not isinstance(volume, np.ndarray) or not isinstance(out, np.ndarray) or volume.dtype != out.dtype \
+            or volume.dtype not in _SUFFIX:
+        raise TypeError("Invalid volume or output type")
+    _need3(volume, "volume")
+    _need3(out, "out")
+    suf = _SUFFIX[volume.dtype]
+    cval = _extract(cval if suf == "f64" else int(cval), suf)
+    n = int(n)
+    if n < 0:
+        raise OverflowError("can't convert negative int to unsigned")
+    sp = np.ascontiguousarray([float(v) for v in spacing], dtype=np.float64)
+    mm = np.ascontiguousarray(m, dtype=np.float64)
+    if sp.shape != (3,) or mm.shape != (4, 4):
+        raise TypeError("spacing must have 3 entries and m must be 4x4")
+    if not out.flags.writeable:
+        raise ValueError("out is read-only")
+    d = dev.to_device(volume)
+    import torch
+    o = torch.empty(out.shape, dtype=d.dtype, device=d.device)
+    ws = dev._workspace(256, d.device)
+    with torch.cuda.device(d.device):
+        _lib.call("b2v_apply_view_matrix_transform", dev._p(d), dev.dtype_code(d), *volume.shape,
+                  C.c_void_p(sp.ctypes.data), C.c_void_p(mm.ctypes.data), n, ORIENTATIONS.get(orientation, 3), int(minterpol),
+                  float(cval), dev._p(o), *out.shape, dev._p(ws), dev._stream())
+    dev.to_host(o, out)
+
+
 # ---- the rest of the crate's surface (invesalius_rs/__init__.py:273-300) ---------------------------
 # The functions above replace the hot path. Everything else the reference imports from
 # `invesalius_rs` under its other aliases (`import invesalius_rs as transforms / cy_mesh / ...`:
@@ -228,12 +264,12 @@ def fast_countour_mip(image, n, axis, wl, ww, tmip, out):
 FORWARDED = (
     "trilin_interpolate_py", "nearest_neighbour_interp", "tricub_interpolate_py", "tricub_interpolate2_py",
     "lanczos_interpolate_py", "floodfill_auto_threshold", "floodfill_voronoi", "jump_flooding",
-    "apply_view_matrix_transform", "convolve_non_zero", "mask_cut", "polygon2mask_rs", "brush_mask_rs", "Mesh",
+    "convolve_non_zero", "mask_cut", "polygon2mask_rs", "brush_mask_rs", "Mesh",
     "ca_smoothing", "count_regions", "_native",
 )
 
 __all__ = ["floodfill", "floodfill_threshold", "floodfill_threshold_inplace", "fill_holes_automatically", "mida", "lmip",
-           "fast_countour_mip", *[n for n in FORWARDED if not n.startswith("_")]]
+           "fast_countour_mip", "apply_view_matrix_transform", *[n for n in FORWARDED if not n.startswith("_")]]
 
 _crate = None
 
@@ -246,7 +282,7 @@ def _load_crate():
             mod = importlib.import_module("invesalius_rs")     # the reference's own package (top level)
         except ImportError as e:
             raise ImportError("the compiled invesalius_rs crate is not installed: only the hot path "
-                              f"({', '.join(__all__[:7])}) is provided by invesalius3_b200") from e
+                              f"({', '.join(__all__[:8])}) is provided by invesalius3_b200") from e
         if mod is globals().get("__spec__") or getattr(mod, "__file__", None) == __file__:
             raise ImportError("invesalius_rs resolves to this shim; install the reference crate under its own name")
         _crate = mod

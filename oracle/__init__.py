@@ -255,6 +255,27 @@ def _mida_f64_f64(image, axis, wl, ww, out):
     raise NotImplementedError("f64 contour-MIDA is outside the GPU core's dtype set")
 
 
+# --------------------------------------------------------------------------- transforms
+ORIENT = {"AXIAL": 0, "CORONAL": 1, "SAGITAL": 2}
+
+
+def apply_view_matrix_transform(volume, spacing, m, n, orientation, minterpol, cval, out):
+    """invesalius_rs/__init__.py:84 -> transforms_py.rs:96-148 -> transforms.rs:9-55 ->
+    interpolation.rs (nearest 0, trilinear 1, tricubic 2, Lanczos-4 otherwise). PARITY UNPINNED
+    (no reference test): restated in oracle/transforms.c."""
+    suf = _SUFFIX.get(volume.dtype)
+    if suf is None or out.dtype != volume.dtype or volume.ndim != 3 or out.ndim != 3:
+        raise TypeError("Invalid volume or output type")
+    cval = _extract(cval if suf == "f64" else int(cval), suf)
+    mm = np.ascontiguousarray(m, dtype=np.float64).reshape(16)
+    sp = np.ascontiguousarray(spacing, dtype=np.float64)
+    fn = getattr(lib(), f"orc_avmt_{suf}")
+    rc = fn(_ptr(volume), _estrides(volume), *map(C.c_int64, volume.shape), _ptr(sp), _ptr(mm), C.c_int64(int(n)),
+            ORIENT.get(orientation, 3), int(minterpol), _CT[suf](cval), _ptr(out), _estrides(out), *map(C.c_int64, out.shape))
+    if rc:
+        raise ValueError("interpolated value not representable in the output type (Rust panic in interpolation.rs)")
+
+
 # --------------------------------------------------------------------------- marching cubes
 def marching_cubes(volume, iso, spacing=(1.0, 1.0, 1.0), origin_index=(0, 0, 0), flip_y=True):
     """Canonical marching cubes (parity unpinned: stands in for vtkContourFilter,
