@@ -324,6 +324,10 @@ def extra_results(peak):
     except Exception as e:   # noqa: BLE001
         res["error_1024"] = f"{type(e).__name__}: {e}"
     try:
+        res["label_512"] = label_results(timeit)
+    except Exception as e:   # noqa: BLE001
+        res["label_512"] = {"error": f"{type(e).__name__}: {e}"}
+    try:
         res["view_transform_512"] = view_transform_results(timeit)
     except Exception as e:   # noqa: BLE001
         res["view_transform_512"] = {"error": f"{type(e).__name__}: {e}"}
@@ -331,6 +335,30 @@ def extra_results(peak):
         res["watershed_512"] = watershed_results()
     except Exception as e:   # noqa: BLE001
         res["watershed_512"] = {"error": f"{type(e).__name__}: {e}"}
+    return res
+
+
+def label_results(timeit):
+    """scipy.ndimage.label of the 512^3 bone-threshold mask and of its complement (what
+    Mask.fill_holes_auto labels), 6-connected, device-resident; SciPy timed on a 64-plane slab."""
+    import torch
+    from scipy import ndimage
+    from invesalius3_b200 import labeling, phantom
+    vol = phantom.ct((512, 512, 512), seed=2)
+    img = (vol >= THR[0]) & (vol <= THR[1])
+    st = ndimage.generate_binary_structure(3, 1)
+    res = {}
+    for name, a in (("bone_mask", img), ("complement", ~img)):
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8)).cuda()
+        ms = timeit(lambda: labeling.label_device(t, st), iters=3, warmup=1)
+        lab, n = labeling.label_device(t, st)
+        slab = np.ascontiguousarray(a[224:288])
+        t0 = time.perf_counter()
+        w, nw = ndimage.label(slab, st, output=np.uint32)
+        cpu = time.perf_counter() - t0
+        g, ng = labeling.label(slab, st)
+        res[name] = {"ms": round(ms, 3), "Mvoxel/s": round(a.size / ms / 1e3, 1), "labels": n,
+                     "scipy_slab64_Mvoxel/s": round(slab.size / cpu / 1e6, 1), "slab_equals_scipy": bool(ng == nw and np.array_equal(g, w))}
     return res
 
 

@@ -178,6 +178,21 @@ int b2v_fcm_volume(const void* img, int dtype, int64_t dz, int64_t dy, int64_t d
 int b2v_fast_countour_mip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, float n, int axis,
                           double wl, double ww, int tmip, void* out, void* workspace, void* stream);
 
+/* ---- connected components ------------------------------------------------------
+ * b2v_label: scipy.ndimage.label(input, structure, output=uint32) as InVesalius calls it
+ * (invesalius/data/mask.py:526-530, 549-552; imagedata_utils.py:717-721): input uint8, non-zero =
+ * feature; strct_host uint8, 1 or 3 wide per axis, centrosymmetric (else B2V_ERR_ARG, SciPy raises
+ * too); labels uint32, numbered in raster order of each component's first voxel like SciPy.
+ * *nlabels_host receives the count. SYNCHRONISES. workspace: b2v_label_workspace_bytes(n voxels).
+ * b2v_count_regions: invesalius_rs.count_regions (count_regions.rs:5-18): out[p] = number of voxels
+ * holding image[p]'s value; values outside [0, number_regions] are B2V_ERR_RANGE (the reference
+ * panics). workspace: 256 + 4 * (number_regions + 1) bytes. */
+int64_t b2v_label_workspace_bytes(int64_t n);
+int b2v_label(const uint8_t* input, int64_t nz, int64_t ny, int64_t nx, const uint8_t* strct_host, int64_t odz, int64_t ody,
+              int64_t odx, uint32_t* labels, void* workspace, void* stream, int64_t* nlabels_host);
+int b2v_count_regions(const void* image, int dtype, int64_t n, uint32_t number_regions, uint32_t* out, void* workspace,
+                      void* stream);
+
 /* ---- view-matrix resampling --------------------------------------------
  * invesalius_rs.apply_view_matrix_transform(volume, spacing, M, n, orientation, minterpol, cval,
  * out): __init__.py:84 -> transforms_py.rs:96-148 -> transforms.rs:9-55 -> interpolation.rs.

@@ -217,6 +217,12 @@ def fast_countour_mip(image, n, axis, wl, ww, tmip, out):
     dev.to_host(res[None], out[None])
 
 
+def count_regions(image, number_regions):
+    """invesalius_rs/__init__.py:108-111 -> count_regions.rs:5-18."""
+    from . import labeling
+    return labeling.count_regions(image, number_regions)
+
+
 ORIENTATIONS = {"AXIAL": 0, "CORONAL": 1, "SAGITAL": 2}
 
 
@@ -265,11 +271,11 @@ FORWARDED = (
     "trilin_interpolate_py", "nearest_neighbour_interp", "tricub_interpolate_py", "tricub_interpolate2_py",
     "lanczos_interpolate_py", "floodfill_auto_threshold", "floodfill_voronoi", "jump_flooding",
     "convolve_non_zero", "mask_cut", "polygon2mask_rs", "brush_mask_rs", "Mesh",
-    "ca_smoothing", "count_regions", "_native",
+    "ca_smoothing", "_native",
 )
 
 __all__ = ["floodfill", "floodfill_threshold", "floodfill_threshold_inplace", "fill_holes_automatically", "mida", "lmip",
-           "fast_countour_mip", "apply_view_matrix_transform", *[n for n in FORWARDED if not n.startswith("_")]]
+           "fast_countour_mip", "apply_view_matrix_transform", "count_regions", *[n for n in FORWARDED if not n.startswith("_")]]
 
 _crate = None
 
@@ -282,7 +288,7 @@ def _load_crate():
             mod = importlib.import_module("invesalius_rs")     # the reference's own package (top level)
         except ImportError as e:
             raise ImportError("the compiled invesalius_rs crate is not installed: only the hot path "
-                              f"({', '.join(__all__[:8])}) is provided by invesalius3_b200") from e
+                              f"({', '.join(__all__[:9])}) is provided by invesalius3_b200") from e
         if mod is globals().get("__spec__") or getattr(mod, "__file__", None) == __file__:
             raise ImportError("invesalius_rs resolves to this shim; install the reference crate under its own name")
         _crate = mod

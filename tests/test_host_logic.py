@@ -129,13 +129,13 @@ def test_non_hot_exports_are_forwarded_to_the_crate(monkeypatch):
         rs.no_such_symbol
     fake = types.ModuleType("invesalius_rs")
     fake.__file__ = "/somewhere/invesalius_rs/__init__.py"
-    fake.count_regions = lambda image, n: ("crate", n)
+    fake.mask_cut = lambda image, n: ("crate", n)
     fake.Mesh = type("Mesh", (), {})
     monkeypatch.setitem(sys.modules, "invesalius_rs", fake)
-    assert rs.count_regions(None, 4) == ("crate", 4) and rs.Mesh is fake.Mesh
+    assert rs.mask_cut(None, 4) == ("crate", 4) and rs.Mesh is fake.Mesh
     for name in ("floodfill", "floodfill_threshold", "floodfill_threshold_inplace", "fill_holes_automatically", "mida",
                  "lmip", "fast_countour_mip"):
         assert callable(getattr(rs, name)) and getattr(rs, name).__module__ == rs.__name__   # hot path: ours
-    assert set(rs.FORWARDED) >= {"convolve_non_zero", "mask_cut", "polygon2mask_rs", "brush_mask_rs", "Mesh", "ca_smoothing",
-                                 "count_regions"}
-    assert "apply_view_matrix_transform" not in rs.FORWARDED and callable(rs.apply_view_matrix_transform)   # ours since 8f-1
+    assert set(rs.FORWARDED) >= {"convolve_non_zero", "mask_cut", "polygon2mask_rs", "brush_mask_rs", "Mesh", "ca_smoothing"}
+    for ours in ("apply_view_matrix_transform", "count_regions"):
+        assert ours not in rs.FORWARDED and callable(getattr(rs, ours))
