@@ -178,6 +178,24 @@ int b2v_fcm_volume(const void* img, int dtype, int64_t dz, int64_t dy, int64_t d
 int b2v_fast_countour_mip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, float n, int axis,
                           double wl, double ww, int tmip, void* out, void* workspace, void* stream);
 
+/* ---- pre-filters and mask algebra -------------------------------------------------
+ * b2v_boolean_op: Slice.do_boolean_op (invesalius/data/slice_.py:1906-1916) on two mask bodies:
+ *   op 0 union, 1 difference, 2 intersection, 3 xor; selected <=> value > 2; out = 0 / 255.
+ * b2v_convolve_non_zero: invesalius_rs.convolve_non_zero (transforms_py.rs:52-93; Slice.calc_mask_area,
+ *   slice_.py:2299-2322): float64 volume and kernel (device), out[p] = sum over the kernel window
+ *   (cval outside the volume) where volume[p] != 0, else 0; summed in the reference's loop order.
+ * b2v_median_filter_i16: scipy.ndimage.median_filter(matrix, size) with size 3 or 5, mode 'reflect'
+ *   (filters.py:9-12). in != out.
+ * b2v_uniform_filter_i16: scipy.ndimage.uniform_filter(matrix, size) on int16 (filters.py:15-18):
+ *   three separable passes, each storing trunc(window sum / size) in int16 as SciPy does when the
+ *   output array is int16. tmp: a third int16 volume. All bit-exact against SciPy. */
+int b2v_boolean_op(const uint8_t* m1, const uint8_t* m2, int64_t n, int op, uint8_t* out, void* stream);
+int b2v_convolve_non_zero(const double* volume, int64_t sz, int64_t sy, int64_t sx, const double* kernel_dev, int64_t skz,
+                          int64_t sky, int64_t skx, double cval, double* out, void* stream);
+int b2v_median_filter_i16(const int16_t* in, int64_t nz, int64_t ny, int64_t nx, int size, int16_t* out, void* stream);
+int b2v_uniform_filter_i16(const int16_t* in, int64_t nz, int64_t ny, int64_t nx, int size, int16_t* out, int16_t* tmp,
+                           void* stream);
+
 /* ---- connected components ------------------------------------------------------
  * b2v_label: scipy.ndimage.label(input, structure, output=uint32) as InVesalius calls it
  * (invesalius/data/mask.py:526-530, 549-552; imagedata_utils.py:717-721): input uint8, non-zero =

@@ -1,0 +1,176 @@
+// Whole-volume pre-filters and mask algebra: the step before threshold
+// (invesalius/data/filters.py:5-66 driven by slice_.py:2330-2432) and elementwise mask operations.
+//   b2v_boolean_op          Slice.do_boolean_op                   slice_.py:1906-1916
+//   b2v_convolve_non_zero   invesalius_rs.convolve_non_zero       transforms_py.rs:52-93 (calc_mask_area, slice_.py:2299-2322)
+//   b2v_median_filter_i16   ndimage.median_filter(matrix, size)   filters.py:9-12 (size 3 or 5, mode 'reflect')
+//   b2v_uniform_filter_i16  ndimage.uniform_filter(matrix, size)  filters.py:15-18 (separable; every pass stores
+//                           trunc(sum / size) in int16 like SciPy's NI_UniformFilter1D writing into an int16 output)
+// All integer results are bit-exact against SciPy / NumPy; convolve_non_zero sums in the reference's
+// loop order (k, j, i) in float64 without FMA.
+#include "b2v_common.cuh"
+
+namespace {
+
+int fgrid(long long n, int per = 256) {
+  long long blocks = ceil_div64(n, per);
+  long long cap = (long long)b2v_sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+__device__ __forceinline__ long long reflect_idx(long long i, long long n) {   // scipy mode='reflect': (d c b a | a b c d | d c b a)
+  if (n == 1) return 0;
+  const long long period = 2 * n;
+  i %= period;
+  if (i < 0) i += period;
+  return i < n ? i : period - 1 - i;
+}
+
+// op: 0 union, 1 difference, 2 intersection, 3 xor; selected <=> value > 2 (slice_.py:1906-1916)
+__global__ void __launch_bounds__(256) k_boolean_op(const uint8_t* __restrict__ m1, const uint8_t* __restrict__ m2, long long n,
+                                                    int op, uint8_t* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const bool a = m1[i] > 2, b = m2[i] > 2;
+    bool r;
+    if (op == 0) r = a || b;
+    else if (op == 1) r = a != (a && b);
+    else if (op == 2) r = a && b;
+    else r = a != b;
+    out[i] = r ? 255 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_convolve_non_zero(const double* __restrict__ vol, int sz, int sy, int sx,
+                                                           const double* __restrict__ ker, int skz, int sky, int skx,
+                                                           double cval, double* __restrict__ out) {
+  const long long n = (long long)sz * sy * sx;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    const int x = (int)(p % sx);
+    const long long r = p / sx;
+    const int y = (int)(r % sy), z = (int)(r / sy);
+    double sum = 0.0;
+    if (vol[p] != 0.0) {
+      for (int k = 0; k < skz; ++k) {
+        const int kz = z - skz / 2 + k;
+        for (int j = 0; j < sky; ++j) {
+          const int ky = y - sky / 2 + j;
+          for (int i = 0; i < skx; ++i) {
+            const int kx = x - skx / 2 + i;
+            const double v = (kz >= 0 && kz < sz && ky >= 0 && ky < sy && kx >= 0 && kx < sx)
+                                 ? vol[((long long)kz * sy + ky) * sx + kx] : cval;
+            sum += v * ker[(k * sky + j) * skx + i];
+          }
+        }
+      }
+    }
+    out[p] = sum;
+  }
+}
+
+// median of the S^3 neighbourhood (reflect borders): radix select on the order-preserving
+// unsigned image of the int16 values, 16 counting passes over the window kept in registers / local memory
+template <int S>
+__global__ void __launch_bounds__(128) k_median_i16(const int16_t* __restrict__ in, int nz, int ny, int nx,
+                                                    int16_t* __restrict__ out) {
+  constexpr int N = S * S * S, R = N / 2, H = S / 2;
+  const long long n = (long long)nz * ny * nx;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    const int x = (int)(p % nx);
+    const long long r = p / nx;
+    const int y = (int)(r % ny), z = (int)(r / ny);
+    unsigned short w[N];
+    int c = 0;
+#pragma unroll
+    for (int kz = 0; kz < S; ++kz) {
+      const long long zz = reflect_idx(z - H + kz, nz);
+#pragma unroll
+      for (int ky = 0; ky < S; ++ky) {
+        const long long yy = reflect_idx(y - H + ky, ny);
+        const int16_t* row = in + (zz * ny + yy) * nx;
+#pragma unroll
+        for (int kx = 0; kx < S; ++kx) w[c++] = (unsigned short)((int)row[reflect_idx(x - H + kx, nx)] + 32768);
+      }
+    }
+    // the largest value v such that at least N - R window entries are >= v  ==  the entry of rank R (0-based, ascending)
+    unsigned int v = 0;
+#pragma unroll 1
+    for (int bit = 15; bit >= 0; --bit) {
+      const unsigned int cand = v | (1u << bit);
+      int ge = 0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) ge += (unsigned int)w[k] >= cand;
+      if (ge >= N - R) v = cand;
+    }
+    out[p] = (int16_t)((int)v - 32768);
+  }
+}
+
+// one separable pass of uniform_filter along `axis`: out = trunc(window sum / size), int16 -> int16
+__global__ void __launch_bounds__(256) k_uniform1d_i16(const int16_t* __restrict__ in, int nz, int ny, int nx, int axis,
+                                                       int size, int16_t* __restrict__ out) {
+  const long long n = (long long)nz * ny * nx;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int len = axis == 0 ? nz : (axis == 1 ? ny : nx);
+  const long long step = axis == 0 ? (long long)ny * nx : (axis == 1 ? nx : 1);
+  const int lo = size / 2;        // window [i - size/2, i + size - 1 - size/2] (origin 0)
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    const int x = (int)(p % nx);
+    const long long r = p / nx;
+    const int y = (int)(r % ny), z = (int)(r / ny);
+    const int i = axis == 0 ? z : (axis == 1 ? y : x);
+    const long long base = p - (long long)i * step;
+    long long sum = 0;
+    for (int k = 0; k < size; ++k) sum += in[base + reflect_idx(i - lo + k, len) * step];
+    out[p] = (int16_t)((double)sum / (double)size);     // NI_UniformFilter1D: tmp / filter_size in double, C cast
+  }
+}
+
+}  // namespace
+
+extern "C" int b2v_boolean_op(const uint8_t* m1, const uint8_t* m2, int64_t n, int op, uint8_t* out, void* stream) {
+  B2V_REQUIRE(m1 && m2 && out && n > 0 && op >= 0 && op <= 3, B2V_ERR_ARG, "boolean_op: bad arguments");
+  k_boolean_op<<<fgrid(n, 1024), 256, 0, (cudaStream_t)stream>>>(m1, m2, n, op, out);
+  return b2v_check_launch("k_boolean_op");
+}
+
+extern "C" int b2v_convolve_non_zero(const double* volume, int64_t sz, int64_t sy, int64_t sx, const double* kernel_dev,
+                                     int64_t skz, int64_t sky, int64_t skx, double cval, double* out, void* stream) {
+  B2V_REQUIRE(volume && kernel_dev && out && sz > 0 && sy > 0 && sx > 0 && skz > 0 && sky > 0 && skx > 0, B2V_ERR_ARG,
+              "convolve_non_zero: bad arguments");
+  B2V_REQUIRE(sz < (1ll << 30) && sy < (1ll << 30) && sx < (1ll << 30) && skz * sky * skx < (1ll << 20), B2V_ERR_ARG,
+              "convolve_non_zero: shape too large");
+  k_convolve_non_zero<<<fgrid(sz * sy * sx), 256, 0, (cudaStream_t)stream>>>(volume, (int)sz, (int)sy, (int)sx, kernel_dev,
+                                                                             (int)skz, (int)sky, (int)skx, cval, out);
+  return b2v_check_launch("k_convolve_non_zero");
+}
+
+extern "C" int b2v_median_filter_i16(const int16_t* in, int64_t nz, int64_t ny, int64_t nx, int size, int16_t* out,
+                                     void* stream) {
+  B2V_REQUIRE(in && out && in != out && nz > 0 && ny > 0 && nx > 0 && nz * ny * nx < (1ll << 40), B2V_ERR_ARG,
+              "median_filter: bad arguments");
+  B2V_REQUIRE(size == 3 || size == 5, B2V_ERR_ARG, "median_filter: size must be 3 or 5 (filters.py:11 caps it there)");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (size == 3) k_median_i16<3><<<fgrid(nz * ny * nx, 128), 128, 0, s>>>(in, (int)nz, (int)ny, (int)nx, out);
+  else k_median_i16<5><<<fgrid(nz * ny * nx, 128), 128, 0, s>>>(in, (int)nz, (int)ny, (int)nx, out);
+  return b2v_check_launch("k_median_i16");
+}
+
+extern "C" int b2v_uniform_filter_i16(const int16_t* in, int64_t nz, int64_t ny, int64_t nx, int size, int16_t* out,
+                                      int16_t* tmp, void* stream) {
+  B2V_REQUIRE(in && out && tmp && in != out && in != tmp && out != tmp && nz > 0 && ny > 0 && nx > 0 && size >= 1,
+              B2V_ERR_ARG, "uniform_filter: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = nz * ny * nx;
+  int rc;
+  // SciPy filters axis 0 first (input -> output), then axes 1, 2 in place on the int16 output
+  k_uniform1d_i16<<<fgrid(n), 256, 0, s>>>(in, (int)nz, (int)ny, (int)nx, 0, size, out);
+  if ((rc = b2v_check_launch("k_uniform1d_i16"))) return rc;
+  k_uniform1d_i16<<<fgrid(n), 256, 0, s>>>(out, (int)nz, (int)ny, (int)nx, 1, size, tmp);
+  if ((rc = b2v_check_launch("k_uniform1d_i16"))) return rc;
+  k_uniform1d_i16<<<fgrid(n), 256, 0, s>>>(tmp, (int)nz, (int)ny, (int)nx, 2, size, out);
+  return b2v_check_launch("k_uniform1d_i16");
+}
