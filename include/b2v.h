@@ -195,6 +195,21 @@ int b2v_convolve_non_zero(const double* volume, int64_t sz, int64_t sy, int64_t 
 int b2v_median_filter_i16(const int16_t* in, int64_t nz, int64_t ny, int64_t nx, int size, int16_t* out, void* stream);
 int b2v_uniform_filter_i16(const int16_t* in, int64_t nz, int64_t ny, int64_t nx, int size, int16_t* out, int16_t* tmp,
                            void* stream);
+/* The Gaussian-based filters of filters.py (gaussian_blur :5-6, sharpening :21-29, despeckle :32-36,
+ * border detection :39-66) are built from scipy.ndimage.correlate1d evaluated exactly as SciPy's
+ * NI_Correlate1D does for symmetric (symmetry = +1) and antisymmetric (-1) odd kernels: tmp = x[c] w[0];
+ * for jj = -radius .. -1: tmp += (x[c + jj] +/- x[c - jj]) w[jj]; float64; 'reflect'; an int16 output
+ * takes the C cast. weights_dev: 2 radius + 1 centred float64 weights on the device (for a Gaussian:
+ * scipy.ndimage._filters._gaussian_kernel1d, reversed). dtype pairs (int16,int16), (int16,float64),
+ * (float64,float64). b2v_sharpen_i16, b2v_sobel_magnitude, b2v_rescale_cast_i16: the elementwise
+ * float64 statements around them, in NumPy's order. Bit-exact against SciPy. */
+int b2v_correlate1d(const void* in, int in_dtype, int64_t nz, int64_t ny, int64_t nx, int axis, const double* weights_dev,
+                    int radius, int symmetry, void* out, int out_dtype, void* stream);
+int b2v_sharpen_i16(const int16_t* img, const double* blurred, int64_t n, double value, double lo, double hi, int16_t* out,
+                    void* stream);
+int b2v_sobel_magnitude(double* sx_inout, const double* sy, const double* sz, int64_t n, void* stream);
+int b2v_rescale_cast_i16(const double* m, int64_t n, int rescale, double mag_min, double mag_range, double span,
+                         double min_val, int16_t* out, void* stream);
 
 /* ---- connected components ------------------------------------------------------
  * b2v_label: scipy.ndimage.label(input, structure, output=uint32) as InVesalius calls it

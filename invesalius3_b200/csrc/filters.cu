@@ -27,6 +27,12 @@ __device__ __forceinline__ long long reflect_idx(long long i, long long n) {   /
   return i < n ? i : period - 1 - i;
 }
 
+// double -> int16 like the x86 code NumPy / SciPy compile to: truncate into int32, keep the low 16 bits
+// (CUDA's direct double -> short conversion would saturate instead); identical for values in range
+template <typename TO> __device__ __forceinline__ TO cast_out(double v);
+template <> __device__ __forceinline__ int16_t cast_out<int16_t>(double v) { return (int16_t)(int)v; }
+template <> __device__ __forceinline__ double cast_out<double>(double v) { return v; }
+
 // op: 0 union, 1 difference, 2 intersection, 3 xor; selected <=> value > 2 (slice_.py:1906-1916)
 __global__ void __launch_bounds__(256) k_boolean_op(const uint8_t* __restrict__ m1, const uint8_t* __restrict__ m2, long long n,
                                                     int op, uint8_t* __restrict__ out) {
@@ -125,7 +131,65 @@ __global__ void __launch_bounds__(256) k_uniform1d_i16(const int16_t* __restrict
     const long long base = p - (long long)i * step;
     long long sum = 0;
     for (int k = 0; k < size; ++k) sum += in[base + reflect_idx(i - lo + k, len) * step];
-    out[p] = (int16_t)((double)sum / (double)size);     // NI_UniformFilter1D: tmp / filter_size in double, C cast
+    out[p] = cast_out<int16_t>((double)sum / (double)size);     // NI_UniformFilter1D: tmp / filter_size in double, C cast
+  }
+}
+
+// scipy.ndimage.correlate1d for symmetric (sym = +1) / antisymmetric (sym = -1) odd kernels, exactly as
+// NI_Correlate1D evaluates them: tmp = x[c] * w[0]; for jj = -r .. -1: tmp += (x[c + jj] (+/-) x[c - jj]) * w[jj],
+// float64, 'reflect' borders; an int16 output receives the C cast of tmp (truncation), as SciPy's line
+// buffer does. w: centred weights on the device (w[r] is the centre).
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) k_correlate1d(const TI* __restrict__ in, int nz, int ny, int nx, int axis,
+                                                     const double* __restrict__ w, int r, int sym, TO* __restrict__ out) {
+  const long long n = (long long)nz * ny * nx;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int len = axis == 0 ? nz : (axis == 1 ? ny : nx);
+  const long long step = axis == 0 ? (long long)ny * nx : (axis == 1 ? nx : 1);
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    const int x = (int)(p % nx);
+    const long long rr = p / nx;
+    const int y = (int)(rr % ny), z = (int)(rr / ny);
+    const int c = axis == 0 ? z : (axis == 1 ? y : x);
+    const long long base = p - (long long)c * step;
+    double tmp = (double)in[p] * w[r];
+    for (int jj = -r; jj < 0; ++jj) {
+      const double lo = (double)in[base + reflect_idx(c + jj, len) * step];
+      const double hi = (double)in[base + reflect_idx(c - jj, len) * step];
+      tmp += (sym > 0 ? lo + hi : lo - hi) * w[r + jj];
+    }
+    out[p] = cast_out<TO>(tmp);
+  }
+}
+
+// sharpening_filter (filters.py:21-29): clip(f + (value * 0.5) * (f - blurred), min, max).astype(int16)
+__global__ void __launch_bounds__(256) k_sharpen(const int16_t* __restrict__ img, const double* __restrict__ blurred, long long n,
+                                                 double half_value, double lo, double hi, int16_t* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double f = (double)img[i];
+    double s = f + half_value * (f - blurred[i]);
+    s = s < lo ? lo : (s > hi ? hi : s);
+    out[i] = cast_out<int16_t>(s);
+  }
+}
+
+// border_detection_filter (filters.py:45-51): sqrt(sx**2 + sy**2 + sz**2), in place into a
+__global__ void __launch_bounds__(256) k_sobel_magnitude(double* a, const double* __restrict__ b, const double* __restrict__ c,
+                                                         long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    a[i] = sqrt((a[i] * a[i] + b[i] * b[i]) + c[i] * c[i]);
+}
+
+// (magnitude - mag_min) / mag_range * span + min_val, cast to int16 (filters.py:56-66); scale = 0: plain cast
+__global__ void __launch_bounds__(256) k_rescale_cast(const double* __restrict__ m, long long n, int rescale, double mag_min,
+                                                      double mag_range, double span, double min_val, int16_t* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double v = m[i];
+    if (rescale) v = (v - mag_min) / mag_range * span + min_val;
+    out[i] = cast_out<int16_t>(v);
   }
 }
 
@@ -173,4 +237,43 @@ extern "C" int b2v_uniform_filter_i16(const int16_t* in, int64_t nz, int64_t ny,
   if ((rc = b2v_check_launch("k_uniform1d_i16"))) return rc;
   k_uniform1d_i16<<<fgrid(n), 256, 0, s>>>(tmp, (int)nz, (int)ny, (int)nx, 2, size, out);
   return b2v_check_launch("k_uniform1d_i16");
+}
+
+// dtype codes: B2V_I16 or B2V_F64 for input and output; in != out
+extern "C" int b2v_correlate1d(const void* in, int in_dtype, int64_t nz, int64_t ny, int64_t nx, int axis,
+                               const double* weights_dev, int radius, int symmetry, void* out, int out_dtype, void* stream) {
+  B2V_REQUIRE(in && out && in != out && weights_dev && nz > 0 && ny > 0 && nx > 0 && axis >= 0 && axis <= 2 && radius >= 0 &&
+                  (symmetry == 1 || symmetry == -1),
+              B2V_ERR_ARG, "correlate1d: bad arguments");
+  B2V_REQUIRE(nz < (1ll << 30) && ny < (1ll << 30) && nx < (1ll << 30), B2V_ERR_ARG, "correlate1d: shape too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = fgrid(nz * ny * nx);
+  if (in_dtype == B2V_I16 && out_dtype == B2V_I16)
+    k_correlate1d<int16_t, int16_t><<<g, 256, 0, s>>>((const int16_t*)in, (int)nz, (int)ny, (int)nx, axis, weights_dev, radius, symmetry, (int16_t*)out);
+  else if (in_dtype == B2V_I16 && out_dtype == B2V_F64)
+    k_correlate1d<int16_t, double><<<g, 256, 0, s>>>((const int16_t*)in, (int)nz, (int)ny, (int)nx, axis, weights_dev, radius, symmetry, (double*)out);
+  else if (in_dtype == B2V_F64 && out_dtype == B2V_F64)
+    k_correlate1d<double, double><<<g, 256, 0, s>>>((const double*)in, (int)nz, (int)ny, (int)nx, axis, weights_dev, radius, symmetry, (double*)out);
+  else B2V_REQUIRE(false, B2V_ERR_ARG, "correlate1d: dtype pair must be (int16,int16), (int16,float64) or (float64,float64)");
+  return b2v_check_launch("k_correlate1d");
+}
+
+extern "C" int b2v_sharpen_i16(const int16_t* img, const double* blurred, int64_t n, double value, double lo, double hi,
+                               int16_t* out, void* stream) {
+  B2V_REQUIRE(img && blurred && out && n > 0, B2V_ERR_ARG, "sharpen: bad arguments");
+  k_sharpen<<<fgrid(n), 256, 0, (cudaStream_t)stream>>>(img, blurred, n, value * 0.5, lo, hi, out);
+  return b2v_check_launch("k_sharpen");
+}
+
+extern "C" int b2v_sobel_magnitude(double* sx_inout, const double* sy, const double* sz, int64_t n, void* stream) {
+  B2V_REQUIRE(sx_inout && sy && sz && n > 0, B2V_ERR_ARG, "sobel_magnitude: bad arguments");
+  k_sobel_magnitude<<<fgrid(n), 256, 0, (cudaStream_t)stream>>>(sx_inout, sy, sz, n);
+  return b2v_check_launch("k_sobel_magnitude");
+}
+
+extern "C" int b2v_rescale_cast_i16(const double* m, int64_t n, int rescale, double mag_min, double mag_range, double span,
+                                    double min_val, int16_t* out, void* stream) {
+  B2V_REQUIRE(m && out && n > 0, B2V_ERR_ARG, "rescale_cast: bad arguments");
+  k_rescale_cast<<<fgrid(n), 256, 0, (cudaStream_t)stream>>>(m, n, rescale, mag_min, mag_range, span, min_val, out);
+  return b2v_check_launch("k_rescale_cast");
 }

@@ -21,8 +21,38 @@ def test_median_and_mean_equal_scipy(shape):
     for value in (0.5, 1.0, 2.0, 3.0):           # sizes 2, 3, 5, 7
         want = ndimage.uniform_filter(a, size=int(2 * value + 1)).astype(a.dtype)
         assert np.array_equal(filters.mean_blur_filter(a, value), want), (shape, value)
-    with pytest.raises(NotImplementedError):
-        filters.gaussian_blur_filter(a, 1.0)
+
+
+def test_gaussian_family_equals_scipy():
+    """filters.py:5-66 statement for statement against SciPy on the host."""
+    from invesalius3_b200 import filters
+    for shape in ((12, 13, 14), (20, 33, 47), (1, 30, 40)):
+        matrix = _img(shape, 3 + sum(shape))
+        for sigma in (0.5, 1.0, 1.7, 3.0):
+            assert np.array_equal(filters.gaussian_blur_filter(matrix, sigma), ndimage.gaussian_filter(matrix, sigma=sigma))
+            assert np.array_equal(filters.despeckle_filter(matrix, sigma), ndimage.gaussian_filter(matrix, sigma=sigma))
+        for value in (1.0, 2.5):
+            dtype = matrix.dtype
+            min_val, max_val = matrix.min(), matrix.max()
+            float_matrix = matrix.astype(float)
+            blurred = ndimage.gaussian_filter(float_matrix, sigma=1.0)
+            detail = float_matrix - blurred
+            sharpened = float_matrix + value * 0.5 * detail
+            want = np.clip(sharpened, min_val, max_val).astype(dtype)
+            assert np.array_equal(filters.sharpening_filter(matrix, value), want), (shape, value)
+        for value, normalize in ((1.0, True), (2.0, True), (1.0, False)):
+            f = ndimage.gaussian_filter(matrix.astype(float), sigma=value)
+            sx, sy, sz = ndimage.sobel(f, axis=0), ndimage.sobel(f, axis=1), ndimage.sobel(f, axis=2)
+            magnitude = np.sqrt(sx**2 + sy**2 + sz**2)
+            if normalize:
+                min_val, max_val = float(matrix.min()), float(matrix.max())
+                mag_min = magnitude.min()
+                mag_range = magnitude.max() - mag_min
+                if mag_range > 0:
+                    magnitude = (magnitude - mag_min) / mag_range * (max_val - min_val) + min_val
+            with np.errstate(invalid="ignore"):
+                want = magnitude.astype(matrix.dtype)
+            assert np.array_equal(filters.border_detection_filter(matrix, value, normalize), want), (shape, value, normalize)
 
 
 def test_boolean_ops_and_convolve_non_zero():
