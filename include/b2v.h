@@ -178,6 +178,20 @@ int b2v_fcm_volume(const void* img, int dtype, int64_t dz, int64_t dy, int64_t d
 int b2v_fast_countour_mip(const void* img, int dtype, int64_t dz, int64_t dy, int64_t dx, float n, int axis,
                           double wl, double ww, int tmip, void* out, void* workspace, void* stream);
 
+/* ---- context-aware mesh smoothing ------------------------------------------------
+ * invesalius_rs.context_aware_smoothing(vertices, faces, normals, T, tmax, bmin, n_iters)
+ * (mesh_py.rs -> mesh.rs:27-395; Mesh.ca_smoothing, invesalius_rs/__init__.py:220-249; caller
+ * invesalius/data/surface_process.py:312-320). vertices float32 [V][3], smoothed in place; faces4
+ * int64 [M][4] with the leading 3; normals float32 [M][3] (per face). order: int64 [4 M], the STABLE
+ * ascending argsort of the 4 M face entries (any stable sort; the host wrapper uses torch.sort).
+ * The reference's quirks are kept (every column of a face row counts as a vertex id in the
+ * vertex->face map; the staircase test flags every vertex that has a face). workspace:
+ * b2v_ca_smoothing_workspace_bytes. SYNCHRONISES. */
+int64_t b2v_ca_smoothing_workspace_bytes(int64_t nverts, int64_t nfaces);
+int b2v_ca_smoothing(float* vertices, int64_t nverts, const int64_t* faces4, int64_t nfaces, const float* normals,
+                     const int64_t* order, double t, double tmax, double bmin, uint32_t n_iters, void* workspace,
+                     void* stream);
+
 /* ---- pre-filters and mask algebra -------------------------------------------------
  * b2v_boolean_op: Slice.do_boolean_op (invesalius/data/slice_.py:1906-1916) on two mask bodies:
  *   op 0 union, 1 difference, 2 intersection, 3 xor; selected <=> value > 2; out = 0 / 255.

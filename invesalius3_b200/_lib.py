@@ -50,6 +50,8 @@ PROTOTYPES = {
     "b2v_fcm_workspace_bytes": (i64, [cint, i64, i64, i64, cint, cint]),
     "b2v_fcm_volume": (cint, [vp, cint, i64, i64, i64, f32, cint, vp, vp, vp]),
     "b2v_fast_countour_mip": (cint, [vp, cint, i64, i64, i64, f32, cint, dbl, dbl, cint, vp, vp, vp]),
+    "b2v_ca_smoothing_workspace_bytes": (i64, [i64, i64]),
+    "b2v_ca_smoothing": (cint, [vp, i64, vp, i64, vp, vp, dbl, dbl, dbl, u32, vp, vp]),
     "b2v_boolean_op": (cint, [vp, vp, i64, cint, vp, vp]),
     "b2v_convolve_non_zero": (cint, [vp, i64, i64, i64, vp, i64, i64, i64, dbl, vp, vp]),
     "b2v_median_filter_i16": (cint, [vp, i64, i64, i64, cint, vp, vp]),

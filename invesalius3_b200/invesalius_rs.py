@@ -223,6 +223,16 @@ def count_regions(image, number_regions):
     return labeling.count_regions(image, number_regions)
 
 
+def _mesh_ops():
+    from . import mesh_ops
+    return mesh_ops
+
+
+def ca_smoothing(mesh, T, tmax, bmin, n_iters):
+    """invesalius_rs/__init__.py:251-270 (Mesh.ca_smoothing -> mesh.rs:27-395)."""
+    mesh.ca_smoothing(T, tmax, bmin, n_iters)
+
+
 def convolve_non_zero(volume, kernel, cval):
     """invesalius_rs/__init__.py -> transforms_py.rs:52-93 (Slice.calc_mask_area, slice_.py:2319)."""
     from . import filters
@@ -276,12 +286,11 @@ def apply_view_matrix_transform(volume, spacing, m, n, orientation, minterpol, c
 FORWARDED = (
     "trilin_interpolate_py", "nearest_neighbour_interp", "tricub_interpolate_py", "tricub_interpolate2_py",
     "lanczos_interpolate_py", "floodfill_auto_threshold", "floodfill_voronoi", "jump_flooding",
-    "mask_cut", "polygon2mask_rs", "brush_mask_rs", "Mesh",
-    "ca_smoothing", "_native",
+    "mask_cut", "polygon2mask_rs", "brush_mask_rs", "_native",
 )
 
 __all__ = ["floodfill", "floodfill_threshold", "floodfill_threshold_inplace", "fill_holes_automatically", "mida", "lmip",
-           "fast_countour_mip", "apply_view_matrix_transform", "count_regions", "convolve_non_zero", *[n for n in FORWARDED if not n.startswith("_")]]
+           "fast_countour_mip", "apply_view_matrix_transform", "count_regions", "convolve_non_zero", "Mesh", "ca_smoothing", *[n for n in FORWARDED if not n.startswith("_")]]
 
 _crate = None
 
@@ -294,7 +303,7 @@ def _load_crate():
             mod = importlib.import_module("invesalius_rs")     # the reference's own package (top level)
         except ImportError as e:
             raise ImportError("the compiled invesalius_rs crate is not installed: only the hot path "
-                              f"({', '.join(__all__[:10])}) is provided by invesalius3_b200") from e
+                              f"({', '.join(__all__[:12])}) is provided by invesalius3_b200") from e
         if mod is globals().get("__spec__") or getattr(mod, "__file__", None) == __file__:
             raise ImportError("invesalius_rs resolves to this shim; install the reference crate under its own name")
         _crate = mod
@@ -302,6 +311,8 @@ def _load_crate():
 
 
 def __getattr__(name):
+    if name == "Mesh":                       # array-based Mesh of mesh_ops (no VTK needed on this side)
+        return _mesh_ops().Mesh
     if name in FORWARDED:
         try:
             return getattr(_load_crate(), name)
