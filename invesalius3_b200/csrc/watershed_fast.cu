@@ -35,7 +35,6 @@ constexpr int kThreads = 256;
 constexpr int kMaxSets = 8;            // sweep sets per visit before the tile re-queues itself
 constexpr uint32_t kInfC = 0xffffffffu;
 constexpr unsigned long long kInfK = ~0ull;
-constexpr unsigned long long kHop = 1ull << 32;
 constexpr uint16_t kSetEmpty = 32768, kSetMulti = 0;
 // phase-2 key: hops above the label. 64 bits hold any label (uint16 code) and any hop count; when
 // the markers carry at most 256 distinct labels the key is hops << 8 | rank of the label (32 bits):

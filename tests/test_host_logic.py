@@ -139,3 +139,35 @@ def test_non_hot_exports_are_forwarded_to_the_crate(monkeypatch):
     assert set(rs.FORWARDED) >= {"mask_cut", "polygon2mask_rs", "brush_mask_rs"}
     for ours in ("apply_view_matrix_transform", "count_regions", "convolve_non_zero", "ca_smoothing", "Mesh"):   # SURVEY 8f-1 .. 8f-4
         assert ours not in rs.FORWARDED and callable(getattr(rs, ours))
+
+
+def test_new_shims_reject_bad_arguments_before_device_work():
+    """The 8f shims validate dtypes / ranges like the reference's PyO3 layer before touching the device."""
+    from invesalius3_b200 import filters, invesalius_rs as rs, labeling, mesh_ops
+    vol = np.zeros((4, 5, 6), np.int16)
+    with pytest.raises(TypeError):        # volume / out dtype mismatch (transforms_py.rs:147)
+        rs.apply_view_matrix_transform(vol, (1, 1, 1), np.eye(4), 0, "AXIAL", 1, 0, np.zeros((1, 5, 6), np.uint8))
+    with pytest.raises(OverflowError):    # cval.extract::<i16>()
+        rs.apply_view_matrix_transform(vol, (1, 1, 1), np.eye(4), 0, "AXIAL", 1, 40000, np.zeros((1, 5, 6), np.int16))
+    with pytest.raises(TypeError):
+        rs.apply_view_matrix_transform(vol, (1, 1), np.eye(4), 0, "AXIAL", 1, 0, np.zeros((1, 5, 6), np.int16))
+    with pytest.raises(TypeError):
+        filters.median_blur_filter(vol.astype(np.float32), 1.0)
+    with pytest.raises(TypeError):
+        filters.boolean_op(filters.BOOLEAN_AND, vol, vol, vol)
+    with pytest.raises(KeyError):
+        filters.boolean_op(9, vol.astype(np.uint8), vol.astype(np.uint8), vol.astype(np.uint8))
+    with pytest.raises(OverflowError):
+        filters.convolve_non_zero(np.zeros((3, 3, 3)), np.ones((3, 3, 3)), 70000)
+    with pytest.raises(NotImplementedError):
+        labeling.label(np.zeros((2, 2, 2, 2), bool))
+    with pytest.raises(RuntimeError):
+        labeling.label(np.zeros((4, 4), bool), np.ones((3, 3, 3), bool))
+    with pytest.raises(TypeError):
+        mesh_ops.context_aware_smoothing(np.zeros((3, 3), np.float64), np.zeros((1, 4), np.int64), np.zeros((1, 3), np.float32), 0.7, 3, 0.1, 1)
+    with pytest.raises(TypeError):
+        mesh_ops.context_aware_smoothing(np.zeros((3, 3), np.float32), np.zeros((1, 4), np.float32), np.zeros((1, 3), np.float32), 0.7, 3, 0.1, 1)
+    with pytest.raises(ValueError):
+        mesh_ops.Mesh()
+    m = mesh_ops.Mesh(vertices=np.zeros((3, 3), np.float32), faces=np.array([[3, 0, 1, 2]]), normals=np.zeros((1, 3), np.float32))
+    assert mesh_ops.Mesh(other=m).faces is not m.faces and rs.Mesh is mesh_ops.Mesh
