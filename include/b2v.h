@@ -198,7 +198,7 @@ int b2v_ca_smoothing(float* vertices, int64_t nverts, const int64_t* faces4, int
  * b2v_convolve_non_zero: invesalius_rs.convolve_non_zero (transforms_py.rs:52-93; Slice.calc_mask_area,
  *   slice_.py:2299-2322): float64 volume and kernel (device), out[p] = sum over the kernel window
  *   (cval outside the volume) where volume[p] != 0, else 0; summed in the reference's loop order.
- * b2v_median_filter_i16: scipy.ndimage.median_filter(matrix, size) with size 3 or 5, mode 'reflect'
+ * b2v_median_filter_i16: scipy.ndimage.median_filter(matrix, size) with size 3, 4 or 5, mode 'reflect'
  *   (filters.py:9-12). in != out.
  * b2v_uniform_filter_i16: scipy.ndimage.uniform_filter(matrix, size) on int16 (filters.py:15-18):
  *   three separable passes, each storing trunc(window sum / size) in int16 as SciPy does when the

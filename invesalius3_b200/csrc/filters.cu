@@ -2,7 +2,7 @@
 // (invesalius/data/filters.py:5-66 driven by slice_.py:2330-2432) and elementwise mask operations.
 //   b2v_boolean_op          Slice.do_boolean_op                   slice_.py:1906-1916
 //   b2v_convolve_non_zero   invesalius_rs.convolve_non_zero       transforms_py.rs:52-93 (calc_mask_area, slice_.py:2299-2322)
-//   b2v_median_filter_i16   ndimage.median_filter(matrix, size)   filters.py:9-12 (size 3 or 5, mode 'reflect')
+//   b2v_median_filter_i16   ndimage.median_filter(matrix, size)   filters.py:9-12 (size 3, 4 or 5, mode 'reflect')
 //   b2v_uniform_filter_i16  ndimage.uniform_filter(matrix, size)  filters.py:15-18 (separable; every pass stores
 //                           trunc(sum / size) in int16 like SciPy's NI_UniformFilter1D writing into an int16 output)
 // All integer results are bit-exact against SciPy / NumPy; convolve_non_zero sums in the reference's
@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256) k_convolve_non_zero(const double* __restr
   }
 }
 
-// median of the S^3 neighbourhood (reflect borders): radix select on the order-preserving
+// median of the S^3 neighbourhood (reflect borders; window [i - S/2, i - S/2 + S) and rank S^3 / 2 as
+// scipy.ndimage.median_filter takes them, even sizes included): radix select on the order-preserving
 // unsigned image of the int16 values, 16 counting passes over the window kept in registers / local memory
 template <int S>
 __global__ void __launch_bounds__(128) k_median_i16(const int16_t* __restrict__ in, int nz, int ny, int nx,
@@ -216,9 +217,10 @@ extern "C" int b2v_median_filter_i16(const int16_t* in, int64_t nz, int64_t ny, 
                                      void* stream) {
   B2V_REQUIRE(in && out && in != out && nz > 0 && ny > 0 && nx > 0 && nz * ny * nx < (1ll << 40), B2V_ERR_ARG,
               "median_filter: bad arguments");
-  B2V_REQUIRE(size == 3 || size == 5, B2V_ERR_ARG, "median_filter: size must be 3 or 5 (filters.py:11 caps it there)");
+  B2V_REQUIRE(size >= 3 && size <= 5, B2V_ERR_ARG, "median_filter: size must be 3, 4 or 5 (filters.py:11 keeps it there)");
   cudaStream_t s = (cudaStream_t)stream;
   if (size == 3) k_median_i16<3><<<fgrid(nz * ny * nx, 128), 128, 0, s>>>(in, (int)nz, (int)ny, (int)nx, out);
+  else if (size == 4) k_median_i16<4><<<fgrid(nz * ny * nx, 128), 128, 0, s>>>(in, (int)nz, (int)ny, (int)nx, out);
   else k_median_i16<5><<<fgrid(nz * ny * nx, 128), 128, 0, s>>>(in, (int)nz, (int)ny, (int)nx, out);
   return b2v_check_launch("k_median_i16");
 }

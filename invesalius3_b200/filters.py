@@ -1,6 +1,6 @@
 """Pre-filters and mask algebra with the reference's signatures, numpy in / numpy out:
 
-  median_blur_filter(matrix, value)   invesalius/data/filters.py:9-12   ndimage.median_filter, size 3 or 5
+  median_blur_filter(matrix, value)   invesalius/data/filters.py:9-12   ndimage.median_filter, size 3, 4 or 5
   mean_blur_filter(matrix, value)     filters.py:15-18                  ndimage.uniform_filter(...).astype(dtype)
   boolean_op(op, m1, m2, out)         Slice.do_boolean_op, slice_.py:1906-1916 (mask bodies)
   convolve_non_zero(volume, kernel, cval)   invesalius_rs.convolve_non_zero (calc_mask_area, slice_.py:2299-2322)
@@ -32,8 +32,6 @@ def _i16_volume(matrix):
 def median_blur_filter(matrix: np.ndarray, value: float) -> np.ndarray:
     a = _i16_volume(matrix)
     size = max(3, min(int(2 * value + 1), 5))
-    if size == 4:
-        raise NotImplementedError("median_filter: even sizes are not built (the reference reaches 3, 4 or 5)")
     t = dev.to_device(a)
     out = torch.empty_like(t)
     with torch.cuda.device(t.device):

@@ -15,7 +15,7 @@ def _img(shape, seed):
 def test_median_and_mean_equal_scipy(shape):
     from invesalius3_b200 import filters
     a = _img(shape, sum(shape))
-    for value in (1.0, 1.4, 2.0, 3.0):           # sizes 3, 3, 5, 5 (capped)
+    for value in (1.0, 1.4, 1.5, 2.0, 3.0):      # sizes 3, 3, 4, 5, 5 (capped)
         size = max(3, min(int(2 * value + 1), 5))
         assert np.array_equal(filters.median_blur_filter(a, value), ndimage.median_filter(a, size=size)), (shape, value)
     for value in (0.5, 1.0, 2.0, 3.0):           # sizes 2, 3, 5, 7
