@@ -802,7 +802,7 @@ __global__ void __launch_bounds__(kFcmThreads, 3) k_fcm_volume(const T* __restri
         const float dd = __fadd_rn(__fadd_rn(__fmul_rn(gxf, dirx), __fmul_rn(gyf, diry)), __fmul_rn(gzf, dirz));
         const float base = __fsub_rn(1.0f, fabsf(__fdiv_rn(dd, gm)));
         // powf of the reference is libm's (<1 ulp); a double pow rounded once is within the same ulp;
-        // n == 1 (InVesalius' default border size) and n == 2 are exact in any libm
+        // n == 1 (InVesalius' default border size) is exact in any libm; n == 2 is x * x here (glibc: <= 1 ulp off)
         const float sf = n == 1.0f ? base : (n == 2.0f ? __fmul_rn(base, base) : (float)pow((double)base, (double)n));
         val = __fmul_rn(gm, sf);
       }

@@ -216,3 +216,81 @@ def test_lmip_small(orc):
     assert out[0, 0] == 900  # first local max after entering [tmin, tmax]
     orc.lmip(img, 0, 3000, 3033, out)
     assert out[0, 0] == 2000  # never entered the window: plain max
+
+
+# ---- wider independent cross-checks of the unpinned projections (no reference test exists for them):
+# second restatements written from mips.rs in vectorised NumPy float32, compared on larger volumes,
+# every dtype pair and axis
+def _lmip_numpy(img, axis, tmin, tmax):
+    a = np.moveaxis(img, axis, 0)
+    tmin, tmax = a.dtype.type(tmin), a.dtype.type(tmax)
+    mv = a[0].copy()
+    start = (a[0] >= tmin) & (a[0] <= tmax)
+    done = np.zeros(mv.shape, bool)
+    for v in a:                      # mips.rs:40-66, all rays of a plane at once
+        act = ~done
+        gt = v > mv
+        stop = act & ~gt & (v < mv) & start
+        mv = np.where(act & gt, v, mv)
+        done |= stop
+        start |= act & ~stop & (v >= tmin) & (v <= tmax)
+    return mv
+
+
+def _fcm_numpy(img, n, axis):
+    f = np.float32
+    def diff(hi, lo):
+        if img.dtype == np.float64:
+            return (hi - lo).astype(f)
+        return (hi.astype(np.int64) - lo.astype(np.int64)).astype(img.dtype).astype(f)   # wraps like the release build
+    p = np.pad(img, 1, mode="edge")
+    gz = diff(p[2:, 1:-1, 1:-1], p[:-2, 1:-1, 1:-1]) / f(2)
+    gy = diff(p[1:-1, 2:, 1:-1], p[1:-1, :-2, 1:-1]) / f(2)
+    gx = diff(p[1:-1, 1:-1, 2:], p[1:-1, 1:-1, :-2]) / f(2)
+    gm = np.sqrt(((gx * gx).astype(f) + (gy * gy).astype(f)).astype(f) + (gz * gz).astype(f)).astype(f)
+    d = [gz, gy, gx][axis]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        base = (f(1) - np.abs((d / gm).astype(f))).astype(f)
+        sf = base if n == 1 else (base * base).astype(f)
+        val = np.where(gm == 0, f(0), (gm * sf).astype(f))
+    return val.astype(img.dtype) if img.dtype != np.float64 else val.astype(np.float64)
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_projections_against_second_restatements(orc, axis):
+    rng = np.random.default_rng(10 + axis)
+    shape = (9, 11, 13)
+    smooth = ndimage.gaussian_filter(rng.normal(size=shape), 1.0)
+    i16 = (smooth / np.abs(smooth).max() * 1800 + 500).astype(np.int16)
+    u8 = ((i16.astype(np.int32) + 1400) // 16).clip(0, 255).astype(np.uint8)
+    f64 = i16.astype(np.float64) * 0.37
+    oshape = [(shape[1], shape[2]), (shape[0], shape[2]), (shape[0], shape[1])][axis]
+    # MIDA: (int16,int16) and (uint8,uint8)
+    for img, wl, ww in ((i16, 300, 600), (u8, 100, 60)):
+        out = np.zeros(oshape, img.dtype)
+        orc.mida(img, axis, wl, ww, out)
+        assert np.array_equal(out, _mida_numpy(img, axis, wl, ww)), img.dtype
+    # LMIP: every image dtype
+    for img, tmin, tmax in ((i16, 700, 3033), (u8, 90, 200), (f64, 100.0, 900.0)):
+        out = np.zeros(oshape, img.dtype)
+        orc.lmip(img, axis, tmin, tmax, out)
+        assert np.array_equal(out, _lmip_numpy(img, axis, tmin, tmax)), img.dtype
+    # contour volume (mips.rs:170-242) for the exact exponents, every dtype; then its projections
+    for img in (i16, u8, f64):
+        for n in (1, 2):
+            got, want = orc.fcm_volume(img, float(n), axis), _fcm_numpy(img, n, axis)
+            if n == 2 and img.dtype == np.float64:
+                # powf(x, 2) of glibc (what the reference's f32::powf calls) is faithfully, not correctly,
+                # rounded: a few values per thousand sit one float32 ulp from x * x
+                ulp = np.spacing(np.abs(want).astype(np.float32)).astype(np.float64)
+                assert (np.abs(got - want) <= ulp).all() and (got != want).mean() < 0.01
+            else:
+                assert np.array_equal(got, want), (img.dtype, n)
+    tmp = _fcm_numpy(i16, 2, axis)
+    out = np.zeros(oshape, np.int16)
+    orc.fast_countour_mip(i16, 2.0, axis, 300, 600, 0, out)
+    assert np.array_equal(out, tmp.max(axis))
+    orc.fast_countour_mip(i16, 2.0, axis, 300, 600, 1, out)
+    assert np.array_equal(out, _lmip_numpy(tmp, axis, 700, 3033))
+    orc.fast_countour_mip(i16, 2.0, axis, 300, 600, 2, out)
+    assert np.array_equal(out, _mida_numpy(tmp, axis, 300, 600))
