@@ -294,3 +294,20 @@ def test_projections_against_second_restatements(orc, axis):
     assert np.array_equal(out, _lmip_numpy(tmp, axis, 700, 3033))
     orc.fast_countour_mip(i16, 2.0, axis, 300, 600, 2, out)
     assert np.array_equal(out, _mida_numpy(tmp, axis, 300, 600))
+
+
+@pytest.mark.parametrize("shape", [(1, 5, 7), (4, 1, 3), (3, 4, 1), (2, 2, 2), (17, 3, 29)])
+def test_projection_restatements_agree_on_thin_and_ragged_volumes(orc, shape):
+    """Single-plane, single-row, single-column and ragged volumes: the ray loops, the clamped
+    differences of the contour volume and the output shapes for every axis."""
+    rng = np.random.default_rng(sum(shape))
+    i16 = rng.integers(-1000, 3000, shape).astype(np.int16)
+    for axis in (0, 1, 2):
+        oshape = tuple(s for a, s in enumerate(shape) if a != axis)
+        out = np.zeros(oshape, np.int16)
+        orc.lmip(i16, axis, 700, 3033, out)
+        assert np.array_equal(out, _lmip_numpy(i16, axis, 700, 3033))
+        orc.mida(i16, axis, 300, 600, out)
+        assert np.array_equal(out, _mida_numpy(i16, axis, 300, 600))
+        for n in (1, 2):
+            assert np.array_equal(orc.fcm_volume(i16, float(n), axis), _fcm_numpy(i16, n, axis))
