@@ -476,7 +476,7 @@ def ws_whole(g, mk, alg, ww_wl):
     return ws_model.flood(pre, m, 1 if alg == "Watershed" else 0)
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_watershed_ranks(orc, world):
     out = run_ranks("rank_watershed", "test_dist_gloo", world=world)
     g, mk = ws_case()
@@ -513,7 +513,7 @@ def rank_fill_holes(rank, world, device):
     return res
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_fill_holes_ranks(orc, world):
     out = run_ranks("rank_fill_holes", "test_dist_gloo", world=world)
     mask, labels, nlabels = fh_case()
@@ -523,3 +523,33 @@ def test_fill_holes_ranks(orc, world):
         got = np.concatenate([out[r][max_size][1] for r in range(world)])
         assert np.array_equal(got, want), max_size
         assert all(out[r][max_size][0] == ret for r in range(world)), max_size
+
+
+# ---- four ranks, uneven slabs (23 planes -> 6, 6, 6, 5): the same protocols across three boundaries
+def test_floodfill_four_ranks(orc):
+    world = 4
+    out = run_ranks("rank_floodfill", "test_dist_gloo", world=world)
+    g = global_volume()
+    for case, (strct, seeds) in enumerate(ff_cases(g)):
+        want = np.zeros(g.shape, np.uint8); want[:, 10, :] = 254
+        orc.floodfill_threshold(g, seeds, 100, 3071, 254, strct, want)
+        assert [out[r][case][0] for r in range(1, world)] == [out[r][case][1] for r in range(world - 1)]
+        got = np.concatenate([out[r][case][2] for r in range(world)])
+        assert np.array_equal(got, want), case
+        grown = (want == 254); grown[:, 10, :] = False
+        assert all(grown[out[r][case][0]:out[r][case][1]].any() for r in range(world))   # every shard takes part
+        assert len({out[r][case][3] for r in range(world)}) == 1                          # one vote, one round count
+
+
+def test_marching_cubes_four_ranks(orc):
+    world = 4
+    out = run_ranks("rank_mc", "test_dist_gloo", world=world)
+    g = global_volume()
+    mask = ((g >= THR[0]) & (g <= THR[1])).astype(np.uint8) * 255
+    V, T = orc.marching_cubes(mask, 127, (0.5, 0.75, 1.5), (-1, -1, 3), True)
+    gv = np.concatenate([out[r][0] for r in range(world)])
+    gt = np.concatenate([out[r][1] for r in range(world)])
+    assert all(out[r][3] == len(V) and out[r][4] == len(T) for r in range(world))
+    assert [out[r][2] for r in range(world)] == np.cumsum([0] + [len(out[r][0]) for r in range(world - 1)]).tolist()
+    assert np.array_equal(gv, V)
+    assert np.array_equal(gt.astype(np.int64), T)
